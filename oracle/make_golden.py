@@ -1,0 +1,299 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt by running the REFERENCE'S OWN
+Python (imported from /root/reference, which exists only in the build container) on seeded
+synthetic inputs.  Run:  python -m oracle.make_golden
+
+What is exercised from the reference, unmodified unless noted:
+  utils/common.py   get_samples, get_samples_by_class, get_rays_from_uv, sample_along_rays,
+                    feature_matching, raw2nerf_color, get_opacity_loss, get_rotation_from_quad
+                    (quad2rotation source-patched P2: ``.to(quad.get_device())`` -> ``.to(quad.device)``)
+  models/decoder.py Decoder / Pos_Encoding / Coarse / Out / Merge (on the tcnn stand-in)
+  slams/tracking.py Tracker.get_target_samples, renderer, compute_*_loss
+  slams/mapping.py  Mapper.get_target_samples, fine_fn, renderer, compute_*_loss, smoothness
+                    (source-patched P1: ``reshape(pts_shape[:3], 1)`` -> ``reshape(*pts_shape[:3], 1)``)
+Stubbed modules: tinycudann (-> oracle.tcnn_standin), mathutils, matplotlib.pyplot, colorama.
+Random draws (torch.randint / torch.rand) are recorded in call order (patch P5) so that the
+restatement in oracle/reference_path.py can replay them.
+"""
+import inspect
+import os
+import sys
+import textwrap
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import tcnn_standin  # noqa: E402
+from oracle import reference_path as rp  # noqa: E402
+from dns_slam_b200 import synthetic as syn  # noqa: E402
+
+REF = "/root/reference"
+
+
+def import_reference():
+    sys.modules["tinycudann"] = tcnn_standin
+    mu = types.ModuleType("mathutils")
+    mu.Matrix = object
+    sys.modules["mathutils"] = mu
+    co = types.ModuleType("colorama")
+    co.Fore = types.SimpleNamespace(MAGENTA="", GREEN="", CYAN="", RED="", YELLOW="", BLUE="")
+    co.Style = types.SimpleNamespace(RESET_ALL="")
+    sys.modules["colorama"] = co
+    mp_, pp = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    mp_.pyplot = pp
+    sys.modules.setdefault("matplotlib", mp_)
+    sys.modules.setdefault("matplotlib.pyplot", pp)
+    sys.path.insert(0, REF)
+    import utils.common as C
+    import models.decoder as D
+    import slams.tracking as T
+    import slams.mapping as M
+    # P2
+    src = inspect.getsource(C.quad2rotation).replace(".to(quad.get_device())", ".to(quad.device)")
+    exec(src, C.__dict__)
+    # P1
+    src = textwrap.dedent(inspect.getsource(M.Mapper.smoothness)).replace(
+        "occ.reshape(pts_shape[:3], 1)", "occ.reshape(*pts_shape[:3], 1)")
+    ns = {}
+    exec(src, M.__dict__, ns)
+    M.Mapper.smoothness = ns["smoothness"]
+    return C, D, T, M
+
+
+class Recorder:
+    """Records every torch.randint / torch.rand result while active."""
+
+    def __init__(self):
+        self.items = []
+
+    def __enter__(self):
+        self._ri, self._r = torch.randint, torch.rand
+
+        def randint(*a, **k):
+            v = self._ri(*a, **k)
+            self.items.append(("randint", v.detach().cpu().clone()))
+            return v
+
+        def rand(*a, **k):
+            v = self._r(*a, **k)
+            self.items.append(("rand", v.detach().cpu().clone()))
+            return v
+
+        torch.randint, torch.rand = randint, rand
+        return self
+
+    def __exit__(self, *exc):
+        torch.randint, torch.rand = self._ri, self._r
+
+
+def build_models(shape, n_class, seed, table_scale=3000.0, expert_classes=()):
+    """Oracle-side models with distinct seeded weights; the hash table is scaled up so that the
+    grid features are O(0.3) and parity tests actually exercise them."""
+    bound = syn.load_bound(syn.SHAPES[shape]["bound"])
+    dec = rp.Decoder(syn.model_cfg(shape), bound, n_class=n_class, seed=seed)
+    with torch.no_grad():
+        dec.pe_fn.grid_fn.params.mul_(table_scale)
+    experts = {int(c): rp.new_expert(seed=seed + 100 + int(c)) for c in expert_classes}
+    return bound, dec, experts
+
+
+def grad_summary(g):
+    """Compact fingerprint of a large gradient (the hash table)."""
+    g = g.detach().reshape(-1)
+    stride = max(g.numel() // 4096, 1)
+    return dict(sum=g.double().sum(), abssum=g.double().abs().sum(), nnz=(g != 0).sum(),
+                strided=g[::stride].clone(), stride=stride)
+
+
+def clone_tree(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().clone()
+    if isinstance(x, dict):
+        return {k: clone_tree(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [clone_tree(v) for v in x]
+    return x
+
+
+def tracking_case(C, D, T, shape="tiny", n_class=6, seed=11):
+    s = syn.SHAPES[shape]
+    gen = torch.Generator().manual_seed(seed)
+    bound, odec, _ = build_models(shape, n_class, seed)
+    dec = D.Decoder(syn.model_cfg(shape), bound, n_class=n_class)
+    dec.load_state_dict(odec.state_dict())
+    cam = syn.camera(shape)
+    poses = syn.trajectory(shape, 6)
+    fr = syn.frame(shape, poses[3], gen, n_class=n_class)
+    feats = syn.pixel_features(shape, 2, gen)
+
+    trk = object.__new__(T.Tracker)
+    trk.device = "cpu"
+    trk.bound = bound
+    for k in ("H", "W", "fx", "fy", "cx", "cy"):
+        setattr(trk, k, cam[k])
+    trk.K = cam["K"]
+    trk.n_pixels, trk.n_samples_ray, trk.n_surface_ray = s["tracking_pixels"], 32, 15
+    trk.decoder = dec
+    trk.lambda_p, trk.lambda_d, trk.lambda_l = s["lambda_color"], s["lambda_depth"], s["lambda_label"]
+
+    est = poses[3].clone()
+    est[:3, 3] += torch.tensor([0.01, -0.02, 0.015])
+    quad = rp.quad_from_matrix(est[:3, :3].numpy()).clone().requires_grad_(True)
+    Tt = est[:3, 3].clone().requires_grad_(True)
+    refer_w2c = torch.inverse(poses[2])
+    bottom = torch.tensor([[0, 0, 0, 1.0]])
+    R = C.get_rotation_from_quad(quad)
+    cur_c2w = torch.cat([torch.cat((R, Tt[:, None]), -1), bottom], 0)
+    est_w2c = torch.stack((refer_w2c, torch.inverse(cur_c2w)), 0)
+    cur = {"gt_color": fr["color"], "gt_depth": fr["depth"], "gt_label": fr["label"],
+           "est_quad": quad, "est_T": Tt}
+    with Recorder() as rec:
+        samples = trk.get_target_samples(cur, {"est_w2c": est_w2c}, [feats])
+    pc, pd, pv, pl = trk.renderer(samples)
+    p = trk.compute_photometric_loss(samples["gt_color"], pc, samples["mask"])
+    d = trk.compute_depth_loss(samples["gt_depth"], pd, pv, samples["mask"])
+    l = trk.compute_label_loss(samples["gt_label"], pl, samples["mask"])
+    loss = trk.lambda_p * p + trk.lambda_d * d + trk.lambda_l * l
+    loss.backward()
+    sd = {k: v for k, v in dec.named_parameters()}
+    out = dict(
+        meta=dict(shape=shape, n_class=n_class, seed=seed, n_samples=32, n_surface=15,
+                  pose_index=3, refer_index=2),
+        quad=quad.detach().clone(), T=Tt.detach().clone(), tape=rec.items,
+        samples={k: (torch.from_numpy(v) if not isinstance(v, torch.Tensor) else v.detach().clone())
+                 for k, v in samples.items()},
+        pred=dict(color=pc.detach(), depth=pd.detach(), var=pv.detach(), logits=pl.detach()),
+        loss=dict(p=p.detach(), d=d.detach(), l=l.detach(), total=loss.detach()),
+        grad=dict(quad=quad.grad.clone(), T=Tt.grad.clone(),
+                  coarse=sd["coarse_fn.decoder.params"].grad.clone(),
+                  color=sd["out_fn.color_decoder.params"].grad.clone(),
+                  logit=sd["out_fn.logit_decoder.params"].grad.clone(),
+                  merge=sd["merge.decoder.params"].grad.clone(),
+                  table=grad_summary(sd["pe_fn.grid_fn.params"].grad)),
+        table_checksum=dec.pe_fn.grid_fn.params.detach().double().sum(),
+    )
+    return out
+
+
+def mapping_case(C, D, M, shape="tiny", n_class=6, seed=23):
+    s = syn.SHAPES[shape]
+    gen = torch.Generator().manual_seed(seed)
+    bound, odec, oexp = build_models(shape, n_class, seed, expert_classes=range(n_class))
+    dec = D.Decoder(syn.model_cfg(shape), bound, n_class=n_class)
+    dec.load_state_dict(odec.state_dict())
+    cam = syn.camera(shape)
+    poses = syn.trajectory(shape, 8)
+    tgt_ids = [1, 4, 6]                      # keyframe ids of the target frames
+    frames = [syn.frame(shape, poses[i], gen, n_class=n_class) for i in tgt_ids]
+    feats = [syn.pixel_features(shape, 3, gen) for _ in tgt_ids]
+
+    mp = object.__new__(M.Mapper)
+    mp.device = "cpu"
+    mp.bound = bound
+    for k in ("H", "W", "fx", "fy", "cx", "cy"):
+        setattr(mp, k, cam[k])
+    mp.K = cam["K"]
+    mp.n_pixels, mp.n_target_frame = s["mapping_pixels"], len(tgt_ids)
+    mp.n_samples_ray, mp.n_surface_ray = 32, 15
+    mp.decoder, mp.hidden_dim = dec, 32
+    mp.fine_decoders = {}
+    for c, net in oexp.items():
+        e = tcnn_standin.Network(80, 33, dict(rp._MLP_CFG))
+        e.load_state_dict(net.state_dict())
+        mp.fine_decoders[c] = e
+    mp.cfg = {"training": {"smooth_pts": s["smooth_pts"], "opacity_sigma": s["opacity_sigma"]}}
+
+    quad_list, T_list = [], []
+    for n, i in enumerate(tgt_ids):
+        est = poses[i].clone()
+        est[:3, 3] += 0.01 * (n + 1)
+        q = rp.quad_from_matrix(est[:3, :3].numpy()).clone()
+        t = est[:3, 3].clone()
+        if n != 0:
+            q.requires_grad_(True)
+            t.requires_grad_(True)
+        quad_list.append(q)
+        T_list.append(t)
+    # reference views: two keyframes + the frame itself (-1); one id is itself a target frame
+    refer_idx = [[0, 4, -1], [1, 2, -1], [4, 5, -1]]
+    refer_c2w = [[poses[k if k >= 0 else tgt_ids[f]].clone() for k in ids] for f, ids in enumerate(refer_idx)]
+    target_frames = {"kf_idx": tgt_ids, "gt_color": [f["color"] for f in frames],
+                     "gt_depth": [f["depth"] for f in frames], "gt_label": [f["label"] for f in frames]}
+    refer_frames = {"kf_idx": refer_idx, "est_c2w": refer_c2w}
+    with Recorder() as rec:
+        samples = mp.get_target_samples(target_frames, quad_list, T_list, refer_frames=refer_frames,
+                                        features=feats)
+        pc, pd, pv, pl, fine, coarse = mp.renderer(samples)
+        d = mp.compute_depth_loss(samples["gt_depth"], pd)
+        p = mp.compute_photometric_loss(samples["gt_color"], pc)
+        l = mp.compute_label_loss(samples["gt_label"], pl)
+        lt = mp.compute_latent_loss(coarse, fine)
+        sm = mp.smoothness(sample_points=s["smooth_pts"])
+        fs, op = C.get_opacity_loss(samples["z_vals"], samples["gt_depth"], fine[..., -1], s["opacity_sigma"])
+    lam_sm = 0.05                      # larger than the yaml value so the TV gradient is visible
+    loss = s["lambda_color"] * p + s["lambda_depth"] * d + s["lambda_label"] * l + 10 * lt \
+        + lam_sm * sm + s["lambda_fs"] * fs + s["lambda_opacity"] * op
+    loss.backward()
+    sd = {k: v for k, v in dec.named_parameters()}
+    out = dict(
+        meta=dict(shape=shape, n_class=n_class, seed=seed, n_samples=32, n_surface=15,
+                  tgt_ids=tgt_ids, refer_idx=refer_idx, lambda_lt=10.0, lambda_sm=lam_sm),
+        quad=[q.detach().clone() for q in quad_list], T=[t.detach().clone() for t in T_list],
+        tape=rec.items, samples=clone_tree(samples),
+        pred=dict(color=pc.detach(), depth=pd.detach(), var=pv.detach(), logits=pl.detach(),
+                  fine=fine.detach(), coarse=coarse.detach()),
+        loss=dict(p=p.detach(), d=d.detach(), l=l.detach(), lt=lt.detach(), sm=sm.detach(),
+                  fs=fs.detach(), op=op.detach(), total=loss.detach()),
+        grad=dict(quad=[None if q.grad is None else q.grad.clone() for q in quad_list],
+                  T=[None if t.grad is None else t.grad.clone() for t in T_list],
+                  coarse=sd["coarse_fn.decoder.params"].grad.clone(),
+                  color=sd["out_fn.color_decoder.params"].grad.clone(),
+                  logit=sd["out_fn.logit_decoder.params"].grad.clone(),
+                  merge=sd["merge.decoder.params"].grad.clone(),
+                  experts={c: (None if e.params.grad is None else e.params.grad.clone())
+                           for c, e in mp.fine_decoders.items()},
+                  table=grad_summary(sd["pe_fn.grid_fn.params"].grad)),
+        table_checksum=dec.pe_fn.grid_fn.params.detach().double().sum(),
+    )
+    return out
+
+
+def kernels_case(C):
+    """Stand-alone known-answer vectors of the small reference functions."""
+    g = torch.Generator().manual_seed(5)
+    quad = torch.randn(5, 4, generator=g)
+    raw = torch.randn(7, 11, 4, generator=g)
+    z = torch.sort(torch.rand(7, 11, generator=g) * 3 + 0.2, -1)[0]
+    rays_d = torch.randn(7, 3, generator=g)
+    depth_map, depth_var, rgb_map, w = C.raw2nerf_color(raw, z, rays_d, device="cpu")
+    gd = torch.rand(7, generator=g) * 3
+    gd[2] = 0.0
+    occ = torch.randn(7 * 11, generator=g)
+    fs, op = C.get_opacity_loss(z, gd, occ, 0.05)
+    depth = torch.rand(9, generator=g) * 4
+    depth[1] = 0.0
+    far_bb = (depth * 1.5 + 0.3).double().unsqueeze(-1)
+    with Recorder() as rec:
+        zv = C.sample_along_rays(depth, 32, 15, far_bb, "cpu")
+    return dict(quad=quad, R=C.quad2rotation(quad), raw=raw, z=z, depth_map=depth_map,
+                depth_var=depth_var, rgb_map=rgb_map, weights=w, gd=gd, occ=occ, fs=fs, op=op,
+                sar_depth=depth, sar_far=far_bb, sar_tape=rec.items, sar_z=zv)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    C, D, T, M = import_reference()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    torch.save(kernels_case(C), os.path.join(out_dir, "kernels.pt"))
+    torch.save(tracking_case(C, D, T), os.path.join(out_dir, "tracking_tiny.pt"))
+    torch.save(mapping_case(C, D, M), os.path.join(out_dir, "mapping_tiny.pt"))
+    for f in sorted(os.listdir(out_dir)):
+        print(f, os.path.getsize(os.path.join(out_dir, f)))
+
+
+if __name__ == "__main__":
+    main()
