@@ -1,0 +1,146 @@
+"""ctypes binding of ``libdns_slam_b200.so`` (C ABI declared in ``include/dns_slam_b200.h``).
+
+The library is a plain nvcc-built shared object living next to this file; it is loaded with
+``ctypes`` (no torch extension machinery at run time).  Tensors cross the boundary as raw
+device pointers (``tensor.data_ptr()``) plus the current CUDA stream.  There is no CPU
+fallback: if the library is missing, or a tensor is not a contiguous CUDA tensor of the
+expected dtype, the call raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdns_slam_b200.so")
+
+MAX_LEVELS = 16
+MODE_TRACK, MODE_MAP = 0, 1
+
+
+class Grid(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("n_features", C.c_int32),
+                ("scale", C.c_float * MAX_LEVELS), ("res", C.c_uint32 * MAX_LEVELS),
+                ("size", C.c_uint32 * MAX_LEVELS), ("offset", C.c_uint32 * (MAX_LEVELS + 1)),
+                ("hashed", C.c_uint32 * MAX_LEVELS)]
+
+
+_P = C.c_void_p
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("n_rays", C.c_int32), ("n_samples", C.c_int32),
+                ("n_class", C.c_int32), ("n_experts", C.c_int32), ("need_dparams", C.c_int32),
+                ("need_drays", C.c_int32), ("need_dfeat", C.c_int32),
+                ("bound", (C.c_double * 2) * 3),
+                ("lambda_p", C.c_float), ("lambda_d", C.c_float), ("lambda_l", C.c_float),
+                ("lambda_lt", C.c_float), ("lambda_fs", C.c_float), ("lambda_op", C.c_float),
+                ("opacity_trunc", C.c_float), ("opacity_sigma", C.c_float),
+                ("grid", Grid),
+                ("rays_o", _P), ("rays_d", _P), ("z_vals", _P), ("gt_color", _P), ("gt_depth", _P),
+                ("gt_label", _P), ("mask", _P), ("features", _P),
+                ("table", _P), ("coarse", _P), ("color", _P), ("logit", _P), ("experts", _P),
+                ("class_to_expert", _P), ("n_class_ids", C.c_int32),
+                ("pred_color", _P), ("pred_depth", _P), ("pred_var", _P), ("pred_logits", _P),
+                ("fine", _P), ("coarse_out", _P), ("losses", _P),
+                ("d_table", _P), ("d_coarse", _P), ("d_color", _P), ("d_logit", _P),
+                ("d_experts", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("d_features", _P),
+                ("workspace", _P), ("workspace_bytes", C.c_int64)]
+
+
+class TvArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("smooth_pts", C.c_int32), ("voxel", C.c_double),
+                ("bound", (C.c_double * 2) * 3), ("offset", C.c_double * 3),
+                ("jitter", C.c_double * 3), ("lambda_sm", C.c_float), ("need_dparams", C.c_int32),
+                ("grid", Grid), ("table", _P), ("coarse", _P), ("loss", _P), ("d_table", _P),
+                ("d_coarse", _P), ("workspace", _P), ("workspace_bytes", C.c_int64)]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("H0", C.c_int32),
+                ("W0", C.c_int32), ("Ww", C.c_int32), ("n_uniform", C.c_int32),
+                ("n_surface", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("bound", (C.c_double * 2) * 3),
+                ("color", _P), ("depth", _P), ("label", _P), ("index", _P), ("R", _P), ("T", _P),
+                ("t_lin", _P), ("t_surface", _P), ("t_zero", _P),
+                ("gt_color", _P), ("gt_depth", _P), ("gt_label", _P), ("rays_o", _P),
+                ("rays_d", _P), ("z_vals", _P), ("pts", _P), ("inside", _P), ("scratch", _P)]
+
+
+_lib = None
+
+# every symbol include/dns_slam_b200.h declares
+SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_oneblob_fwd", "dns_oneblob_bwd",
+           "dns_hashgrid_fwd", "dns_hashgrid_bwd", "dns_hashgrid_indices", "dns_mlp_fwd",
+           "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd",
+           "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
+           "dns_adam_step"]
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C dns_slam_b200/csrc`). dns_slam_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.dns_last_error.restype = C.c_char_p
+    L.dns_render_workspace_bytes.restype = C.c_int64
+    L.dns_tv_workspace_bytes.restype = C.c_int64
+    i64, i32, f32 = C.c_int64, C.c_int, C.c_float
+    L.dns_struct_sizes.argtypes = [C.POINTER(C.c_int64)]
+    L.dns_oneblob_fwd.argtypes = [_P, i64, i32, i32, _P, _P]
+    L.dns_oneblob_bwd.argtypes = [_P, _P, i64, i32, i32, _P, _P]
+    L.dns_hashgrid_fwd.argtypes = [C.POINTER(Grid), _P, _P, i64, _P, _P]
+    L.dns_hashgrid_bwd.argtypes = [C.POINTER(Grid), _P, _P, _P, i64, _P, _P, _P]
+    L.dns_hashgrid_indices.argtypes = [C.POINTER(Grid), _P, i64, _P, _P]
+    L.dns_mlp_fwd.argtypes = [_P, _P, i64, i32, i32, _P, _P, _P]
+    L.dns_mlp_bwd.argtypes = [_P, _P, _P, _P, i64, i32, i32, _P, _P, _P, _P]
+    L.dns_render_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.dns_render_fwd_bwd.argtypes = [C.POINTER(RenderArgs), _P]
+    L.dns_tv_workspace_bytes.argtypes = [i32]
+    L.dns_tv_fwd_bwd.argtypes = [C.POINTER(TvArgs), _P]
+    L.dns_sample_rays.argtypes = [C.POINTER(SampleArgs), _P]
+    L.dns_feature_gather.argtypes = [_P, i64, _P, i32, _P, i32, i32, _P, i32, i32, i32, _P, _P, _P, _P]
+    L.dns_adam_step.argtypes = [_P, _P, _P, _P, i64, f32, f32, f32, f32, i32, _P]
+    sizes = (C.c_int64 * 4)()
+    L.dns_struct_sizes(sizes)
+    mine = [C.sizeof(Grid), C.sizeof(RenderArgs), C.sizeof(TvArgs), C.sizeof(SampleArgs)]
+    if list(sizes) != mine:
+        raise RuntimeError(f"ctypes struct layout {mine} != C layout {list(sizes)}; rebuild the library")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("dns_slam_b200: " + lib().dns_last_error().decode())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, dtype=None, allow_none=False):
+    """Raw device pointer of a contiguous CUDA tensor (raises otherwise: no host fallback)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("dns_slam_b200: required tensor is None")
+    if not t.is_cuda:
+        raise RuntimeError("dns_slam_b200 runs on CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("dns_slam_b200: tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"dns_slam_b200: expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def fill_bound(dst, bound):
+    b = bound.detach().double().cpu()
+    for a in range(3):
+        dst[a][0] = float(b[a, 0])
+        dst[a][1] = float(b[a, 1])

@@ -1,0 +1,239 @@
+// Shared device helpers of the dns_slam_b200 kernels (sm_100a).
+//
+// Encodings follow the tiny-cuda-nn algorithms the reference reaches through
+// models/pos_encoding.py:31-46 (HashGrid) and :61-71 (OneBlob); MLPs follow
+// models/decoder.py:58-65 (bias-free 1-hidden-layer ReLU networks of width 32).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dns_slam_b200.h"
+
+namespace dns {
+
+constexpr int kTile = 128;   // slots per point tile / threads per point CTA
+constexpr int kXld = 81;     // odd leading dimension of the [slot][80] smem tile: conflict free
+constexpr int kIn1 = 80;     // OneBlob 48 + grid 32
+constexpr int kIn2 = 112;    // OneBlob 48 + latent 32 + pixel feature 32
+constexpr int kOutP = 36;    // 33 latent channels padded to a multiple of 4
+constexpr int kNetT = kIn1 * 32 + 32 * kOutP;  // transposed coarse/expert block in the workspace
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+// ---------------------------------------------------------------------------------------
+// OneBlob (16-bin periodic quartic kernel)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float q_cdf(float u) {
+  float u2 = u * u, u4 = u2 * u2;
+  float v = (15.0f / 16.0f) * u * (1.0f - (2.0f / 3.0f) * u2 + (1.0f / 5.0f) * u4) + 0.5f;
+  return fminf(fmaxf(v, 0.0f), 1.0f);
+}
+__device__ __forceinline__ float q_pdf(float u) {  // d q_cdf / du (0 where the clamp is active)
+  float t = 1.0f - u * u;
+  return fabsf(u) < 1.0f ? (15.0f / 16.0f) * t * t : 0.0f;
+}
+__device__ __forceinline__ float cdf3(float d, float nb) {
+  return q_cdf(d * nb) + q_cdf((d - 1.0f) * nb) + q_cdf((d + 1.0f) * nb);
+}
+__device__ __forceinline__ float pdf3(float d, float nb) {
+  return q_pdf(d * nb) + q_pdf((d - 1.0f) * nb) + q_pdf((d + 1.0f) * nb);
+}
+// out[b] = cdf3((b+1)/nb - x) - cdf3(b/nb - x), b = 0..nb-1, written with stride `st`
+__device__ __forceinline__ void oneblob_fwd(float x, int nb, float* out, int st) {
+  float fnb = (float)nb;
+  float prev = cdf3(0.0f - x, fnb);
+  for (int b = 0; b < nb; ++b) {
+    float cur = cdf3((float)(b + 1) / fnb - x, fnb);
+    out[b * st] = cur - prev;
+    prev = cur;
+  }
+}
+// dL/dx = sum_b d_out[b] * -(nb) * (pdf3(right - x) - pdf3(left - x))
+__device__ __forceinline__ float oneblob_bwd(float x, int nb, const float* d_out, int st) {
+  float fnb = (float)nb;
+  float prev = pdf3(0.0f - x, fnb);
+  float acc = 0.0f;
+  for (int b = 0; b < nb; ++b) {
+    float cur = pdf3((float)(b + 1) / fnb - x, fnb);
+    acc += d_out[b * st] * (cur - prev);
+    prev = cur;
+  }
+  return -fnb * acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Hash grid
+// ---------------------------------------------------------------------------------------
+// pos = fmaf(scale, x, 0.5) emulated through double so that CPU oracle and GPU agree bit for
+// bit (the double product of two floats is exact).
+__device__ __forceinline__ void grid_pos(float x, float scale, uint32_t& g, float& w) {
+  double pd = (double)x * (double)scale + 0.5;
+  float pos = (float)pd;
+  float fl = floorf(pos);
+  g = (uint32_t)(int)fl;
+  w = pos - fl;
+}
+__device__ __forceinline__ uint32_t corner_index(const dns_grid& G, int l, uint32_t cx, uint32_t cy,
+                                                 uint32_t cz) {
+  uint32_t size = G.size[l], idx;
+  if (G.hashed[l]) {
+    idx = (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (size - 1u);  // size == 2^log2_T
+  } else {
+    uint32_t res = G.res[l];
+    idx = cx + cy * res + cz * (res * res);
+    if (idx >= size) idx %= size;
+  }
+  return idx + G.offset[l];
+}
+
+// forward of all levels for one point; out[2l+f] written with stride st
+__device__ __forceinline__ void hashgrid_fwd(const dns_grid& G, const float2* __restrict__ table,
+                                             const float x[3], float* out, int st) {
+#pragma unroll 2
+  for (int l = 0; l < G.n_levels; ++l) {
+    uint32_t g[3];
+    float w[3];
+    float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      v[c] = __ldg(table + corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+      a0 += wt * v[c].x;
+      a1 += wt * v[c].y;
+    }
+    out[(2 * l) * st] = a0;
+    out[(2 * l + 1) * st] = a1;
+  }
+}
+
+// backward of all levels for one point: scatter into d_table (if non-null) and return dL/dx
+// (if want_dx).  d_out[2l+f] read with stride st.
+__device__ __forceinline__ void hashgrid_bwd(const dns_grid& G, const float2* __restrict__ table,
+                                             float2* d_table, const float x[3], const float* d_out,
+                                             int st, bool want_dx, float dx[3]) {
+  dx[0] = dx[1] = dx[2] = 0.f;
+#pragma unroll 1
+  for (int l = 0; l < G.n_levels; ++l) {
+    float g0 = d_out[(2 * l) * st], g1 = d_out[(2 * l + 1) * st];
+    if (g0 == 0.f && g1 == 0.f) continue;
+    uint32_t g[3];
+    float w[3];
+    float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    uint32_t idx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      idx[c] = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+    if (d_table) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+        atomicAdd(d_table + idx[c], make_float2(wt * g0, wt * g1));
+      }
+    }
+    if (want_dx) {
+      float s[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float2 v = __ldg(table + idx[c]);
+        s[c] = v.x * g0 + v.y * g1;
+      }
+      float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
+      // d/dw_x: corners differing in bit 0
+      dx[0] += sc * (wy0 * wz0 * (s[1] - s[0]) + w[1] * wz0 * (s[3] - s[2]) + wy0 * w[2] * (s[5] - s[4]) +
+                     w[1] * w[2] * (s[7] - s[6]));
+      dx[1] += sc * (wx0 * wz0 * (s[2] - s[0]) + w[0] * wz0 * (s[3] - s[1]) + wx0 * w[2] * (s[6] - s[4]) +
+                     w[0] * w[2] * (s[7] - s[5]));
+      dx[2] += sc * (wx0 * wy0 * (s[4] - s[0]) + w[0] * wy0 * (s[5] - s[1]) + wx0 * w[1] * (s[6] - s[2]) +
+                     w[0] * w[1] * (s[7] - s[3]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// point geometry (slams/tracking.py:160,189-190; slams/mapping.py:531,604-608)
+// ---------------------------------------------------------------------------------------
+struct Bound {
+  double lo[3];
+  double ext[3];  // hi - lo, float64
+};
+// pts = o + d * z in fp32 (separate multiply and add, as torch evaluates it), then
+// x = float((double(pts) - lo) / (hi - lo))
+__device__ __forceinline__ void point_from_ray(const float* __restrict__ o, const float* __restrict__ d,
+                                               float z, const Bound& B, float x[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float pt = __fadd_rn(o[a], __fmul_rn(d[a], z));
+    x[a] = (float)(((double)pt - B.lo[a]) / B.ext[a]);
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+
+// ---------------------------------------------------------------------------------------
+// thread-per-point MLP pieces; weights in shared memory, k-major (W1T [K][32]) so that
+// every lane reads the same 16 bytes (broadcast), activations in registers.
+// ---------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void zero(float (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = 0.f;
+}
+// h[0..31] += sum_k x[k*xs] * W1T[(k0+k)*ld + col0 + j]
+template <int NOUT>
+__device__ __forceinline__ void accum_layer(const float* __restrict__ x, int xs, int K,
+                                            const float* __restrict__ WT, int ld, float (&h)[NOUT]) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    float xv = x[k * xs];
+    const float4* w = reinterpret_cast<const float4*>(WT + k * ld);
+#pragma unroll
+    for (int q = 0; q < NOUT / 4; ++q) {
+      float4 v = w[q];
+      h[4 * q + 0] = fmaf(xv, v.x, h[4 * q + 0]);
+      h[4 * q + 1] = fmaf(xv, v.y, h[4 * q + 1]);
+      h[4 * q + 2] = fmaf(xv, v.z, h[4 * q + 2]);
+      h[4 * q + 3] = fmaf(xv, v.w, h[4 * q + 3]);
+    }
+  }
+}
+// dot of a register vector with one row of a k-major weight matrix: sum_j v[j] * W[row*ld + j]
+template <int N>
+__device__ __forceinline__ float dot_row(const float (&v)[N], const float* __restrict__ Wrow) {
+  const float4* w = reinterpret_cast<const float4*>(Wrow);
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    float4 t = w[q];
+    acc = fmaf(v[4 * q + 0], t.x, acc);
+    acc = fmaf(v[4 * q + 1], t.y, acc);
+    acc = fmaf(v[4 * q + 2], t.z, acc);
+    acc = fmaf(v[4 * q + 3], t.w, acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red /*[32]*/) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  v = (l < nw) ? red[l] : 0.f;
+  if (w == 0)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;  // valid in warp 0
+}
+
+}  // namespace dns

@@ -1,0 +1,1184 @@
+// Fused render + loss + backward of the DNS-SLAM inner loop (sm_100a).
+//
+// Restates, as three point/ray kernels plus weight-gradient GEMMs:
+//   Tracker.renderer + losses   slams/tracking.py:188-214, 85-96, 326-338
+//   Mapper.renderer + fine_fn   slams/mapping.py:590-635   (class(p) = label[p mod N] quirk)
+//   mapping losses              slams/mapping.py:110-126, 891-907; utils/common.py:769-802
+//   occupancy compositing       utils/common.py:506-537
+//   Mapper.smoothness           slams/mapping.py:129-159 (TV of the coarse occupancy)
+//
+// Pipeline for one chunk of rays (slots = points regrouped so that every 128-slot tile has
+// ONE semantic class -> one expert MLP per tile, weights broadcast from shared memory):
+//   k_point_fwd   encode (OneBlob + hash grid) -> coarse MLP [-> expert MLP] -> latents, lt/fs/op
+//   k_ray         out_fn (colour + logit layer 1 per point, logit layer 2 per RAY: it is linear,
+//                 so it commutes with compositing) -> compositing -> p/d/l losses -> backward
+//                 down to d(latents), d(features), d(rays)
+//   k_point_bwd   lt/fs/op gradients + d(latents) -> MLP backward -> hash-table scatter, d(rays)
+//   k_dw_gemm     dW = X^T dH for every MLP from stashed activations (ops.cu)
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dns {
+
+int launch_dw_gemm(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows,
+                   const int* n_tiles_dev, int n_tiles_host, const int* tile_class, float* C, int ldc,
+                   int64_t c_stride, cudaStream_t st);
+
+enum { kTrack = 0, kMap = 1, kTv = 2 };
+// counts[] slots
+enum { cMask = 0, cDpos = 1, cFront = 2, cBand = 3, cTiles = 4, cErr = 5 };
+// raw loss sums
+enum { rP = 0, rD = 1, rL = 2, rLt = 3, rFs = 4, rOp = 5 };
+
+// ---------------------------------------------------------------------------------------
+// weight re-layout (once per call): tcnn row-major -> k-major blocks read with broadcast LDS.128
+// ---------------------------------------------------------------------------------------
+// params [n][4096] = W1[32][80] | W2[48][32]  ->  WT [n][kNetT] = W1T[80][32] | W2T[32][36]
+__global__ void k_transpose_net80(const float* __restrict__ params, float* __restrict__ WT) {
+  const float* p = params + (int64_t)blockIdx.x * 4096;
+  float* w = WT + (int64_t)blockIdx.x * kNetT;
+  for (int i = threadIdx.x; i < 2560; i += blockDim.x) {
+    int k = i >> 5, j = i & 31;
+    w[i] = p[j * 80 + k];
+  }
+  for (int i = threadIdx.x; i < 32 * kOutP; i += blockDim.x) {
+    int j = i / kOutP, c = i - j * kOutP;
+    w[2560 + i] = c < DNS_LATENT ? p[2560 + c * 32 + j] : 0.f;
+  }
+}
+// colour / logit nets: W1T2 [112][64] (cols 0..31 colour hidden, 32..63 logit hidden), W2cT [32][4]
+__global__ void k_transpose_out(const float* __restrict__ color, const float* __restrict__ logit,
+                                float* __restrict__ W1T2, float* __restrict__ W2cT) {
+  for (int i = threadIdx.x; i < kIn2 * 64; i += blockDim.x) {
+    int k = i >> 6, j = i & 63;
+    W1T2[i] = j < 32 ? color[j * kIn2 + k] : logit[(j - 32) * kIn2 + k];
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    int j = i >> 2, c = i & 3;
+    W2cT[i] = c < 3 ? color[32 * kIn2 + c * 32 + j] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// batch-global counts (loss denominators and the count_nonzero guards of common.py:794)
+// ---------------------------------------------------------------------------------------
+__global__ void k_counts(const float* __restrict__ gt_depth, const float* __restrict__ z, const uint8_t* __restrict__ mask,
+                         int64_t N, int S, float trunc, int* counts) {
+  int n_mask = 0, n_dpos = 0, n_front = 0, n_band = 0;
+  int64_t P = N * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / S;
+    float d = gt_depth[r], zv = z[i];
+    bool front = zv < __fsub_rn(d, trunc), back = zv > __fadd_rn(d, trunc);
+    n_front += front;
+    n_band += (!front && !back && d > 0.f);
+    if (i - r * S == 0) {
+      n_dpos += d > 0.f;
+      n_mask += mask ? (mask[r] != 0) : 1;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_mask += __shfl_xor_sync(0xffffffffu, n_mask, o);
+    n_dpos += __shfl_xor_sync(0xffffffffu, n_dpos, o);
+    n_front += __shfl_xor_sync(0xffffffffu, n_front, o);
+    n_band += __shfl_xor_sync(0xffffffffu, n_band, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_mask) atomicAdd(counts + cMask, n_mask);
+    if (n_dpos) atomicAdd(counts + cDpos, n_dpos);
+    if (n_front) atomicAdd(counts + cFront, n_front);
+    if (n_band) atomicAdd(counts + cBand, n_band);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// class-homogeneous slot tiles (MAP): counting sort of the chunk's points by label[p mod N]
+// ---------------------------------------------------------------------------------------
+__global__ void k_class_hist(const int64_t* __restrict__ label, int64_t N, int64_t p0, int64_t Pc, int nci,
+                             int* hist, int* counts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Pc; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = label[(p0 + i) % N];
+    if (c < 0 || c >= nci) {
+      counts[cErr] = 1;
+      c = 0;
+    }
+    unsigned m = __match_any_sync(__activemask(), (int)c);
+    if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(hist + c, __popc(m));
+  }
+}
+// one block: slot_start[c] (in slots), number of tiles, tile -> expert row
+__global__ void k_class_scan(const int* __restrict__ hist, int nci, const int* __restrict__ class_to_expert,
+                             int* slot_start, int* cursor, int* tile_class, int* counts) {
+  if (threadIdx.x == 0) {
+    int tiles = 0;
+    for (int c = 0; c < nci; ++c) {
+      slot_start[c] = tiles * kTile;
+      cursor[c] = 0;
+      int nt = (hist[c] + kTile - 1) / kTile;
+      if (nt > 0 && class_to_expert[c] < 0) counts[cErr] = 2;  // "Fine decoders does NOT have class" (mapping.py:595)
+      tiles += nt;
+    }
+    slot_start[nci] = tiles * kTile;
+    counts[cTiles] = tiles;
+  }
+  __syncthreads();
+  for (int c = 0; c < nci; ++c) {
+    int t0 = slot_start[c] / kTile, t1 = slot_start[c + 1] / kTile, e = class_to_expert[c];
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) tile_class[t] = e;
+  }
+}
+__global__ void k_class_scatter(const int64_t* __restrict__ label, int64_t N, int64_t p0, int64_t Pc, int nci,
+                                const int* __restrict__ slot_start, int* cursor, int* perm) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Pc; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c64 = label[(p0 + i) % N];
+    int c = (c64 < 0 || c64 >= nci) ? 0 : (int)c64;
+    unsigned m = __match_any_sync(__activemask(), c);
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cursor + c, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    perm[slot_start[c] + base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// point kernels
+// ---------------------------------------------------------------------------------------
+struct PointArgs {
+  // geometry
+  const float* rays_o;
+  const float* rays_d;
+  const float* z;
+  const float* gt_depth;
+  int S;
+  int64_t N_total, P_total;  // whole batch (loss denominators, class quirk)
+  int64_t p0, Pc;            // this chunk: global offset and number of points
+  Bound B;
+  dns_grid G;
+  const float2* table;
+  // TV lattice
+  int n;
+  double voxel, jit[3], off[3];
+  // slots
+  const int* perm;        // slot -> chunk-local point, -1 = padding; NULL = identity
+  const int* tile_class;  // tile -> expert row (MAP)
+  const int* counts;      // device counts (n_tiles at cTiles when perm != NULL)
+  int n_tiles_host;
+  // weights (k-major blocks)
+  const float* WTc;
+  const float* WTe;
+  // latents in point order, padded rows of 36
+  float* fine36;
+  float* coarse36;
+  float* dfine36;
+  float* occ;   // TV: [n^3]
+  float* docc;  // TV
+  // stashes in slot order
+  float* Xst;   // [Q][80]
+  float* Hc;    // [Q][32]
+  float* Hf;
+  float* dHc;
+  float* dHf;
+  float* dOc;   // [Q][36]
+  float* dOf;
+  // losses / gradients
+  float lam_lt, lam_fs, lam_op, trunc, sigma;
+  float* raw;
+  float2* d_table;
+  float* d_rays_o;
+  float* d_rays_d;
+  int need_dparams, need_drays;
+};
+
+template <int MODE>
+__device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_t& i, int64_t& r, float& zv, float x[3]) {
+  if (MODE == kTv) {
+    int64_t n = a.n, n3 = n * n * n;
+    if (q >= n3) return false;
+    i = q;
+    int64_t idx[3] = {q / (n * n), (q / n) % n, q % n};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double pt = (((double)idx[c] + a.jit[c]) * a.voxel + a.B.lo[c]) + a.off[c];
+      x[c] = (float)((pt - a.B.lo[c]) / a.B.ext[c]);
+    }
+    r = 0;
+    zv = 0.f;
+    return true;
+  } else {
+    i = a.perm ? (int64_t)a.perm[q] : q;
+    if (i < 0 || i >= a.Pc) return false;
+    int64_t p = a.p0 + i;
+    r = p / a.S;
+    zv = a.z[p];
+    point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
+    return true;
+  }
+}
+
+__device__ __forceinline__ void load_block(float* dst, const float* __restrict__ src, int n4) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+  float4* d = reinterpret_cast<float4*>(dst);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) d[i] = s[i];
+}
+
+// 80 -> 32 (ReLU) -> 36: h and out in registers
+__device__ __forceinline__ void net80_fwd(const float* xrow, const float* W1T, const float* W2T, float (&h)[32],
+                                          float (&out)[kOutP]) {
+  zero(h);
+  accum_layer<32>(xrow, 1, kIn1, W1T, 32, h);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
+  zero(out);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float4* w = reinterpret_cast<const float4*>(W2T + j * kOutP);
+#pragma unroll
+    for (int q = 0; q < kOutP / 4; ++q) {
+      float4 v = w[q];
+      out[4 * q + 0] = fmaf(h[j], v.x, out[4 * q + 0]);
+      out[4 * q + 1] = fmaf(h[j], v.y, out[4 * q + 1]);
+      out[4 * q + 2] = fmaf(h[j], v.z, out[4 * q + 2]);
+      out[4 * q + 3] = fmaf(h[j], v.w, out[4 * q + 3]);
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_row(float* dst, const float (&v)[N]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+template <int N>
+__device__ __forceinline__ void load_row(const float* src, float (&v)[N]) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    float4 t = s[q];
+    v[4 * q] = t.x;
+    v[4 * q + 1] = t.y;
+    v[4 * q + 2] = t.z;
+    v[4 * q + 3] = t.w;
+  }
+}
+
+// fs / opacity masks of one sample (utils/common.py:786-792)
+__device__ __forceinline__ void opacity_masks(float zv, float d, float trunc, float& front, float& band, float& valid) {
+  bool f = zv < __fsub_rn(d, trunc), b = zv > __fadd_rn(d, trunc);
+  valid = d > 0.f ? 1.f : 0.f;
+  front = f ? 1.f : 0.f;
+  band = (!f && !b) ? valid : 0.f;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTile) k_point_fwd(PointArgs a) {
+  extern __shared__ float sm[];
+  float* XS = sm;                    // [128][81]
+  float* Wc = XS + kTile * kXld;     // coarse block
+  float* Wf = Wc + kNetT;            // expert block (MAP)
+  __shared__ float red[32];
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int n_tiles = a.perm ? a.counts[cTiles] : a.n_tiles_host;
+  if (tile >= n_tiles) return;
+  int expert = -1;
+  load_block(Wc, a.WTc, kNetT / 4);
+  if (MODE == kMap) {
+    expert = a.tile_class[tile];
+    if (expert >= 0) load_block(Wf, a.WTe + (int64_t)expert * kNetT, kNetT / 4);
+  }
+  const int64_t q = (int64_t)tile * kTile + tid;
+  int64_t i, r;
+  float zv, x[3];
+  const bool valid = slot_point<MODE>(a, q, i, r, zv, x);
+  float* xrow = XS + tid * kXld;
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) oneblob_fwd(x[c], 16, xrow + 16 * c, 1);
+    hashgrid_fwd(a.G, a.table, x, xrow + DNS_PE_DIM, 1);
+  } else {
+    for (int k = 0; k < kIn1; ++k) xrow[k] = 0.f;
+  }
+  __syncthreads();
+  float h[32], out[kOutP];
+  net80_fwd(xrow, Wc, Wc + 2560, h, out);
+  store_row(a.Hc + q * 32, h);
+  float lt = 0.f, fs = 0.f, op = 0.f;
+  if (MODE == kTv) {
+    if (valid) a.occ[q] = out[0];
+  } else if (MODE == kTrack) {
+    if (valid) store_row(a.fine36 + (a.p0 + i) * kOutP, out);
+  } else {
+    float fo[kOutP];
+    if (valid) store_row(a.coarse36 + (a.p0 + i) * kOutP, out);
+    if (expert >= 0) {
+      net80_fwd(xrow, Wf, Wf + 2560, h, fo);
+    } else {
+      zero(h);
+      zero(fo);
+    }
+    store_row(a.Hf + q * 32, h);
+    if (valid) {
+      store_row(a.fine36 + (a.p0 + i) * kOutP, fo);
+#pragma unroll
+      for (int c = 0; c < DNS_LATENT; ++c) {
+        float d = out[c] - fo[c];
+        lt = fmaf(d, d, lt);
+      }
+      float front, band, vd, d = a.gt_depth[r];
+      opacity_masks(zv, d, a.trunc, front, band, vd);
+      float o = sigmoidf_(10.f * fo[32]);
+      float t = o * front * vd;
+      fs = t * t;
+      float u = (zv - d) / a.sigma;
+      float ps = 0.5f * __expf(-0.5f * u * u);
+      float e = o * band - ps * band;
+      op = e * e;
+    }
+  }
+  if (a.need_dparams) {  // X stash: the tile is one contiguous [128][80] block
+    __syncthreads();
+    float* dst = a.Xst + (int64_t)tile * kTile * kIn1;
+    for (int e = tid; e < kTile * kIn1; e += kTile) {
+      int rr = e / kIn1, k = e - rr * kIn1;
+      dst[e] = XS[rr * kXld + k];
+    }
+  }
+  if (MODE == kMap) {
+    lt = block_reduce_sum(lt, red);
+    fs = block_reduce_sum(fs, red);
+    op = block_reduce_sum(op, red);
+    if (tid == 0) {
+      atomicAdd(a.raw + rLt, lt);
+      atomicAdd(a.raw + rFs, fs);
+      atomicAdd(a.raw + rOp, op);
+    }
+  }
+}
+
+// dh = relu'(h) * (W2^T d_out);  d_in[k] (+)= sum_j dh[j] W1T[k][j]
+__device__ __forceinline__ void net80_bwd(const float (&d_out)[kOutP], const float* hrow, const float* W1T,
+                                          const float* W2T, float* xrow, bool accumulate, float* dh_st, float* do_st) {
+  float h[32], dh[32];
+  load_row(hrow, h);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) dh[j] = h[j] > 0.f ? dot_row<kOutP>(d_out, W2T + j * kOutP) : 0.f;
+  if (dh_st) store_row(dh_st, dh);
+  if (do_st) store_row(do_st, d_out);
+#pragma unroll 4
+  for (int k = 0; k < kIn1; ++k) {
+    float v = dot_row<32>(dh, W1T + k * 32);
+    xrow[k] = accumulate ? xrow[k] + v : v;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTile) k_point_bwd(PointArgs a) {
+  extern __shared__ float sm[];
+  float* XS = sm;
+  float* Wc = XS + kTile * kXld;
+  float* Wf = Wc + kNetT;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int n_tiles = a.perm ? a.counts[cTiles] : a.n_tiles_host;
+  if (tile >= n_tiles) return;
+  int expert = -1;
+  load_block(Wc, a.WTc, kNetT / 4);
+  if (MODE == kMap) {
+    expert = a.tile_class[tile];
+    if (expert >= 0) load_block(Wf, a.WTe + (int64_t)expert * kNetT, kNetT / 4);
+  }
+  __syncthreads();
+  const int64_t q = (int64_t)tile * kTile + tid;
+  int64_t i, r;
+  float zv, x[3];
+  const bool valid = slot_point<MODE>(a, q, i, r, zv, x);
+  float* xrow = XS + tid * kXld;
+  float d_out[kOutP];
+  zero(d_out);
+  float* dHc = a.need_dparams ? a.dHc + q * 32 : nullptr;
+  float* dOc = a.need_dparams ? a.dOc + q * kOutP : nullptr;
+  if (MODE == kTv) {
+    if (valid) d_out[0] = a.docc[q];
+    net80_bwd(d_out, a.Hc + q * 32, Wc, Wc + 2560, xrow, false, dHc, dOc);
+  } else if (MODE == kTrack) {
+    if (valid) load_row(a.dfine36 + (a.p0 + i) * kOutP, d_out);
+    net80_bwd(d_out, a.Hc + q * 32, Wc, Wc + 2560, xrow, false, dHc, dOc);
+  } else {
+    float g_lt = 2.f * a.lam_lt / (33.f * (float)a.P_total);
+    float co[kOutP], fo[kOutP];
+    zero(co);
+    zero(fo);
+    if (valid) {
+      const int64_t p = a.p0 + i;
+      load_row(a.dfine36 + p * kOutP, d_out);
+      load_row(a.coarse36 + p * kOutP, co);
+      load_row(a.fine36 + p * kOutP, fo);
+#pragma unroll
+      for (int c = 0; c < DNS_LATENT; ++c) d_out[c] -= g_lt * (co[c] - fo[c]);
+      if (a.counts[cFront] > 0 && a.counts[cBand] > 0) {
+        float front, band, vd, d = a.gt_depth[r];
+        opacity_masks(zv, d, a.trunc, front, band, vd);
+        float o = sigmoidf_(10.f * fo[32]);
+        float u = (zv - d) / a.sigma;
+        float ps = 0.5f * __expf(-0.5f * u * u);
+        float inv_p = 1.f / (float)a.P_total;
+        float d_o = 2.f * a.lam_fs * inv_p * o * front * vd + 2.f * a.lam_op * inv_p * (o - ps) * band;
+        d_out[32] += d_o * 10.f * o * (1.f - o);
+      }
+    }
+    if (expert >= 0) {
+      net80_bwd(d_out, a.Hf + q * 32, Wf, Wf + 2560, xrow, false, a.need_dparams ? a.dHf + q * 32 : nullptr,
+                a.need_dparams ? a.dOf + q * kOutP : nullptr);
+    } else {
+      for (int k = 0; k < kIn1; ++k) xrow[k] = 0.f;
+    }
+    // coarse net: only the latent loss reaches it in mapping (mapping.py:624-626 render from fine)
+#pragma unroll
+    for (int c = 0; c < kOutP; ++c) d_out[c] = (valid && c < DNS_LATENT) ? g_lt * (co[c] - fo[c]) : 0.f;
+    net80_bwd(d_out, a.Hc + q * 32, Wc, Wc + 2560, xrow, true, dHc, dOc);
+  }
+  if (!valid) return;
+  float dx[3] = {0.f, 0.f, 0.f}, dxg[3];
+  if (a.need_drays) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dx[c] = oneblob_bwd(x[c], 16, xrow + 16 * c, 1);
+  }
+  hashgrid_bwd(a.G, a.table, a.need_dparams ? a.d_table : nullptr, x, xrow + DNS_PE_DIM, 1, a.need_drays != 0, dxg);
+  if (a.need_drays && MODE != kTv) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float g = (dx[c] + dxg[c]) / (float)a.B.ext[c];
+      atomicAdd(a.d_rays_o + 3 * r + c, g);
+      atomicAdd(a.d_rays_d + 3 * r + c, g * zv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// ray kernel: out_fn + compositing + losses + backward (thread per sample point)
+// ---------------------------------------------------------------------------------------
+struct RayArgs {
+  int mode;
+  int S, T, RPC, C, C4;
+  int64_t N_total, ray0, Nc;  // chunk of rays [ray0, ray0 + Nc)
+  Bound B;
+  const float* rays_o;
+  const float* rays_d;
+  const float* z;
+  const float* gt_color;
+  const float* gt_depth;
+  const int64_t* gt_label;
+  const uint8_t* mask;
+  const float* features;
+  const float* fine36;
+  const float* W1T2;
+  const float* W2cT;
+  const float* logit;  // tcnn layout; W2l = logit + 32*112, [Cpad][32]
+  const int* counts;
+  float lam_p, lam_d, lam_l;
+  float* pred_color;
+  float* pred_depth;
+  float* pred_var;
+  float* pred_logits;
+  float* raw;
+  float* dfine36;
+  float* d_features;
+  float* d_rays_o;
+  float* d_rays_d;
+  // stashes (point / ray order of the chunk)
+  float* X2;     // [Pc][112]
+  float* dH2;    // [Pc][64]
+  float* Hcol;   // [Pc][32]
+  float* dpre;   // [Pc][4]
+  float* dlogit; // [Nc][C4]
+  float* Hbar;   // [Nc][32]
+  int need_dparams, need_drays, need_dfeat;
+};
+
+__global__ void __launch_bounds__(256) k_ray(RayArgs a) {
+  extern __shared__ float sm[];
+  const int T = a.T, S = a.S, RPC = a.RPC, C = a.C, C4 = a.C4, ld = T + 1;
+  float* W1 = sm;                       // [112][64]
+  float* W2c = W1 + kIn2 * 64;          // [32][4]
+  float* XC = W2c + 128;                // [48][T+1] per-thread columns / staging
+  float* bs = XC + 48 * ld;             // [T]
+  float* us = bs + T;                   // [T]
+  float* ws = us + T;                   // [T]
+  float* HB = ws + T;                   // [RPC][32]
+  float* QV = HB + RPC * 32;            // [RPC][32]
+  float* RO = QV + RPC * 32;            // [RPC][8] ray outputs
+  float* RG = RO + RPC * 8;             // [RPC][8] ray gradients
+  float* LG = RG + RPC * 8;             // [RPC][C4] logits, then d_logits
+  float* LS = LG + RPC * C4;            // [4] CTA loss partial sums
+  const int t = threadIdx.x;
+  load_block(W1, a.W1T2, kIn2 * 64 / 4);
+  load_block(W2c, a.W2cT, 32);
+  if (t < 4) LS[t] = 0.f;
+  const int lr = t / S, s = t - lr * S;
+  const int64_t rl = (int64_t)blockIdx.x * RPC + lr;      // chunk-local ray
+  const bool valid = lr < RPC && rl < a.Nc;
+  const int64_t r = a.ray0 + rl;                          // global ray
+  const int64_t pl = rl * S + s, p = r * S + s;           // chunk-local / global point
+  const int rb = lr * S;                                  // first thread of my ray
+  float* xc = XC + t;
+  float x[3] = {0.f, 0.f, 0.f}, zv = 0.f, occ = 0.f;
+  float h[64];
+  zero(h);
+  __syncthreads();
+  if (valid) {
+    zv = a.z[p];
+    point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
+    // segment 1: OneBlob(x) -> 48
+#pragma unroll
+    for (int c = 0; c < 3; ++c) oneblob_fwd(x[c], 16, xc + 16 * c * ld, ld);
+    if (a.need_dparams)
+      for (int k = 0; k < 48; ++k) a.X2[pl * kIn2 + k] = xc[k * ld];
+    accum_layer<64>(xc, ld, 48, W1, 64, h);
+    // segment 2: latent channels 1..32 of the fine (TRACK: coarse) output
+    {
+      float row[kOutP];
+      load_row(a.fine36 + p * kOutP, row);
+      occ = row[0];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) xc[k * ld] = row[1 + k];
+      if (a.need_dparams)
+        for (int k = 0; k < 32; ++k) a.X2[pl * kIn2 + 48 + k] = row[1 + k];
+    }
+    accum_layer<64>(xc, ld, 32, W1 + 48 * 64, 64, h);
+    // segment 3: merged pixel feature
+    {
+      float row[32];
+      if (a.features) load_row(a.features + p * 32, row);
+      else zero(row);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) xc[k * ld] = row[k];
+      if (a.need_dparams) store_row(a.X2 + pl * kIn2 + 80, row);
+    }
+    accum_layer<64>(xc, ld, 32, W1 + 80 * 64, 64, h);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) h[j] = fmaxf(h[j], 0.f);
+  }
+  // colour head: 32 -> 3, sigmoid (decoder.py:123)
+  float rgb[3] = {0.f, 0.f, 0.f};
+  {
+    float pre[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float4 w = *reinterpret_cast<const float4*>(W2c + 4 * j);
+      pre[0] = fmaf(h[j], w.x, pre[0]);
+      pre[1] = fmaf(h[j], w.y, pre[1]);
+      pre[2] = fmaf(h[j], w.z, pre[2]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] = sigmoidf_(pre[c]);
+  }
+  // occupancy compositing (common.py:524-532)
+  const float alpha = valid ? sigmoidf_(10.f * occ) : 0.f;
+  const float b = __fadd_rn(1.f - alpha, 1e-10f);
+  bs[t] = b;
+  __syncthreads();
+  float Ts = 1.f;
+  if (valid)
+    for (int j = 0; j < s; ++j) Ts *= bs[rb + j];
+  const float u = alpha * Ts;
+  us[t] = u;
+  __syncthreads();
+  float sumu = 0.f;
+  if (valid)
+    for (int j = 0; j < S; ++j) sumu += us[rb + j];
+  const float w = valid ? u / sumu : 0.f;
+  __syncthreads();
+  // stage w * {logit hidden (32), rgb (3), z} and reduce per ray
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xc[j * ld] = w * h[32 + j];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xc[(32 + c) * ld] = w * rgb[c];
+    xc[35 * ld] = w * zv;
+  }
+  __syncthreads();
+  for (int e = t; e < RPC * 36; e += T) {
+    int l2 = e / 36, o = e - l2 * 36;
+    if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
+      const float* col = XC + o * ld + l2 * S;
+      float acc = 0.f;
+      for (int j = 0; j < S; ++j) acc += col[j];
+      if (o < 32) HB[l2 * 32 + o] = acc;
+      else RO[l2 * 8 + (o - 32)] = acc;  // 0..2 rgb, 3 depth
+    }
+  }
+  __syncthreads();
+  const float dz = valid ? zv - RO[lr * 8 + 3] : 0.f;
+  bs[t] = w * dz * dz;
+  us[t] = w * dz;
+  // semantic head layer 2 on the composited hidden state (linear => commutes with compositing)
+  const float* W2l = a.logit + 32 * kIn2;
+  for (int e = t; e < RPC * C; e += T) {
+    int l2 = e / C, c = e - l2 * C;
+    if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
+      const float4* wr = reinterpret_cast<const float4*>(W2l + c * 32);
+      const float* hb = HB + l2 * 32;
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v = __ldg(wr + q);
+        acc = fmaf(hb[4 * q], v.x, acc);
+        acc = fmaf(hb[4 * q + 1], v.y, acc);
+        acc = fmaf(hb[4 * q + 2], v.z, acc);
+        acc = fmaf(hb[4 * q + 3], v.w, acc);
+      }
+      LG[l2 * C4 + c] = acc;
+    }
+  }
+  __syncthreads();
+  // per-ray losses and their gradients (one thread per ray)
+  if (valid && s == 0) {
+    float var = 0.f, swdz = 0.f;
+    for (int j = 0; j < S; ++j) {
+      var += bs[rb + j];
+      swdz += us[rb + j];
+    }
+    float* ro = RO + lr * 8;
+    float* rg = RG + lr * 8;
+    float* lg = LG + lr * C4;
+    const float dhat = ro[3];
+    a.pred_color[3 * r] = ro[0];
+    a.pred_color[3 * r + 1] = ro[1];
+    a.pred_color[3 * r + 2] = ro[2];
+    a.pred_depth[r] = dhat;
+    a.pred_var[r] = var;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      a.pred_logits[r * C + c] = lg[c];
+      mx = fmaxf(mx, lg[c]);
+    }
+    const float gd = a.gt_depth[r];
+    const int64_t lab = a.gt_label[r];
+    const bool track = a.mode == kTrack;
+    const bool m = track ? (a.mask ? a.mask[r] != 0 : true) : true;
+    const float n_ray = track ? (float)a.counts[cMask] : (float)a.N_total;
+    float lp = 0.f, ldp = 0.f, ll = 0.f;
+    float g_rgb[3] = {0.f, 0.f, 0.f}, g_d = 0.f, g_var = 0.f, g_ce = 0.f;
+    if (m) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float e = ro[c] - a.gt_color[3 * r + c];
+        lp = fmaf(e, e, lp);
+        g_rgb[c] = a.lam_p * 2.f * e / (3.f * n_ray);
+      }
+      float diff = dhat - gd;
+      float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+      if (track) {  // tracking.py:89-92: |d - d^| / sqrt(var + 1e-10)
+        float vv = var + 1e-10f, inv = rsqrtf(vv);
+        ldp = fabsf(diff) * inv;
+        g_d = a.lam_d * sgn * inv / n_ray;
+        g_var = a.lam_d * fabsf(diff) * (-0.5f) * inv / vv / n_ray;
+        g_d += g_var * (-2.f) * swdz;
+      } else if (gd > 0.f) {  // mapping.py:114-117
+        ldp = fabsf(diff);
+        g_d = a.lam_d * sgn / (float)a.counts[cDpos];
+      }
+      float se = 0.f;
+      for (int c = 0; c < C; ++c) se += __expf(lg[c] - mx);
+      float lse = logf(se) + mx;
+      ll = lse - lg[lab];
+      g_ce = a.lam_l / n_ray;
+      for (int c = 0; c < C; ++c) lg[c] = g_ce * (__expf(lg[c] - lse) - (c == lab ? 1.f : 0.f));
+    } else {
+      for (int c = 0; c < C; ++c) lg[c] = 0.f;
+    }
+    for (int c = C; c < C4; ++c) lg[c] = 0.f;
+    rg[0] = g_rgb[0];
+    rg[1] = g_rgb[1];
+    rg[2] = g_rgb[2];
+    rg[3] = g_d;
+    rg[4] = g_var;
+    atomicAdd(LS + 0, lp);
+    atomicAdd(LS + 1, ldp);
+    atomicAdd(LS + 2, ll);
+    if (a.need_dparams) {
+      for (int c = 0; c < C4; ++c) a.dlogit[rl * C4 + c] = lg[c];
+      for (int j = 0; j < 32; ++j) a.Hbar[rl * 32 + j] = HB[lr * 32 + j];
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    atomicAdd(a.raw + rP, LS[0]);
+    atomicAdd(a.raw + rD, LS[1]);
+    atomicAdd(a.raw + rL, LS[2]);
+  }
+  // QV[ray][j] = sum_c d_logit[c] * W2l[c][j]
+  for (int e = t; e < RPC * 32; e += T) {
+    int l2 = e >> 5, j = e & 31;
+    if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
+      const float* lg = LG + l2 * C4;
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) acc = fmaf(lg[c], __ldg(W2l + c * 32 + j), acc);
+      QV[e] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- per-point backward
+  float d_w = 0.f;
+  if (valid) {
+    const float* rg = RG + lr * 8;
+    const float* qv = QV + lr * 32;
+    d_w = rg[0] * rgb[0] + rg[1] * rgb[1] + rg[2] * rgb[2] + rg[3] * zv + rg[4] * dz * dz;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d_w = fmaf(h[32 + j], qv[j], d_w);
+  }
+  bs[t] = w * d_w;
+  ws[t] = b;
+  __syncthreads();
+  float G = 0.f;
+  if (valid)
+    for (int j = 0; j < S; ++j) G += bs[rb + j];
+  const float d_u = valid ? (d_w - G) / sumu : 0.f;
+  us[t] = d_u * u;
+  __syncthreads();
+  float d_occ = 0.f;
+  if (valid) {
+    float suf = 0.f;
+    for (int j = s + 1; j < S; ++j) suf += us[rb + j];
+    float d_alpha = d_u * Ts - suf / b;
+    d_occ = d_alpha * 10.f * alpha * (1.f - alpha);
+  }
+  if (valid) {
+    const float* rg = RG + lr * 8;
+    const float* qv = QV + lr * 32;
+    float dp[4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dp[c] = w * rg[c] * rgb[c] * (1.f - rgb[c]);
+    dp[3] = 0.f;
+    if (a.need_dparams) {
+      float hc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) hc[j] = h[j];
+      store_row(a.Hcol + pl * 32, hc);
+      store_row(a.dpre + pl * 4, dp);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float4 wv = *reinterpret_cast<const float4*>(W2c + 4 * j);
+      h[j] = h[j] > 0.f ? dp[0] * wv.x + dp[1] * wv.y + dp[2] * wv.z : 0.f;
+      h[32 + j] = h[32 + j] > 0.f ? w * qv[j] : 0.f;
+    }
+    if (a.need_dparams) store_row(a.dH2 + pl * 64, h);
+    // d(latent) -> dfine row, channel 0 = d(occupancy)
+    {
+      float row[kOutP];
+      row[0] = d_occ;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) row[1 + k] = dot_row<64>(h, W1 + (48 + k) * 64);
+      row[33] = row[34] = row[35] = 0.f;
+      store_row(a.dfine36 + p * kOutP, row);
+    }
+    if (a.need_dfeat) {
+      float row[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) row[k] = dot_row<64>(h, W1 + (80 + k) * 64);
+      store_row(a.d_features + p * 32, row);
+    }
+  }
+  if (a.need_drays) {
+    __syncthreads();
+    if (valid) {
+      for (int k = 0; k < 48; ++k) xc[k * ld] = dot_row<64>(h, W1 + k * 64);
+      float g[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] = oneblob_bwd(x[c], 16, xc + 16 * c * ld, ld) / (float)a.B.ext[c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        xc[c * ld] = g[c];
+        xc[(3 + c) * ld] = g[c] * zv;
+      }
+    }
+    __syncthreads();
+    for (int e = t; e < RPC * 6; e += T) {
+      int l2 = e / 6, o = e - l2 * 6;
+      int64_t rr = (int64_t)blockIdx.x * RPC + l2;
+      if (rr < a.Nc) {
+        const float* col = XC + o * ld + l2 * S;
+        float acc = 0.f;
+        for (int j = 0; j < S; ++j) acc += col[j];
+        if (o < 3) a.d_rays_o[3 * (a.ray0 + rr) + o] = acc;
+        else a.d_rays_d[3 * (a.ray0 + rr) + o - 3] = acc;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+__global__ void k_finalize(int mode, const float* raw, const int* counts, int64_t N, int64_t P, float lp, float ld,
+                           float ll, float llt, float lfs, float lop, float* losses) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float p, d, l, lt = 0.f, fs = 0.f, op = 0.f, nv;
+  if (mode == kTrack) {
+    nv = (float)counts[cMask];
+    p = raw[rP] / (3.f * nv);
+    d = raw[rD] / nv;
+    l = raw[rL] / nv;
+  } else {
+    nv = (float)N;
+    p = raw[rP] / (3.f * nv);
+    d = raw[rD] / (float)counts[cDpos];
+    l = raw[rL] / nv;
+    lt = raw[rLt] / (33.f * (float)P);
+    if (counts[cFront] > 0 && counts[cBand] > 0) {
+      fs = raw[rFs] / (float)P;
+      op = raw[rOp] / (float)P;
+    }
+  }
+  losses[0] = p;
+  losses[1] = d;
+  losses[2] = l;
+  losses[3] = lt;
+  losses[4] = fs;
+  losses[5] = op;
+  losses[6] = lp * p + ld * d + ll * l + llt * lt + lfs * fs + lop * op;
+  losses[7] = counts[cErr] ? -(float)counts[cErr] : nv;
+}
+__global__ void k_unpad33(const float* __restrict__ src36, float* __restrict__ dst33, int64_t P) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * DNS_LATENT) return;
+  int64_t p = i / DNS_LATENT;
+  dst33[i] = src36[p * kOutP + (i - p * DNS_LATENT)];
+}
+// TV stencil (mapping.py:153-157): loss and d(loss)/d(occ)
+__global__ void k_tv_stencil(const float* __restrict__ occ, int n, float inv_norm, float lambda, float* docc,
+                             float* loss) {
+  __shared__ float red[32];
+  int64_t n3 = (int64_t)n * n * n;
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (q < n3) {
+    int ix = (int)(q / ((int64_t)n * n)), iy = (int)((q / n) % n), iz = (int)(q % n);
+    float v = occ[q], g = 0.f;
+    const int64_t st[3] = {(int64_t)n * n, n, 1};
+    const int id[3] = {ix, iy, iz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (id[c] + 1 < n) {
+        float d = occ[q + st[c]] - v;
+        acc = fmaf(d, d, acc);
+        g -= 2.f * d;
+      }
+      if (id[c] > 0) g += 2.f * (v - occ[q - st[c]]);
+    }
+    docc[q] = g * inv_norm * lambda;
+  }
+  acc = block_reduce_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * inv_norm);
+}
+
+// ---------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  int64_t off;
+  template <typename Tp>
+  Tp* take(int64_t n) {
+    off = (off + 255) & ~(int64_t)255;
+    Tp* p = base ? reinterpret_cast<Tp*>(base + off) : nullptr;
+    off += n * (int64_t)sizeof(Tp);
+    return p;
+  }
+};
+struct RenderWs {
+  int* counts;
+  float* raw;
+  int *hist, *slot_start, *cursor;
+  float *WTc, *WTe, *W1T2, *W2cT;
+  int *perm, *tile_class;
+  float *fine36, *coarse36, *dfine36;
+  float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf;
+  float *X2, *dH2, *Hcol, *dpre, *dlogit, *Hbar;
+  int64_t Q, tiles;
+};
+static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C, int nci) {
+  Carver c{base, 0};
+  const int64_t Pc = Nc * S;
+  const bool map = mode == DNS_MODE_MAP;
+  w.tiles = (Pc + kTile - 1) / kTile + (map ? nci : 0);
+  w.Q = w.tiles * kTile;
+  const int C4 = (C + 3) & ~3;
+  w.counts = c.take<int>(16);
+  w.raw = c.take<float>(16);
+  w.hist = c.take<int>(nci + 1);
+  w.slot_start = c.take<int>(nci + 2);
+  w.cursor = c.take<int>(nci + 1);
+  w.WTc = c.take<float>(kNetT);
+  w.WTe = c.take<float>((int64_t)kNetT * (map ? nci : 0) + 4);
+  w.W1T2 = c.take<float>(kIn2 * 64);
+  w.W2cT = c.take<float>(128);
+  w.perm = c.take<int>(map ? w.Q : 4);
+  w.tile_class = c.take<int>(w.tiles);
+  w.fine36 = c.take<float>(Pc * kOutP);
+  w.coarse36 = c.take<float>(map ? Pc * kOutP : 4);
+  w.dfine36 = c.take<float>(Pc * kOutP);
+  w.Xst = c.take<float>(w.Q * kIn1);
+  w.Hc = c.take<float>(w.Q * 32);
+  w.Hf = c.take<float>(map ? w.Q * 32 : 4);
+  w.dHc = c.take<float>(w.Q * 32);
+  w.dHf = c.take<float>(map ? w.Q * 32 : 4);
+  w.dOc = c.take<float>(w.Q * kOutP);
+  w.dOf = c.take<float>(map ? w.Q * kOutP : 4);
+  w.X2 = c.take<float>(Pc * kIn2);
+  w.dH2 = c.take<float>(Pc * 64);
+  w.Hcol = c.take<float>(Pc * 32);
+  w.dpre = c.take<float>(Pc * 4);
+  w.dlogit = c.take<float>(Nc * C4);
+  w.Hbar = c.take<float>(Nc * 32);
+  return c.off + 256;
+}
+constexpr int64_t kMaxChunkRays = 1 << 17;
+
+static void pick_ray_block(int S, int& T, int& RPC) {
+  int best_r = 1;
+  double best = 0.0;
+  int rmax = 256 / S;
+  if (rmax < 1) rmax = 1;
+  if (rmax > 16) rmax = 16;
+  for (int rr = 1; rr <= rmax; ++rr) {
+    int tt = (rr * S + 31) & ~31;
+    double eff = (double)(rr * S) / tt;
+    if (eff >= best - 1e-9) {
+      best = eff;
+      best_r = rr;
+    }
+  }
+  RPC = best_r;
+  T = (RPC * S + 31) & ~31;
+}
+
+}  // namespace dns
+
+using namespace dns;
+
+extern "C" {
+
+int64_t dns_render_workspace_bytes(int mode, int n_rays, int n_samples, int n_class, int n_class_ids) {
+  RenderWs w;
+  int64_t nc = n_rays < kMaxChunkRays ? n_rays : kMaxChunkRays;
+  if (nc < 1) nc = 1;
+  return carve(w, nullptr, mode, nc, n_samples, n_class, n_class_ids < 1 ? 1 : n_class_ids);
+}
+
+int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = a->mode, S = a->n_samples, C = a->n_class;
+  const int64_t N = a->n_rays;
+  if (mode != DNS_MODE_TRACK && mode != DNS_MODE_MAP) {
+    set_error("render: bad mode %d", mode);
+    return DNS_ERR_ARG;
+  }
+  if (N <= 0 || S <= 0 || S > 256 || C < 1 || C > 128) {
+    set_error("render: need n_rays > 0, 1 <= n_samples <= 256, 1 <= n_class <= 128 (got %lld, %d, %d)", (long long)N, S, C);
+    return DNS_ERR_UNSUPPORTED;
+  }
+  if (a->grid.n_levels != 16 || a->grid.n_features != 2) {
+    set_error("render: the fused path is built for 16 levels x 2 features");
+    return DNS_ERR_UNSUPPORTED;
+  }
+  const bool map = mode == DNS_MODE_MAP;
+  const int nci = map ? (a->n_class_ids < 1 ? 1 : a->n_class_ids) : 1;
+  if (map && (!a->experts || !a->class_to_expert || a->n_experts < 1 || a->n_experts > nci)) {
+    set_error("render: MAP mode needs experts, class_to_expert and 1 <= n_experts <= n_class_ids");
+    return DNS_ERR_ARG;
+  }
+  // largest chunk whose scratch fits the workspace
+  RenderWs w;
+  int64_t Nc = N < kMaxChunkRays ? N : kMaxChunkRays;
+  while (Nc > 1 && carve(w, nullptr, mode, Nc, S, C, nci) > a->workspace_bytes) Nc = (Nc + 1) / 2;
+  if (!a->workspace || carve(w, nullptr, mode, Nc, S, C, nci) > a->workspace_bytes) {
+    set_error("render: workspace too small (%lld bytes)", (long long)a->workspace_bytes);
+    return DNS_ERR_ARG;
+  }
+  carve(w, (char*)a->workspace, mode, Nc, S, C, nci);
+  const int C4 = (C + 3) & ~3;
+  const int64_t P = N * S;
+  Bound B;
+  for (int c = 0; c < 3; ++c) {
+    B.lo[c] = a->bound[c][0];
+    B.ext[c] = a->bound[c][1] - a->bound[c][0];
+  }
+  cudaMemsetAsync(w.counts, 0, 16 * sizeof(int), st);
+  cudaMemsetAsync(w.raw, 0, 16 * sizeof(float), st);
+  k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, w.WTc);
+  if (map) k_transpose_net80<<<a->n_experts, 256, 0, st>>>(a->experts, w.WTe);
+  k_transpose_out<<<1, 256, 0, st>>>(a->color, a->logit, w.W1T2, w.W2cT);
+  {
+    int64_t blocks = (P + 255) / 256;
+    k_counts<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(a->gt_depth, a->z_vals, map ? nullptr : a->mask, N, S,
+                                                                  a->opacity_trunc, w.counts);
+  }
+  if (int e = check_launch("render prep")) return e;
+
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_point_fwd<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_point_fwd<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_point_fwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_point_bwd<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_point_bwd<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_point_bwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_ray, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr = true;
+  }
+  const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT * (map ? 2 : 1));
+  int T, RPC;
+  pick_ray_block(S, T, RPC);
+  const size_t smem_ray =
+      sizeof(float) * (kIn2 * 64 + 128 + 48 * (T + 1) + 3 * T + RPC * (32 + 32 + 8 + 8 + C4) + 8);
+
+  for (int64_t ray0 = 0; ray0 < N; ray0 += Nc) {
+    const int64_t nc = (N - ray0) < Nc ? (N - ray0) : Nc;
+    const int64_t p0 = ray0 * S, Pc = nc * S;
+    const int tiles_max = (int)((Pc + kTile - 1) / kTile + (map ? nci : 0));
+    PointArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.rays_o = a->rays_o; pa.rays_d = a->rays_d; pa.z = a->z_vals; pa.gt_depth = a->gt_depth;
+    pa.S = S; pa.N_total = N; pa.P_total = P; pa.p0 = p0; pa.Pc = Pc; pa.B = B; pa.G = a->grid;
+    pa.table = (const float2*)a->table;
+    pa.counts = w.counts; pa.n_tiles_host = tiles_max;
+    pa.WTc = w.WTc; pa.WTe = w.WTe;
+    // point-order buffers are indexed with GLOBAL point ids: shift the chunk-local base
+    pa.fine36 = w.fine36 - p0 * kOutP; pa.coarse36 = w.coarse36 - p0 * kOutP; pa.dfine36 = w.dfine36 - p0 * kOutP;
+    pa.Xst = w.Xst; pa.Hc = w.Hc; pa.Hf = w.Hf; pa.dHc = w.dHc; pa.dHf = w.dHf; pa.dOc = w.dOc; pa.dOf = w.dOf;
+    pa.lam_lt = a->lambda_lt; pa.lam_fs = a->lambda_fs; pa.lam_op = a->lambda_op;
+    pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
+    pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
+    pa.need_dparams = a->need_dparams; pa.need_drays = a->need_drays;
+    if (map) {
+      cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);
+      cudaMemsetAsync(w.perm, 0xFF, (size_t)tiles_max * kTile * sizeof(int), st);
+      int64_t blocks = (Pc + 255) / 256;
+      int grid = (int)(blocks < 592 ? blocks : 592);
+      k_class_hist<<<grid, 256, 0, st>>>(a->gt_label, N, p0, Pc, nci, w.hist, w.counts);
+      k_class_scan<<<1, 256, 0, st>>>(w.hist, nci, a->class_to_expert, w.slot_start, w.cursor, w.tile_class, w.counts);
+      k_class_scatter<<<grid, 256, 0, st>>>(a->gt_label, N, p0, Pc, nci, w.slot_start, w.cursor, w.perm);
+      pa.perm = w.perm; pa.tile_class = w.tile_class;
+      k_point_fwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
+    } else {
+      k_point_fwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
+    }
+    if (int e = check_launch("point_fwd")) return e;
+
+    RayArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.mode = mode; ra.S = S; ra.T = T; ra.RPC = RPC; ra.C = C; ra.C4 = C4;
+    ra.N_total = N; ra.ray0 = ray0; ra.Nc = nc; ra.B = B;
+    ra.rays_o = a->rays_o; ra.rays_d = a->rays_d; ra.z = a->z_vals; ra.gt_color = a->gt_color;
+    ra.gt_depth = a->gt_depth; ra.gt_label = a->gt_label; ra.mask = map ? nullptr : a->mask; ra.features = a->features;
+    ra.fine36 = pa.fine36; ra.W1T2 = w.W1T2; ra.W2cT = w.W2cT; ra.logit = a->logit; ra.counts = w.counts;
+    ra.lam_p = a->lambda_p; ra.lam_d = a->lambda_d; ra.lam_l = a->lambda_l;
+    ra.pred_color = a->pred_color; ra.pred_depth = a->pred_depth; ra.pred_var = a->pred_var;
+    ra.pred_logits = a->pred_logits; ra.raw = w.raw; ra.dfine36 = pa.dfine36; ra.d_features = a->d_features;
+    ra.d_rays_o = a->d_rays_o; ra.d_rays_d = a->d_rays_d;
+    ra.X2 = w.X2; ra.dH2 = w.dH2; ra.Hcol = w.Hcol; ra.dpre = w.dpre; ra.dlogit = w.dlogit; ra.Hbar = w.Hbar;
+    ra.need_dparams = a->need_dparams; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d;
+    ra.need_dfeat = a->need_dfeat && a->d_features;
+    pa.need_drays = ra.need_drays;
+    k_ray<<<(int)((nc + RPC - 1) / RPC), T, smem_ray, st>>>(ra);
+    if (int e = check_launch("ray")) return e;
+
+    if (map) k_point_bwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
+    else k_point_bwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
+    if (int e = check_launch("point_bwd")) return e;
+
+    if (a->fine) k_unpad33<<<(int)((Pc * DNS_LATENT + 255) / 256), 256, 0, st>>>(w.fine36, a->fine + p0 * DNS_LATENT, Pc);
+    if (map && a->coarse_out)
+      k_unpad33<<<(int)((Pc * DNS_LATENT + 255) / 256), 256, 0, st>>>(w.coarse36, a->coarse_out + p0 * DNS_LATENT, Pc);
+
+    if (a->need_dparams) {
+      const int64_t Qrows = (int64_t)tiles_max * kTile;
+      const int* ntd = map ? w.counts + cTiles : nullptr;
+      int e = 0;
+      // coarse net (all slots): dW1 = dH^T X, dW2 = dOut^T H
+      e |= launch_dw_gemm(w.dHc, 32, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, nullptr, a->d_coarse, kIn1, 0, st);
+      e |= launch_dw_gemm(w.dOc, kOutP, DNS_LATENT, w.Hc, 32, 32, Qrows, ntd, tiles_max, nullptr, a->d_coarse + 2560, 32, 0, st);
+      if (map) {
+        e |= launch_dw_gemm(w.dHf, 32, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, w.tile_class, a->d_experts, kIn1, 4096, st);
+        e |= launch_dw_gemm(w.dOf, kOutP, DNS_LATENT, w.Hf, 32, 32, Qrows, ntd, tiles_max, w.tile_class, a->d_experts + 2560, 32, 4096, st);
+      }
+      const int pt_tiles = (int)((Pc + kTile - 1) / kTile), ray_tiles = (int)((nc + kTile - 1) / kTile);
+      e |= launch_dw_gemm(w.dH2, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_color, kIn2, 0, st);
+      e |= launch_dw_gemm(w.dH2 + 32, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_logit, kIn2, 0, st);
+      e |= launch_dw_gemm(w.dpre, 4, 3, w.Hcol, 32, 32, Pc, nullptr, pt_tiles, nullptr, a->d_color + 32 * kIn2, 32, 0, st);
+      e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st);
+      if (e) return DNS_ERR_CUDA;
+    }
+  }
+  k_finalize<<<1, 32, 0, st>>>(mode, w.raw, w.counts, N, P, a->lambda_p, a->lambda_d, a->lambda_l, a->lambda_lt,
+                               a->lambda_fs, a->lambda_op, a->losses);
+  return check_launch("finalize");
+}
+
+int64_t dns_tv_workspace_bytes(int n) {
+  int64_t n3 = (int64_t)n * n * n;
+  int64_t Q = ((n3 + kTile - 1) / kTile) * kTile;
+  return 4096 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 32 + kOutP)) + 8 * 256;
+}
+
+int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = a->n;
+  if (n < 2 || n > 512) {
+    set_error("tv: lattice size out of range (%d)", n);
+    return DNS_ERR_ARG;
+  }
+  if (!a->workspace || a->workspace_bytes < dns_tv_workspace_bytes(n)) {
+    set_error("tv: workspace too small");
+    return DNS_ERR_ARG;
+  }
+  const int64_t n3 = (int64_t)n * n * n;
+  const int tiles = (int)((n3 + kTile - 1) / kTile);
+  const int64_t Q = (int64_t)tiles * kTile;
+  Carver c{(char*)a->workspace, 0};
+  float* WTc = c.take<float>(kNetT);
+  float* occ = c.take<float>(n3);
+  float* docc = c.take<float>(n3);
+  float* Xst = c.take<float>(Q * kIn1);
+  float* Hc = c.take<float>(Q * 32);
+  float* dHc = c.take<float>(Q * 32);
+  float* dOc = c.take<float>(Q * kOutP);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_point_fwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_point_bwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, WTc);
+  cudaMemsetAsync(a->loss, 0, sizeof(float), st);
+  PointArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  for (int k = 0; k < 3; ++k) {
+    pa.B.lo[k] = a->bound[k][0];
+    pa.B.ext[k] = a->bound[k][1] - a->bound[k][0];
+    pa.jit[k] = a->jitter[k];
+    pa.off[k] = a->offset[k];
+  }
+  pa.n = n; pa.voxel = a->voxel; pa.G = a->grid; pa.table = (const float2*)a->table;
+  pa.n_tiles_host = tiles; pa.WTc = WTc; pa.occ = occ; pa.docc = docc;
+  pa.Xst = Xst; pa.Hc = Hc; pa.dHc = dHc; pa.dOc = dOc;
+  pa.d_table = (float2*)a->d_table; pa.need_dparams = a->need_dparams; pa.need_drays = 0;
+  const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT);
+  k_point_fwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
+  const float inv_norm = 1.0f / ((float)a->smooth_pts * (float)a->smooth_pts * (float)a->smooth_pts);
+  k_tv_stencil<<<(int)((n3 + 255) / 256), 256, 0, st>>>(occ, n, inv_norm, a->lambda_sm, docc, a->loss);
+  if (int e = check_launch("tv fwd")) return e;
+  if (a->need_dparams) {
+    k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
+    if (int e = check_launch("tv bwd")) return e;
+    int e = 0;
+    e |= launch_dw_gemm(dHc, 32, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st);
+    e |= launch_dw_gemm(dOc, kOutP, 1, Hc, 32, 32, Q, nullptr, tiles, nullptr, a->d_coarse + 2560, 32, 0, st);
+    if (e) return DNS_ERR_CUDA;
+  }
+  return DNS_OK;
+}
+
+}  // extern "C"

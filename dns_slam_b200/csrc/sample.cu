@@ -1,0 +1,191 @@
+// Ray / point sampling and the pixel-feature gather (sm_100a).
+//
+//   dns_sample_rays     utils/common.py:248-304 (get_samples, get_rays_from_uv),
+//                       slams/tracking.py:148-160 / slams/mapping.py:519-531 (far plane, points),
+//                       utils/common.py:561-599 (sample_along_rays)
+//   dns_feature_gather  utils/common.py:632-670 (projection, rounding, masks, gather) with the
+//                       bilinear up-sampling of :646 evaluated on the fly at the rounded pixel
+//
+// Integer / index work is bit exact against the oracle: every fp32 / fp64 operation is issued
+// in the reference's order with explicit round-to-nearest intrinsics (no FMA contraction).
+#include "common.cuh"
+
+namespace dns {
+
+__global__ void k_sample_gather(dns_sample_args a) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n) return;
+  int64_t idx = a.index[r];
+  int hh = a.H0 + (int)(idx / a.Ww), ww = a.W0 + (int)(idx % a.Ww);
+  int64_t pix = (int64_t)hh * a.W + ww;
+  float d = a.depth[pix];
+  a.gt_color[3 * r + 0] = a.color[3 * pix + 0];
+  a.gt_color[3 * r + 1] = a.color[3 * pix + 1];
+  a.gt_color[3 * r + 2] = a.color[3 * pix + 2];
+  a.gt_depth[r] = d;
+  a.gt_label[r] = a.label[pix];
+  float i = (float)ww, j = (float)hh;
+  float dir[3] = {__fdiv_rn(__fsub_rn(i, a.cx), a.fx), __fdiv_rn(-__fsub_rn(j, a.cy), a.fy), -1.0f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = __fadd_rn(__fadd_rn(__fmul_rn(dir[0], a.R[3 * c]), __fmul_rn(dir[1], a.R[3 * c + 1])),
+                        __fmul_rn(dir[2], a.R[3 * c + 2]));
+    a.rays_d[3 * r + c] = v;
+    a.rays_o[3 * r + c] = a.T[c];
+  }
+  // batch-global max depth (common.py:581,591); depths are >= 0 so the int ordering is the float ordering
+  atomicMax(reinterpret_cast<int*>(a.scratch), __float_as_int(fmaxf(d, 0.f)));
+}
+
+__global__ void k_sample_z(dns_sample_args a) {
+  extern __shared__ float sm[];  // [S][blockDim.x]
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  if (r >= a.n) return;
+  const int S = a.n_uniform + a.n_surface;
+  const float d = a.gt_depth[r];
+  const float maxd = a.scratch[0];
+  // far plane in float64 (tracking.py:151-156)
+  double far_bb = INFINITY;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double o = (double)a.rays_o[3 * r + c], dd = (double)a.rays_d[3 * r + c];
+    double t0 = (a.bound[c][0] - o) / dd, t1 = (a.bound[c][1] - o) / dd;
+    double m = fmax(t0, t1);
+    far_bb = fmin(far_bb, m);
+  }
+  a.inside[r] = far_bb >= (double)d ? 1 : 0;
+  far_bb += 0.01;
+  float* col = sm + tid;
+  // depth-guided samples
+  if (d > 0.f) {
+    float lo = __fmul_rn(0.95f, d), hi = __fmul_rn(1.05f, d);
+    for (int k = 0; k < a.n_surface; ++k) {
+      float t = a.t_surface[k];
+      col[(a.n_uniform + k) * bd] = __fadd_rn(__fmul_rn(lo, __fsub_rn(1.0f, t)), __fmul_rn(hi, t));
+    }
+  } else {
+    for (int k = 0; k < a.n_surface; ++k) {
+      float t = a.t_zero[k];
+      col[(a.n_uniform + k) * bd] = __fadd_rn(__fmul_rn(0.001f, __fsub_rn(1.0f, t)), __fmul_rn(maxd, t));
+    }
+  }
+  // uniform samples: near fp32, far fp64 (clamped), blended in fp64, rounded to fp32 at the end
+  {
+    float near = __fmul_rn(d, 0.001f);
+    double hi = (double)__fmul_rn(maxd, 1.2f);
+    double far = fmin(fmax(far_bb, 0.0), hi);
+    for (int k = 0; k < a.n_uniform; ++k) {
+      float t = a.t_lin[k];
+      double v = (double)__fmul_rn(near, __fsub_rn(1.0f, t)) + far * (double)t;
+      col[k * bd] = (float)v;
+    }
+  }
+  // ascending sort by rank (ties broken by position; equal values are interchangeable)
+  for (int i = 0; i < S; ++i) {
+    float v = col[i * bd];
+    int rank = 0;
+    for (int j = 0; j < S; ++j) {
+      float u = col[j * bd];
+      rank += (u < v) || (u == v && j < i);
+    }
+    a.z_vals[(int64_t)r * S + rank] = v;
+  }
+  if (a.pts) {
+    for (int i = 0; i < S; ++i) {
+      float z = a.z_vals[(int64_t)r * S + i];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        a.pts[((int64_t)r * S + i) * 3 + c] = __fadd_rn(a.rays_o[3 * r + c], __fmul_rn(a.rays_d[3 * r + c], z));
+    }
+  }
+}
+
+// one warp per (view, point); feats are channels-last [R][h][w][C], C == 64
+__global__ void k_feature_gather(const float* __restrict__ pts, int64_t P, const float* __restrict__ w2c, int R,
+                                 const float* __restrict__ K, int H, int W, const float* __restrict__ feats, int C,
+                                 int h, int w, float* __restrict__ code, int64_t* __restrict__ uv_out,
+                                 uint8_t* __restrict__ mask_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (int64_t)R * P) return;
+  const int v = (int)(wid / P);
+  const int64_t p = wid - (int64_t)v * P;
+  const float* M = w2c + 16 * v;
+  const float px = pts[3 * p], py = pts[3 * p + 1], pz = pts[3 * p + 2];
+  float cam[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) cam[c] = fmaf(M[4 * c + 2], pz, fmaf(M[4 * c + 1], py, fmaf(M[4 * c], px, M[4 * c + 3])));
+  cam[1] = -cam[1];
+  cam[2] = -cam[2];
+  float img[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) img[c] = fmaf(K[3 * c + 2], cam[2], fmaf(K[3 * c + 1], cam[1], K[3 * c] * cam[0]));
+  float den = img[2] + 1e-5f;
+  float u = rintf(img[0] / den), vv = rintf(img[1] / den);
+  bool m = (u > 0.f) && (u < (float)(W - 1)) && (vv > 0.f) && (vv < (float)(H - 1)) && (cam[2] > 0.f);
+  int64_t ui = m ? (int64_t)u : 0, vi = m ? (int64_t)vv : 0;
+  if (lane == 0) {
+    if (uv_out) {
+      uv_out[2 * wid] = ui;
+      uv_out[2 * wid + 1] = vi;
+    }
+    if (mask_out) mask_out[wid] = m ? 1 : 0;
+  }
+  float* dst = code + wid * C;
+  if (!m) {
+    for (int c = lane; c < C; c += 32) dst[c] = 0.f;
+    return;
+  }
+  // F.interpolate(..., mode='bilinear', align_corners=True) sampled at integer pixel (vi, ui)
+  float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  float fy = sy * (float)vi, fx = sx * (float)ui;
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+  const float* f = feats + (int64_t)v * h * w * C;
+  const float* f00 = f + ((int64_t)y0 * w + x0) * C;
+  const float* f01 = f + ((int64_t)y0 * w + x1) * C;
+  const float* f10 = f + ((int64_t)y1 * w + x0) * C;
+  const float* f11 = f + ((int64_t)y1 * w + x1) * C;
+  for (int c = lane; c < C; c += 32)
+    dst[c] = ly0 * (lx0 * __ldg(f00 + c) + lx1 * __ldg(f01 + c)) + ly1 * (lx0 * __ldg(f10 + c) + lx1 * __ldg(f11 + c));
+}
+
+}  // namespace dns
+
+using namespace dns;
+
+extern "C" {
+
+int dns_sample_rays(const dns_sample_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = a->n_uniform + a->n_surface;
+  if (a->n <= 0) return DNS_OK;
+  if (S < 1 || S > 256 || a->n_uniform < 0 || a->n_surface < 0) {
+    set_error("sample: need 1 <= n_uniform + n_surface <= 256");
+    return DNS_ERR_UNSUPPORTED;
+  }
+  cudaMemsetAsync(a->scratch, 0, 2 * sizeof(float), st);
+  k_sample_gather<<<(a->n + 127) / 128, 128, 0, st>>>(*a);
+  const int bd = 64;
+  size_t smem = sizeof(float) * S * bd;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_sample_z, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    attr = true;
+  }
+  k_sample_z<<<(a->n + bd - 1) / bd, bd, smem, st>>>(*a);
+  return check_launch("sample_rays");
+}
+
+int dns_feature_gather(const float* pts, int64_t P, const float* w2c, int R, const float* K, int H, int W,
+                       const float* feats, int C, int h, int w, float* code, int64_t* uv, uint8_t* mask, void* stream) {
+  if (P <= 0 || R <= 0) return DNS_OK;
+  int64_t warps = (int64_t)R * P;
+  int64_t blocks = (warps * 32 + 255) / 256;
+  k_feature_gather<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pts, P, w2c, R, K, H, W, feats, C, h, w, code, uv,
+                                                                       mask);
+  return check_launch("feature_gather");
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+"""Fused path: sampling, render + loss + backward, TV smoothness, feature matching, Adam.
+
+Python mirrors of the reference call sites, each a thin wrapper over ONE C-ABI call:
+
+    sample_rays        get_samples / far plane / sample_along_rays  (common.py:296-304,561-599;
+                                                                      tracking.py:137-160)
+    render_and_loss    Tracker.renderer + losses + backward          (tracking.py:188-214,85-96)
+                       Mapper.renderer + losses + backward           (mapping.py:590-635,110-126,891-909)
+    tv_loss            Mapper.smoothness                             (mapping.py:129-159)
+    feature_matching   utils.common.feature_matching                 (common.py:645-679)
+    adam_step          torch.optim.Adam.step over a flat buffer      (mapping.py:464-466,910)
+
+``render_and_loss`` is an autograd Function: forward runs the fused forward AND backward
+kernels (the loss is a scalar whose normalisers depend on inputs only), ``backward`` scales the
+stored gradients by the incoming gradient, so ``loss.backward()`` fills ``.grad`` of the
+decoder parameters and of the pose leaves exactly like the reference loop.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+LOSS_KEYS = ("p_loss", "d_loss", "l_loss", "lt_loss", "fs_loss", "opacity_loss", "total", "n_valid")
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    """Cached, growing scratch buffer (caller-owned memory of the C ABI)."""
+    key = (device.type, device.index)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _ws_cache[key] = buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
+    return buf
+
+
+# ----------------------------------------------------------------------------------------
+# sampling
+# ----------------------------------------------------------------------------------------
+def fix_surface_draw(t, n_surface):
+    """common.py:572-573: force one offset to 0.5 unless the draw already holds one."""
+    t = t.clone()
+    if not torch.any(t == 0.5):
+        t[n_surface // 2 + 1] = 0.5
+    return t
+
+
+def sample_rays(cam, bound, frame, idx, window, R, T, n_samples, n_surface, t_surface, t_zero,
+                want_pts=False, t_lin=None):
+    """frame: dict(color [H,W,3] f32, depth [H,W] f32, label [H,W] i64) on the GPU; idx: flat
+    window indices [n] int64 (the draws of common.py:274 / :327); window = (H0, H1, W0, W1).
+    Returns the ``samples`` fields of tracking.py:177-185 plus ``inside``."""
+    dev = frame["color"].device
+    n = idx.numel()
+    S = n_samples + n_surface
+    a = _lib.SampleArgs()
+    H0, H1, W0, W1 = window
+    a.n, a.H, a.W, a.H0, a.W0, a.Ww = n, cam["H"], cam["W"], H0, W0, W1 - W0
+    a.n_uniform, a.n_surface = n_samples, n_surface
+    a.fx, a.fy, a.cx, a.cy = cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    _lib.fill_bound(a.bound, bound)
+    if t_lin is None:
+        t_lin = torch.linspace(0.0, 1.0, steps=n_samples) if n_samples > 0 else torch.zeros(0)
+    keep = [frame["color"], frame["depth"], frame["label"], idx.contiguous(),
+            R.detach().to(dev, torch.float32).contiguous(), T.detach().to(dev, torch.float32).contiguous(),
+            t_lin.to(dev, torch.float32).contiguous(), t_surface.to(dev, torch.float32).contiguous(),
+            t_zero.to(dev, torch.float32).contiguous()]
+    a.color, a.depth = _lib.ptr(keep[0], torch.float32), _lib.ptr(keep[1], torch.float32)
+    a.label, a.index = _lib.ptr(keep[2], torch.int64), _lib.ptr(keep[3], torch.int64)
+    a.R, a.T, a.t_lin, a.t_surface, a.t_zero = (_lib.ptr(k) for k in keep[4:])
+    out = dict(gt_color=torch.empty(n, 3, device=dev), gt_depth=torch.empty(n, device=dev),
+               gt_label=torch.empty(n, dtype=torch.int64, device=dev), rays_o=torch.empty(n, 3, device=dev),
+               rays_d=torch.empty(n, 3, device=dev), z_vals=torch.empty(n, S, device=dev),
+               inside=torch.empty(n, dtype=torch.uint8, device=dev))
+    if want_pts:
+        out["pts"] = torch.empty(n, S, 3, device=dev)
+    scratch = torch.empty(2, device=dev)
+    for k in ("gt_color", "gt_depth", "gt_label", "rays_o", "rays_d", "z_vals", "inside"):
+        setattr(a, k, _lib.ptr(out[k]))
+    a.pts = _lib.ptr(out.get("pts"), allow_none=True)
+    a.scratch = _lib.ptr(scratch)
+    _lib.check(_lib.lib().dns_sample_rays(C.byref(a), _lib.stream()))
+    out["inside"] = out["inside"].bool()
+    return out
+
+
+def pixel_dirs(cam, idx, window):
+    """Camera-frame directions of the sampled pixels (common.py:257-258)."""
+    H0, H1, W0, W1 = window
+    Ww = W1 - W0
+    i = (W0 + idx % Ww).to(torch.float32)
+    j = (H0 + torch.div(idx, Ww, rounding_mode="floor")).to(torch.float32)
+    return torch.stack([(i - cam["cx"]) / cam["fx"], -(j - cam["cy"]) / cam["fy"], -torch.ones_like(i)], -1)
+
+
+def attach_pose_grad(rays_o, rays_d, dirs, R, T):
+    """Values stay the kernel's (bit exact); gradients flow to R / T through the torch expression
+    of get_rays_from_uv (common.py:262-263):  v + (e - e.detach()) == v exactly."""
+    e_d = torch.sum(dirs[:, None, :] * R, -1)
+    e_o = T.expand(e_d.shape)
+    return rays_o + (e_o - e_o.detach()), rays_d + (e_d - e_d.detach())
+
+
+# ----------------------------------------------------------------------------------------
+# fused render + loss + backward
+# ----------------------------------------------------------------------------------------
+class RenderConfig:
+    """Non-differentiable inputs and knobs of one fused call."""
+
+    def __init__(self, mode, bound, gstruct, z_vals, gt_color, gt_depth, gt_label, mask=None,
+                 class_to_expert=None, n_class=40, lambdas=None, opacity_trunc=0.05, opacity_sigma=0.05,
+                 want_latents=False):
+        self.mode, self.bound, self.gstruct = mode, bound, gstruct
+        self.z_vals, self.gt_color, self.gt_depth, self.gt_label = z_vals, gt_color, gt_depth, gt_label
+        self.mask, self.class_to_expert, self.n_class = mask, class_to_expert, n_class
+        lam = dict(p=5.0, d=5.0, l=0.1, lt=0.0, fs=0.0, op=0.0)
+        lam.update(lambdas or {})
+        self.lam = lam
+        self.opacity_trunc, self.opacity_sigma = opacity_trunc, opacity_sigma
+        self.want_latents = want_latents
+
+
+def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, features, grads, need_drays,
+               need_dfeat):
+    """One ``dns_render_fwd_bwd`` call.  ``grads``: dict with optional device buffers
+    ``table/coarse/color/logit/experts`` that are ACCUMULATED into (None => no parameter grads).
+    Returns (losses[8], preds dict, d_rays_o, d_rays_d, d_features)."""
+    dev = rays_o.device
+    N, S = cfg.z_vals.shape
+    Cn = cfg.n_class
+    a = _lib.RenderArgs()
+    a.mode, a.n_rays, a.n_samples, a.n_class = cfg.mode, N, S, Cn
+    need_dparams = grads is not None
+    a.need_dparams, a.need_drays, a.need_dfeat = int(need_dparams), int(need_drays), int(need_dfeat)
+    _lib.fill_bound(a.bound, cfg.bound)
+    a.lambda_p, a.lambda_d, a.lambda_l = cfg.lam["p"], cfg.lam["d"], cfg.lam["l"]
+    a.lambda_lt, a.lambda_fs, a.lambda_op = cfg.lam["lt"], cfg.lam["fs"], cfg.lam["op"]
+    a.opacity_trunc, a.opacity_sigma = cfg.opacity_trunc, cfg.opacity_sigma
+    a.grid = cfg.gstruct
+    f32, i64 = torch.float32, torch.int64
+    a.rays_o, a.rays_d = _lib.ptr(rays_o, f32), _lib.ptr(rays_d, f32)
+    a.z_vals, a.gt_color = _lib.ptr(cfg.z_vals, f32), _lib.ptr(cfg.gt_color, f32)
+    a.gt_depth, a.gt_label = _lib.ptr(cfg.gt_depth, f32), _lib.ptr(cfg.gt_label, i64)
+    mask8 = None
+    if cfg.mode == _lib.MODE_TRACK and cfg.mask is not None:
+        mask8 = cfg.mask.to(torch.uint8).contiguous()
+    a.mask = _lib.ptr(mask8, allow_none=True)
+    a.features = _lib.ptr(features, f32, allow_none=True)
+    a.table, a.coarse = _lib.ptr(table, f32), _lib.ptr(coarse, f32)
+    a.color, a.logit = _lib.ptr(color, f32), _lib.ptr(logit, f32)
+    n_ids = 1
+    if cfg.mode == _lib.MODE_MAP:
+        if experts is None or cfg.class_to_expert is None:
+            raise ValueError("mapping mode needs the expert bank and class_to_expert")
+        a.experts = _lib.ptr(experts, f32)
+        a.n_experts = experts.shape[0]
+        a.class_to_expert = _lib.ptr(cfg.class_to_expert, torch.int32)
+        n_ids = cfg.class_to_expert.numel()
+    a.n_class_ids = n_ids
+    preds = dict(color=torch.empty(N, 3, device=dev), depth=torch.empty(N, device=dev),
+                 var=torch.empty(N, device=dev), logits=torch.empty(N, Cn, device=dev))
+    a.pred_color, a.pred_depth = _lib.ptr(preds["color"]), _lib.ptr(preds["depth"])
+    a.pred_var, a.pred_logits = _lib.ptr(preds["var"]), _lib.ptr(preds["logits"])
+    if cfg.want_latents:
+        preds["fine"] = torch.empty(N * S, 33, device=dev)
+        a.fine = _lib.ptr(preds["fine"])
+        if cfg.mode == _lib.MODE_MAP:
+            preds["coarse"] = torch.empty(N * S, 33, device=dev)
+            a.coarse_out = _lib.ptr(preds["coarse"])
+    losses = torch.empty(8, device=dev)
+    a.losses = _lib.ptr(losses)
+    if need_dparams:
+        a.d_table, a.d_coarse = _lib.ptr(grads["table"], f32), _lib.ptr(grads["coarse"], f32)
+        a.d_color, a.d_logit = _lib.ptr(grads["color"], f32), _lib.ptr(grads["logit"], f32)
+        if cfg.mode == _lib.MODE_MAP:
+            a.d_experts = _lib.ptr(grads["experts"], f32)
+    d_o = torch.empty(N, 3, device=dev) if need_drays else None
+    d_d = torch.empty(N, 3, device=dev) if need_drays else None
+    d_f = torch.empty(N, S, 32, device=dev) if need_dfeat else None
+    a.d_rays_o, a.d_rays_d = _lib.ptr(d_o, allow_none=True), _lib.ptr(d_d, allow_none=True)
+    a.d_features = _lib.ptr(d_f, allow_none=True)
+    L = _lib.lib()
+    nbytes = L.dns_render_workspace_bytes(cfg.mode, N, S, Cn, n_ids)
+    ws = workspace(nbytes, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _lib.check(L.dns_render_fwd_bwd(C.byref(a), _lib.stream()))
+    return losses, preds, d_o, d_d, d_f
+
+
+class _RenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, table, coarse, color, logit, experts, rays_o, rays_d, features):
+        need = ctx.needs_input_grad
+        need_dparams = any(need[1:6])
+        need_drays = need[6] or need[7]
+        need_dfeat = features is not None and need[8]
+        grads = None
+        if need_dparams:
+            grads = dict(table=torch.zeros_like(table), coarse=torch.zeros_like(coarse),
+                         color=torch.zeros_like(color), logit=torch.zeros_like(logit),
+                         experts=torch.zeros_like(experts) if experts is not None else None)
+        feats = features.detach().to(torch.float32).contiguous() if features is not None else None
+        losses, preds, d_o, d_d, d_f = render_raw(
+            cfg, table.detach(), coarse.detach(), color.detach(), logit.detach(),
+            experts.detach() if experts is not None else None, rays_o.detach().contiguous(),
+            rays_d.detach().contiguous(), feats, grads, need_drays, need_dfeat)
+        ctx.grads, ctx.d_rays, ctx.d_f = grads, (d_o, d_d), d_f
+        total = losses[6].clone()
+        outs = (total, losses, preds["color"], preds["depth"], preds["var"], preds["logits"],
+                preds.get("fine"), preds.get("coarse"))
+        ctx.mark_non_differentiable(*[o for o in outs[1:] if o is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_total, *unused):
+        g, need = ctx.grads, ctx.needs_input_grad
+
+        def sc(t, flag):
+            return g_total * t if (flag and t is not None) else None
+
+        gp = g or {}
+        return (None, sc(gp.get("table"), need[1]), sc(gp.get("coarse"), need[2]), sc(gp.get("color"), need[3]),
+                sc(gp.get("logit"), need[4]), sc(gp.get("experts"), need[5]), sc(ctx.d_rays[0], need[6]),
+                sc(ctx.d_rays[1], need[7]), sc(ctx.d_f, need[8]))
+
+
+def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_sigma=0.05, want_latents=False):
+    """Fused drop-in for ``renderer(samples)`` + the loss block of the iteration bodies.
+
+    ``samples``: the dict of tracking.py:177-185 / mapping.py:579-586 (``pts`` is not needed: points
+    are rebuilt from rays and z).  Returns ``(loss_dict, preds)`` where ``loss_dict['total']`` is
+    differentiable w.r.t. the decoder parameters, ``samples['rays_o'/'rays_d']`` and
+    ``samples['features']``; the other entries are detached scalars (mapping.py:942-947 keys)."""
+    cfg = RenderConfig(mode, decoder.bound, decoder.pe_fn.grid_fn.gstruct, samples["z_vals"].contiguous(),
+                       samples["gt_color"].contiguous(), samples["gt_depth"].contiguous(),
+                       samples["gt_label"].contiguous(), samples.get("mask"),
+                       decoder.class_to_expert if mode == _lib.MODE_MAP else None,
+                       n_class or decoder.n_class, lambdas, opacity_trunc=opacity_sigma, want_latents=want_latents)
+    experts = decoder.expert_params if mode == _lib.MODE_MAP else None
+    feats = samples.get("features")
+    out = _RenderFn.apply(cfg, decoder.pe_fn.grid_fn.params, decoder.coarse_fn.decoder.params,
+                          decoder.out_fn.color_decoder.params, decoder.out_fn.logit_decoder.params, experts,
+                          samples["rays_o"], samples["rays_d"], feats)
+    total, losses = out[0], out[1]
+    ld = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
+    ld["total"] = total
+    preds = dict(color=out[2], depth=out[3], var=out[4], logits=out[5], fine=out[6], coarse=out[7])
+    return ld, preds
+
+
+# ----------------------------------------------------------------------------------------
+# TV smoothness
+# ----------------------------------------------------------------------------------------
+def tv_offsets(bound, sample_points, rand3, rand113, voxel_size=0.1, margin=0.05):
+    """float64 offset / jitter exactly as mapping.py:133-140 builds them (host side, tiny)."""
+    b = bound.detach().double().cpu()
+    volume = b[:, 1] - b[:, 0]
+    offset_max = volume - (sample_points - 1) * voxel_size - 2 * margin
+    offset = rand3.detach().cpu().to(offset_max) * offset_max + margin
+    jitter = rand113.detach().cpu().reshape(3).to(volume)
+    return offset, jitter
+
+
+def tv_raw(gstruct, bound, table, coarse, sample_points, offset, jitter, lambda_sm, d_table, d_coarse):
+    dev = table.device
+    a = _lib.TvArgs()
+    a.n, a.smooth_pts, a.voxel = sample_points - 1, sample_points, 0.1
+    _lib.fill_bound(a.bound, bound)
+    for k in range(3):
+        a.offset[k], a.jitter[k] = float(offset[k]), float(jitter[k])
+    a.lambda_sm = lambda_sm
+    a.need_dparams = int(d_table is not None)
+    a.grid = gstruct
+    a.table, a.coarse = _lib.ptr(table, torch.float32), _lib.ptr(coarse, torch.float32)
+    loss = torch.empty(1, device=dev)
+    a.loss = _lib.ptr(loss)
+    a.d_table, a.d_coarse = _lib.ptr(d_table, allow_none=True), _lib.ptr(d_coarse, allow_none=True)
+    L = _lib.lib()
+    ws = workspace(L.dns_tv_workspace_bytes(a.n), dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _lib.check(L.dns_tv_fwd_bwd(C.byref(a), _lib.stream()))
+    return loss[0]
+
+
+class _TvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, coarse, gstruct, bound, sample_points, offset, jitter):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_t = torch.zeros_like(table) if need else None
+        d_c = torch.zeros_like(coarse) if need else None
+        loss = tv_raw(gstruct, bound, table.detach(), coarse.detach(), sample_points, offset, jitter, 1.0, d_t, d_c)
+        ctx.g = (d_t, d_c)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        d_t, d_c = ctx.g
+        return (g * d_t if d_t is not None else None, g * d_c if d_c is not None else None, None, None, None, None, None)
+
+
+def tv_loss(decoder, sample_points, rand3, rand113):
+    """Mapper.smoothness(sample_points) with the two CPU draws of mapping.py:138,140 as inputs."""
+    offset, jitter = tv_offsets(decoder.bound, sample_points, rand3, rand113)
+    return _TvFn.apply(decoder.pe_fn.grid_fn.params, decoder.coarse_fn.decoder.params,
+                       decoder.pe_fn.grid_fn.gstruct, decoder.bound, sample_points, offset, jitter)
+
+
+# ----------------------------------------------------------------------------------------
+# pixel-feature branch
+# ----------------------------------------------------------------------------------------
+def channels_last(features):
+    """[R,C,h,w] -> contiguous [R,h,w,C]; done once per frame, not per iteration."""
+    return features.permute(0, 2, 3, 1).contiguous()
+
+
+def feature_gather(H, W, K, pts, refer_w2c, feats_cl):
+    """Projection + rounding + masks + bilinear fetch (common.py:646-670,676).  Non-differentiable
+    (the reference's ``torch.round`` cuts the gradient).  Returns code [R,P,C], uv [R,P,2], mask [R,P]."""
+    dev = pts.device
+    P, R = pts.shape[0], refer_w2c.shape[0]
+    _, h, w, Cc = feats_cl.shape
+    code = torch.empty(R, P, Cc, device=dev)
+    uv = torch.empty(R, P, 2, dtype=torch.int64, device=dev)
+    mask = torch.empty(R, P, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().dns_feature_gather(
+        _lib.ptr(pts.detach().to(torch.float32).contiguous()), P,
+        _lib.ptr(refer_w2c.detach().to(torch.float32).contiguous()), R,
+        _lib.ptr(K.detach().to(dev, torch.float32).contiguous()), H, W, _lib.ptr(feats_cl, torch.float32), Cc, h, w,
+        _lib.ptr(code), _lib.ptr(uv), _lib.ptr(mask), _lib.stream()))
+    return code, uv, mask.bool()
+
+
+def feature_matching(H, W, K, pts_, refer_w2c, feats_cl, merge_fn):
+    """utils.common.feature_matching with channels-last features (no 209 MB/view up-sample)."""
+    code, _, _ = feature_gather(H, W, K, pts_, refer_w2c, feats_cl)
+    refer_c2w = torch.inverse(refer_w2c)
+    refer_o = refer_c2w[:, :3, 3]
+    refer_p = pts_[None, :, :] - refer_o[:, None, :]
+    return merge_fn(refer_p, refer_o, code)
+
+
+# ----------------------------------------------------------------------------------------
+# Adam
+# ----------------------------------------------------------------------------------------
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8):
+    """In-place torch.optim.Adam step (defaults) over flat fp32 buffers."""
+    _lib.check(_lib.lib().dns_adam_step(_lib.ptr(params, torch.float32), _lib.ptr(grads, torch.float32),
+                                        _lib.ptr(exp_avg, torch.float32), _lib.ptr(exp_avg_sq, torch.float32),
+                                        params.numel(), lr, betas[0], betas[1], eps, step, _lib.stream()))

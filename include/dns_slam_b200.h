@@ -1,0 +1,231 @@
+/*
+ * dns_slam_b200 -- C ABI of the B200-native (sm_100a) DNS-SLAM render-and-optimise hot path.
+ *
+ * Plain C, raw DEVICE pointers + explicit cudaStream_t (passed as void*), int error codes
+ * (0 = ok; dns_last_error() gives the text), caller-owned memory, no hidden allocations
+ * (scratch comes from a caller-provided workspace sized by dns_render_workspace_bytes /
+ * dns_tv_workspace_bytes), no global state.  There is NO CPU fallback: every entry point
+ * launches CUDA kernels.
+ *
+ * The reference (li-kunyi/dns-slam) has no FFI of its own; its native boundary is the
+ * un-vendored `tinycudann` torch binding.  Each entry point below cites the reference
+ * interface it replaces (paths relative to the reference root).
+ */
+#ifndef DNS_SLAM_B200_H
+#define DNS_SLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNS_MAX_LEVELS 16
+#define DNS_HIDDEN 32      /* n_neurons of every MLP on the path (configs/slam.yaml:18) */
+#define DNS_PE_DIM 48      /* OneBlob 3 x 16 bins  (models/pos_encoding.py:61-71) */
+#define DNS_GRID_DIM 32    /* 16 levels x 2 features (models/pos_encoding.py:31-46) */
+#define DNS_LATENT 33      /* occupancy logit + 32 latent channels (models/decoder.py:85) */
+#define DNS_FEAT_DIM 32    /* merged pixel feature width (models/decoder.py:59) */
+
+enum { DNS_OK = 0, DNS_ERR_ARG = 1, DNS_ERR_CUDA = 2, DNS_ERR_UNSUPPORTED = 3 };
+enum { DNS_MODE_TRACK = 0, DNS_MODE_MAP = 1 };
+
+/* Multi-resolution hash grid geometry; computed ONCE on the host (fp32 emulation of
+ * tiny-cuda-nn grid_scale / grid_resolution) and shared with the oracle so that the hash
+ * indices are bit exact.  Replaces the encoding_config dict of
+ * models/pos_encoding.py:34-45. */
+typedef struct dns_grid {
+  int32_t n_levels;                     /* <= DNS_MAX_LEVELS */
+  int32_t n_features;                   /* 2 */
+  float scale[DNS_MAX_LEVELS];          /* pos = fma(scale, x, 0.5) */
+  uint32_t res[DNS_MAX_LEVELS];         /* grid resolution of the level */
+  uint32_t size[DNS_MAX_LEVELS];        /* entries in the level (multiple of 8, <= 2^log2_T) */
+  uint32_t offset[DNS_MAX_LEVELS + 1];  /* running sum of size[], in entries */
+  uint32_t hashed[DNS_MAX_LEVELS];      /* 1: coherent-prime hash, 0: dense index */
+} dns_grid;
+
+const char* dns_last_error(void);
+int dns_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Operator surface == the tinycudann module API the reference calls
+ * ------------------------------------------------------------------------------------- */
+
+/* tcnn.Encoding(otype=OneBlob).forward / backward  (models/pos_encoding.py:61-71,
+ * called at models/decoder.py:46,71).  x [P,D] f32 -> out [P,D*n_bins] f32. */
+int dns_oneblob_fwd(const float* x, int64_t P, int D, int n_bins, float* out, void* stream);
+int dns_oneblob_bwd(const float* x, const float* d_out, int64_t P, int D, int n_bins, float* d_x,
+                    void* stream);
+
+/* tcnn.Encoding(otype=HashGrid).forward / backward (models/pos_encoding.py:31-46, called at
+ * models/decoder.py:47).  x [P,3] f32 in [0,1], table [n_entries,2] f32 -> out [P,2L].
+ * bwd ACCUMULATES into d_table (atomics) and, if d_x != NULL, writes dL/dx [P,3]. */
+int dns_hashgrid_fwd(const dns_grid* g, const float* x, const float* table, int64_t P, float* out,
+                     void* stream);
+int dns_hashgrid_bwd(const dns_grid* g, const float* x, const float* table, const float* d_out,
+                     int64_t P, float* d_table, float* d_x, void* stream);
+/* bit-exactness probe used by the parity tests: table indices of the 8 corners,
+ * idx [P, L, 8] uint32 (absolute entry index incl. level offset). */
+int dns_hashgrid_indices(const dns_grid* g, const float* x, int64_t P, uint32_t* idx, void* stream);
+
+/* tcnn.Network(CutlassMLP, 1 hidden layer of 32, ReLU, no bias).forward / backward
+ * (models/decoder.py:58-65,84-91,101-117; slams/mapping.py:737-744).
+ * params = [W1 (32 x n_in) | W2 (out_pad x 32)] row-major, n_in % 16 == 0.
+ * hidden [P,32] (post-ReLU) is written by fwd and consumed by bwd.
+ * bwd writes d_hidden [P,32] (caller-owned scratch), ACCUMULATES into d_params (may be NULL)
+ * and writes d_x [P,n_in] (may be NULL). */
+int dns_mlp_fwd(const float* x, const float* params, int64_t P, int n_in, int n_out, float* out,
+                float* hidden, void* stream);
+int dns_mlp_bwd(const float* x, const float* params, const float* hidden, const float* d_out,
+                int64_t P, int n_in, int n_out, float* d_hidden, float* d_x, float* d_params,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused path == the bodies of Tracker.renderer + losses + backward
+ * (slams/tracking.py:188-214,85-96,326-338) and Mapper.renderer + losses + backward
+ * (slams/mapping.py:590-635,110-126,891-909; utils/common.py:506-537,769-802)
+ * ------------------------------------------------------------------------------------- */
+typedef struct dns_render_args {
+  int32_t mode;          /* DNS_MODE_TRACK | DNS_MODE_MAP */
+  int32_t n_rays;        /* N (after the inside-mask compaction in MAP mode) */
+  int32_t n_samples;     /* S = n_samples_ray + n_surface_ray */
+  int32_t n_class;       /* C: width of the semantic head */
+  int32_t n_experts;     /* MAP: rows of `experts` */
+  int32_t need_dparams;  /* accumulate hash-table / MLP gradients */
+  int32_t need_drays;    /* write d_rays_o / d_rays_d (pose gradients) */
+  int32_t need_dfeat;    /* write d_features (gradient into the Merge branch) */
+  double bound[3][2];    /* float64 scene bound (slams/dns_slam.py:100-107) */
+  /* loss weights: lambda_color, lambda_depth, lambda_label, lambda_lt, lambda_fs,
+   * lambda_opacity (slams/mapping.py:906-907, slams/tracking.py:329) */
+  float lambda_p, lambda_d, lambda_l, lambda_lt, lambda_fs, lambda_op;
+  float opacity_trunc;   /* = cfg opacity_sigma: lands in the truncation slot (mapping.py:896) */
+  float opacity_sigma;   /* = 0.05 default of utils/common.py:769 */
+  dns_grid grid;
+  /* inputs (device) */
+  const float* rays_o;     /* [N,3] */
+  const float* rays_d;     /* [N,3] */
+  const float* z_vals;     /* [N,S] */
+  const float* gt_color;   /* [N,3] */
+  const float* gt_depth;   /* [N] */
+  const int64_t* gt_label; /* [N] */
+  const uint8_t* mask;     /* TRACK: [N] valid-ray mask (tracking.py:174-175); NULL = all */
+  const float* features;   /* [N,S,32] merged pixel features, may be NULL (= zeros) */
+  /* parameters (device) */
+  const float* table;      /* [n_entries,2] */
+  const float* coarse;     /* 80->32->33(48)   W1[32][80] | W2[48][32] */
+  const float* color;      /* 112->32->3(16) */
+  const float* logit;      /* 112->32->C(pad16) */
+  const float* experts;    /* MAP: [n_experts][3616+...] same layout as coarse */
+  const int32_t* class_to_expert; /* MAP: [n_class_ids] expert row of a label id, -1 = none */
+  int32_t n_class_ids;
+  /* outputs (device) */
+  float* pred_color;   /* [N,3] */
+  float* pred_depth;   /* [N] */
+  float* pred_var;     /* [N] */
+  float* pred_logits;  /* [N,C] */
+  float* fine;         /* [P,33] (MAP; TRACK: the coarse latents), may be NULL */
+  float* coarse_out;   /* [P,33] (MAP), may be NULL */
+  float* losses;       /* [8]: p, d, l, lt, fs, op, total, n_valid */
+  /* gradients of `total` (device); accumulated (+=) unless noted */
+  float* d_table;
+  float* d_coarse;
+  float* d_color;
+  float* d_logit;
+  float* d_experts;    /* [n_experts][...] */
+  float* d_rays_o;     /* [N,3] overwritten */
+  float* d_rays_d;     /* [N,3] overwritten */
+  float* d_features;   /* [N,S,32] overwritten */
+  /* scratch */
+  void* workspace;
+  int64_t workspace_bytes;
+} dns_render_args;
+
+int64_t dns_render_workspace_bytes(int mode, int n_rays, int n_samples, int n_class, int n_class_ids);
+int dns_render_fwd_bwd(const dns_render_args* a, void* stream);
+
+/* Mapper.smoothness forward + backward (slams/mapping.py:129-159, oracle patch P1): TV of the
+ * coarse occupancy on an n^3 lattice (n = smooth_pts - 1).  Point (i,j,k) is
+ *   x_a = ((((double)idx_a + jitter[a]) * voxel + bound_lo[a]) + offset[a] - bound_lo[a]) / extent[a]
+ * loss = sum of squared forward differences / smooth_pts^3, gradients scaled by lambda. */
+typedef struct dns_tv_args {
+  int32_t n;              /* lattice points per axis = smooth_pts - 1 */
+  int32_t smooth_pts;
+  double voxel;           /* 0.1 */
+  double bound[3][2];
+  double offset[3];       /* rand(3) * offset_max + margin, float64 */
+  double jitter[3];       /* rand(1,1,1,3) as float64 */
+  float lambda_sm;
+  int32_t need_dparams;
+  dns_grid grid;
+  const float* table;
+  const float* coarse;
+  float* loss;            /* [1] unweighted TV loss */
+  float* d_table;         /* += */
+  float* d_coarse;        /* += */
+  void* workspace;
+  int64_t workspace_bytes;
+} dns_tv_args;
+
+int64_t dns_tv_workspace_bytes(int n);
+int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Sampling == get_samples / get_rays_from_uv / far plane / sample_along_rays / point build
+ * (utils/common.py:248-304,561-599; slams/tracking.py:137-160; slams/mapping.py:497-531)
+ * ------------------------------------------------------------------------------------- */
+typedef struct dns_sample_args {
+  int32_t n;              /* rays */
+  int32_t H, W;           /* image size */
+  int32_t H0, W0, Ww;     /* window origin and width: flat index -> (H0 + idx / Ww, W0 + idx % Ww) */
+  int32_t n_uniform;      /* linspace samples (n_samples_ray) */
+  int32_t n_surface;      /* depth-guided samples (n_surface_ray) */
+  float fx, fy, cx, cy;
+  double bound[3][2];
+  const float* color;     /* [H,W,3] */
+  const float* depth;     /* [H,W] */
+  const int64_t* label;   /* [H,W] */
+  const int64_t* index;   /* [n] flat window indices (draws hoisted, oracle patch P5) */
+  const float* R;         /* [3,3] row-major c2w rotation */
+  const float* T;         /* [3] */
+  const float* t_lin;     /* [n_uniform] torch.linspace(0,1) */
+  const float* t_surface; /* [n_surface] first draw (element n_surface/2+1 already forced to 0.5) */
+  const float* t_zero;    /* [n_surface] second draw (zero-depth rays) */
+  float* gt_color;        /* [n,3] */
+  float* gt_depth;        /* [n] */
+  int64_t* gt_label;      /* [n] */
+  float* rays_o;          /* [n,3] */
+  float* rays_d;          /* [n,3] */
+  float* z_vals;          /* [n,S] ascending */
+  float* pts;             /* [n,S,3] or NULL */
+  uint8_t* inside;        /* [n] far_bb >= gt_depth */
+  float* scratch;         /* [2] device scratch: batch max depth */
+} dns_sample_args;
+
+int dns_sample_rays(const dns_sample_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pixel-feature branch == utils/common.py:645-679 without the 209 MB/view upsample:
+ * project P points into R views, round, mask, 4-tap bilinear fetch of the half-res feature
+ * map at the rounded full-res pixel (align_corners=True).
+ * ------------------------------------------------------------------------------------- */
+int dns_feature_gather(const float* pts, int64_t P, const float* w2c /*[R,4,4]*/, int R,
+                       const float* K /*[3,3]*/, int H, int W,
+                       const float* feats /*[R,h,w,C] channels-last*/,
+                       int C, int h, int w, float* code /*[R,P,C]*/, int64_t* uv /*[R,P,2] or NULL*/,
+                       uint8_t* mask /*[R,P] or NULL*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Adam == torch.optim.Adam defaults over a flat fp32 buffer
+ * (slams/tracking.py:119-124,339; slams/mapping.py:464-466,910)
+ * ------------------------------------------------------------------------------------- */
+int dns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+/* sizeof(dns_grid), sizeof(dns_render_args), sizeof(dns_tv_args), sizeof(dns_sample_args): lets a
+ * foreign-language binding assert that its struct mirror matches this header. */
+void dns_struct_sizes(int64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNS_SLAM_B200_H */
