@@ -40,7 +40,9 @@ def test_oneblob(P):
     w = torch.randn(P, 48, generator=g)
     (yo * w).sum().backward()
     (yg * w.to(dev)).sum().backward()
-    close(xg.grad, xo.grad, rtol=1e-3, atol=1e-4, name="oneblob bwd")
+    # sums of 48 signed terms of magnitude ~30: compare norm-wise (1e-3 bar) and element-wise against the scale
+    assert rel_err(xg.grad, xo.grad) < 1e-4
+    close(xg.grad, xo.grad, rtol=1e-3, atol=1e-4 * float(xo.grad.abs().max()), name="oneblob bwd")
 
 
 @pytest.mark.parametrize("hash_size,res", [(13, 124), (16, 592)])
@@ -101,7 +103,8 @@ def test_network(n_in, n_out, P):
     w = torch.randn(P, n_out, generator=g)
     (yo * w).sum().backward()
     (yg * w.to(dev)).sum().backward()
-    close(xg.grad, xo.grad, rtol=1e-3, atol=1e-4, name="mlp dx")
+    assert rel_err(xg.grad, xo.grad) < 1e-4
+    close(xg.grad, xo.grad, rtol=1e-3, atol=1e-4 * float(xo.grad.abs().max()), name="mlp dx")
     assert rel_err(net.params.grad, net_o.params.grad) < 1e-4
 
 
