@@ -70,7 +70,7 @@ class SampleArgs(C.Structure):
 _lib = None
 
 # every symbol include/dns_slam_b200.h declares
-SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_oneblob_fwd", "dns_oneblob_bwd",
+SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_oneblob_fwd", "dns_oneblob_bwd",
            "dns_hashgrid_fwd", "dns_hashgrid_bwd", "dns_hashgrid_indices", "dns_mlp_fwd",
            "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd",
            "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
@@ -92,6 +92,8 @@ def lib():
     L.dns_tv_workspace_bytes.restype = C.c_int64
     i64, i32, f32 = C.c_int64, C.c_int, C.c_float
     L.dns_struct_sizes.argtypes = [C.POINTER(C.c_int64)]
+    L.dns_profile_enable.argtypes = [C.c_int]
+    L.dns_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     L.dns_oneblob_fwd.argtypes = [_P, i64, i32, i32, _P, _P]
     L.dns_oneblob_bwd.argtypes = [_P, _P, i64, i32, i32, _P, _P]
     L.dns_hashgrid_fwd.argtypes = [C.POINTER(Grid), _P, _P, i64, _P, _P]
@@ -113,6 +115,22 @@ def lib():
         raise RuntimeError(f"ctypes struct layout {mine} != C layout {list(sizes)}; rebuild the library")
     _lib = L
     return L
+
+
+PHASES = ("prep", "class_prep", "point_fwd", "ray", "point_bwd", "dw_gemm", "finalize", "adam", "tv_fwd",
+          "tv_bwd", "sample", "feature", "ops")
+
+
+def profile_enable(on):
+    lib().dns_profile_enable(int(on))
+
+
+def profile_read(reset=True):
+    """(ms per phase, launches per phase) accumulated since the last reset."""
+    ms = (C.c_double * 16)()
+    ln = (C.c_longlong * 16)()
+    n = lib().dns_profile_read(ms, ln, int(reset))
+    return {PHASES[i]: ms[i] for i in range(n)}, {PHASES[i]: ln[i] for i in range(n)}
 
 
 def check(rc):

@@ -22,6 +22,18 @@ constexpr int kNetT = kIn1 * 32 + 32 * kOutP;  // transposed coarse/expert block
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Phase accounting: kernel-launch counters (always) and CUDA-event timing on the launching stream
+// (when enabled through dns_profile_enable) -- this is what bench.py's roofline numbers come from.
+enum Phase { phPrep = 0, phClassPrep, phPointFwd, phRay, phPointBwd, phDwGemm, phFinalize, phAdam, phTvFwd,
+             phTvBwd, phSample, phFeature, phOps, phCount };
+struct PhaseScope {
+  int phase;
+  cudaStream_t st;
+  int slot;
+  PhaseScope(int phase, cudaStream_t st, int n_launches);
+  ~PhaseScope();
+};
+
 // ---------------------------------------------------------------------------------------
 // OneBlob (16-bin periodic quartic kernel)
 // ---------------------------------------------------------------------------------------

@@ -25,6 +25,31 @@ int check_launch(const char* what) {
 }
 
 // ---------------------------------------------------------------------------------------
+// phase accounting
+// ---------------------------------------------------------------------------------------
+static bool g_profile = false;
+static long long g_launches[phCount] = {0};
+struct EvPair {
+  int phase;
+  cudaEvent_t a, b;
+};
+static EvPair g_events[4096];
+static int g_n_events = 0;
+PhaseScope::PhaseScope(int phase_, cudaStream_t st_, int n_launches) : phase(phase_), st(st_), slot(-1) {
+  g_launches[phase] += n_launches;
+  if (g_profile && g_n_events < 4096) {
+    slot = g_n_events++;
+    g_events[slot].phase = phase;
+    cudaEventCreate(&g_events[slot].a);
+    cudaEventCreate(&g_events[slot].b);
+    cudaEventRecord(g_events[slot].a, st);
+  }
+}
+PhaseScope::~PhaseScope() {
+  if (slot >= 0) cudaEventRecord(g_events[slot].b, st);
+}
+
+// ---------------------------------------------------------------------------------------
 // OneBlob
 // ---------------------------------------------------------------------------------------
 __global__ void k_oneblob_fwd(const float* __restrict__ x, int64_t n /*P*D*/, int nb, float* __restrict__ out) {
@@ -324,6 +349,28 @@ using namespace dns;
 
 extern "C" {
 
+void dns_profile_enable(int on) { g_profile = on != 0; }
+// Adds the elapsed milliseconds of every recorded phase interval to ms[phase] and copies the launch
+// counters; waits for the recorded events.  reset != 0 clears counters and intervals.
+int dns_profile_read(double* ms, long long* launches, int reset) {
+  for (int i = 0; i < g_n_events; ++i) {
+    float t = 0.f;
+    cudaEventSynchronize(g_events[i].b);
+    if (cudaEventElapsedTime(&t, g_events[i].a, g_events[i].b) == cudaSuccess && ms) ms[g_events[i].phase] += t;
+  }
+  if (launches)
+    for (int i = 0; i < phCount; ++i) launches[i] = g_launches[i];
+  if (reset) {
+    for (int i = 0; i < g_n_events; ++i) {
+      cudaEventDestroy(g_events[i].a);
+      cudaEventDestroy(g_events[i].b);
+    }
+    g_n_events = 0;
+    for (int i = 0; i < phCount; ++i) g_launches[i] = 0;
+  }
+  return phCount;
+}
+
 const char* dns_last_error(void) { return g_err; }
 int dns_version(void) { return 100; }
 void dns_struct_sizes(int64_t out[4]) {
@@ -336,12 +383,14 @@ void dns_struct_sizes(int64_t out[4]) {
 int dns_oneblob_fwd(const float* x, int64_t P, int D, int n_bins, float* out, void* stream) {
   int64_t n = P * D;
   if (n <= 0) return DNS_OK;
+  PhaseScope ph(phOps, (cudaStream_t)stream, 1);
   k_oneblob_fwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, n_bins, out);
   return check_launch("oneblob_fwd");
 }
 int dns_oneblob_bwd(const float* x, const float* d_out, int64_t P, int D, int n_bins, float* d_x, void* stream) {
   int64_t n = P * D;
   if (n <= 0) return DNS_OK;
+  PhaseScope ph(phOps, (cudaStream_t)stream, 1);
   k_oneblob_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, d_out, n, n_bins, d_x);
   return check_launch("oneblob_bwd");
 }
@@ -351,6 +400,7 @@ int dns_hashgrid_fwd(const dns_grid* g, const float* x, const float* table, int6
     return DNS_ERR_UNSUPPORTED;
   }
   if (P <= 0) return DNS_OK;
+  PhaseScope ph(phOps, (cudaStream_t)stream, 1);
   k_hashgrid_fwd<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*g, x, (const float2*)table, P, out);
   return check_launch("hashgrid_fwd");
 }
@@ -361,6 +411,7 @@ int dns_hashgrid_bwd(const dns_grid* g, const float* x, const float* table, cons
     return DNS_ERR_UNSUPPORTED;
   }
   if (P <= 0) return DNS_OK;
+  PhaseScope ph(phOps, (cudaStream_t)stream, 1);
   k_hashgrid_bwd<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*g, x, (const float2*)table, d_out, P,
                                                                              (float2*)d_table, d_x);
   return check_launch("hashgrid_bwd");
@@ -387,6 +438,7 @@ int dns_mlp_fwd(const float* x, const float* params, int64_t P, int n_in, int n_
   cudaFuncSetAttribute(k_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
   int64_t tiles = (P + kTile - 1) / kTile;
   int grid = (int)(tiles < 444 ? tiles : 444);
+  PhaseScope ph(phOps, (cudaStream_t)stream, 1);
   k_mlp_fwd<<<grid, kTile, smem, (cudaStream_t)stream>>>(x, params, P, n_in, n_out, out, hidden);
   return check_launch("mlp_fwd");
 }
@@ -399,6 +451,7 @@ int dns_mlp_bwd(const float* x, const float* params, const float* hidden, const 
   cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   int64_t tiles = (P + kTile - 1) / kTile;
   int grid = (int)(tiles < 592 ? tiles : 592);
+  PhaseScope ph(phOps, st, d_params ? 3 : 1);
   k_mlp_bwd<<<grid, kTile, smem, st>>>(params, hidden, d_out, P, n_in, n_out, d_hidden, d_x);
   if (int e = check_launch("mlp_bwd")) return e;
   if (d_params) {
@@ -419,6 +472,7 @@ int dns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   int64_t blocks = (n + 255) / 256;
   int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+  PhaseScope ph(phAdam, (cudaStream_t)stream, 1);
   k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                  (float)bc1, (float)sqrt(bc2));
   return check_launch("adam");

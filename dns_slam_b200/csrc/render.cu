@@ -1005,6 +1005,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     B.lo[c] = a->bound[c][0];
     B.ext[c] = a->bound[c][1] - a->bound[c][0];
   }
+  PhaseScope* ph = new PhaseScope(phPrep, st, map ? 6 : 5);
   cudaMemsetAsync(w.counts, 0, 16 * sizeof(int), st);
   cudaMemsetAsync(w.raw, 0, 16 * sizeof(float), st);
   k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, w.WTc);
@@ -1015,6 +1016,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     k_counts<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(a->gt_depth, a->z_vals, map ? nullptr : a->mask, N, S,
                                                                   a->opacity_trunc, w.counts);
   }
+  delete ph;
   if (int e = check_launch("render prep")) return e;
 
   static bool attr = false;
@@ -1053,6 +1055,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
     pa.need_dparams = a->need_dparams; pa.need_drays = a->need_drays;
     if (map) {
+      PhaseScope phc(phClassPrep, st, 5);
       cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);
       cudaMemsetAsync(w.perm, 0xFF, (size_t)tiles_max * kTile * sizeof(int), st);
       int64_t blocks = (Pc + 255) / 256;
@@ -1061,9 +1064,11 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       k_class_scan<<<1, 256, 0, st>>>(w.hist, nci, a->class_to_expert, w.slot_start, w.cursor, w.tile_class, w.counts);
       k_class_scatter<<<grid, 256, 0, st>>>(a->gt_label, N, p0, Pc, nci, w.slot_start, w.cursor, w.perm);
       pa.perm = w.perm; pa.tile_class = w.tile_class;
-      k_point_fwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
-    } else {
-      k_point_fwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
+    }
+    {
+      PhaseScope php(phPointFwd, st, 1);
+      if (map) k_point_fwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
+      else k_point_fwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
     }
     if (int e = check_launch("point_fwd")) return e;
 
@@ -1082,11 +1087,16 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.need_dparams = a->need_dparams; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d;
     ra.need_dfeat = a->need_dfeat && a->d_features;
     pa.need_drays = ra.need_drays;
-    k_ray<<<(int)((nc + RPC - 1) / RPC), T, smem_ray, st>>>(ra);
+    {
+      PhaseScope phr(phRay, st, 1);
+      k_ray<<<(int)((nc + RPC - 1) / RPC), T, smem_ray, st>>>(ra);
+    }
     if (int e = check_launch("ray")) return e;
-
-    if (map) k_point_bwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
-    else k_point_bwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
+    {
+      PhaseScope phb(phPointBwd, st, 1);
+      if (map) k_point_bwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
+      else k_point_bwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
+    }
     if (int e = check_launch("point_bwd")) return e;
 
     if (a->fine) k_unpad33<<<(int)((Pc * DNS_LATENT + 255) / 256), 256, 0, st>>>(w.fine36, a->fine + p0 * DNS_LATENT, Pc);
@@ -1094,6 +1104,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       k_unpad33<<<(int)((Pc * DNS_LATENT + 255) / 256), 256, 0, st>>>(w.coarse36, a->coarse_out + p0 * DNS_LATENT, Pc);
 
     if (a->need_dparams) {
+      PhaseScope phg(phDwGemm, st, map ? 8 : 6);
       const int64_t Qrows = (int64_t)tiles_max * kTile;
       const int* ntd = map ? w.counts + cTiles : nullptr;
       int e = 0;
@@ -1112,6 +1123,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       if (e) return DNS_ERR_CUDA;
     }
   }
+  PhaseScope phf(phFinalize, st, 1);
   k_finalize<<<1, 32, 0, st>>>(mode, w.raw, w.counts, N, P, a->lambda_p, a->lambda_d, a->lambda_l, a->lambda_lt,
                                a->lambda_fs, a->lambda_op, a->losses);
   return check_launch("finalize");
@@ -1166,11 +1178,14 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   pa.Xst = Xst; pa.Hc = Hc; pa.dHc = dHc; pa.dOc = dOc;
   pa.d_table = (float2*)a->d_table; pa.need_dparams = a->need_dparams; pa.need_drays = 0;
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT);
+  PhaseScope* pht = new PhaseScope(phTvFwd, st, 4);
   k_point_fwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
   const float inv_norm = 1.0f / ((float)a->smooth_pts * (float)a->smooth_pts * (float)a->smooth_pts);
   k_tv_stencil<<<(int)((n3 + 255) / 256), 256, 0, st>>>(occ, n, inv_norm, a->lambda_sm, docc, a->loss);
+  delete pht;
   if (int e = check_launch("tv fwd")) return e;
   if (a->need_dparams) {
+    PhaseScope phtb(phTvBwd, st, 3);
     k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
     if (int e = check_launch("tv bwd")) return e;
     int e = 0;

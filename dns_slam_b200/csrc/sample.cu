@@ -165,6 +165,7 @@ int dns_sample_rays(const dns_sample_args* a, void* stream) {
     set_error("sample: need 1 <= n_uniform + n_surface <= 256");
     return DNS_ERR_UNSUPPORTED;
   }
+  PhaseScope ph(phSample, st, 3);
   cudaMemsetAsync(a->scratch, 0, 2 * sizeof(float), st);
   k_sample_gather<<<(a->n + 127) / 128, 128, 0, st>>>(*a);
   const int bd = 64;
@@ -183,6 +184,7 @@ int dns_feature_gather(const float* pts, int64_t P, const float* w2c, int R, con
   if (P <= 0 || R <= 0) return DNS_OK;
   int64_t warps = (int64_t)R * P;
   int64_t blocks = (warps * 32 + 255) / 256;
+  PhaseScope ph(phFeature, (cudaStream_t)stream, 1);
   k_feature_gather<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pts, P, w2c, R, K, H, W, feats, C, h, w, code, uv,
                                                                        mask);
   return check_launch("feature_gather");

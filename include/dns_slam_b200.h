@@ -221,6 +221,13 @@ int dns_feature_gather(const float* pts, int64_t P, const float* w2c /*[R,4,4]*/
 int dns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, void* stream);
 
+/* Phase accounting for benchmarks: per-phase kernel-launch counters (always on) and, when
+ * enabled, CUDA-event timing of each phase on the launching stream.  Phases: 0 prep, 1 class
+ * prep, 2 point_fwd, 3 ray, 4 point_bwd, 5 dw_gemm, 6 finalize, 7 adam, 8 tv_fwd, 9 tv_bwd,
+ * 10 sample, 11 feature, 12 operator kernels.  dns_profile_read returns the number of phases. */
+void dns_profile_enable(int on);
+int dns_profile_read(double* ms /*[16]*/, long long* launches /*[16]*/, int reset);
+
 /* sizeof(dns_grid), sizeof(dns_render_args), sizeof(dns_tv_args), sizeof(dns_sample_args): lets a
  * foreign-language binding assert that its struct mirror matches this header. */
 void dns_struct_sizes(int64_t out[4]);
