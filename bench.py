@@ -170,7 +170,16 @@ def main():
     _, samples = bench_util.synthetic_batch(args.shape, "map", R, S, C, dev, seed=100 + rank, dec=dec)
     lam = dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0, fs=s["lambda_fs"],
                op=s["lambda_opacity"])
-    ms = stepmod.MappingStep(dec, s["lr"], lam, s["opacity_sigma"], pg, world)
+    if world > 1:   # rays [rank*R, (rank+1)*R) of ONE global batch of R*world rays
+        sh = stepmod.ShardedMappingStep(dec, s["lr"], stepmod.TorchComm(pg), rank, world, lambdas=lam,
+                                        opacity_sigma=s["opacity_sigma"])
+
+        class _Ms:          # same .step(samples) surface as MappingStep
+            def step(self, smp):
+                return sh.step_sharded(smp, R * world)
+        ms = _Ms()
+    else:
+        ms = stepmod.MappingStep(dec, s["lr"], lam, s["opacity_sigma"])
 
     def barrier():
         if world > 1:
@@ -243,7 +252,8 @@ def main():
     traffic = None
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tj):
-        traffic = json.load(open(tj)).get(dom)
+        bpp = json.load(open(tj)).get("bytes_per_point", {}).get(dom)   # ncu --set full, per sample point
+        traffic = bpp * R * S if bpp is not None else None
     step_alg = R * (S * 3332 + 252)
     roof = {"bound": "hbm", "kernel": {"point_fwd": "k_point_fwd", "ray": "k_ray", "point_bwd": "k_point_bwd"}[dom],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -45,7 +45,9 @@ class RenderArgs(C.Structure):
                 ("fine", _P), ("coarse_out", _P), ("losses", _P),
                 ("d_table", _P), ("d_coarse", _P), ("d_color", _P), ("d_logit", _P),
                 ("d_experts", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("d_features", _P),
-                ("workspace", _P), ("workspace_bytes", C.c_int64)]
+                ("workspace", _P), ("workspace_bytes", C.c_int64),
+                ("n_rays_total", C.c_int64), ("ray_offset", C.c_int64), ("gt_label_all", _P),
+                ("global_counts", _P)]
 
 
 class TvArgs(C.Structure):
@@ -72,7 +74,7 @@ _lib = None
 # every symbol include/dns_slam_b200.h declares
 SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_oneblob_fwd", "dns_oneblob_bwd",
            "dns_hashgrid_fwd", "dns_hashgrid_bwd", "dns_hashgrid_indices", "dns_mlp_fwd",
-           "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd",
+           "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd", "dns_render_counts",
            "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
            "dns_adam_step"]
 
@@ -103,6 +105,7 @@ def lib():
     L.dns_mlp_bwd.argtypes = [_P, _P, _P, _P, i64, i32, i32, _P, _P, _P, _P]
     L.dns_render_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.dns_render_fwd_bwd.argtypes = [C.POINTER(RenderArgs), _P]
+    L.dns_render_counts.argtypes = [C.POINTER(RenderArgs), _P, _P]
     L.dns_tv_workspace_bytes.argtypes = [i32]
     L.dns_tv_fwd_bwd.argtypes = [C.POINTER(TvArgs), _P]
     L.dns_sample_rays.argtypes = [C.POINTER(SampleArgs), _P]

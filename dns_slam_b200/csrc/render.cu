@@ -999,7 +999,11 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   }
   carve(w, (char*)a->workspace, mode, Nc, S, C, nci);
   const int C4 = (C + 3) & ~3;
-  const int64_t P = N * S;
+  const bool sharded = a->n_rays_total > 0;
+  const int64_t Ntot = sharded ? a->n_rays_total : N;           // global batch (denominators, class rule)
+  const int64_t goff = sharded ? a->ray_offset * S : 0;         // global id of local point 0
+  const int64_t* lab_all = (sharded && a->gt_label_all) ? a->gt_label_all : a->gt_label;
+  const int64_t P = Ntot * S;
   Bound B;
   for (int c = 0; c < 3; ++c) {
     B.lo[c] = a->bound[c][0];
@@ -1012,9 +1016,13 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   if (map) k_transpose_net80<<<a->n_experts, 256, 0, st>>>(a->experts, w.WTe);
   k_transpose_out<<<1, 256, 0, st>>>(a->color, a->logit, w.W1T2, w.W2cT);
   {
-    int64_t blocks = (P + 255) / 256;
-    k_counts<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(a->gt_depth, a->z_vals, map ? nullptr : a->mask, N, S,
-                                                                  a->opacity_trunc, w.counts);
+    if (a->global_counts) {
+      cudaMemcpyAsync(w.counts, a->global_counts, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    } else {
+      int64_t blocks = (N * S + 255) / 256;
+      k_counts<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(a->gt_depth, a->z_vals, map ? nullptr : a->mask, N,
+                                                                    S, a->opacity_trunc, w.counts);
+    }
   }
   delete ph;
   if (int e = check_launch("render prep")) return e;
@@ -1043,7 +1051,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     PointArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.rays_o = a->rays_o; pa.rays_d = a->rays_d; pa.z = a->z_vals; pa.gt_depth = a->gt_depth;
-    pa.S = S; pa.N_total = N; pa.P_total = P; pa.p0 = p0; pa.Pc = Pc; pa.B = B; pa.G = a->grid;
+    pa.S = S; pa.N_total = Ntot; pa.P_total = P; pa.p0 = p0; pa.Pc = Pc; pa.B = B; pa.G = a->grid;
     pa.table = (const float2*)a->table;
     pa.counts = w.counts; pa.n_tiles_host = tiles_max;
     pa.WTc = w.WTc; pa.WTe = w.WTe;
@@ -1060,9 +1068,9 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       cudaMemsetAsync(w.perm, 0xFF, (size_t)tiles_max * kTile * sizeof(int), st);
       int64_t blocks = (Pc + 255) / 256;
       int grid = (int)(blocks < 592 ? blocks : 592);
-      k_class_hist<<<grid, 256, 0, st>>>(a->gt_label, N, p0, Pc, nci, w.hist, w.counts);
+      k_class_hist<<<grid, 256, 0, st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.hist, w.counts);
       k_class_scan<<<1, 256, 0, st>>>(w.hist, nci, a->class_to_expert, w.slot_start, w.cursor, w.tile_class, w.counts);
-      k_class_scatter<<<grid, 256, 0, st>>>(a->gt_label, N, p0, Pc, nci, w.slot_start, w.cursor, w.perm);
+      k_class_scatter<<<grid, 256, 0, st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.slot_start, w.cursor, w.perm);
       pa.perm = w.perm; pa.tile_class = w.tile_class;
     }
     {
@@ -1075,7 +1083,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     RayArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.mode = mode; ra.S = S; ra.T = T; ra.RPC = RPC; ra.C = C; ra.C4 = C4;
-    ra.N_total = N; ra.ray0 = ray0; ra.Nc = nc; ra.B = B;
+    ra.N_total = Ntot; ra.ray0 = ray0; ra.Nc = nc; ra.B = B;
     ra.rays_o = a->rays_o; ra.rays_d = a->rays_d; ra.z = a->z_vals; ra.gt_color = a->gt_color;
     ra.gt_depth = a->gt_depth; ra.gt_label = a->gt_label; ra.mask = map ? nullptr : a->mask; ra.features = a->features;
     ra.fine36 = pa.fine36; ra.W1T2 = w.W1T2; ra.W2cT = w.W2cT; ra.logit = a->logit; ra.counts = w.counts;
@@ -1124,9 +1132,24 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     }
   }
   PhaseScope phf(phFinalize, st, 1);
-  k_finalize<<<1, 32, 0, st>>>(mode, w.raw, w.counts, N, P, a->lambda_p, a->lambda_d, a->lambda_l, a->lambda_lt,
+  k_finalize<<<1, 32, 0, st>>>(mode, w.raw, w.counts, Ntot, P, a->lambda_p, a->lambda_d, a->lambda_l, a->lambda_lt,
                                a->lambda_fs, a->lambda_op, a->losses);
   return check_launch("finalize");
+}
+
+int dns_render_counts(const dns_render_args* a, int32_t* counts4, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = a->n_rays, S = a->n_samples;
+  if (N <= 0 || S <= 0 || !counts4) {
+    set_error("render_counts: bad arguments");
+    return DNS_ERR_ARG;
+  }
+  PhaseScope ph(phPrep, st, 2);
+  cudaMemsetAsync(counts4, 0, 4 * sizeof(int), st);
+  int64_t blocks = (N * S + 255) / 256;
+  k_counts<<<(int)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(
+      a->gt_depth, a->z_vals, a->mode == DNS_MODE_MAP ? nullptr : a->mask, N, (int)S, a->opacity_trunc, counts4);
+  return check_launch("render_counts");
 }
 
 int64_t dns_tv_workspace_bytes(int n) {

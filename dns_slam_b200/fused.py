@@ -119,6 +119,43 @@ class RenderConfig:
         self.lam = lam
         self.opacity_trunc, self.opacity_sigma = opacity_trunc, opacity_sigma
         self.want_latents = want_latents
+        # ray sharding: set by shard(); None => single-GPU call
+        self.n_rays_total = self.ray_offset = self.gt_label_all = self.global_counts = None
+
+    def shard(self, n_rays_total, ray_offset, gt_label_all, global_counts):
+        """This call holds rays [ray_offset, ray_offset + N) of a batch of n_rays_total rays."""
+        self.n_rays_total, self.ray_offset = int(n_rays_total), int(ray_offset)
+        self.gt_label_all, self.global_counts = gt_label_all, global_counts
+        return self
+
+
+def _fill_inputs(a, cfg):
+    f32, i64 = torch.float32, torch.int64
+    N, S = cfg.z_vals.shape
+    a.mode, a.n_rays, a.n_samples, a.n_class = cfg.mode, N, S, cfg.n_class
+    a.opacity_trunc, a.opacity_sigma = cfg.opacity_trunc, cfg.opacity_sigma
+    a.z_vals, a.gt_color = _lib.ptr(cfg.z_vals, f32), _lib.ptr(cfg.gt_color, f32)
+    a.gt_depth, a.gt_label = _lib.ptr(cfg.gt_depth, f32), _lib.ptr(cfg.gt_label, i64)
+    mask8 = None
+    if cfg.mode == _lib.MODE_TRACK and cfg.mask is not None:
+        mask8 = cfg.mask.to(torch.uint8).contiguous()
+    a.mask = _lib.ptr(mask8, allow_none=True)
+    if cfg.n_rays_total is not None:
+        a.n_rays_total, a.ray_offset = cfg.n_rays_total, cfg.ray_offset
+        a.gt_label_all = _lib.ptr(cfg.gt_label_all, i64)
+        a.global_counts = _lib.ptr(cfg.global_counts, torch.int32, allow_none=True)
+    return mask8
+
+
+def render_counts(cfg):
+    """Local {n_mask, n_depth>0, n_front, n_band} (int32[4] on the device): all-reduce them across
+    ranks and hand the sum to ``RenderConfig.shard`` (``dns_render_counts``)."""
+    a = _lib.RenderArgs()
+    keep = _fill_inputs(a, cfg)
+    out = torch.zeros(4, dtype=torch.int32, device=cfg.z_vals.device)
+    _lib.check(_lib.lib().dns_render_counts(C.byref(a), _lib.ptr(out), _lib.stream()))
+    del keep
+    return out
 
 
 def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, features, grads, need_drays,
@@ -130,22 +167,15 @@ def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, featur
     N, S = cfg.z_vals.shape
     Cn = cfg.n_class
     a = _lib.RenderArgs()
-    a.mode, a.n_rays, a.n_samples, a.n_class = cfg.mode, N, S, Cn
+    mask8 = _fill_inputs(a, cfg)
     need_dparams = grads is not None
     a.need_dparams, a.need_drays, a.need_dfeat = int(need_dparams), int(need_drays), int(need_dfeat)
     _lib.fill_bound(a.bound, cfg.bound)
     a.lambda_p, a.lambda_d, a.lambda_l = cfg.lam["p"], cfg.lam["d"], cfg.lam["l"]
     a.lambda_lt, a.lambda_fs, a.lambda_op = cfg.lam["lt"], cfg.lam["fs"], cfg.lam["op"]
-    a.opacity_trunc, a.opacity_sigma = cfg.opacity_trunc, cfg.opacity_sigma
     a.grid = cfg.gstruct
     f32, i64 = torch.float32, torch.int64
     a.rays_o, a.rays_d = _lib.ptr(rays_o, f32), _lib.ptr(rays_d, f32)
-    a.z_vals, a.gt_color = _lib.ptr(cfg.z_vals, f32), _lib.ptr(cfg.gt_color, f32)
-    a.gt_depth, a.gt_label = _lib.ptr(cfg.gt_depth, f32), _lib.ptr(cfg.gt_label, i64)
-    mask8 = None
-    if cfg.mode == _lib.MODE_TRACK and cfg.mask is not None:
-        mask8 = cfg.mask.to(torch.uint8).contiguous()
-    a.mask = _lib.ptr(mask8, allow_none=True)
     a.features = _lib.ptr(features, f32, allow_none=True)
     a.table, a.coarse = _lib.ptr(table, f32), _lib.ptr(coarse, f32)
     a.color, a.logit = _lib.ptr(color, f32), _lib.ptr(logit, f32)

@@ -37,13 +37,17 @@ class MappingStep:
         out["experts"] = buf[a:a + n].view(-1, EXPERT_PARAMS)
         return out
 
-    def forward_backward(self, samples, need_drays=True, need_dfeat=True):
+    def _config(self, samples):
+        dec = self.dec
+        return fused.RenderConfig(_lib.MODE_MAP, dec.bound, dec.pe_fn.grid_fn.gstruct, samples["z_vals"],
+                                  samples["gt_color"], samples["gt_depth"], samples["gt_label"], None,
+                                  dec.class_to_expert, dec.n_class, self.lambdas, opacity_trunc=self.opacity_sigma)
+
+    def forward_backward(self, samples, need_drays=True, need_dfeat=True, cfg=None):
         """Fills ``self.grad`` (flat) and returns (losses[8], preds, d_rays_o, d_rays_d, d_features)."""
         dec = self.dec
         self.grad.zero_()
-        cfg = fused.RenderConfig(_lib.MODE_MAP, dec.bound, dec.pe_fn.grid_fn.gstruct, samples["z_vals"],
-                                 samples["gt_color"], samples["gt_depth"], samples["gt_label"], None,
-                                 dec.class_to_expert, dec.n_class, self.lambdas, opacity_trunc=self.opacity_sigma)
+        cfg = cfg or self._config(samples)
         p = self._views(dec.flat)
         return fused.render_raw(cfg, p["table"], p["coarse"], p["color"], p["logit"], p["experts"],
                                 samples["rays_o"], samples["rays_d"], samples.get("features"),
@@ -56,6 +60,79 @@ class MappingStep:
         self.t += 1
         fused.adam_step(self.dec.flat, self.grad, self.m, self.v, self.lr, self.t)
         return out
+
+
+def shard_bounds(n_total, world, rank):
+    """Contiguous, balanced ray ranges: rank r owns [lo, hi)."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedMappingStep(MappingStep):
+    """One mapping batch sharded by rays over the ranks of ``process_group``.
+
+    Every rank holds the full decoder (replicated) and ITS slice of the ray batch.  Per step:
+    (1) labels of the whole batch are all-gathered once (the class rule ``class(p) = label[p mod N]``
+    of mapping.py:612-613 reaches across shards) and the four batch-global counts are all-reduced
+    (tiny); (2) each rank runs the fused kernels on its rays with GLOBAL denominators, so partial
+    losses and gradients SUM to the single-GPU values; (3) ONE all-reduce of the flat gradient
+    buffer (+ 8 loss partials appended to it); (4) identical fused Adam on every rank -- no
+    parameter broadcast.  ``comm`` is any object with all_reduce_sum(tensor) / all_gather(tensor)
+    (torch.distributed over NCCL on GPUs; the CPU tests plug gloo)."""
+
+    def __init__(self, decoder, lr, comm, rank, world, **kw):
+        super().__init__(decoder, lr, **kw)
+        self.comm, self.rank, self.world_n = comm, rank, world
+        self.packed = torch.zeros(self.grad.numel() + 8, device=self.grad.device)
+        self.grad = self.packed[:-8]                 # gradients and loss partials travel together
+
+    def step_sharded(self, local_samples, n_total, need_drays=True, need_dfeat=True):
+        lo, hi = shard_bounds(n_total, self.world_n, self.rank)
+        assert local_samples["z_vals"].shape[0] == hi - lo, "local batch does not match the shard bounds"
+        labels_all = self.comm.all_gather(local_samples["gt_label"].contiguous())
+        cfg = self._config(local_samples)
+        counts = self._local_counts(cfg)
+        self.comm.all_reduce_sum(counts)
+        cfg.shard(n_total, lo, labels_all, counts)
+        out = self.forward_backward(local_samples, need_drays, need_dfeat, cfg=cfg)
+        self.packed[-8:] = out[0]
+        self.comm.all_reduce_sum(self.packed)
+        losses = self.packed[-8:].clone()
+        self.t += 1
+        self._adam()
+        return (losses,) + tuple(out[1:])
+
+    # the two device calls besides forward_backward (overridden by the CPU host-logic tests)
+    def _local_counts(self, cfg):
+        return fused.render_counts(cfg)
+
+    def _adam(self):
+        fused.adam_step(self.dec.flat, self.grad, self.m, self.v, self.lr, self.t)
+
+
+class TorchComm:
+    """torch.distributed adapter (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def all_reduce_sum(self, t):
+        torch.distributed.all_reduce(t, group=self.group)
+        return t
+
+    def all_gather(self, t):
+        """Concatenation over ranks of possibly different-length 1-D tensors."""
+        world = torch.distributed.get_world_size(self.group)
+        n = torch.tensor([t.numel()], device=t.device)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        torch.distributed.all_gather(sizes, n, group=self.group)
+        mx = int(max(int(s) for s in sizes))
+        pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+        pad[:t.numel()] = t
+        outs = [torch.zeros_like(pad) for _ in range(world)]
+        torch.distributed.all_gather(outs, pad, group=self.group)
+        return torch.cat([o[:int(s)] for o, s in zip(outs, sizes)])
 
 
 class TrackingStep:

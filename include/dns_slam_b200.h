@@ -138,10 +138,23 @@ typedef struct dns_render_args {
   /* scratch */
   void* workspace;
   int64_t workspace_bytes;
+  /* ray sharding across GPUs; all zero / NULL for a single-GPU call.  The n_rays
+   * local rays are rays [ray_offset, ray_offset + n_rays) of a batch of n_rays_total: loss
+   * denominators, the count_nonzero guards and the class rule class(p) = label[p mod N]
+   * (mapping.py:612-613) use the GLOBAL batch, so per-rank losses / gradients SUM to the
+   * single-GPU result. */
+  int64_t n_rays_total;
+  int64_t ray_offset;
+  const int64_t* gt_label_all;   /* [n_rays_total] labels of the whole batch */
+  const int32_t* global_counts;  /* [4] all-reduced dns_render_counts output */
 } dns_render_args;
 
 int64_t dns_render_workspace_bytes(int mode, int n_rays, int n_samples, int n_class, int n_class_ids);
 int dns_render_fwd_bwd(const dns_render_args* a, void* stream);
+/* Local batch counts {n_mask, n_depth>0, n_front, n_band} (int32[4], device) that the loss
+ * denominators / guards of dns_render_fwd_bwd use; all-reduce (sum) them across ranks and pass
+ * the result as global_counts. */
+int dns_render_counts(const dns_render_args* a, int32_t* counts4, void* stream);
 
 /* Mapper.smoothness forward + backward (slams/mapping.py:129-159, oracle patch P1): TV of the
  * coarse occupancy on an n^3 lattice (n = smooth_pts - 1).  Point (i,j,k) is

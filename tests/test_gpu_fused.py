@@ -189,3 +189,32 @@ def test_full_size_properties(mode, N, S, C):
     z = samples["z_vals"]
     assert bool((p1["depth"] >= z.min(1)[0] - 1e-4).all()) and bool((p1["depth"] <= z.max(1)[0] + 1e-4).all())
     assert 0 < int((gt1 != 0).sum()) <= N * S * 16 * 8 * 2
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ranks_emulated_on_one_gpu(world):
+    """the ray-sharded call with GLOBAL denominators and the global
+    class rule, run shard by shard on ONE GPU (no collectives), sums to the single-call result."""
+    from dns_slam_b200 import bench_util, fused, step as stepmod
+    dev = _dev()
+    N, S, C = 601, 47, 12
+    dec, samples = bench_util.synthetic_batch("tiny", "map", N, S, C, dev, seed=5, n_frames=2)
+    samples = {k: v for k, v in samples.items() if k != "mask"}
+    ms = stepmod.MappingStep(dec, 5e-3, dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0))
+    full = ms.forward_backward(samples)
+    g_full, l_full = ms.grad.clone(), full[0].clone()
+    shards = [stepmod.shard_bounds(N, world, r) for r in range(world)]
+    local = [{k: v[lo:hi].contiguous() for k, v in samples.items()} for lo, hi in shards]
+    counts = sum(fused.render_counts(ms._config(s)) for s in local)
+    assert torch.equal(counts.cpu(), fused.render_counts(ms._config(samples)).cpu())
+    g_sum, l_sum = torch.zeros_like(g_full), torch.zeros(8, device=dev)
+    d_o = []
+    for (lo, hi), s in zip(shards, local):
+        cfg = ms._config(s).shard(N, lo, samples["gt_label"], counts)
+        out = ms.forward_backward(s, cfg=cfg)
+        g_sum += ms.grad
+        l_sum += out[0]
+        d_o.append(out[2])
+    close(l_sum[:7], l_full[:7], rtol=1e-4, atol=1e-7, name="sharded losses")
+    assert rel_err(g_sum, g_full) < 1e-4
+    close(torch.cat(d_o, 0), full[2], rtol=1e-3, atol=1e-6 * float(full[2].abs().max()) + 1e-9, name="d_rays_o")
