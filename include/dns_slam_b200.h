@@ -234,6 +234,13 @@ int dns_feature_gather(const float* pts, int64_t P, const float* w2c /*[R,4,4]*/
 int dns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, void* stream);
 
+/* 1 (default): MLP weight-gradient GEMMs run on tcgen05 tensor cores (bf16 hi+lo split, three
+ * products, fp32 accumulation in TMEM); 0: fp32 SIMT path, kept for A/B comparison. */
+void dns_set_tensor_cores(int on);
+/* Test entry of the tcgen05 GEMM: C[m][n] (row stride N) += sum_p A[p][m] * B[p][n]. */
+int dns_debug_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows,
+                      float* C, void* stream);
+
 /* Phase accounting for benchmarks: per-phase kernel-launch counters (always on) and, when
  * enabled, CUDA-event timing of each phase on the launching stream.  Phases: 0 prep, 1 class
  * prep, 2 point_fwd, 3 ray, 4 point_bwd, 5 dw_gemm, 6 finalize, 7 adam, 8 tv_fwd, 9 tv_bwd,

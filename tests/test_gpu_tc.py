@@ -1,0 +1,50 @@
+"""tcgen05 weight-gradient GEMM (bf16 hi+lo split, fp32 TMEM accumulation) against float64 matmul."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,lda,N,ldb,rows", [(32, 32, 80, 80, 1000), (33, 36, 32, 32, 640), (32, 64, 112, 112, 4097),
+                                               (3, 4, 32, 32, 130), (40, 40, 32, 32, 77), (128, 128, 32, 32, 300),
+                                               (1, 36, 32, 32, 512), (64, 64, 112, 112, 128 * 9)])
+def test_dw_gemm_tc(M, lda, N, ldb, rows):
+    from dns_slam_b200 import _lib
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M * 1000 + N)
+    A = (torch.randn(rows, lda, generator=g) * torch.rand(rows, 1, generator=g) * 3).to(dev)
+    B = torch.randn(rows, ldb, generator=g).to(dev)
+    C = torch.zeros(M, N, device=dev)
+    L = _lib.lib()
+    for _ in range(2):      # accumulates: two calls = 2x
+        _lib.check(L.dns_debug_gemm_tc(_lib.ptr(A), lda, M, _lib.ptr(B), ldb, N, rows, _lib.ptr(C), _lib.stream()))
+    torch.cuda.synchronize()
+    want = 2 * (A[:, :M].double().t() @ B[:, :N].double())
+    err = float((C.double() - want).norm() / want.norm())
+    assert err < 2e-5, f"relative error {err:.3e}"
+    assert float((C.double() - want).abs().max()) < 1e-3 * float(want.abs().max())
+
+
+def test_fused_gradients_same_with_and_without_tensor_cores():
+    """The dW GEMMs of the fused path: tcgen05 vs the fp32 SIMT kernel on the same stash."""
+    from dns_slam_b200 import _lib, bench_util, step as stepmod
+    dev = torch.device("cuda:0")
+    dec, samples = bench_util.synthetic_batch("tiny", "map", 700, 47, 9, dev, seed=2, n_frames=2)
+    samples = {k: v for k, v in samples.items() if k != "mask"}
+    ms = stepmod.MappingStep(dec, 5e-3)
+    L = _lib.lib()
+    try:
+        L.dns_set_tensor_cores(0)
+        ms.forward_backward(samples)
+        g0 = ms.grad.clone()
+        L.dns_set_tensor_cores(1)
+        ms.forward_backward(samples)
+        g1 = ms.grad.clone()
+    finally:
+        L.dns_set_tensor_cores(1)
+    lay = dec.layout
+    for k in ("coarse", "color", "logit", "experts"):
+        a, n = lay[k]
+        e = float((g1[a:a + n] - g0[a:a + n]).norm() / (g0[a:a + n].norm() + 1e-30))
+        assert e < 1e-4, (k, e)
