@@ -34,6 +34,25 @@ struct PhaseScope {
   ~PhaseScope();
 };
 
+// tcgen05 weight-gradient GEMM (tc.cu):  out[l][c] += sum_p L[p][l] * Cc[p][c]
+struct DwArgs {
+  const float* L;   // lane-side operand [rows][ldl] (nL <= 128)
+  int ldl, nL;
+  const float* Cc;  // column-side operand [rows][ldcc] (nC <= 128)
+  int ldcc, nC;
+  int64_t n_rows;
+  const int* n_tiles_dev;
+  int n_tiles_host;
+  const int* tile_class;
+  // output 0 takes columns [0, split), output 1 columns [split, nC); element (l, c) -> o[l*sl + c*sc]
+  float* out0;
+  float* out1;
+  int split;
+  int64_t sl0, sc0, cls0, sl1, sc1, cls1;
+};
+int launch_dw_gemm_tc2(DwArgs a, cudaStream_t st);
+bool use_tensor_cores();
+
 // ---------------------------------------------------------------------------------------
 // OneBlob (16-bin periodic quartic kernel)
 // ---------------------------------------------------------------------------------------

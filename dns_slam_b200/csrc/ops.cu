@@ -194,7 +194,9 @@ bool use_tensor_cores();
 int launch_dw_gemm(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows,
                    const int* n_tiles_dev, int n_tiles_host, const int* tile_class, float* C, int ldc,
                    int64_t c_stride, cudaStream_t st) {
-  if (use_tensor_cores() && M <= 128 && N <= 128)
+  // the tcgen05 kernel stages rows with 16-byte loads: rows must be float4-aligned and padded
+  if (use_tensor_cores() && M <= 128 && N <= 128 && (lda & 3) == 0 && (ldb & 3) == 0 && ((M + 3) & ~3) <= lda &&
+      ((N + 3) & ~3) <= ldb && (((uintptr_t)A | (uintptr_t)B) & 15) == 0)
     return launch_dw_gemm_tc(A, lda, M, B, ldb, N, n_rows, n_tiles_dev, n_tiles_host, tile_class, C, ldc, c_stride, st);
   int Ms = (M + 3) & ~3, Ns = (N + 3) & ~3;
   if ((Ms >> 2) * (Ns >> 2) > 256) {

@@ -17,7 +17,7 @@
 //   k_dw_gemm     dW = X^T dH for every MLP from stashed activations (ops.cu)
 #include <string.h>
 
-#include "common.cuh"
+#include "render.cuh"
 
 namespace dns {
 
@@ -25,11 +25,6 @@ int launch_dw_gemm(const float* A, int lda, int M, const float* B, int ldb, int 
                    const int* n_tiles_dev, int n_tiles_host, const int* tile_class, float* C, int ldc,
                    int64_t c_stride, cudaStream_t st);
 
-enum { kTrack = 0, kMap = 1, kTv = 2 };
-// counts[] slots
-enum { cMask = 0, cDpos = 1, cFront = 2, cBand = 3, cTiles = 4, cErr = 5 };
-// raw loss sums
-enum { rP = 0, rD = 1, rL = 2, rLt = 3, rFs = 4, rOp = 5 };
 
 // ---------------------------------------------------------------------------------------
 // weight re-layout (once per call): tcnn row-major -> k-major blocks read with broadcast LDS.128
@@ -395,7 +390,7 @@ __global__ void __launch_bounds__(kTile) k_point_bwd(PointArgs a) {
   float* xrow = XS + tid * kXld;
   float d_out[kOutP];
   zero(d_out);
-  float* dHc = a.need_dparams ? a.dHc + q * 32 : nullptr;
+  float* dHc = a.need_dparams ? a.dHc + q * 64 : nullptr;
   float* dOc = a.need_dparams ? a.dOc + q * kOutP : nullptr;
   if (MODE == kTv) {
     if (valid) d_out[0] = a.docc[q];
@@ -427,7 +422,7 @@ __global__ void __launch_bounds__(kTile) k_point_bwd(PointArgs a) {
       }
     }
     if (expert >= 0) {
-      net80_bwd(d_out, a.Hf + q * 32, Wf, Wf + 2560, xrow, false, a.need_dparams ? a.dHf + q * 32 : nullptr,
+      net80_bwd(d_out, a.Hf + q * 32, Wf, Wf + 2560, xrow, false, a.need_dparams ? a.dHc + q * 64 + 32 : nullptr,
                 a.need_dparams ? a.dOf + q * kOutP : nullptr);
     } else {
       for (int k = 0; k < kIn1; ++k) xrow[k] = 0.f;
@@ -457,43 +452,6 @@ __global__ void __launch_bounds__(kTile) k_point_bwd(PointArgs a) {
 // ---------------------------------------------------------------------------------------
 // ray kernel: out_fn + compositing + losses + backward (thread per sample point)
 // ---------------------------------------------------------------------------------------
-struct RayArgs {
-  int mode;
-  int S, T, RPC, C, C4;
-  int64_t N_total, ray0, Nc;  // chunk of rays [ray0, ray0 + Nc)
-  Bound B;
-  const float* rays_o;
-  const float* rays_d;
-  const float* z;
-  const float* gt_color;
-  const float* gt_depth;
-  const int64_t* gt_label;
-  const uint8_t* mask;
-  const float* features;
-  const float* fine36;
-  const float* W1T2;
-  const float* W2cT;
-  const float* logit;  // tcnn layout; W2l = logit + 32*112, [Cpad][32]
-  const int* counts;
-  float lam_p, lam_d, lam_l;
-  float* pred_color;
-  float* pred_depth;
-  float* pred_var;
-  float* pred_logits;
-  float* raw;
-  float* dfine36;
-  float* d_features;
-  float* d_rays_o;
-  float* d_rays_d;
-  // stashes (point / ray order of the chunk)
-  float* X2;     // [Pc][112]
-  float* dH2;    // [Pc][64]
-  float* Hcol;   // [Pc][32]
-  float* dpre;   // [Pc][4]
-  float* dlogit; // [Nc][C4]
-  float* Hbar;   // [Nc][32]
-  int need_dparams, need_drays, need_dfeat;
-};
 
 __global__ void __launch_bounds__(256) k_ray(RayArgs a) {
   extern __shared__ float sm[];
@@ -892,6 +850,7 @@ struct RenderWs {
   float* raw;
   int *hist, *slot_start, *cursor;
   float *WTc, *WTe, *W1T2, *W2cT;
+  uint4 *W1o_hi, *W1o_lo;   // bf16 hi / lo chunk tiles of the colour|logit layer-1 weights (tcgen05 path)
   int *perm, *tile_class;
   float *fine36, *coarse36, *dfine36;
   float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf;
@@ -914,6 +873,8 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.WTe = c.take<float>((int64_t)kNetT * (map ? nci : 0) + 4);
   w.W1T2 = c.take<float>(kIn2 * 64);
   w.W2cT = c.take<float>(128);
+  w.W1o_hi = c.take<uint4>(14 * 64);
+  w.W1o_lo = c.take<uint4>(14 * 64);
   w.perm = c.take<int>(map ? w.Q : 4);
   w.tile_class = c.take<int>(w.tiles);
   w.fine36 = c.take<float>(Pc * kOutP);
@@ -922,8 +883,8 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.Xst = c.take<float>(w.Q * kIn1);
   w.Hc = c.take<float>(w.Q * 32);
   w.Hf = c.take<float>(map ? w.Q * 32 : 4);
-  w.dHc = c.take<float>(w.Q * 32);
-  w.dHf = c.take<float>(map ? w.Q * 32 : 4);
+  w.dHc = c.take<float>(w.Q * 64);   // [Q][64]: columns 0..31 coarse, 32..63 class expert
+  w.dHf = w.dHc ? w.dHc + 32 : nullptr;
   w.dOc = c.take<float>(w.Q * kOutP);
   w.dOf = c.take<float>(map ? w.Q * kOutP : 4);
   w.X2 = c.take<float>(Pc * kIn2);
@@ -1040,7 +1001,9 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   }
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT * (map ? 2 : 1));
   int T, RPC;
-  pick_ray_block(S, T, RPC);
+  const bool tc = use_tensor_cores();
+  if (tc) pick_ray_block_tc(S, T, RPC);
+  else pick_ray_block(S, T, RPC);
   const size_t smem_ray =
       sizeof(float) * (kIn2 * 64 + 128 + 48 * (T + 1) + 3 * T + RPC * (32 + 32 + 8 + 8 + C4) + 8);
 
@@ -1097,7 +1060,11 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.need_drays = ra.need_drays;
     {
       PhaseScope phr(phRay, st, 1);
-      k_ray<<<(int)((nc + RPC - 1) / RPC), T, smem_ray, st>>>(ra);
+      if (tc) {
+        if (int e = launch_ray_tc(ra, a->color, a->logit, w.W1o_hi, w.W1o_lo, ray0 == 0, nc, st)) return e;
+      } else {
+        k_ray<<<(int)((nc + RPC - 1) / RPC), T, smem_ray, st>>>(ra);
+      }
     }
     if (int e = check_launch("ray")) return e;
     {
@@ -1116,16 +1083,33 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       const int64_t Qrows = (int64_t)tiles_max * kTile;
       const int* ntd = map ? w.counts + cTiles : nullptr;
       int e = 0;
-      // coarse net (all slots): dW1 = dH^T X, dW2 = dOut^T H
-      e |= launch_dw_gemm(w.dHc, 32, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, nullptr, a->d_coarse, kIn1, 0, st);
-      e |= launch_dw_gemm(w.dOc, kOutP, DNS_LATENT, w.Hc, 32, 32, Qrows, ntd, tiles_max, nullptr, a->d_coarse + 2560, 32, 0, st);
-      if (map) {
-        e |= launch_dw_gemm(w.dHf, 32, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, w.tile_class, a->d_experts, kIn1, 4096, st);
-        e |= launch_dw_gemm(w.dOf, kOutP, DNS_LATENT, w.Hf, 32, 32, Qrows, ntd, tiles_max, w.tile_class, a->d_experts + 2560, 32, 4096, st);
-      }
       const int pt_tiles = (int)((Pc + kTile - 1) / kTile), ray_tiles = (int)((nc + kTile - 1) / kTile);
-      e |= launch_dw_gemm(w.dH2, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_color, kIn2, 0, st);
-      e |= launch_dw_gemm(w.dH2 + 32, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_logit, kIn2, 0, st);
+      if (use_tensor_cores()) {
+        // layer-1 weight gradients on tcgen05, the shared input operand read once:
+        //   X80^T [dHc | dHf] -> coarse W1 (+ class-expert W1);  X112^T [dH colour | dH logit] -> colour / logit W1
+        DwArgs g;
+        memset(&g, 0, sizeof(g));
+        g.L = w.Xst; g.ldl = kIn1; g.nL = kIn1; g.Cc = w.dHc; g.ldcc = 64; g.nC = map ? 64 : 32;
+        g.n_rows = Qrows; g.n_tiles_dev = ntd; g.n_tiles_host = tiles_max; g.tile_class = map ? w.tile_class : nullptr;
+        g.out0 = a->d_coarse; g.split = 32; g.sl0 = 1; g.sc0 = kIn1; g.cls0 = 0;
+        g.out1 = map ? a->d_experts : nullptr; g.sl1 = 1; g.sc1 = kIn1; g.cls1 = 4096;
+        e |= launch_dw_gemm_tc2(g, st);
+        memset(&g, 0, sizeof(g));
+        g.L = w.X2; g.ldl = kIn2; g.nL = kIn2; g.Cc = w.dH2; g.ldcc = 64; g.nC = 64;
+        g.n_rows = Pc; g.n_tiles_host = pt_tiles;
+        g.out0 = a->d_color; g.split = 32; g.sl0 = 1; g.sc0 = kIn2; g.out1 = a->d_logit; g.sl1 = 1; g.sc1 = kIn2;
+        e |= launch_dw_gemm_tc2(g, st);
+      } else {
+        e |= launch_dw_gemm(w.dHc, 64, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, nullptr, a->d_coarse, kIn1, 0, st);
+        if (map)
+          e |= launch_dw_gemm(w.dHf, 64, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, w.tile_class, a->d_experts, kIn1, 4096, st);
+        e |= launch_dw_gemm(w.dH2, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_color, kIn2, 0, st);
+        e |= launch_dw_gemm(w.dH2 + 32, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_logit, kIn2, 0, st);
+      }
+      // layer-2 weight gradients: dOut^T H
+      e |= launch_dw_gemm(w.dOc, kOutP, DNS_LATENT, w.Hc, 32, 32, Qrows, ntd, tiles_max, nullptr, a->d_coarse + 2560, 32, 0, st);
+      if (map)
+        e |= launch_dw_gemm(w.dOf, kOutP, DNS_LATENT, w.Hf, 32, 32, Qrows, ntd, tiles_max, w.tile_class, a->d_experts + 2560, 32, 4096, st);
       e |= launch_dw_gemm(w.dpre, 4, 3, w.Hcol, 32, 32, Pc, nullptr, pt_tiles, nullptr, a->d_color + 32 * kIn2, 32, 0, st);
       e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st);
       if (e) return DNS_ERR_CUDA;
@@ -1155,7 +1139,7 @@ int dns_render_counts(const dns_render_args* a, int32_t* counts4, void* stream) 
 int64_t dns_tv_workspace_bytes(int n) {
   int64_t n3 = (int64_t)n * n * n;
   int64_t Q = ((n3 + kTile - 1) / kTile) * kTile;
-  return 4096 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 32 + kOutP)) + 8 * 256;
+  return 4096 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + kOutP)) + 8 * 256;
 }
 
 int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
@@ -1178,7 +1162,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   float* docc = c.take<float>(n3);
   float* Xst = c.take<float>(Q * kIn1);
   float* Hc = c.take<float>(Q * 32);
-  float* dHc = c.take<float>(Q * 32);
+  float* dHc = c.take<float>(Q * 64);
   float* dOc = c.take<float>(Q * kOutP);
   static bool attr = false;
   if (!attr) {
@@ -1212,7 +1196,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
     k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
     if (int e = check_launch("tv bwd")) return e;
     int e = 0;
-    e |= launch_dw_gemm(dHc, 32, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st);
+    e |= launch_dw_gemm(dHc, 64, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st);
     e |= launch_dw_gemm(dOc, kOutP, 1, Hc, 32, 32, Q, nullptr, tiles, nullptr, a->d_coarse + 2560, 32, 0, st);
     if (e) return DNS_ERR_CUDA;
   }

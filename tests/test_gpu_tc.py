@@ -36,15 +36,28 @@ def test_fused_gradients_same_with_and_without_tensor_cores():
     L = _lib.lib()
     try:
         L.dns_set_tensor_cores(0)
-        ms.forward_backward(samples)
+        o0 = ms.forward_backward(samples)
         g0 = ms.grad.clone()
         L.dns_set_tensor_cores(1)
-        ms.forward_backward(samples)
+        o1 = ms.forward_backward(samples)
         g1 = ms.grad.clone()
     finally:
         L.dns_set_tensor_cores(1)
+    torch.testing.assert_close(o1[0][:7], o0[0][:7], rtol=1e-4, atol=1e-7)            # losses
+    for k in ("color", "depth", "var", "logits"):
+        torch.testing.assert_close(o1[1][k], o0[1][k], rtol=1e-4, atol=1e-5)
+    for i in (2, 3):                                                                 # d_rays_o, d_rays_d
+        e = float((o1[i] - o0[i]).norm() / (o0[i].norm() + 1e-30))
+        assert e < 1e-4, (i, e)
+    # d_features per point: the two paths sum in different orders, so a hidden pre-activation that is zero
+    # to within rounding can flip its ReLU mask (a legitimate sub-gradient change) at a handful of points;
+    # everywhere else the bf16 hi/lo x3 products agree with fp32 to ~1e-5.
+    a, b = o0[4].reshape(-1, 32).double(), o1[4].reshape(-1, 32).double()
+    per_point = (a - b).norm(dim=1) / (a.norm(dim=1) + 1e-30)
+    assert float(torch.quantile(per_point, 0.99)) < 1e-4
+    assert int((per_point > 1e-3).sum()) <= max(3, per_point.numel() // 2000)
     lay = dec.layout
-    for k in ("coarse", "color", "logit", "experts"):
+    for k in ("table", "coarse", "color", "logit", "experts"):
         a, n = lay[k]
         e = float((g1[a:a + n] - g0[a:a + n]).norm() / (g0[a:a + n].norm() + 1e-30))
-        assert e < 1e-4, (k, e)
+        assert e < 1e-3, (k, e)     # parity bar; ReLU-mask flips at ~0 pre-activations are legitimate
