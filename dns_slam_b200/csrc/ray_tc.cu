@@ -15,8 +15,7 @@
 // reads its accumulator row back with tcgen05.ld.32x32b.  The SAME shared-memory copy of W1
 // ([feature chunk][hidden row][8 features]) is the K-major B operand of the forward GEMM and the
 // MN-major B operand of the backward GEMM, so no transposed copy exists.
-#include "render.cuh"
-#include "umma.cuh"
+#include "tc_common.cuh"
 
 namespace dns {
 
@@ -34,33 +33,6 @@ __global__ void k_prep_w1o_tc(const float* __restrict__ color, const float* __re
   split8(a, b, h, l);
   hi[i] = h;
   lo[i] = l;
-}
-
-__device__ __forceinline__ void oneblob16(float x, float (&o)[16]) {
-  float prev = cdf3(0.0f - x, 16.0f);
-#pragma unroll
-  for (int b = 0; b < 16; ++b) {
-    float cur = cdf3((float)(b + 1) / 16.0f - x, 16.0f);
-    o[b] = cur - prev;
-    prev = cur;
-  }
-}
-__device__ __forceinline__ float oneblob16_bwd(float x, const float (&d)[16]) {
-  float prev = pdf3(0.0f - x, 16.0f), acc = 0.f;
-#pragma unroll
-  for (int b = 0; b < 16; ++b) {
-    float cur = pdf3((float)(b + 1) / 16.0f - x, 16.0f);
-    acc += d[b] * (cur - prev);
-    prev = cur;
-  }
-  return -16.0f * acc;
-}
-__device__ __forceinline__ void put_chunk(unsigned char* hi_tile, unsigned char* lo_tile, int chunk, int cs, int point,
-                                          const float* v8) {
-  uint4 h, l;
-  split8(make_float4(v8[0], v8[1], v8[2], v8[3]), make_float4(v8[4], v8[5], v8[6], v8[7]), h, l);
-  *reinterpret_cast<uint4*>(hi_tile + chunk * cs + point * 16) = h;
-  *reinterpret_cast<uint4*>(lo_tile + chunk * cs + point * 16) = l;
 }
 
 __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restrict__ w1_hi, const uint4* __restrict__ w1_lo) {

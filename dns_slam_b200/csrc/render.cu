@@ -140,132 +140,6 @@ __global__ void k_class_scatter(const int64_t* __restrict__ label, int64_t N, in
 // ---------------------------------------------------------------------------------------
 // point kernels
 // ---------------------------------------------------------------------------------------
-struct PointArgs {
-  // geometry
-  const float* rays_o;
-  const float* rays_d;
-  const float* z;
-  const float* gt_depth;
-  int S;
-  int64_t N_total, P_total;  // whole batch (loss denominators, class quirk)
-  int64_t p0, Pc;            // this chunk: global offset and number of points
-  Bound B;
-  dns_grid G;
-  const float2* table;
-  // TV lattice
-  int n;
-  double voxel, jit[3], off[3];
-  // slots
-  const int* perm;        // slot -> chunk-local point, -1 = padding; NULL = identity
-  const int* tile_class;  // tile -> expert row (MAP)
-  const int* counts;      // device counts (n_tiles at cTiles when perm != NULL)
-  int n_tiles_host;
-  // weights (k-major blocks)
-  const float* WTc;
-  const float* WTe;
-  // latents in point order, padded rows of 36
-  float* fine36;
-  float* coarse36;
-  float* dfine36;
-  float* occ;   // TV: [n^3]
-  float* docc;  // TV
-  // stashes in slot order
-  float* Xst;   // [Q][80]
-  float* Hc;    // [Q][32]
-  float* Hf;
-  float* dHc;
-  float* dHf;
-  float* dOc;   // [Q][36]
-  float* dOf;
-  // losses / gradients
-  float lam_lt, lam_fs, lam_op, trunc, sigma;
-  float* raw;
-  float2* d_table;
-  float* d_rays_o;
-  float* d_rays_d;
-  int need_dparams, need_drays;
-};
-
-template <int MODE>
-__device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_t& i, int64_t& r, float& zv, float x[3]) {
-  if (MODE == kTv) {
-    int64_t n = a.n, n3 = n * n * n;
-    if (q >= n3) return false;
-    i = q;
-    int64_t idx[3] = {q / (n * n), (q / n) % n, q % n};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      double pt = (((double)idx[c] + a.jit[c]) * a.voxel + a.B.lo[c]) + a.off[c];
-      x[c] = (float)((pt - a.B.lo[c]) / a.B.ext[c]);
-    }
-    r = 0;
-    zv = 0.f;
-    return true;
-  } else {
-    i = a.perm ? (int64_t)a.perm[q] : q;
-    if (i < 0 || i >= a.Pc) return false;
-    int64_t p = a.p0 + i;
-    r = p / a.S;
-    zv = a.z[p];
-    point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
-    return true;
-  }
-}
-
-__device__ __forceinline__ void load_block(float* dst, const float* __restrict__ src, int n4) {
-  const float4* s = reinterpret_cast<const float4*>(src);
-  float4* d = reinterpret_cast<float4*>(dst);
-  for (int i = threadIdx.x; i < n4; i += blockDim.x) d[i] = s[i];
-}
-
-// 80 -> 32 (ReLU) -> 36: h and out in registers
-__device__ __forceinline__ void net80_fwd(const float* xrow, const float* W1T, const float* W2T, float (&h)[32],
-                                          float (&out)[kOutP]) {
-  zero(h);
-  accum_layer<32>(xrow, 1, kIn1, W1T, 32, h);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
-  zero(out);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float4* w = reinterpret_cast<const float4*>(W2T + j * kOutP);
-#pragma unroll
-    for (int q = 0; q < kOutP / 4; ++q) {
-      float4 v = w[q];
-      out[4 * q + 0] = fmaf(h[j], v.x, out[4 * q + 0]);
-      out[4 * q + 1] = fmaf(h[j], v.y, out[4 * q + 1]);
-      out[4 * q + 2] = fmaf(h[j], v.z, out[4 * q + 2]);
-      out[4 * q + 3] = fmaf(h[j], v.w, out[4 * q + 3]);
-    }
-  }
-}
-template <int N>
-__device__ __forceinline__ void store_row(float* dst, const float (&v)[N]) {
-  float4* d = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int q = 0; q < N / 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-}
-template <int N>
-__device__ __forceinline__ void load_row(const float* src, float (&v)[N]) {
-  const float4* s = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int q = 0; q < N / 4; ++q) {
-    float4 t = s[q];
-    v[4 * q] = t.x;
-    v[4 * q + 1] = t.y;
-    v[4 * q + 2] = t.z;
-    v[4 * q + 3] = t.w;
-  }
-}
-
-// fs / opacity masks of one sample (utils/common.py:786-792)
-__device__ __forceinline__ void opacity_masks(float zv, float d, float trunc, float& front, float& band, float& valid) {
-  bool f = zv < __fsub_rn(d, trunc), b = zv > __fadd_rn(d, trunc);
-  valid = d > 0.f ? 1.f : 0.f;
-  front = f ? 1.f : 0.f;
-  band = (!f && !b) ? valid : 0.f;
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(kTile) k_point_fwd(PointArgs a) {
   extern __shared__ float sm[];
@@ -851,6 +725,7 @@ struct RenderWs {
   int *hist, *slot_start, *cursor;
   float *WTc, *WTe, *W1T2, *W2cT;
   uint4 *W1o_hi, *W1o_lo;   // bf16 hi / lo chunk tiles of the colour|logit layer-1 weights (tcgen05 path)
+  uint4 *wc_tc, *we_tc;     // bf16 hi / lo tiles of the coarse net and of every class expert (1024 uint4 each)
   int *perm, *tile_class;
   float *fine36, *coarse36, *dfine36;
   float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf;
@@ -875,6 +750,8 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.W2cT = c.take<float>(128);
   w.W1o_hi = c.take<uint4>(14 * 64);
   w.W1o_lo = c.take<uint4>(14 * 64);
+  w.wc_tc = c.take<uint4>(1024);
+  w.we_tc = c.take<uint4>((int64_t)1024 * (map ? nci : 0) + 4);
   w.perm = c.take<int>(map ? w.Q : 4);
   w.tile_class = c.take<int>(w.tiles);
   w.fine36 = c.take<float>(Pc * kOutP);
@@ -987,6 +864,9 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   }
   delete ph;
   if (int e = check_launch("render prep")) return e;
+  const bool tc = use_tensor_cores();
+  if (tc)
+    if (int e = prep_nets_tc(a->coarse, map ? a->experts : nullptr, map ? a->n_experts : 0, w.wc_tc, w.we_tc, st)) return e;
 
   static bool attr = false;
   if (!attr) {
@@ -1001,7 +881,6 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   }
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT * (map ? 2 : 1));
   int T, RPC;
-  const bool tc = use_tensor_cores();
   if (tc) pick_ray_block_tc(S, T, RPC);
   else pick_ray_block(S, T, RPC);
   const size_t smem_ray =
@@ -1038,7 +917,9 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     }
     {
       PhaseScope php(phPointFwd, st, 1);
-      if (map) k_point_fwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
+      if (tc) {
+        if (int e = launch_point_fwd_tc(map ? kMap : kTrack, pa, tiles_max, w.wc_tc, w.we_tc, st)) return e;
+      } else if (map) k_point_fwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
       else k_point_fwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
     }
     if (int e = check_launch("point_fwd")) return e;
@@ -1069,7 +950,9 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     if (int e = check_launch("ray")) return e;
     {
       PhaseScope phb(phPointBwd, st, 1);
-      if (map) k_point_bwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
+      if (tc) {
+        if (int e = launch_point_bwd_tc(map ? kMap : kTrack, pa, tiles_max, w.wc_tc, w.we_tc, st)) return e;
+      } else if (map) k_point_bwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
       else k_point_bwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
     }
     if (int e = check_launch("point_bwd")) return e;
@@ -1139,7 +1022,7 @@ int dns_render_counts(const dns_render_args* a, int32_t* counts4, void* stream) 
 int64_t dns_tv_workspace_bytes(int n) {
   int64_t n3 = (int64_t)n * n * n;
   int64_t Q = ((n3 + kTile - 1) / kTile) * kTile;
-  return 4096 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + kOutP)) + 8 * 256;
+  return 4096 + 16384 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + kOutP)) + 10 * 256;
 }
 
 int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
@@ -1164,6 +1047,8 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   float* Hc = c.take<float>(Q * 32);
   float* dHc = c.take<float>(Q * 64);
   float* dOc = c.take<float>(Q * kOutP);
+  uint4* wc_tc = c.take<uint4>(1024);
+  const bool tc = use_tensor_cores();
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_point_fwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -1186,14 +1071,20 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   pa.d_table = (float2*)a->d_table; pa.need_dparams = a->need_dparams; pa.need_drays = 0;
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT);
   PhaseScope* pht = new PhaseScope(phTvFwd, st, 4);
-  k_point_fwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
+  if (tc) {
+    prep_nets_tc(a->coarse, nullptr, 0, wc_tc, nullptr, st);
+    launch_point_fwd_tc(kTv, pa, tiles, wc_tc, wc_tc, st);
+  } else {
+    k_point_fwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
+  }
   const float inv_norm = 1.0f / ((float)a->smooth_pts * (float)a->smooth_pts * (float)a->smooth_pts);
   k_tv_stencil<<<(int)((n3 + 255) / 256), 256, 0, st>>>(occ, n, inv_norm, a->lambda_sm, docc, a->loss);
   delete pht;
   if (int e = check_launch("tv fwd")) return e;
   if (a->need_dparams) {
     PhaseScope phtb(phTvBwd, st, 3);
-    k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
+    if (tc) launch_point_bwd_tc(kTv, pa, tiles, wc_tc, wc_tc, st);
+    else k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
     if (int e = check_launch("tv bwd")) return e;
     int e = 0;
     e |= launch_dw_gemm(dHc, 64, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st);

@@ -48,6 +48,138 @@ struct RayArgs {
   int need_dparams, need_drays, need_dfeat;
 };
 
+struct PointArgs {
+  // geometry
+  const float* rays_o;
+  const float* rays_d;
+  const float* z;
+  const float* gt_depth;
+  int S;
+  int64_t N_total, P_total;  // whole batch (loss denominators, class quirk)
+  int64_t p0, Pc;            // this chunk: global offset and number of points
+  Bound B;
+  dns_grid G;
+  const float2* table;
+  // TV lattice
+  int n;
+  double voxel, jit[3], off[3];
+  // slots
+  const int* perm;        // slot -> chunk-local point, -1 = padding; NULL = identity
+  const int* tile_class;  // tile -> expert row (MAP)
+  const int* counts;      // device counts (n_tiles at cTiles when perm != NULL)
+  int n_tiles_host;
+  // weights (k-major blocks)
+  const float* WTc;
+  const float* WTe;
+  // latents in point order, padded rows of 36
+  float* fine36;
+  float* coarse36;
+  float* dfine36;
+  float* occ;   // TV: [n^3]
+  float* docc;  // TV
+  // stashes in slot order
+  float* Xst;   // [Q][80]
+  float* Hc;    // [Q][32]
+  float* Hf;
+  float* dHc;
+  float* dHf;
+  float* dOc;   // [Q][36]
+  float* dOf;
+  // losses / gradients
+  float lam_lt, lam_fs, lam_op, trunc, sigma;
+  float* raw;
+  float2* d_table;
+  float* d_rays_o;
+  float* d_rays_d;
+  int need_dparams, need_drays;
+};
+
+template <int MODE>
+__device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_t& i, int64_t& r, float& zv, float x[3]) {
+  if (MODE == kTv) {
+    int64_t n = a.n, n3 = n * n * n;
+    if (q >= n3) return false;
+    i = q;
+    int64_t idx[3] = {q / (n * n), (q / n) % n, q % n};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double pt = (((double)idx[c] + a.jit[c]) * a.voxel + a.B.lo[c]) + a.off[c];
+      x[c] = (float)((pt - a.B.lo[c]) / a.B.ext[c]);
+    }
+    r = 0;
+    zv = 0.f;
+    return true;
+  } else {
+    i = a.perm ? (int64_t)a.perm[q] : q;
+    if (i < 0 || i >= a.Pc) return false;
+    int64_t p = a.p0 + i;
+    r = p / a.S;
+    zv = a.z[p];
+    point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
+    return true;
+  }
+}
+
+__device__ __forceinline__ void load_block(float* dst, const float* __restrict__ src, int n4) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+  float4* d = reinterpret_cast<float4*>(dst);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) d[i] = s[i];
+}
+
+// 80 -> 32 (ReLU) -> 36: h and out in registers
+__device__ __forceinline__ void net80_fwd(const float* xrow, const float* W1T, const float* W2T, float (&h)[32],
+                                          float (&out)[kOutP]) {
+  zero(h);
+  accum_layer<32>(xrow, 1, kIn1, W1T, 32, h);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
+  zero(out);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float4* w = reinterpret_cast<const float4*>(W2T + j * kOutP);
+#pragma unroll
+    for (int q = 0; q < kOutP / 4; ++q) {
+      float4 v = w[q];
+      out[4 * q + 0] = fmaf(h[j], v.x, out[4 * q + 0]);
+      out[4 * q + 1] = fmaf(h[j], v.y, out[4 * q + 1]);
+      out[4 * q + 2] = fmaf(h[j], v.z, out[4 * q + 2]);
+      out[4 * q + 3] = fmaf(h[j], v.w, out[4 * q + 3]);
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_row(float* dst, const float (&v)[N]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+template <int N>
+__device__ __forceinline__ void load_row(const float* src, float (&v)[N]) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    float4 t = s[q];
+    v[4 * q] = t.x;
+    v[4 * q + 1] = t.y;
+    v[4 * q + 2] = t.z;
+    v[4 * q + 3] = t.w;
+  }
+}
+
+// fs / opacity masks of one sample (utils/common.py:786-792)
+__device__ __forceinline__ void opacity_masks(float zv, float d, float trunc, float& front, float& band, float& valid) {
+  bool f = zv < __fsub_rn(d, trunc), b = zv > __fadd_rn(d, trunc);
+  valid = d > 0.f ? 1.f : 0.f;
+  front = f ? 1.f : 0.f;
+  band = (!f && !b) ? valid : 0.f;
+}
+
+
+// tcgen05 point kernels (point_tc.cu); wc / we: bf16 hi/lo weight tiles, 1024 uint4 per net
+int prep_nets_tc(const float* coarse, const float* experts, int n_experts, uint4* wc, uint4* we, cudaStream_t st);
+int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
+int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
+
 // tcgen05 ray kernel (ray_tc.cu)
 void pick_ray_block_tc(int S, int& T, int& RPC);
 size_t ray_tc_smem_bytes(int T, int RPC, int C4);
