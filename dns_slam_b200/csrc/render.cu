@@ -728,7 +728,7 @@ struct RenderWs {
   uint4 *wc_tc, *we_tc;     // bf16 hi / lo tiles of the coarse net and of every class expert (1024 uint4 each)
   int *perm, *tile_class;
   float *fine36, *coarse36, *dfine36;
-  float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf;
+  float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf, *Jst;
   float *X2, *dH2, *Hcol, *dpre, *dlogit, *Hbar;
   int64_t Q, tiles;
 };
@@ -757,6 +757,7 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.fine36 = c.take<float>(Pc * kOutP);
   w.coarse36 = c.take<float>(map ? Pc * kOutP : 4);
   w.dfine36 = c.take<float>(Pc * kOutP);
+  w.Jst = nullptr;   // (a per-level Jacobian stash was measured slower than re-gathering the corners)
   w.Xst = c.take<float>(w.Q * kIn1);
   w.Hc = c.take<float>(w.Q * 32);
   w.Hf = c.take<float>(map ? w.Q * 32 : 4);
@@ -899,7 +900,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.WTc = w.WTc; pa.WTe = w.WTe;
     // point-order buffers are indexed with GLOBAL point ids: shift the chunk-local base
     pa.fine36 = w.fine36 - p0 * kOutP; pa.coarse36 = w.coarse36 - p0 * kOutP; pa.dfine36 = w.dfine36 - p0 * kOutP;
-    pa.Xst = w.Xst; pa.Hc = w.Hc; pa.Hf = w.Hf; pa.dHc = w.dHc; pa.dHf = w.dHf; pa.dOc = w.dOc; pa.dOf = w.dOf;
+    pa.Jst = w.Jst; pa.Xst = w.Xst; pa.Hc = w.Hc; pa.Hf = w.Hf; pa.dHc = w.dHc; pa.dHf = w.dHf; pa.dOc = w.dOc; pa.dOf = w.dOf;
     pa.lam_lt = a->lambda_lt; pa.lam_fs = a->lambda_fs; pa.lam_op = a->lambda_op;
     pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;

@@ -78,6 +78,7 @@ struct PointArgs {
   float* occ;   // TV: [n^3]
   float* docc;  // TV
   // stashes in slot order
+  float* Jst;   // [Q][96] d grid feature / d x (tcgen05 path, only when ray gradients are wanted)
   float* Xst;   // [Q][80]
   float* Hc;    // [Q][32]
   float* Hf;
