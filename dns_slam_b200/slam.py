@@ -185,3 +185,151 @@ class MapperCore:
         ld["smooth_loss"] = sm.detach()
         ld["total"] = ld["total"] + self.lambda_sm * sm
         return ld, preds, samples
+
+
+# ----------------------------------------------------------------------------------------
+# whole-loop drop-ins: the optimisation loops around the iteration bodies
+# ----------------------------------------------------------------------------------------
+def quad_from_matrix(R):
+    """Rotation matrix -> quaternion (w,x,y,z) (utils/common.py:485-504 without ``mathutils``; the sign
+    is immaterial because quad2rotation uses 2/|q|^2)."""
+    import numpy as np
+    R = np.asarray(R.detach().cpu() if isinstance(R, torch.Tensor) else R, dtype=np.float64)
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = [0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s]
+    elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+        s = np.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2]) * 2
+        q = [(R[2, 1] - R[1, 2]) / s, 0.25 * s, (R[0, 1] + R[1, 0]) / s, (R[0, 2] + R[2, 0]) / s]
+    elif R[1, 1] > R[2, 2]:
+        s = np.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2]) * 2
+        q = [(R[0, 2] - R[2, 0]) / s, (R[0, 1] + R[1, 0]) / s, 0.25 * s, (R[1, 2] + R[2, 1]) / s]
+    else:
+        s = np.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]) * 2
+        q = [(R[1, 0] - R[0, 1]) / s, (R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s]
+    return torch.tensor(q, dtype=torch.float32)
+
+
+def uniq_class_indices(tables, n, class_list, draws):
+    """common.py:375-393 (get_samples_by_uniq_class): n rays spread over the GIVEN classes; class 0 of
+    the list takes the remainder, a class with one pixel is repeated, an absent class is skipped."""
+    classes, order, starts, counts = tables
+    lookup = {int(c): k for k, c in enumerate(classes.tolist())}
+    counts_h, starts_h = counts.tolist(), starts.tolist()
+    n_class = len(class_list)
+    n_k = n // n_class
+    out, di = [], 0
+    for pos, cid in enumerate(class_list):
+        m = n - n_k * (n_class - 1) if pos == 0 else n_k
+        k = lookup.get(int(cid))
+        if k is None:
+            continue
+        if counts_h[k] == 1:
+            out.append(order[starts_h[k]].reshape(1).repeat(m))
+        else:
+            out.append(order[starts_h[k] + draws[di].to(order.device)])
+            di += 1
+    return torch.cat(out, -1), di
+
+
+def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR=False):
+    """The pose-optimisation loop of ``Tracker.run`` (slams/tracking.py:304-346): Adam over
+    (translation, quaternion), the best-loss pose is kept.  The ``loss < current_min_loss`` test that
+    costs the reference a host sync per iteration (tracking.py:331) stays on the device.
+    ``draws_fn(it)`` -> dict(idx, t_surface, t_zero).  Returns (best [quad|T] 7-vector, best loss)."""
+    dev = tracker.decoder.bound.device
+    quad = quad_from_matrix(est_c2w[:3, :3]).to(dev).requires_grad_(True)
+    T = est_c2w[:3, 3].detach().clone().to(dev).requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
+                            {"params": [quad], "lr": cam_lr}])
+    best_loss = torch.full((), 1e10, device=dev)
+    best = torch.cat((quad, T), 0).detach().clone()
+    cur = dict(frame, est_quad=quad, est_T=T)
+    history = []
+    for it in range(n_iters):
+        opt.zero_grad()
+        cur_w2c = torch.inverse(c2w_from_quad_T(quad, T))
+        est_w2c = torch.stack((refer_w2c.to(dev), cur_w2c), 0)
+        ld, _, _ = tracker.iteration(cur, {"est_w2c": est_w2c}, features_cl, draws_fn(it))
+        loss = ld["total"]
+        with torch.no_grad():
+            better = loss < best_loss
+            best_loss = torch.where(better, loss, best_loss)
+            best = torch.where(better, torch.cat((quad, T), 0), best)
+        history.append(loss.detach())
+        loss.backward()
+        opt.step()
+    return best, best_loss, torch.stack(history)
+
+
+def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,
+                 new_decoders, draws_fn, tv_draws_fn):
+    """The optimisation loop of ``Mapper.optimize`` (slams/mapping.py:868-910): one Adam over the decoder
+    (hash grid + MLPs), the class experts present and -- when ``is_BA`` -- quaternion / translation of every
+    target frame but the oldest (mapping.py:457); lambda_lt follows the schedule of mapping.py:898-904.
+    Returns (quad_list, T_list, loss dict of the last iteration)."""
+    dec = mapper.decoder
+    dev = dec.bound.device
+    n_t = len(target_frames["frames"])
+    quad_list, T_list = [], []
+    for f in range(n_t):
+        c2w = est_c2w_list[f]
+        q = quad_from_matrix(c2w[:3, :3]).to(dev)
+        t = c2w[:3, 3].detach().clone().to(dev)
+        if (n_t == 1 or f != 0) and is_BA:
+            q.requires_grad_(True)
+            t.requires_grad_(True)
+        quad_list.append(q)
+        T_list.append(t)
+    net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
+    cam_lr = BA_cam_lr * float(is_BA)
+    opt = torch.optim.Adam([{"params": net, "lr": lr},
+                            {"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
+                            {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}])
+    ld = None
+    for it in range(n_iters):
+        opt.zero_grad()
+        lam_lt = (10.0 if it > n_iters // 2 else 0.0) if len(new_decoders) > 0 else 10.0
+        ld, _, _ = mapper.iteration(target_frames, quad_list, T_list, refer_frames, features_cl, draws_fn(it),
+                                    tv_draws_fn(it), lambda_lt=lam_lt)
+        ld["total"].backward()
+        opt.step()
+    return quad_list, T_list, ld
+
+
+def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, lr, draws_fn, tv_draws_fn,
+                 n_iters=100, n_rays=300):
+    """``Mapper.decoder_init`` (slams/mapping.py:764-836): warm-up of freshly created class experts on the
+    current frame: rays spread over the new classes (get_samples_by_uniq_class), losses p + d + l + fs +
+    opacity + TV (no latent term), Adam over the decoder and the new experts."""
+    dec = mapper.decoder
+    dev = dec.bound.device
+    for c in decoder_idx:
+        dec.activate_expert(c)
+    net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
+    opt = torch.optim.Adam([{"params": net, "lr": lr}])
+    R, T = cur_c2w[:3, :3].to(dev), cur_c2w[:3, 3].to(dev)
+    window = (0, mapper.H, 0, mapper.W)
+    w2c = torch.inverse(cur_c2w.to(dev)).unsqueeze(0)
+    lam = dict(mapper.lambdas, lt=0.0)
+    ld = None
+    for it in range(n_iters):
+        opt.zero_grad()
+        d = draws_fn(it)
+        idx, _ = uniq_class_indices(class_table, n_rays, decoder_idx, d["class_draws"])
+        s = fused.sample_rays(mapper.cam, dec.bound, frame, idx, window, R, T, mapper.n_samples_ray,
+                              mapper.n_surface_ray, fused.fix_surface_draw(d["t_surface"], mapper.n_surface_ray),
+                              d["t_zero"])
+        z = s["z_vals"]
+        pts = s["rays_o"][:, None, :] + s["rays_d"][:, None, :] * z[:, :, None]
+        code = fused.feature_matching(mapper.H, mapper.W, mapper.K, pts.flatten(0, 1), w2c, features_cl, dec.merge)
+        samples = {"gt_color": s["gt_color"], "gt_depth": s["gt_depth"], "gt_label": s["gt_label"],
+                   "rays_o": s["rays_o"], "rays_d": s["rays_d"], "z_vals": z,
+                   "features": code.reshape(pts.shape[0], pts.shape[1], -1)}   # no trunc mask here (mapping.py:807-809)
+        ld, _ = fused.render_and_loss(dec, samples, _lib.MODE_MAP, lambdas=lam, opacity_sigma=mapper.opacity_sigma)
+        tv = tv_draws_fn(it)
+        sm = fused.tv_loss(dec, mapper.smooth_pts, tv[0], tv[1])
+        (ld["total"] + mapper.lambda_sm * sm).backward()
+        opt.step()
+    return ld

@@ -99,6 +99,7 @@ class ShardedMappingStep(MappingStep):
         self.packed[-8:] = out[0]
         self.comm.all_reduce_sum(self.packed)
         losses = self.packed[-8:].clone()
+        losses[7] = losses[7] / self.world_n          # n_valid is a batch constant, not a partial sum
         self.t += 1
         self._adam()
         return (losses,) + tuple(out[1:])

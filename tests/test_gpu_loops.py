@@ -1,0 +1,148 @@
+"""Whole-loop drop-ins against the CPU oracle: the pose-optimisation loop of
+Tracker.run (slams/tracking.py:304-346) and the optimisation loop of Mapper.optimize
+(slams/mapping.py:868-910), a few iterations each with identical draws.  Adam amplifies rounding
+differences, so the bar is 2e-3 on the loss trajectory / poses after 3 steps."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import close, frame_to, product_decoder_from_oracle, rel_err  # noqa: E402
+
+META_T = dict(shape="tiny", n_class=6, seed=31, n_samples=32, n_surface=15, pose_index=3, refer_index=2)
+META_M = dict(shape="tiny", n_class=6, seed=37, n_samples=32, n_surface=15, tgt_ids=[1, 4, 6],
+              refer_idx=[[0, 4, -1], [1, 2, -1], [4, 5, -1]], lambda_lt=10.0, lambda_sm=0.05)
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def test_tracking_loop_vs_oracle():
+    from oracle import cases, reference_path as rp
+    from dns_slam_b200 import fused, slam, synthetic as syn
+    dev = _dev()
+    s = syn.SHAPES["tiny"]
+    inp = cases.tracking_inputs(META_T)
+    cam = inp["cam"]
+    n_it, lr = 3, 1e-3
+    g = torch.Generator().manual_seed(5)
+    n_win = (cam["H"] - 40) * (cam["W"] - 40)
+    draws = [dict(idx=torch.randint(n_win, (s["tracking_pixels"],), generator=g), t_surface=torch.rand(15, generator=g),
+                  t_zero=torch.rand(15, generator=g)) for _ in range(n_it)]
+    est = inp["poses"][3].clone()
+    est[:3, 3] += torch.tensor([0.02, -0.01, 0.015])
+    refer_w2c = torch.inverse(inp["poses"][2])
+    # ---- oracle loop (CPU)
+    odec, bound = inp["decoder"], inp["bound"]
+    quad = rp.quad_from_matrix(est[:3, :3].numpy()).clone().requires_grad_(True)
+    T = est[:3, 3].clone().requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [T], "lr": lr}, {"params": [quad], "lr": lr}])
+    hist_o = []
+    for it in range(n_it):
+        opt.zero_grad()
+        w2c = torch.stack((refer_w2c, torch.inverse(rp.c2w_from_quad_T(quad, T))), 0)
+        tape = rp.DrawTape([("randint", draws[it]["idx"]), ("rand", draws[it]["t_surface"]), ("rand", draws[it]["t_zero"])])
+        smp = rp.tracker_get_target_samples(cam, bound, odec, inp["frame"], quad, T, w2c, inp["feats"],
+                                            s["tracking_pixels"], 32, 15, tape)
+        pc, pd, pv, pl = rp.tracker_renderer(odec, bound, smp)
+        p, d, l = rp.tracking_losses(smp, pc, pd, pv, pl)
+        loss = s["lambda_color"] * p + s["lambda_depth"] * d + s["lambda_label"] * l
+        hist_o.append(loss.detach())
+        loss.backward()
+        opt.step()
+    # ---- native loop
+    dec = product_decoder_from_oracle("tiny", odec, n_class=6)
+    trk = slam.TrackerCore(cam, dec, s["tracking_pixels"], 32, 15, s["lambda_color"], s["lambda_depth"], s["lambda_label"])
+    best, best_loss, hist = slam.track_frame(trk, frame_to(inp["frame"], dev), refer_w2c, fused.channels_last(inp["feats"].to(dev)),
+                                             est, n_it, lr, lambda it: draws[it])
+    close(hist, torch.stack(hist_o), rtol=2e-3, atol=1e-5, name="tracking loss trajectory")
+    k = int(torch.argmin(torch.stack(hist_o)))
+    assert abs(float(best_loss) - float(hist_o[k])) < 2e-3 * abs(float(hist_o[k]))
+
+
+def test_mapping_loop_vs_oracle():
+    from oracle import cases, reference_path as rp
+    from dns_slam_b200 import fused, slam, synthetic as syn
+    dev = _dev()
+    s = syn.SHAPES["tiny"]
+    meta = META_M
+    inp = cases.mapping_inputs(meta)
+    cam, bound = inp["cam"], inp["bound"]
+    n_it, lr, cam_lr = 2, 5e-3, 5e-4
+    n_t = len(meta["tgt_ids"])
+    npf = s["mapping_pixels"] // n_t
+    g = torch.Generator().manual_seed(9)
+    draws, tv = [], []
+    for _ in range(n_it):
+        per = []
+        for fr in inp["frames"]:
+            lab = fr["label"].reshape(-1)
+            classes, counts = torch.unique(lab, return_counts=True)
+            n_c, n_k = classes.numel(), (npf // 3) // classes.numel()
+            cd = []
+            for c in range(n_c):
+                m = (npf // 3) - n_k * (n_c - 1) if c == 0 else n_k
+                if int(counts[c]) != 1:
+                    cd.append(torch.randint(int(counts[c]), (m,), generator=g))
+            per.append(dict(idx_uniform=torch.randint(cam["H"] * cam["W"], (npf // 3 * 2,), generator=g), class_draws=cd,
+                            t_surface=torch.rand(15, generator=g), t_zero=torch.rand(15, generator=g)))
+        draws.append(per)
+        tv.append((torch.rand(3, generator=g), torch.rand(1, 1, 1, 3, generator=g)))
+    est = [inp["poses"][i].clone() for i in meta["tgt_ids"]]
+    for n, e in enumerate(est):
+        e[:3, 3] += 0.01 * (n + 1)
+    lam = dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0, fs=s["lambda_fs"], op=s["lambda_opacity"])
+    # ---- oracle loop (CPU)
+    odec, oexp = inp["decoder"], inp["experts"]
+    ql = [rp.quad_from_matrix(e[:3, :3].numpy()).clone().requires_grad_(i != 0) for i, e in enumerate(est)]
+    Tl = [e[:3, 3].clone().requires_grad_(i != 0) for i, e in enumerate(est)]
+    net = list(odec.parameters()) + [e.params for e in oexp.values()]
+    opt = torch.optim.Adam([{"params": net, "lr": lr}, {"params": ql[1:], "lr": cam_lr}, {"params": Tl[1:], "lr": cam_lr}])
+    losses_o = []
+    for it in range(n_it):
+        opt.zero_grad()
+        items = []
+        for d in draws[it]:
+            items.append(("randint", d["idx_uniform"]))
+            items += [("randint", c) for c in d["class_draws"]]
+            items += [("rand", d["t_surface"]), ("rand", d["t_zero"])]
+        items += [("rand", tv[it][0]), ("rand", tv[it][1])]
+        tape = rp.DrawTape(items)
+        smp = rp.mapper_get_target_samples(cam, bound, odec, inp["frames"], ql, Tl, meta["refer_idx"], meta["tgt_ids"],
+                                           inp["refer_c2w"], inp["feats"], s["mapping_pixels"], 32, 15, tape)
+        pc, pd, pv, pl, fine, coarse = rp.mapper_renderer(odec, oexp, bound, smp)
+        p, d, l, lt, fs, op = rp.mapping_losses(smp, pc, pd, pl, fine, coarse, s["opacity_sigma"])
+        sm = rp.smoothness(odec, bound, s["smooth_pts"], tape)
+        loss = lam["p"] * p + lam["d"] * d + lam["l"] * l + lam["lt"] * lt + meta["lambda_sm"] * sm + lam["fs"] * fs + lam["op"] * op
+        losses_o.append(loss.detach())
+        loss.backward()
+        opt.step()
+    # ---- native loop
+    # the oracle decoder has already been stepped: rebuild identical initial weights for the native side
+    inp2 = cases.mapping_inputs(meta)
+    dec = product_decoder_from_oracle("tiny", inp2["decoder"], inp2["experts"], n_class=6)
+    mp = slam.MapperCore(cam, dec, s["mapping_pixels"], 32, 15, lambdas=lam, opacity_sigma=s["opacity_sigma"],
+                         smooth_pts=s["smooth_pts"], lambda_sm=meta["lambda_sm"])
+    frames = [frame_to(f, dev) for f in inp["frames"]]
+    target = dict(kf_idx=meta["tgt_ids"], frames=frames, class_tables=[slam.class_tables(f["label"]) for f in frames])
+    refer = dict(kf_idx=meta["refer_idx"], est_c2w=[[c.to(dev) for c in row] for row in inp["refer_c2w"]])
+    feats = [fused.channels_last(f.to(dev)) for f in inp["feats"]]
+    hist = []
+    orig_iter = mp.iteration
+
+    def rec(*a, **k):
+        out = orig_iter(*a, **k)
+        hist.append(out[0]["total"].detach())
+        return out
+    mp.iteration = rec
+    quad_list, T_list, ld = slam.map_optimize(mp, target, refer, feats, est, n_it, lr, cam_lr, True, [],
+                                              lambda it: draws[it], lambda it: tv[it])
+    close(torch.stack(hist), torch.stack(losses_o), rtol=2e-3, atol=1e-5, name="mapping loss trajectory")
+    for i in range(1, n_t):
+        close(quad_list[i], ql[i], rtol=2e-3, atol=2e-5, name=f"quad[{i}] after BA")
+        close(T_list[i], Tl[i], rtol=2e-3, atol=2e-5, name=f"T[{i}] after BA")
+    # parameters after two Adam steps: the update direction is sign-like, so compare the net displacement
+    assert rel_err(dec.coarse_fn.decoder.params, odec.coarse_fn.decoder.params) < 1e-3
+    assert rel_err(dec.pe_fn.grid_fn.params, odec.pe_fn.grid_fn.params) < 1e-3
