@@ -372,7 +372,58 @@ def _extra_configs(args, dev):
     t1 = _time_cuda(lambda: ts.forward_backward(smp1), 50, 10)
     out["config1_tracking_1024x96"] = {"ms_per_iteration": t1, "rays_per_s": 1024 / (t1 * 1e-3),
                                        "ms_per_10_iterations": 10 * t1}
+    # T_iter: whole iterations incl. sampling, feature matching + Merge, TV, Adam
+    for shape in ("replica", "scannet"):
+        out["iteration_" + shape] = _iteration_timings(shape, args.n_class, dev)
     return out
+
+
+def _iteration_timings(shape, n_class, dev):
+    """ms per tracking / mapping ITERATION at the reference's default sizes (replica.yaml / scannet.yaml):
+    the loops of slams/tracking.py:313-340 and slams/mapping.py:881-910 through the drop-in host mirror."""
+    from dns_slam_b200 import bench_util, slam, synthetic as syn
+    s = syn.SHAPES[shape]
+    dec = bench_util.make_decoder(shape, n_class, dev, seed=1)
+    sc = bench_util.slam_scene(shape, n_class, dev, seed=2)
+    cam = sc["cam"]
+    trk = slam.TrackerCore(cam, dec, s["tracking_pixels"], 32, 15, s["lambda_color"], s["lambda_depth"], s["lambda_label"],
+                           freeze_decoder=True)
+    n_it = 10
+    td = bench_util.tracking_draws(cam, s["tracking_pixels"], n_it)
+    est = sc["poses"][3].clone()
+    est[:3, 3] += 0.01
+    refer_w2c = torch.inverse(sc["poses"][2])
+    feats2 = sc["feats"][1][:2].contiguous()
+
+    def track():
+        slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, n_it, s["cam_lr"], lambda it: td[it])
+    t_track = _time_cuda(track, 3, 1) / n_it
+    # marginal cost of a CUDA-graph-replayed iteration: (210 - 110 iterations) / 100, capture cost cancels out
+    def track_graph(n):
+        return lambda: slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, n, s["cam_lr"], lambda it: td[it % n_it],
+                                        use_graph=True)
+    track_graph(20)()
+    t_long = min(_time_cuda(track_graph(210), 1, 0) for _ in range(2))
+    t_short = min(_time_cuda(track_graph(110), 1, 0) for _ in range(2))
+    t_track_graph = (t_long - t_short) / 100.0
+    mp = slam.MapperCore(cam, dec, s["mapping_pixels"], 32, 15,
+                         lambdas=dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0,
+                                      fs=s["lambda_fs"], op=s["lambda_opacity"]),
+                         opacity_sigma=s["opacity_sigma"], smooth_pts=s["smooth_pts"], lambda_sm=s["lambda_smooth"])
+    m_it = 5
+    md, tv = bench_util.mapping_draws(sc, s["mapping_pixels"], m_it)
+    target = dict(kf_idx=sc["kf_idx"], frames=sc["frames"], class_tables=sc["class_tables"])
+    refer = dict(kf_idx=sc["refer_idx"], est_c2w=sc["refer_c2w"])
+    est_list = [sc["poses"][2 * f + 1].clone() for f in range(len(sc["frames"]))]
+
+    def mapit():
+        slam.map_optimize(mp, target, refer, sc["feats"], est_list, m_it, s["lr"], s["BA_cam_lr"], True, [],
+                          lambda it: md[it], lambda it: tv[it])
+    t_map = _time_cuda(mapit, 2, 1) / m_it
+    return {"tracking_ms_per_iteration": t_track, "tracking_ms_per_iteration_cuda_graph": t_track_graph,
+            "tracking_rays": s["tracking_pixels"],
+            "mapping_ms_per_iteration": t_map, "mapping_rays": s["mapping_pixels"], "tv_lattice": (s["smooth_pts"] - 1) ** 3,
+            "n_samples": 47, "note": "autograd drop-in path (render_and_loss + torch Adam), sampling + feature matching + TV included"}
 
 
 if __name__ == "__main__":

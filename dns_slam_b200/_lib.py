@@ -163,7 +163,16 @@ def ptr(t, dtype=None, allow_none=False):
 
 
 def fill_bound(dst, bound):
-    b = bound.detach().double().cpu()
+    """float64 scene bound -> C struct.  The bound never changes after construction, so its host copy is
+    cached ON the tensor object (a ``.cpu()`` per call would put a device sync in every iteration; a cache
+    keyed by data_ptr could alias a freed tensor)."""
+    b = getattr(bound, "_dns_host", None)
+    if b is None:
+        b = bound.detach().double().cpu()
+        try:
+            bound._dns_host = b
+        except AttributeError:
+            pass
     for a in range(3):
         dst[a][0] = float(b[a, 0])
         dst[a][1] = float(b[a, 1])

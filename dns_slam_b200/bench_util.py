@@ -61,3 +61,53 @@ def synthetic_batch(shape, mode, N, S, C, device, seed=0, n_frames=None, dec=Non
                    rays_o=cat["rays_o"], rays_d=cat["rays_d"], z_vals=cat["z_vals"], features=feats,
                    mask=(cat["gt_depth"] > 0.01) * cat["inside"])
     return dec, samples
+
+
+def slam_scene(shape, n_class, device, seed=0, n_target=4, n_refer=3):
+    """Synthetic keyframes for whole-iteration timings: target frames with class tables, reference
+    poses and channels-last pixel features (one [R,h,w,64] block per target frame)."""
+    cam = syn.camera(shape)
+    gen = torch.Generator().manual_seed(seed)
+    poses = syn.trajectory(shape, n_target * 2 + 2)
+    frames, feats, refer_c2w, refer_idx = [], [], [], []
+    for f in range(n_target):
+        fr = syn.frame(shape, poses[2 * f + 1], gen, n_class=n_class)
+        frames.append({k: v.to(device).contiguous() for k, v in fr.items()})
+        feats.append(fused.channels_last(syn.pixel_features(shape, n_refer, gen).to(device)))
+        refer_idx.append([100 + 2 * f, 101 + 2 * f, -1][:n_refer])          # ids that are not target frames
+        refer_c2w.append([poses[2 * f].to(device), poses[2 * f + 2].to(device), poses[2 * f + 1].to(device)][:n_refer])
+    tables = [slam.class_tables(fr["label"]) for fr in frames]
+    return dict(cam=cam, poses=poses, frames=frames, feats=feats, refer_idx=refer_idx, refer_c2w=refer_c2w,
+                class_tables=tables, kf_idx=list(range(n_target)))
+
+
+def tracking_draws(cam, n_pixels, n_iters, seed=0, n_surface=15):
+    g = torch.Generator().manual_seed(seed)
+    n_win = (cam["H"] - 40) * (cam["W"] - 40)
+    return [dict(idx=torch.randint(n_win, (n_pixels,), generator=g), t_surface=torch.rand(n_surface, generator=g),
+                 t_zero=torch.rand(n_surface, generator=g)) for _ in range(n_iters)]
+
+
+def mapping_draws(scene, n_pixels, n_iters, seed=0, n_surface=15):
+    """Draw tapes of mapping iterations in the reference's order, pre-generated on the host."""
+    g = torch.Generator().manual_seed(seed)
+    cam = scene["cam"]
+    n_t = len(scene["frames"])
+    npf = n_pixels // n_t
+    out, tv = [], []
+    for _ in range(n_iters):
+        per = []
+        for tab in scene["class_tables"]:
+            counts = tab[3].tolist()
+            n_c = len(counts)
+            n_k = (npf // 3) // n_c
+            cd = []
+            for c in range(n_c):
+                m = (npf // 3) - n_k * (n_c - 1) if c == 0 else n_k
+                if counts[c] != 1:
+                    cd.append(torch.randint(counts[c], (m,), generator=g))
+            per.append(dict(idx_uniform=torch.randint(cam["H"] * cam["W"], (npf // 3 * 2,), generator=g), class_draws=cd,
+                            t_surface=torch.rand(n_surface, generator=g), t_zero=torch.rand(n_surface, generator=g)))
+        out.append(per)
+        tv.append((torch.rand(3, generator=g), torch.rand(1, 1, 1, 3, generator=g)))
+    return out, tv

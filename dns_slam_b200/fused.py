@@ -24,6 +24,7 @@ from . import _lib
 LOSS_KEYS = ("p_loss", "d_loss", "l_loss", "lt_loss", "fs_loss", "opacity_loss", "total", "n_valid")
 
 _ws_cache = {}
+_tlin_cache = {}
 
 
 def workspace(nbytes, device):
@@ -40,10 +41,9 @@ def workspace(nbytes, device):
 # ----------------------------------------------------------------------------------------
 def fix_surface_draw(t, n_surface):
     """common.py:572-573: force one offset to 0.5 unless the draw already holds one."""
-    t = t.clone()
-    if not torch.any(t == 0.5):
-        t[n_surface // 2 + 1] = 0.5
-    return t
+    forced = t.clone()
+    forced[n_surface // 2 + 1:n_surface // 2 + 2].fill_(0.5)      # fill kernel: no H2D scalar copy (graph capturable)
+    return torch.where((t == 0.5).any(), t, forced)      # no host sync
 
 
 def sample_rays(cam, bound, frame, idx, window, R, T, n_samples, n_surface, t_surface, t_zero,
@@ -61,7 +61,11 @@ def sample_rays(cam, bound, frame, idx, window, R, T, n_samples, n_surface, t_su
     a.fx, a.fy, a.cx, a.cy = cam["fx"], cam["fy"], cam["cx"], cam["cy"]
     _lib.fill_bound(a.bound, bound)
     if t_lin is None:
-        t_lin = torch.linspace(0.0, 1.0, steps=n_samples) if n_samples > 0 else torch.zeros(0)
+        key = (n_samples, dev.type, dev.index)
+        t_lin = _tlin_cache.get(key)
+        if t_lin is None:   # torch.linspace evaluated on the CPU as the oracle does, uploaded once
+            t_lin = (torch.linspace(0.0, 1.0, steps=n_samples) if n_samples > 0 else torch.zeros(0)).to(dev)
+            _tlin_cache[key] = t_lin
     keep = [frame["color"], frame["depth"], frame["label"], idx.contiguous(),
             R.detach().to(dev, torch.float32).contiguous(), T.detach().to(dev, torch.float32).contiguous(),
             t_lin.to(dev, torch.float32).contiguous(), t_surface.to(dev, torch.float32).contiguous(),
@@ -255,7 +259,8 @@ class _RenderFn(torch.autograd.Function):
                 sc(ctx.d_rays[1], need[7]), sc(ctx.d_f, need[8]))
 
 
-def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_sigma=0.05, want_latents=False):
+def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_sigma=0.05, want_latents=False,
+                    freeze_decoder=False):
     """Fused drop-in for ``renderer(samples)`` + the loss block of the iteration bodies.
 
     ``samples``: the dict of tracking.py:177-185 / mapping.py:579-586 (``pts`` is not needed: points
@@ -269,9 +274,11 @@ def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_
                        n_class or decoder.n_class, lambdas, opacity_trunc=opacity_sigma, want_latents=want_latents)
     experts = decoder.expert_params if mode == _lib.MODE_MAP else None
     feats = samples.get("features")
-    out = _RenderFn.apply(cfg, decoder.pe_fn.grid_fn.params, decoder.coarse_fn.decoder.params,
-                          decoder.out_fn.color_decoder.params, decoder.out_fn.logit_decoder.params, experts,
-                          samples["rays_o"], samples["rays_d"], feats)
+    prm = [decoder.pe_fn.grid_fn.params, decoder.coarse_fn.decoder.params, decoder.out_fn.color_decoder.params,
+           decoder.out_fn.logit_decoder.params, experts]
+    if freeze_decoder:   # tracking only moves the pose (tracking.py:108-126): skip every parameter gradient
+        prm = [p.detach() if p is not None else None for p in prm]
+    out = _RenderFn.apply(cfg, prm[0], prm[1], prm[2], prm[3], prm[4], samples["rays_o"], samples["rays_d"], feats)
     total, losses = out[0], out[1]
     ld = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
     ld["total"] = total
@@ -361,11 +368,33 @@ def feature_gather(H, W, K, pts, refer_w2c, feats_cl):
     return code, uv, mask.bool()
 
 
+_bottom_cache = {}
+
+
+def bottom_row(device):
+    """[[0,0,0,1]] on ``device``, uploaded once (an H2D copy per call would break CUDA-graph capture)."""
+    key = (device.type, device.index)
+    b = _bottom_cache.get(key)
+    if b is None:
+        b = _bottom_cache[key] = torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=torch.float32).to(device)
+    return b
+
+
+def rigid_inverse(M):
+    """Inverse of rigid transforms [..,4,4] ([R t; 0 1] -> [R^T, -R^T t]); replaces the cuSOLVER-backed
+    ``torch.inverse`` of tracking.py:318 / common.py:672 on the native path (same result to fp32 rounding,
+    no library launch, CUDA-graph capturable)."""
+    R = M[..., :3, :3].transpose(-1, -2)
+    t = -(R @ M[..., :3, 3:4])
+    top = torch.cat((R, t), -1)
+    bottom = M[..., 3:4, :].detach() * 0 + bottom_row(M.device)
+    return torch.cat((top, bottom), -2)
+
+
 def feature_matching(H, W, K, pts_, refer_w2c, feats_cl, merge_fn):
     """utils.common.feature_matching with channels-last features (no 209 MB/view up-sample)."""
     code, _, _ = feature_gather(H, W, K, pts_, refer_w2c, feats_cl)
-    refer_c2w = torch.inverse(refer_w2c)
-    refer_o = refer_c2w[:, :3, 3]
+    refer_o = rigid_inverse(refer_w2c)[:, :3, 3]
     refer_p = pts_[None, :, :] - refer_o[:, None, :]
     return merge_fn(refer_p, refer_o, code)
 

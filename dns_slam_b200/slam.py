@@ -31,8 +31,7 @@ def get_rotation_from_quad(quad):
 
 def c2w_from_quad_T(quad, T):
     R = get_rotation_from_quad(quad)
-    bottom = torch.tensor([BOTTOM], dtype=torch.float32, device=quad.device)
-    return torch.cat([torch.cat((R, T[:, None]), -1), bottom], 0)
+    return torch.cat([torch.cat((R, T[:, None]), -1), fused.bottom_row(quad.device)], 0)
 
 
 def trunc_mask(z, gt_depth):
@@ -43,6 +42,16 @@ def trunc_mask(z, gt_depth):
     return (1.0 - front) * (1.0 - back) * (d > 0.0).to(z.dtype)
 
 
+class ClassTables(tuple):
+    """(classes, order, starts, counts) with host copies of the small per-class lists made ONCE per frame,
+    so that the per-iteration index draw needs no device->host read."""
+
+    def __new__(cls, classes, order, starts, counts):
+        self = super().__new__(cls, (classes, order, starts, counts))
+        self.classes_h, self.starts_h, self.counts_h = classes.tolist(), starts.tolist(), counts.tolist()
+        return self
+
+
 def class_tables(label_win):
     """Per-frame tables for the class-balanced draw (common.py:312-322): labels do not change
     between iterations, so ``unique`` / ``nonzero`` are done once per frame, not per iteration.
@@ -51,16 +60,16 @@ def class_tables(label_win):
     order = torch.sort(flat, stable=True)[1]
     classes, counts = torch.unique_consecutive(flat[order], return_counts=True)
     starts = torch.cumsum(counts, 0) - counts
-    return classes, order, starts, counts
+    return ClassTables(classes, order, starts, counts)
 
 
 def class_balanced_indices(tables, n, draws):
     """common.py:315-330 with the per-class randint draws supplied in order (a class with one
     pixel consumes no draw)."""
     classes, order, starts, counts = tables
-    n_class = classes.numel()
+    counts_h, starts_h = tables.counts_h, tables.starts_h
+    n_class = len(counts_h)
     n_k = n // n_class
-    counts_h, starts_h = counts.tolist(), starts.tolist()
     out, di = [], 0
     for c in range(n_class):
         m = n - n_k * (n_class - 1) if c == 0 else n_k
@@ -76,8 +85,8 @@ class TrackerCore:
     """The part of ``Tracker`` that sits on the hot path."""
 
     def __init__(self, cam, decoder, n_pixels, n_samples_ray=32, n_surface_ray=15, lambda_p=5.0,
-                 lambda_d=5.0, lambda_l=0.1):
-        self.cam, self.decoder = cam, decoder
+                 lambda_d=5.0, lambda_l=0.1, freeze_decoder=False):
+        self.cam, self.decoder, self.freeze_decoder = cam, decoder, freeze_decoder
         self.H, self.W = cam["H"], cam["W"]
         self.K = cam["K"].to(decoder.bound.device)
         self.n_pixels, self.n_samples_ray, self.n_surface_ray = n_pixels, n_samples_ray, n_surface_ray
@@ -107,7 +116,8 @@ class TrackerCore:
         """Body of tracking.py:322-329; returns (loss dict, preds, samples)."""
         samples = self.get_target_samples(cur_frames, refer_frames, features_cl, draws)
         ld, preds = fused.render_and_loss(self.decoder, samples, _lib.MODE_TRACK,
-                                          lambdas=dict(p=self.lambda_p, d=self.lambda_d, l=self.lambda_l))
+                                          lambdas=dict(p=self.lambda_p, d=self.lambda_d, l=self.lambda_l),
+                                          freeze_decoder=self.freeze_decoder)
         return ld, preds, samples
 
 
@@ -158,7 +168,7 @@ class MapperCore:
                     c2w = c2w_from_quad_T(quad_list[t], T_list[t]).detach()
                 else:
                     c2w = refer_frames["est_c2w"][i][k].detach()
-                w2c.append(torch.inverse(c2w))
+                w2c.append(fused.rigid_inverse(c2w))
             code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), torch.stack(w2c, 0),
                                           features_cl[i], self.decoder.merge)
             code = code.reshape(pts.shape[0], pts.shape[1], -1) * trunc_mask(z, s["gt_depth"])[..., None]
@@ -215,8 +225,8 @@ def uniq_class_indices(tables, n, class_list, draws):
     """common.py:375-393 (get_samples_by_uniq_class): n rays spread over the GIVEN classes; class 0 of
     the list takes the remainder, a class with one pixel is repeated, an absent class is skipped."""
     classes, order, starts, counts = tables
-    lookup = {int(c): k for k, c in enumerate(classes.tolist())}
-    counts_h, starts_h = counts.tolist(), starts.tolist()
+    lookup = {int(c): k for k, c in enumerate(tables.classes_h)}
+    counts_h, starts_h = tables.counts_h, tables.starts_h
     n_class = len(class_list)
     n_k = n // n_class
     out, di = [], 0
@@ -233,11 +243,17 @@ def uniq_class_indices(tables, n, class_list, draws):
     return torch.cat(out, -1), di
 
 
-def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR=False):
+def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR=False,
+                use_graph=False):
     """The pose-optimisation loop of ``Tracker.run`` (slams/tracking.py:304-346): Adam over
     (translation, quaternion), the best-loss pose is kept.  The ``loss < current_min_loss`` test that
     costs the reference a host sync per iteration (tracking.py:331) stays on the device.
-    ``draws_fn(it)`` -> dict(idx, t_surface, t_zero).  Returns (best [quad|T] 7-vector, best loss)."""
+    ``draws_fn(it)`` -> dict(idx, t_surface, t_zero).  Returns (best [quad|T] 7-vector, best loss, losses).
+    ``use_graph``: capture ONE iteration (sampling, feature matching, fused render + backward, Adam, best
+    pose) in a CUDA graph after three eager warm-up iterations and replay it -- the loop is launch bound
+    (hundreds of tiny launches per iteration), not GPU bound."""
+    if use_graph:
+        return _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR)
     dev = tracker.decoder.bound.device
     quad = quad_from_matrix(est_c2w[:3, :3]).to(dev).requires_grad_(True)
     T = est_c2w[:3, 3].detach().clone().to(dev).requires_grad_(True)
@@ -249,7 +265,7 @@ def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr
     history = []
     for it in range(n_iters):
         opt.zero_grad()
-        cur_w2c = torch.inverse(c2w_from_quad_T(quad, T))
+        cur_w2c = fused.rigid_inverse(c2w_from_quad_T(quad, T))
         est_w2c = torch.stack((refer_w2c.to(dev), cur_w2c), 0)
         ld, _, _ = tracker.iteration(cur, {"est_w2c": est_w2c}, features_cl, draws_fn(it))
         loss = ld["total"]
@@ -261,6 +277,57 @@ def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr
         loss.backward()
         opt.step()
     return best, best_loss, torch.stack(history)
+
+
+def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR):
+    dev = tracker.decoder.bound.device
+    quad = quad_from_matrix(est_c2w[:3, :3]).to(dev).requires_grad_(True)
+    T = est_c2w[:3, 3].detach().clone().to(dev).requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
+                            {"params": [quad], "lr": cam_lr}], capturable=True)
+    d0 = draws_fn(0)
+    static = {k: v.to(dev).clone() for k, v in d0.items()}
+    best_loss = torch.full((), 1e10, device=dev)
+    best = torch.cat((quad, T), 0).detach().clone()
+    hist = torch.zeros(n_iters, device=dev)
+    slot = torch.zeros((), dtype=torch.int64, device=dev)
+    refer = refer_w2c.to(dev)
+    cur = dict(frame, est_quad=quad, est_T=T)
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        est_w2c = torch.stack((refer, fused.rigid_inverse(c2w_from_quad_T(quad, T))), 0)
+        ld, _, _ = tracker.iteration(cur, {"est_w2c": est_w2c}, features_cl, static)
+        loss = ld["total"]
+        with torch.no_grad():
+            better = loss < best_loss
+            best.copy_(torch.where(better, torch.cat((quad, T), 0), best))
+            best_loss.copy_(torch.where(better, loss, best_loss))
+            hist.index_copy_(0, slot.reshape(1), loss.detach().reshape(1))
+            slot.add_(1)
+        loss.backward()
+        opt.step()
+
+    n_warm = min(3, n_iters)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for it in range(n_warm):
+            for k, v in draws_fn(it).items():
+                static[k].copy_(v)
+            one()
+    torch.cuda.current_stream().wait_stream(side)
+    if n_iters > n_warm:
+        for k, v in draws_fn(n_warm).items():
+            static[k].copy_(v)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one()
+        for it in range(n_warm, n_iters):          # capture only records: the captured iteration is replayed too
+            for k, v in draws_fn(it).items():
+                static[k].copy_(v, non_blocking=True)
+            graph.replay()
+    return best, best_loss, hist
 
 
 def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,

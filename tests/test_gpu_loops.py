@@ -60,6 +60,18 @@ def test_tracking_loop_vs_oracle():
     close(hist, torch.stack(hist_o), rtol=2e-3, atol=1e-5, name="tracking loss trajectory")
     k = int(torch.argmin(torch.stack(hist_o)))
     assert abs(float(best_loss) - float(hist_o[k])) < 2e-3 * abs(float(hist_o[k]))
+    # CUDA-graph replay of the same loop (frozen decoder: tracking only moves the pose) == eager loop
+    n2 = 6
+    g2 = torch.Generator().manual_seed(6)
+    draws2 = [dict(idx=torch.randint(n_win, (s["tracking_pixels"],), generator=g2), t_surface=torch.rand(15, generator=g2),
+                   t_zero=torch.rand(15, generator=g2)) for _ in range(n2)]
+    trk2 = slam.TrackerCore(cam, dec, s["tracking_pixels"], 32, 15, s["lambda_color"], s["lambda_depth"], s["lambda_label"],
+                            freeze_decoder=True)
+    fr, fcl = frame_to(inp["frame"], dev), fused.channels_last(inp["feats"].to(dev))
+    b_e, l_e, h_e = slam.track_frame(trk2, fr, refer_w2c, fcl, est, n2, lr, lambda it: draws2[it])
+    b_g, l_g, h_g = slam.track_frame(trk2, fr, refer_w2c, fcl, est, n2, lr, lambda it: draws2[it], use_graph=True)
+    close(h_g, h_e, rtol=1e-4, atol=1e-6, name="graph vs eager loss trajectory")
+    close(b_g, b_e, rtol=1e-5, atol=1e-6, name="graph vs eager best pose")
 
 
 def test_mapping_loop_vs_oracle():
