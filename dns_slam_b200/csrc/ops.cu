@@ -33,15 +33,20 @@ struct EvPair {
   int phase;
   cudaEvent_t a, b;
 };
-static EvPair g_events[4096];
-static int g_n_events = 0;
+constexpr int kMaxEvents = 4096;
+static EvPair g_events[kMaxEvents];
+static int g_n_events = 0;      // intervals recorded since the last reset
+static int g_n_created = 0;     // events are created once and re-used: no driver calls besides the records
 PhaseScope::PhaseScope(int phase_, cudaStream_t st_, int n_launches) : phase(phase_), st(st_), slot(-1) {
   g_launches[phase] += n_launches;
-  if (g_profile && g_n_events < 4096) {
+  if (g_profile && g_n_events < kMaxEvents) {
     slot = g_n_events++;
+    if (slot >= g_n_created) {
+      cudaEventCreate(&g_events[slot].a);
+      cudaEventCreate(&g_events[slot].b);
+      g_n_created = slot + 1;
+    }
     g_events[slot].phase = phase;
-    cudaEventCreate(&g_events[slot].a);
-    cudaEventCreate(&g_events[slot].b);
     cudaEventRecord(g_events[slot].a, st);
   }
 }
@@ -358,7 +363,15 @@ using namespace dns;
 
 extern "C" {
 
-void dns_profile_enable(int on) { g_profile = on != 0; }
+void dns_profile_enable(int on) {
+  g_profile = on != 0;
+  if (g_profile) {
+    for (; g_n_created < 512; ++g_n_created) {
+      cudaEventCreate(&g_events[g_n_created].a);
+      cudaEventCreate(&g_events[g_n_created].b);
+    }
+  }
+}
 // Adds the elapsed milliseconds of every recorded phase interval to ms[phase] and copies the launch
 // counters; waits for the recorded events.  reset != 0 clears counters and intervals.
 int dns_profile_read(double* ms, long long* launches, int reset) {
@@ -370,10 +383,6 @@ int dns_profile_read(double* ms, long long* launches, int reset) {
   if (launches)
     for (int i = 0; i < phCount; ++i) launches[i] = g_launches[i];
   if (reset) {
-    for (int i = 0; i < g_n_events; ++i) {
-      cudaEventDestroy(g_events[i].a);
-      cudaEventDestroy(g_events[i].b);
-    }
     g_n_events = 0;
     for (int i = 0; i < phCount; ++i) g_launches[i] = 0;
   }

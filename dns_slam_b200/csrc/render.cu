@@ -137,6 +137,77 @@ __global__ void k_class_scatter(const int64_t* __restrict__ label, int64_t N, in
   }
 }
 
+// Whole-batch fast path: when the call covers the complete, unsharded batch every ray index occurs exactly S
+// times among {p mod N}, so the class-c points are {r + k N : r in rays_c, 0 <= k < S}.  A counting sort of the
+// N RAYS (N atomics instead of N*S) plus a closed-form slot -> point map replaces the per-point sort.
+__global__ void k_ray_hist(const int64_t* __restrict__ label, int64_t N, int nci, int* ray_cnt, int* counts) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = label[r];
+    if (c < 0 || c >= nci) {
+      counts[cErr] = 1;
+      c = 0;
+    }
+    unsigned m = __match_any_sync(__activemask(), (int)c);
+    if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(ray_cnt + c, __popc(m));
+  }
+}
+__global__ void k_class_scan_rays(const int* __restrict__ ray_cnt, int nci, int S, const int* __restrict__ class_to_expert,
+                                  int* slot_start, int* ray_start, int* cursor, int* tile_class, int* counts) {
+  if (threadIdx.x == 0) {
+    int tiles = 0, rays = 0;
+    for (int c = 0; c < nci; ++c) {
+      slot_start[c] = tiles * kTile;
+      ray_start[c] = rays;
+      cursor[c] = 0;
+      int nt = (int)(((int64_t)ray_cnt[c] * S + kTile - 1) / kTile);
+      if (nt > 0 && class_to_expert[c] < 0) counts[cErr] = 2;
+      tiles += nt;
+      rays += ray_cnt[c];
+    }
+    slot_start[nci] = tiles * kTile;
+    ray_start[nci] = rays;
+    counts[cTiles] = tiles;
+  }
+  __syncthreads();
+  for (int c = 0; c < nci; ++c) {
+    int t0 = slot_start[c] / kTile, t1 = slot_start[c + 1] / kTile, e = class_to_expert[c];
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) tile_class[t] = e;
+  }
+}
+__global__ void k_ray_scatter(const int64_t* __restrict__ label, int64_t N, int nci, const int* __restrict__ ray_start,
+                              int* cursor, int* rays_sorted) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c64 = label[r];
+    int c = (c64 < 0 || c64 >= nci) ? 0 : (int)c64;
+    unsigned m = __match_any_sync(__activemask(), c);
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cursor + c, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    rays_sorted[ray_start[c] + base + __popc(m & ((1u << lane) - 1u))] = (int)r;
+  }
+}
+// one CTA per tile: slot q -> point r + k N of the tile's class, -1 for the padding tail of the class
+__global__ void __launch_bounds__(kTile) k_perm_fill(const int* __restrict__ slot_start, const int* __restrict__ ray_start,
+                                                     const int* __restrict__ ray_cnt, const int* __restrict__ rays_sorted,
+                                                     int nci, int S, int64_t N, const int* __restrict__ counts, int* perm) {
+  __shared__ int cls;
+  const int tile = blockIdx.x;
+  if (tile >= counts[cTiles]) return;
+  const int q0 = tile * kTile;
+  if (threadIdx.x == 0) {
+    int c = 0;
+    while (c + 1 < nci && slot_start[c + 1] <= q0) ++c;
+    cls = c;
+  }
+  __syncthreads();
+  const int c = cls, nc = ray_cnt[c];
+  const int64_t t = (int64_t)q0 + threadIdx.x - slot_start[c];
+  int p = -1;
+  if (nc > 0 && t < (int64_t)nc * S) p = (int)(rays_sorted[ray_start[c] + (int)(t % nc)] + (t / nc) * N);
+  perm[q0 + threadIdx.x] = p;
+}
+
 // ---------------------------------------------------------------------------------------
 // point kernels
 // ---------------------------------------------------------------------------------------
@@ -722,7 +793,7 @@ struct Carver {
 struct RenderWs {
   int* counts;
   float* raw;
-  int *hist, *slot_start, *cursor;
+  int *hist, *slot_start, *cursor, *ray_start, *rays_sorted;
   float *WTc, *WTe, *W1T2, *W2cT;
   uint4 *W1o_hi, *W1o_lo;   // bf16 hi / lo chunk tiles of the colour|logit layer-1 weights (tcgen05 path)
   uint4 *wc_tc, *we_tc;     // bf16 hi / lo tiles of the coarse net and of every class expert (1024 uint4 each)
@@ -744,6 +815,8 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.hist = c.take<int>(nci + 1);
   w.slot_start = c.take<int>(nci + 2);
   w.cursor = c.take<int>(nci + 1);
+  w.ray_start = c.take<int>(nci + 2);
+  w.rays_sorted = c.take<int>(map ? Nc : 4);
   w.WTc = c.take<float>(kNetT);
   w.WTe = c.take<float>((int64_t)kNetT * (map ? nci : 0) + 4);
   w.W1T2 = c.take<float>(kIn2 * 64);
@@ -908,12 +981,23 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     if (map) {
       PhaseScope phc(phClassPrep, st, 5);
       cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);
+      const bool whole = !sharded && ray0 == 0 && nc == N && (int64_t)N * S < 2147483647LL;
+      if (whole) {
+        int rblocks = (int)((N + 255) / 256);
+        rblocks = rblocks < 592 ? rblocks : 592;
+        k_ray_hist<<<rblocks, 256, 0, st>>>(a->gt_label, N, nci, w.hist, w.counts);
+        k_class_scan_rays<<<1, 256, 0, st>>>(w.hist, nci, S, a->class_to_expert, w.slot_start, w.ray_start, w.cursor,
+                                            w.tile_class, w.counts);
+        k_ray_scatter<<<rblocks, 256, 0, st>>>(a->gt_label, N, nci, w.ray_start, w.cursor, w.rays_sorted);
+        k_perm_fill<<<tiles_max, kTile, 0, st>>>(w.slot_start, w.ray_start, w.hist, w.rays_sorted, nci, S, N, w.counts, w.perm);
+      } else {
       cudaMemsetAsync(w.perm, 0xFF, (size_t)tiles_max * kTile * sizeof(int), st);
       int64_t blocks = (Pc + 255) / 256;
       int grid = (int)(blocks < 592 ? blocks : 592);
       k_class_hist<<<grid, 256, 0, st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.hist, w.counts);
       k_class_scan<<<1, 256, 0, st>>>(w.hist, nci, a->class_to_expert, w.slot_start, w.cursor, w.tile_class, w.counts);
       k_class_scatter<<<grid, 256, 0, st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.slot_start, w.cursor, w.perm);
+      }
       pa.perm = w.perm; pa.tile_class = w.tile_class;
     }
     {
