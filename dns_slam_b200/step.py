@@ -152,3 +152,46 @@ class TrackingStep:
                                  None, dec.n_class, self.lambdas)
         return fused.render_raw(cfg, dec.view("table"), dec.view("coarse"), dec.view("color"), dec.view("logit"), None,
                                 samples["rays_o"], samples["rays_d"], samples.get("features"), None, True, need_dfeat)
+
+
+class HostBatchPipeline:
+    """Feeds ray batches that live in PINNED HOST memory to a step function, double buffered: the H2D copy
+    of batch k+1 runs on a copy stream while the kernels of batch k run on the compute stream, and the loss
+    vector of every step is read back into pinned memory.  Used for the end-to-end number of bench.py (every
+    step's inputs really cross PCIe inside the timed region) and for hosts that sample on the CPU."""
+
+    def __init__(self, template_host_batch, device):
+        self.dev = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.bufs = [{k: torch.empty_like(v, device=device) for k, v in template_host_batch.items()} for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # H2D of buffer i finished
+        self.free = [torch.cuda.Event() for _ in range(2)]       # compute on buffer i finished
+        self.result_host = torch.empty(8, pin_memory=True)
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in template_host_batch.values())
+        for e in self.free:
+            e.record(torch.cuda.current_stream(device))
+
+    def _upload(self, host_batch, i):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[i])
+            for k, v in host_batch.items():
+                self.bufs[i][k].copy_(v, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+
+    def run(self, host_batches, step_fn):
+        """host_batches: sequence of dicts of pinned host tensors (may repeat the same object);
+        step_fn(device_batch) -> tuple whose first element is the loss vector [8]."""
+        cur = torch.cuda.current_stream(self.dev)
+        n = len(host_batches)
+        if n == 0:
+            return self.result_host
+        self._upload(host_batches[0], 0)
+        for k in range(n):
+            i = k & 1
+            if k + 1 < n:
+                self._upload(host_batches[k + 1], (k + 1) & 1)
+            cur.wait_event(self.ready[i])
+            out = step_fn(self.bufs[i])
+            self.free[i].record(cur)
+            self.result_host.copy_(out[0], non_blocking=True)
+        return self.result_host
