@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t corner_index(const dns_grid& G, int l, uint3
 // forward of all levels for one point; out[2l+f] written with stride st
 __device__ __forceinline__ void hashgrid_fwd(const dns_grid& G, const float2* __restrict__ table,
                                              const float x[3], float* out, int st) {
-#pragma unroll 4
+#pragma unroll 8
   for (int l = 0; l < G.n_levels; ++l) {
     uint32_t g[3];
     float w[3];

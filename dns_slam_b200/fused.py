@@ -260,7 +260,7 @@ class _RenderFn(torch.autograd.Function):
 
 
 def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_sigma=0.05, want_latents=False,
-                    freeze_decoder=False):
+                    freeze_decoder=False, strict=False):
     """Fused drop-in for ``renderer(samples)`` + the loss block of the iteration bodies.
 
     ``samples``: the dict of tracking.py:177-185 / mapping.py:579-586 (``pts`` is not needed: points
@@ -280,6 +280,10 @@ def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_
         prm = [p.detach() if p is not None else None for p in prm]
     out = _RenderFn.apply(cfg, prm[0], prm[1], prm[2], prm[3], prm[4], samples["rays_o"], samples["rays_d"], feats)
     total, losses = out[0], out[1]
+    if strict:   # one device->host read: the reference raises on the spot (mapping.py:594-595)
+        flag = float(losses[7])
+        if flag < 0:
+            raise ValueError("Fine decoders does NOT have class" if flag <= -2 else "label outside [0, n_class_ids)")
     ld = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
     ld["total"] = total
     preds = dict(color=out[2], depth=out[3], var=out[4], logits=out[5], fine=out[6], coarse=out[7])
