@@ -120,13 +120,17 @@ __global__ void __launch_bounds__(kTile) k_point_fwd_tc(PointArgs a, const uint4
       oneblob16(x[c], pe);
       put_chunk(X_hi, X_lo, 2 * c, 2048, tid, pe);
       put_chunk(X_hi, X_lo, 2 * c + 1, 2048, tid, pe + 8);
-      if (a.need_dparams) store_row(a.Xst + q * kIn1 + 16 * c, pe);
+      if (a.need_dparams && !(a.dbg & 2)) store_row(a.Xst + q * kIn1 + 16 * c, pe);
     }
     float g[32];
-    hashgrid_fwd(a.G, a.table, x, g, 1);
+    if (a.dbg & 1) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) g[k] = x[k % 3] * 0.01f * k;
+    } else
+    hashgrid_fwd_regs(a.G, a.table, x, g);
 #pragma unroll
     for (int c = 0; c < 4; ++c) put_chunk(X_hi, X_lo, 6 + c, 2048, tid, g + 8 * c);
-    if (a.need_dparams) store_row(a.Xst + q * kIn1 + DNS_PE_DIM, g);
+    if (a.need_dparams && !(a.dbg & 2)) store_row(a.Xst + q * kIn1 + DNS_PE_DIM, g);
   } else {
     const uint4 z4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(kTile) k_point_fwd_tc(PointArgs a, const uint4
       for (int k = 0; k < 16; ++k) h[16 * g4 + k] = fmaxf(v[k], 0.f);
     }
     // hidden activations: stash (ReLU mask + dW2 of the backward) and stage as the next A operand
-    {
+    if (!(a.dbg & 2)) {
       float4* hp = reinterpret_cast<float4*>(a.Hc + q * 32);
 #pragma unroll
       for (int k = 0; k < 8; ++k) hp[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(kTile) k_point_bwd_tc(PointArgs a, const uint4
       for (int k = 0; k < 48; ++k) df[k] = 0.f;
     }
   }
-  if (a.need_dparams) {
+  if (a.need_dparams && !(a.dbg & 2)) {
     float4* oc = reinterpret_cast<float4*>(a.dOc + q * kOutP);
 #pragma unroll
     for (int k = 0; k < kOutP / 4; ++k) oc[k] = make_float4(dc[4 * k], dc[4 * k + 1], dc[4 * k + 2], dc[4 * k + 3]);
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(kTile) k_point_bwd_tc(PointArgs a, const uint4
         }
       }
     }
-    if (a.need_dparams) {
+    if (a.need_dparams && !(a.dbg & 2)) {
       float4* d4 = reinterpret_cast<float4*>(a.dHc + q * 64);
 #pragma unroll
       for (int k = 0; k < (MODE == kMap ? 16 : 8); ++k) d4[k] = make_float4(dh[4 * k], dh[4 * k + 1], dh[4 * k + 2], dh[4 * k + 3]);
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(kTile) k_point_bwd_tc(PointArgs a, const uint4
   if (warp == 0) tmem_dealloc(tmem_d, 128);
   if (!valid) return;
   float dxg[3];
-  hashgrid_bwd(a.G, a.table, a.need_dparams ? a.d_table : nullptr, x, dg, 1, a.need_drays != 0, dxg);
+  hashgrid_bwd_regs(a.G, a.table, (a.need_dparams && !(a.dbg & 4)) ? a.d_table : nullptr, x, dg, a.need_drays != 0 && !(a.dbg & 8), dxg);
   if (a.need_drays && MODE != kTv) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

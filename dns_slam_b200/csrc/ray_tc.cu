@@ -108,8 +108,9 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
 #pragma unroll
       for (int c = 0; c < 4; ++c) put_chunk(X_hi, X_lo, 6 + c, cs, t, row + 1 + 8 * c);
       if (a.need_dparams) {
+        float4* d4 = reinterpret_cast<float4*>(a.X2 + pl * kIn2 + 48);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) a.X2[pl * kIn2 + 48 + k] = row[1 + k];
+        for (int q = 0; q < 8; ++q) d4[q] = make_float4(row[1 + 4 * q], row[2 + 4 * q], row[3 + 4 * q], row[4 + 4 * q]);
       }
     }
     {

@@ -15,6 +15,7 @@
 //                 down to d(latents), d(features), d(rays)
 //   k_point_bwd   lt/fs/op gradients + d(latents) -> MLP backward -> hash-table scatter, d(rays)
 //   k_dw_gemm     dW = X^T dH for every MLP from stashed activations (ops.cu)
+#include <stdlib.h>
 #include <string.h>
 
 #include "render.cuh"
@@ -978,6 +979,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
     pa.need_dparams = a->need_dparams; pa.need_drays = a->need_drays;
+    { const char* e = getenv("DNS_DBG"); pa.dbg = e ? atoi(e) : 0; }
     if (map) {
       PhaseScope phc(phClassPrep, st, 5);
       cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);

@@ -93,6 +93,7 @@ struct PointArgs {
   float* d_rays_o;
   float* d_rays_d;
   int need_dparams, need_drays;
+  int dbg;   // experiment switches (DNS_DBG env): 1 no gather, 2 no stash stores, 4 no table atomics, 8 no regather
 };
 
 template <int MODE>

@@ -55,6 +55,72 @@ __device__ __forceinline__ float oneblob16_bwd(float x, const float (&d)[16]) {
   }
   return -16.0f * acc;
 }
+// Register-resident hash-grid forward / backward for the tcgen05 kernels: the 16-level loop is FULLY unrolled so
+// that the 32 features (or their gradients) are compile-time-indexed registers.  (A dynamically indexed per-thread
+// array lives in local memory; ncu showed 53 % of k_point_bwd_tc's stall samples on the first use of such a load.)
+__device__ __forceinline__ void hashgrid_fwd_regs(const dns_grid& G, const float2* __restrict__ table, const float x[3],
+                                                  float (&out)[32]) {
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    uint32_t g[3];
+    float w[3];
+    const float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      v[c] = __ldg(table + corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+      a0 += wt * v[c].x;
+      a1 += wt * v[c].y;
+    }
+    out[2 * l] = a0;
+    out[2 * l + 1] = a1;
+  }
+}
+__device__ __forceinline__ void hashgrid_bwd_regs(const dns_grid& G, const float2* __restrict__ table, float2* d_table,
+                                                  const float x[3], const float (&dg)[32], bool want_dx, float dx[3]) {
+  dx[0] = dx[1] = dx[2] = 0.f;
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    const float g0 = dg[2 * l], g1 = dg[2 * l + 1];
+    if (g0 == 0.f && g1 == 0.f) continue;
+    uint32_t g[3];
+    float w[3];
+    const float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    uint32_t idx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      idx[c] = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+    if (d_table) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+        atomicAdd(d_table + idx[c], make_float2(wt * g0, wt * g1));
+      }
+    }
+    if (want_dx) {
+      float s[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float2 v = __ldg(table + idx[c]);
+        s[c] = v.x * g0 + v.y * g1;
+      }
+      const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
+      dx[0] += sc * (wy0 * wz0 * (s[1] - s[0]) + w[1] * wz0 * (s[3] - s[2]) + wy0 * w[2] * (s[5] - s[4]) + w[1] * w[2] * (s[7] - s[6]));
+      dx[1] += sc * (wx0 * wz0 * (s[2] - s[0]) + w[0] * wz0 * (s[3] - s[1]) + wx0 * w[2] * (s[6] - s[4]) + w[0] * w[2] * (s[7] - s[5]));
+      dx[2] += sc * (wx0 * wy0 * (s[4] - s[0]) + w[0] * wy0 * (s[5] - s[1]) + wx0 * w[1] * (s[6] - s[2]) + w[0] * w[1] * (s[7] - s[3]));
+    }
+  }
+}
 __device__ __forceinline__ void put_chunk(unsigned char* hi_tile, unsigned char* lo_tile, int chunk, int cs, int point,
                                           const float* v8) {
   uint4 h, l;
