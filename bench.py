@@ -410,9 +410,19 @@ def _iteration_timings(shape, n_class, dev):
         slam.map_optimize(mp, target, refer, sc["feats"], est_list, m_it, s["lr"], s["BA_cam_lr"], True, [],
                           lambda it: md[it], lambda it: tv[it])
     t_map = _time_cuda(mapit, 2, 1) / m_it
+    big, small = 64, 34
+    mdg, tvg = bench_util.mapping_draws(sc, s["mapping_pixels"], 8)
+
+    def map_graph(n):
+        return lambda: slam.map_optimize(mp, target, refer, sc["feats"], est_list, n, s["lr"], s["BA_cam_lr"], True, [],
+                                         lambda it: mdg[it % 8], lambda it: tvg[it % 8], use_graph=True)
+    map_graph(6)()
+    t_map_graph = (min(_time_cuda(map_graph(big), 1, 0) for _ in range(2))
+                   - min(_time_cuda(map_graph(small), 1, 0) for _ in range(2))) / (big - small)
     return {"tracking_ms_per_iteration": t_track, "tracking_ms_per_iteration_cuda_graph": t_track_graph,
             "tracking_rays": s["tracking_pixels"],
-            "mapping_ms_per_iteration": t_map, "mapping_rays": s["mapping_pixels"], "tv_lattice": (s["smooth_pts"] - 1) ** 3,
+            "mapping_ms_per_iteration": t_map, "mapping_ms_per_iteration_cuda_graph": t_map_graph,
+            "mapping_graph_ok": bool(getattr(mp, "last_graph_ok", False)), "mapping_rays": s["mapping_pixels"], "tv_lattice": (s["smooth_pts"] - 1) ** 3,
             "n_samples": 47, "note": "autograd drop-in path (render_and_loss + torch Adam), sampling + feature matching + TV included"}
 
 

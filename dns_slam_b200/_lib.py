@@ -55,7 +55,7 @@ class TvArgs(C.Structure):
                 ("bound", (C.c_double * 2) * 3), ("offset", C.c_double * 3),
                 ("jitter", C.c_double * 3), ("lambda_sm", C.c_float), ("need_dparams", C.c_int32),
                 ("grid", Grid), ("table", _P), ("coarse", _P), ("loss", _P), ("d_table", _P),
-                ("d_coarse", _P), ("workspace", _P), ("workspace_bytes", C.c_int64)]
+                ("d_coarse", _P), ("workspace", _P), ("workspace_bytes", C.c_int64), ("offset_jitter_dev", _P)]
 
 
 class SampleArgs(C.Structure):
@@ -72,7 +72,7 @@ class SampleArgs(C.Structure):
 _lib = None
 
 # every symbol include/dns_slam_b200.h declares
-SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_set_tensor_cores", "dns_debug_gemm_tc", "dns_oneblob_fwd", "dns_oneblob_bwd",
+SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_set_tensor_cores", "dns_debug_gemm_tc", "dns_debug_gemm_img", "dns_oneblob_fwd", "dns_oneblob_bwd",
            "dns_hashgrid_fwd", "dns_hashgrid_bwd", "dns_hashgrid_indices", "dns_mlp_fwd",
            "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd", "dns_render_counts",
            "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
@@ -97,6 +97,7 @@ def lib():
     L.dns_profile_enable.argtypes = [C.c_int]
     L.dns_set_tensor_cores.argtypes = [C.c_int]
     L.dns_debug_gemm_tc.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int64, _P, _P]
+    L.dns_debug_gemm_img.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]
     L.dns_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     L.dns_oneblob_fwd.argtypes = [_P, i64, i32, i32, _P, _P]
     L.dns_oneblob_bwd.argtypes = [_P, _P, i64, i32, i32, _P, _P]

@@ -51,6 +51,29 @@ struct DwArgs {
   int64_t sl0, sc0, cls0, sl1, sc1, cls1;
 };
 int launch_dw_gemm_tc2(DwArgs a, cudaStream_t st);
+
+// Operand already stored as a bf16 hi/lo UMMA tile IMAGE: [sub-tile][half: hi, lo][chunk][RS rows] of 16-byte
+// (8 x bf16) elements; a sub-tile is RS consecutive rows (points), RS % 16 == 0.
+struct DwImg {
+  const uint4* ptr;
+  int chunks_total;  // chunks per half in the image
+  int chunk0;        // first chunk used by this GEMM
+  int chunks_used;
+  int n_valid;       // valid features (lanes / columns) among chunks_used * 8
+};
+struct DwImgArgs {
+  DwImg L, Cc;       // lane-side / column-side operand
+  int RS;            // rows per sub-tile
+  int subs_per_tile; // sub-tiles per class tile (tile_class is indexed by tile)
+  const int* n_tiles_dev;
+  int n_tiles_host;  // class tiles (NOT sub-tiles)
+  const int* tile_class;
+  float* out0;
+  float* out1;
+  int split;
+  int64_t sl0, sc0, cls0, sl1, sc1, cls1;
+};
+int launch_dw_img(const DwImgArgs& a, cudaStream_t st);
 bool use_tensor_cores();
 
 // ---------------------------------------------------------------------------------------

@@ -1152,6 +1152,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
     pa.jit[k] = a->jitter[k];
     pa.off[k] = a->offset[k];
   }
+  pa.tv_oj = a->offset_jitter_dev;
   pa.n = n; pa.voxel = a->voxel; pa.G = a->grid; pa.table = (const float2*)a->table;
   pa.n_tiles_host = tiles; pa.WTc = WTc; pa.occ = occ; pa.docc = docc;
   pa.Xst = Xst; pa.Hc = Hc; pa.dHc = dHc; pa.dOc = dOc;

@@ -63,6 +63,7 @@ struct PointArgs {
   // TV lattice
   int n;
   double voxel, jit[3], off[3];
+  const double* tv_oj;   // device override: off[3] | jit[3]
   // slots
   const int* perm;        // slot -> chunk-local point, -1 = padding; NULL = identity
   const int* tile_class;  // tile -> expert row (MAP)
@@ -105,7 +106,8 @@ __device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_
     int64_t idx[3] = {q / (n * n), (q / n) % n, q % n};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      double pt = (((double)idx[c] + a.jit[c]) * a.voxel + a.B.lo[c]) + a.off[c];
+      const double jit = a.tv_oj ? a.tv_oj[3 + c] : a.jit[c], off = a.tv_oj ? a.tv_oj[c] : a.off[c];
+      double pt = (((double)idx[c] + jit) * a.voxel + a.B.lo[c]) + off;
       x[c] = (float)((pt - a.B.lo[c]) / a.B.ext[c]);
     }
     r = 0;

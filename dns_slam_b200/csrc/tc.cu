@@ -21,6 +21,8 @@
 //
 // One CTA owns a contiguous range of tiles, keeps the accumulator in TMEM across them and flushes it
 // with atomics once per range (or when the class of a class-grouped tile stream changes).
+#include <string.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -155,6 +157,142 @@ __global__ void __launch_bounds__(kTile) k_dw_gemm_tc(DwArgs a) {
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------
+// Image version: operands arrive as ready-made bf16 hi/lo tile images (written by the producers straight from
+// their shared-memory operand tiles), so this kernel is a pure  bulk-copy -> tcgen05.mma  pipeline:
+// thread 0 streams sub-tiles with cp.async.bulk into a ring of NS stages (mbarrier expect_tx / complete_tx),
+// issues the MMAs of a stage as soon as it has landed and releases the stage with tcgen05.commit; the
+// accumulator stays in TMEM across a run of equal-class tiles and is flushed once per run with atomics.
+// ---------------------------------------------------------------------------------------
+constexpr int kImgMaxStages = 6;
+__global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int stage_bytes) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t full[kImgMaxStages], empty[kImgMaxStages], done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int RS = a.RS, cs = RS * 16;                         // bytes per chunk of a sub-tile
+  const int nC16 = (a.Cc.n_valid + 15) & ~15;
+  const int l_bytes = a.L.chunks_used * cs, c_bytes = a.Cc.chunks_used * cs;   // one half each
+  const int n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles_host;
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = min(n_tiles, t0 + per);
+  if (t0 >= t1) return;
+  const uint32_t tmem_cols = nC16 <= 32 ? 32 : (nC16 <= 64 ? 64 : 128);
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&done, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t idesc = umma_idesc_bf16(128, nC16, 1, 1);
+  const int64_t l_sub = (int64_t)2 * a.L.chunks_total * RS, c_sub = (int64_t)2 * a.Cc.chunks_total * RS;  // uint4 per sub-tile
+  uint32_t gi = 0, done_phase = 0;   // sub-tiles streamed so far (stage / phase bookkeeping), flushes so far
+
+  int t = t0;
+  while (t < t1) {
+    const int cls = a.tile_class ? a.tile_class[t] : 0;
+    int te = t + 1;
+    while (te < t1 && (a.tile_class ? a.tile_class[te] : 0) == cls) ++te;   // run of equal-class tiles [t, te)
+    if (cls >= 0) {
+      if (tid == 0) {
+        const int n = (te - t) * a.subs_per_tile;
+        const int64_t sub0 = (int64_t)t * a.subs_per_tile;
+        int prod = 0, cons = 0;
+        while (cons < n) {
+          while (prod < n && prod - cons < n_stages) {
+            const uint32_t g = gi + prod, s = g % n_stages, ph = (g / n_stages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            unsigned char* st = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full[s], 2 * (l_bytes + c_bytes));
+            const uint4* lsrc = a.L.ptr + (sub0 + prod) * l_sub + (int64_t)a.L.chunk0 * RS;
+            const uint4* csrc = a.Cc.ptr + (sub0 + prod) * c_sub + (int64_t)a.Cc.chunk0 * RS;
+            bulk_g2s(st, lsrc, l_bytes, &full[s]);                                             // L hi
+            bulk_g2s(st + l_bytes, lsrc + (int64_t)a.L.chunks_total * RS, l_bytes, &full[s]);  // L lo
+            bulk_g2s(st + 2 * l_bytes, csrc, c_bytes, &full[s]);                               // C hi
+            bulk_g2s(st + 2 * l_bytes + c_bytes, csrc + (int64_t)a.Cc.chunks_total * RS, c_bytes, &full[s]);
+            ++prod;
+          }
+          const uint32_t g = gi + cons, s = g % n_stages, ph = (g / n_stages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll 1
+          for (int k = 0; k < RS / 16; ++k) {
+            const uint32_t koff = k * 256;
+            const uint64_t a_hi = umma_desc(base + koff, 128, cs), a_lo = umma_desc(base + l_bytes + koff, 128, cs);
+            const uint64_t b_hi = umma_desc(base + 2 * l_bytes + koff, 128, cs),
+                           b_lo = umma_desc(base + 2 * l_bytes + c_bytes + koff, 128, cs);
+            umma_bf16(tmem_d, a_hi, b_hi, idesc, (cons > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+            umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          ++cons;
+        }
+        gi += n;
+        umma_commit(&done);
+        mbar_wait(&done, done_phase);
+      }
+      done_phase ^= 1;
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      {
+        float* o0 = a.out0 + (int64_t)cls * a.cls0;
+        float* o1 = a.out1 ? a.out1 + (int64_t)cls * a.cls1 : nullptr;
+        const int l = tid;
+        for (int c0 = 0; c0 < nC16; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+          if (l < a.L.n_valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + i;
+              if (c < a.Cc.n_valid && v[i] != 0.f) {
+                if (c < a.split) atomicAdd(o0 + (int64_t)l * a.sl0 + (int64_t)c * a.sc0, v[i]);
+                else if (o1) atomicAdd(o1 + (int64_t)l * a.sl1 + (int64_t)(c - a.split) * a.sc1, v[i]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+    t = te;
+  }
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+int launch_dw_img(const DwImgArgs& a, cudaStream_t st) {
+  if (a.n_tiles_host <= 0) return DNS_OK;
+  const int cs = a.RS * 16;
+  const int stage = 2 * (a.L.chunks_used + a.Cc.chunks_used) * cs;
+  // the MMA footprint of the lane operand spans 16 chunks from the start of each half: keep it inside the allocation
+  const int tail = 16 * cs;
+  int ns = (200 * 1024 - tail) / stage;
+  if (ns > kImgMaxStages) ns = kImgMaxStages;
+  if (ns < 1 || (a.RS & 15) || a.L.chunks_used > 16 || ((a.Cc.n_valid + 15) & ~15) > a.Cc.chunks_used * 8) {
+    set_error("dw_img: unsupported shape (RS %d, chunks %d/%d, nC %d)", a.RS, a.L.chunks_used, a.Cc.chunks_used, a.Cc.n_valid);
+    return DNS_ERR_UNSUPPORTED;
+  }
+  size_t smem = (size_t)ns * stage + tail;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_dw_img, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    attr = true;
+  }
+  int grid = a.n_tiles_host < 148 ? a.n_tiles_host : 148;
+  k_dw_img<<<grid, kTile, smem, st>>>(a, ns, stage);
+  return check_launch("dw_img");
+}
+
 static bool g_use_tc = true;
 bool use_tensor_cores() { return g_use_tc; }
 
@@ -222,7 +360,55 @@ int launch_dw_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, i
 
 }  // namespace dns
 
+namespace dns {
+// test helper: fp32 rows -> bf16 hi/lo tile image  [sub][half][chunk][RS]
+__global__ void k_make_image(const float* __restrict__ src, int ld, int n, int64_t rows, int RS, int chunks, uint4* __restrict__ img) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n_sub = (rows + RS - 1) / RS;
+  if (i >= n_sub * chunks * RS) return;
+  int r = (int)(i % RS);
+  int c = (int)((i / RS) % chunks);
+  int64_t sub = i / ((int64_t)RS * chunks);
+  int64_t row = sub * RS + r;
+  float x[8];
+  for (int k = 0; k < 8; ++k) x[k] = (row < rows && 8 * c + k < n) ? src[row * ld + 8 * c + k] : 0.f;
+  uint4 h, l;
+  split8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), h, l);
+  img[((sub * 2 + 0) * chunks + c) * RS + r] = h;
+  img[((sub * 2 + 1) * chunks + c) * RS + r] = l;
+}
+}  // namespace dns
+
 extern "C" {
+// test entry of the image pipeline: C[m][n] (ldc = N) += sum_p A[p][m] B[p][n]; images are built in temporary buffers
+int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows, int RS, float* C,
+                       void* stream) {
+  using namespace dns;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int lch = (M + 7) / 8, cch = (((N + 15) & ~15) + 7) / 8;
+  const int64_t n_sub = (rows + RS - 1) / RS;
+  uint4 *li = nullptr, *ci = nullptr;
+  cudaMalloc(&li, sizeof(uint4) * n_sub * 2 * lch * RS);
+  cudaMalloc(&ci, sizeof(uint4) * n_sub * 2 * cch * RS);
+  k_make_image<<<(unsigned)((n_sub * lch * RS + 255) / 256), 256, 0, st>>>(A, lda, M, rows, RS, lch, li);
+  k_make_image<<<(unsigned)((n_sub * cch * RS + 255) / 256), 256, 0, st>>>(B, ldb, N, rows, RS, cch, ci);
+  DwImgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = DwImg{li, lch, 0, lch, M};
+  a.Cc = DwImg{ci, cch, 0, cch, N};
+  a.RS = RS;
+  a.subs_per_tile = 1;
+  a.n_tiles_host = (int)n_sub;
+  a.out0 = C;
+  a.split = N;
+  a.sl0 = N;   // lanes = m -> row stride N
+  a.sc0 = 1;
+  int e = launch_dw_img(a, st);
+  cudaStreamSynchronize(st);
+  cudaFree(li);
+  cudaFree(ci);
+  return e;
+}
 // 1: weight-gradient GEMMs on tcgen05 (default); 0: fp32 SIMT path (A/B comparisons)
 void dns_set_tensor_cores(int on) { dns::g_use_tc = on != 0; }
 

@@ -303,13 +303,26 @@ def tv_offsets(bound, sample_points, rand3, rand113, voxel_size=0.1, margin=0.05
     return offset, jitter
 
 
-def tv_raw(gstruct, bound, table, coarse, sample_points, offset, jitter, lambda_sm, d_table, d_coarse):
+def tv_offsets_device(bound, sample_points, rand3, rand113, voxel_size=0.1, margin=0.05):
+    """Same float64 arithmetic as ``tv_offsets`` evaluated on the device: [offset(3) | jitter(3)] float64 tensor
+    (no host round trip, CUDA-graph capturable)."""
+    b = bound.detach().double()
+    volume = b[:, 1] - b[:, 0]
+    offset_max = volume - (sample_points - 1) * voxel_size - 2 * margin
+    offset = rand3.to(offset_max) * offset_max + margin
+    return torch.cat((offset, rand113.reshape(3).to(volume))).contiguous()
+
+
+def tv_raw(gstruct, bound, table, coarse, sample_points, offset, jitter, lambda_sm, d_table, d_coarse, oj_dev=None):
     dev = table.device
     a = _lib.TvArgs()
     a.n, a.smooth_pts, a.voxel = sample_points - 1, sample_points, 0.1
     _lib.fill_bound(a.bound, bound)
-    for k in range(3):
-        a.offset[k], a.jitter[k] = float(offset[k]), float(jitter[k])
+    if oj_dev is not None:
+        a.offset_jitter_dev = _lib.ptr(oj_dev, torch.float64)
+    else:
+        for k in range(3):
+            a.offset[k], a.jitter[k] = float(offset[k]), float(jitter[k])
     a.lambda_sm = lambda_sm
     a.need_dparams = int(d_table is not None)
     a.grid = gstruct
@@ -326,22 +339,27 @@ def tv_raw(gstruct, bound, table, coarse, sample_points, offset, jitter, lambda_
 
 class _TvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, table, coarse, gstruct, bound, sample_points, offset, jitter):
+    def forward(ctx, table, coarse, gstruct, bound, sample_points, offset, jitter, oj_dev=None):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         d_t = torch.zeros_like(table) if need else None
         d_c = torch.zeros_like(coarse) if need else None
-        loss = tv_raw(gstruct, bound, table.detach(), coarse.detach(), sample_points, offset, jitter, 1.0, d_t, d_c)
+        loss = tv_raw(gstruct, bound, table.detach(), coarse.detach(), sample_points, offset, jitter, 1.0, d_t, d_c, oj_dev)
         ctx.g = (d_t, d_c)
         return loss.clone()
 
     @staticmethod
     def backward(ctx, g):
         d_t, d_c = ctx.g
-        return (g * d_t if d_t is not None else None, g * d_c if d_c is not None else None, None, None, None, None, None)
+        return (g * d_t if d_t is not None else None, g * d_c if d_c is not None else None, None, None, None, None, None,
+                None)
 
 
 def tv_loss(decoder, sample_points, rand3, rand113):
     """Mapper.smoothness(sample_points) with the two CPU draws of mapping.py:138,140 as inputs."""
+    if rand3.is_cuda:    # draws already on the device: offsets computed there (no host sync, graph capturable)
+        oj = tv_offsets_device(decoder.bound, sample_points, rand3, rand113)
+        return _TvFn.apply(decoder.pe_fn.grid_fn.params, decoder.coarse_fn.decoder.params,
+                           decoder.pe_fn.grid_fn.gstruct, decoder.bound, sample_points, None, None, oj)
     offset, jitter = tv_offsets(decoder.bound, sample_points, rand3, rand113)
     return _TvFn.apply(decoder.pe_fn.grid_fn.params, decoder.coarse_fn.decoder.params,
                        decoder.pe_fn.grid_fn.gstruct, decoder.bound, sample_points, offset, jitter)

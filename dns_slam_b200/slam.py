@@ -134,7 +134,8 @@ class MapperCore:
         self.lambdas.update(lambdas or {})
         self.opacity_sigma, self.smooth_pts, self.lambda_sm = opacity_sigma, smooth_pts, lambda_sm
 
-    def get_target_samples(self, target_frames, quad_list, T_list, refer_frames, features_cl, draws):
+    def get_target_samples(self, target_frames, quad_list, T_list, refer_frames, features_cl, draws,
+                           assume_inside=False):
         """target_frames: dict(kf_idx, frames=[dict(color,depth,label)], class_tables=[...]);
         refer_frames: dict(kf_idx=[[...]], est_c2w=[[...]]); features_cl[i]: [R,h,w,64];
         draws[i] = dict(idx_uniform, class_draws=[...], t_surface, t_zero)."""
@@ -178,14 +179,19 @@ class MapperCore:
                 acc[k].append(v)
         cat = {k: torch.cat(v, 0) for k, v in acc.items()}
         m = cat.pop("mask")
+        if assume_inside:          # graph replay: no compaction; the flag is checked once after the loop
+            ok = m.all()
+            self.inside_ok = ok if getattr(self, "inside_ok", None) is None else self.inside_ok & ok
+            return cat
         if bool(m.all()):          # one small D2H read; the reference syncs here too (mapping.py:576)
             return cat
         return {k: v[m] for k, v in cat.items()}
 
     def iteration(self, target_frames, quad_list, T_list, refer_frames, features_cl, draws, tv_draws,
-                  lambda_lt=None, want_latents=False):
+                  lambda_lt=None, want_latents=False, assume_inside=False):
         """Body of mapping.py:884-907; returns (loss dict incl. smooth_loss and total, preds, samples)."""
-        samples = self.get_target_samples(target_frames, quad_list, T_list, refer_frames, features_cl, draws)
+        samples = self.get_target_samples(target_frames, quad_list, T_list, refer_frames, features_cl, draws,
+                                          assume_inside=assume_inside)
         lam = dict(self.lambdas)
         if lambda_lt is not None:
             lam["lt"] = lambda_lt
@@ -331,11 +337,20 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
 
 
 def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,
-                 new_decoders, draws_fn, tv_draws_fn):
+                 new_decoders, draws_fn, tv_draws_fn, use_graph=False):
     """The optimisation loop of ``Mapper.optimize`` (slams/mapping.py:868-910): one Adam over the decoder
     (hash grid + MLPs), the class experts present and -- when ``is_BA`` -- quaternion / translation of every
     target frame but the oldest (mapping.py:457); lambda_lt follows the schedule of mapping.py:898-904.
-    Returns (quad_list, T_list, loss dict of the last iteration)."""
+    Returns (quad_list, T_list, loss dict of the last iteration).
+    ``use_graph``: after three eager iterations ONE iteration (4 frames of sampling + feature matching, fused
+    render/backward, TV, Adam) is captured in a CUDA graph and replayed with fresh draws.  Replay needs static
+    shapes, so it assumes every sampled ray passes the inside test of mapping.py:525 (checked once at the end;
+    the call falls back to the eager loop from the saved state otherwise) and a constant lambda_lt."""
+    if use_graph and len(new_decoders) == 0 and n_iters > 4:
+        out = _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr,
+                                  is_BA, draws_fn, tv_draws_fn)
+        if out is not None:
+            return out
     dec = mapper.decoder
     dev = dec.bound.device
     n_t = len(target_frames["frames"])
@@ -400,3 +415,88 @@ def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, 
         (ld["total"] + mapper.lambda_sm * sm).backward()
         opt.step()
     return ld
+
+
+def _to_static(d, dev):
+    if isinstance(d, torch.Tensor):
+        return d.to(dev).clone()
+    if isinstance(d, dict):
+        return {k: _to_static(v, dev) for k, v in d.items()}
+    return [_to_static(v, dev) for v in d]
+
+
+def _copy_static(dst, src):
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_static(dst[k], src[k])
+    else:
+        for a, b in zip(dst, src):
+            _copy_static(a, b)
+
+
+def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,
+                        draws_fn, tv_draws_fn):
+    dec = mapper.decoder
+    dev = dec.bound.device
+    n_t = len(target_frames["frames"])
+    saved = dec.flat.detach().clone()
+    quad_list, T_list = [], []
+    for f in range(n_t):
+        c2w = est_c2w_list[f]
+        q = quad_from_matrix(c2w[:3, :3]).to(dev)
+        t = c2w[:3, 3].detach().clone().to(dev)
+        if (n_t == 1 or f != 0) and is_BA:
+            q.requires_grad_(True)
+            t.requires_grad_(True)
+        quad_list.append(q)
+        T_list.append(t)
+    net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
+    cam_lr = BA_cam_lr * float(is_BA)
+    groups = [{"params": net, "lr": lr}]
+    if any(q.requires_grad for q in quad_list):
+        groups += [{"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
+                   {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}]
+    opt = torch.optim.Adam(groups, capturable=True)
+    static_d = _to_static(draws_fn(0), dev)
+    static_tv = _to_static(list(tv_draws_fn(0)), dev)
+    mapper.inside_ok = None
+    last = {}
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        ld, _, _ = mapper.iteration(target_frames, quad_list, T_list, refer_frames, features_cl, static_d, static_tv,
+                                    lambda_lt=10.0, assume_inside=True)
+        ld["total"].backward()
+        opt.step()
+        for k, v in ld.items():
+            if k not in last:
+                last[k] = torch.zeros_like(v.detach())
+            last[k].copy_(v.detach())
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for it in range(3):
+            _copy_static(static_d, draws_fn(it))
+            _copy_static(static_tv, list(tv_draws_fn(it)))
+            one()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    _copy_static(static_d, draws_fn(3))
+    _copy_static(static_tv, list(tv_draws_fn(3)))
+    with torch.cuda.graph(graph):
+        one()
+    for it in range(3, n_iters):
+        _copy_static(static_d, draws_fn(it))
+        _copy_static(static_tv, list(tv_draws_fn(it)))
+        graph.replay()
+    ok = bool(mapper.inside_ok)          # the single host read of the loop
+    mapper.inside_ok = None
+    mapper.last_graph_ok = ok
+    if not ok:                           # some ray left the bound: static shapes were wrong, redo eagerly
+        with torch.no_grad():
+            dec.flat.copy_(saved)
+        return None
+    return quad_list, T_list, dict(last)

@@ -177,6 +177,9 @@ typedef struct dns_tv_args {
   float* d_coarse;        /* += */
   void* workspace;
   int64_t workspace_bytes;
+  /* optional: offset[3] | jitter[3] as float64 in DEVICE memory (overrides the by-value fields), so that a
+   * captured CUDA graph can be replayed with new draws */
+  const double* offset_jitter_dev;
 } dns_tv_args;
 
 int64_t dns_tv_workspace_bytes(int n);
@@ -240,6 +243,11 @@ void dns_set_tensor_cores(int on);
 /* Test entry of the tcgen05 GEMM: C[m][n] (row stride N) += sum_p A[p][m] * B[p][n]. */
 int dns_debug_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows,
                       float* C, void* stream);
+
+/* Test entry of the tile-image GEMM pipeline (cp.async.bulk -> tcgen05.mma): same contract as
+ * dns_debug_gemm_tc, operands converted to bf16 hi/lo tile images of RS rows first. */
+int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows,
+                       int RS, float* C, void* stream);
 
 /* Phase accounting for benchmarks: per-phase kernel-launch counters (always on) and, when
  * enabled, CUDA-event timing of each phase on the launching stream.  Phases: 0 prep, 1 class

@@ -158,3 +158,33 @@ def test_mapping_loop_vs_oracle():
     # parameters after two Adam steps: the update direction is sign-like, so compare the net displacement
     assert rel_err(dec.coarse_fn.decoder.params, odec.coarse_fn.decoder.params) < 1e-3
     assert rel_err(dec.pe_fn.grid_fn.params, odec.pe_fn.grid_fn.params) < 1e-3
+
+
+def test_mapping_loop_cuda_graph_equals_eager():
+    """CUDA-graph replay of the mapping loop (static shapes, device-side TV offsets) == the eager loop."""
+    from dns_slam_b200 import bench_util, slam, synthetic as syn
+    dev = _dev()
+    s = syn.SHAPES["tiny"]
+    n_it = 7
+    sc = bench_util.slam_scene("tiny", 6, dev, seed=3, n_target=3)
+    md, tv = bench_util.mapping_draws(sc, s["mapping_pixels"], n_it, seed=4)
+    target = dict(kf_idx=sc["kf_idx"], frames=sc["frames"], class_tables=sc["class_tables"])
+    refer = dict(kf_idx=sc["refer_idx"], est_c2w=sc["refer_c2w"])
+    est = [sc["poses"][2 * f + 1].clone() for f in range(3)]
+    lam = dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0)
+    res = []
+    for use_graph in (False, True):
+        dec = bench_util.make_decoder("tiny", 6, dev, seed=1)
+        mp = slam.MapperCore(sc["cam"], dec, s["mapping_pixels"], 32, 15, lambdas=lam, opacity_sigma=0.05,
+                             smooth_pts=s["smooth_pts"], lambda_sm=0.05)
+        ql, tl, ld = slam.map_optimize(mp, target, refer, sc["feats"], est, n_it, 5e-3, 5e-4, True, [],
+                                       lambda it: md[it], lambda it: tv[it], use_graph=use_graph)
+        if use_graph:
+            assert getattr(mp, "last_graph_ok", False), "graph path fell back to eager (rays outside the bound)"
+        res.append((ql, tl, ld, dec.flat.clone()))
+    (q0, t0, l0, f0), (q1, t1, l1, f1) = res
+    close(l1["total"], l0["total"], rtol=1e-3, atol=1e-6, name="last loss")
+    for i in range(1, 3):
+        close(q1[i], q0[i], rtol=1e-3, atol=1e-5, name="quad")
+        close(t1[i], t0[i], rtol=1e-3, atol=1e-5, name="T")
+    assert rel_err(f1, f0) < 1e-3

@@ -61,3 +61,20 @@ def test_fused_gradients_same_with_and_without_tensor_cores():
         a, n = lay[k]
         e = float((g1[a:a + n] - g0[a:a + n]).norm() / (g0[a:a + n].norm() + 1e-30))
         assert e < 1e-3, (k, e)     # parity bar; ReLU-mask flips at ~0 pre-activations are legitimate
+
+
+@pytest.mark.parametrize("M,N,rows,RS", [(80, 64, 1000, 64), (112, 64, 128 * 40, 80), (33, 32, 640, 64), (32, 3, 300, 48),
+                                         (80, 32, 64 * 500 + 7, 64)])
+def test_dw_gemm_image_pipeline(M, N, rows, RS):
+    """cp.async.bulk -> tcgen05.mma pipeline on bf16 hi/lo tile images against float64 matmul."""
+    from dns_slam_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M * 100 + N)
+    A = torch.randn(rows, M, generator=g).to(dev)
+    B = (torch.randn(rows, N, generator=g) * torch.rand(rows, 1, generator=g)).to(dev)
+    C = torch.zeros(M, N, device=dev)
+    _lib.check(_lib.lib().dns_debug_gemm_img(_lib.ptr(A), M, M, _lib.ptr(B), N, N, rows, RS, _lib.ptr(C), _lib.stream()))
+    torch.cuda.synchronize()
+    want = A.double().t() @ B.double()
+    err = float((C.double() - want).norm() / want.norm())
+    assert err < 2e-5, f"relative error {err:.3e}"
