@@ -113,14 +113,16 @@ __global__ void __launch_bounds__(kTile) k_point_fwd_tc(PointArgs a, const uint4
   int64_t i, r;
   float zv, x[3];
   const bool valid = slot_point<MODE>(a, q, i, r, zv, x);
+  // encoded inputs of the tile: MMA operand in shared memory + (for the weight gradients) a global tile image
+  uint4* ximg = (a.need_dparams && !(a.dbg & 2)) ? a.Ximg + (int64_t)tile * (20 * kTile) + tid : nullptr;
+#define XIMG(c) (ximg ? ximg + (c) * kTile : nullptr), (ximg ? ximg + (10 + (c)) * kTile : nullptr)
   if (valid) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float pe[16];
       oneblob16(x[c], pe);
-      put_chunk(X_hi, X_lo, 2 * c, 2048, tid, pe);
-      put_chunk(X_hi, X_lo, 2 * c + 1, 2048, tid, pe + 8);
-      if (a.need_dparams && !(a.dbg & 2)) store_row(a.Xst + q * kIn1 + 16 * c, pe);
+      put_chunk_img(X_hi, X_lo, 2 * c, 2048, tid, pe, XIMG(2 * c));
+      put_chunk_img(X_hi, X_lo, 2 * c + 1, 2048, tid, pe + 8, XIMG(2 * c + 1));
     }
     float g[32];
     if (a.dbg & 1) {
@@ -129,21 +131,17 @@ __global__ void __launch_bounds__(kTile) k_point_fwd_tc(PointArgs a, const uint4
     } else
     hashgrid_fwd_regs(a.G, a.table, x, g);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) put_chunk(X_hi, X_lo, 6 + c, 2048, tid, g + 8 * c);
-    if (a.need_dparams && !(a.dbg & 2)) store_row(a.Xst + q * kIn1 + DNS_PE_DIM, g);
+    for (int c = 0; c < 4; ++c) put_chunk_img(X_hi, X_lo, 6 + c, 2048, tid, g + 8 * c, XIMG(6 + c));
   } else {
     const uint4 z4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int c = 0; c < 10; ++c) {
       *reinterpret_cast<uint4*>(X_hi + c * 2048 + tid * 16) = z4;
       *reinterpret_cast<uint4*>(X_lo + c * 2048 + tid * 16) = z4;
-    }
-    if (a.need_dparams) {
-      float4* d4 = reinterpret_cast<float4*>(a.Xst + q * kIn1);
-#pragma unroll
-      for (int k = 0; k < kIn1 / 4; ++k) d4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ximg) ximg[c * kTile] = ximg[(10 + c) * kTile] = z4;
     }
   }
+#undef XIMG
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -175,20 +173,12 @@ __global__ void __launch_bounds__(kTile) k_point_fwd_tc(PointArgs a, const uint4
 #pragma unroll
       for (int k = 0; k < 16; ++k) h[16 * g4 + k] = fmaxf(v[k], 0.f);
     }
-    // hidden activations: stash (ReLU mask + dW2 of the backward) and stage as the next A operand
-    if (!(a.dbg & 2)) {
-      float4* hp = reinterpret_cast<float4*>(a.Hc + q * 32);
+    // hidden activations: the next A operand, and a global tile image (ReLU mask + dW2 of the backward)
+    uint4* himg = (a.dbg & 2) ? nullptr : a.Himg + (int64_t)tile * (2 * (NH / 8) * kTile) + tid;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) hp[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
-      if (MODE == kMap) {
-        float4* hf = reinterpret_cast<float4*>(a.Hf + q * 32);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          hf[k] = make_float4(h[NH - 32 + 4 * k], h[NH - 32 + 4 * k + 1], h[NH - 32 + 4 * k + 2], h[NH - 32 + 4 * k + 3]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NH / 8; ++c) put_chunk(H_hi, H_lo, c, 2048, tid, h + 8 * c);
+    for (int c = 0; c < NH / 8; ++c)
+      put_chunk_img(H_hi, H_lo, c, 2048, tid, h + 8 * c, himg ? himg + c * kTile : nullptr,
+                    himg ? himg + (NH / 8 + c) * kTile : nullptr);
   }
   fence_async_smem();
   tc_fence_before();
@@ -364,20 +354,18 @@ __global__ void __launch_bounds__(kTile) k_point_bwd_tc(PointArgs a, const uint4
       for (int k = 0; k < 48; ++k) df[k] = 0.f;
     }
   }
-  if (a.need_dparams && !(a.dbg & 2)) {
-    float4* oc = reinterpret_cast<float4*>(a.dOc + q * kOutP);
-#pragma unroll
-    for (int k = 0; k < kOutP / 4; ++k) oc[k] = make_float4(dc[4 * k], dc[4 * k + 1], dc[4 * k + 2], dc[4 * k + 3]);
-    if (MODE == kMap) {
-      float4* of = reinterpret_cast<float4*>(a.dOf + q * kOutP);
-#pragma unroll
-      for (int k = 0; k < kOutP / 4; ++k) of[k] = make_float4(df[4 * k], df[4 * k + 1], df[4 * k + 2], df[4 * k + 3]);
-    }
-  }
+  constexpr int DOCH = MODE == kMap ? 10 : 5;   // chunks per half of the dOut image: 5 (40 >= 33 channels) per net
+  constexpr int HCH = MODE == kMap ? 8 : 4;     // chunks per half of the H / dH images
+  const bool stash = a.need_dparams && !(a.dbg & 2);
+  uint4* doimg = stash ? a.dOimg + (int64_t)tile * (2 * DOCH * kTile) + tid : nullptr;
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
-    put_chunk(DOc_hi, DOc_lo, c, 2048, tid, dc + 8 * c);
-    if (MODE == kMap) put_chunk(DOf_hi, DOf_lo, c, 2048, tid, df + 8 * c);
+    const bool gi = stash && c < 5;
+    put_chunk_img(DOc_hi, DOc_lo, c, 2048, tid, dc + 8 * c, gi ? doimg + c * kTile : nullptr,
+                  gi ? doimg + (DOCH + c) * kTile : nullptr);
+    if (MODE == kMap)
+      put_chunk_img(DOf_hi, DOf_lo, c, 2048, tid, df + 8 * c, gi ? doimg + (5 + c) * kTile : nullptr,
+                    gi ? doimg + (DOCH + 5 + c) * kTile : nullptr);
   }
   fence_async_smem();
   tc_fence_before();
@@ -407,30 +395,32 @@ __global__ void __launch_bounds__(kTile) k_point_bwd_tc(PointArgs a, const uint4
   const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
   {
     float dh[64];
+    // ReLU mask: the bf16 hi half of the stashed activations is non-zero exactly where the activation was positive
+    const uint4* himg = a.Himg + (int64_t)tile * (2 * HCH * kTile) + tid;
 #pragma unroll
     for (int net = 0; net < 2; ++net) {
       const bool on = net == 0 || fine;
-      const float* hrow = (net ? a.Hf : a.Hc) + q * 32;
 #pragma unroll
       for (int g2 = 0; g2 < 2; ++g2) {
         float v[16];
         if (on) tmem_ld16(lane_addr + net * 32 + 16 * g2, v);   // `on` is uniform over the CTA
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          float4 hv = on ? *reinterpret_cast<const float4*>(hrow + 16 * g2 + 4 * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const uint4 hv = on ? himg[(net * 4 + 2 * g2 + c2) * kTile] : make_uint4(0, 0, 0, 0);
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) dh[32 * net + 16 * g2 + 4 * k4 + e] = (on && hh[e] > 0.f) ? v[4 * k4 + e] : 0.f;
+          for (int e = 0; e < 8; ++e)
+            dh[32 * net + 16 * g2 + 8 * c2 + e] = (on && ((hw[e >> 1] >> (16 * (e & 1))) & 0x7fffu)) ? v[8 * c2 + e] : 0.f;
         }
       }
     }
-    if (a.need_dparams && !(a.dbg & 2)) {
-      float4* d4 = reinterpret_cast<float4*>(a.dHc + q * 64);
+    uint4* dhimg = stash ? a.dHimg + (int64_t)tile * (2 * HCH * kTile) + tid : nullptr;
 #pragma unroll
-      for (int k = 0; k < (MODE == kMap ? 16 : 8); ++k) d4[k] = make_float4(dh[4 * k], dh[4 * k + 1], dh[4 * k + 2], dh[4 * k + 3]);
+    for (int c = 0; c < 8; ++c) {
+      const bool gi = stash && c < HCH;
+      put_chunk_img(DH_hi, DH_lo, c, 2048, tid, dh + 8 * c, gi ? dhimg + c * kTile : nullptr,
+                    gi ? dhimg + (HCH + c) * kTile : nullptr);
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) put_chunk(DH_hi, DH_lo, c, 2048, tid, dh + 8 * c);
   }
   fence_async_smem();
   tc_fence_before();

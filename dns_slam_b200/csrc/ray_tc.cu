@@ -75,10 +75,16 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   const int64_t rl = (int64_t)blockIdx.x * RPC + lr;      // chunk-local ray
   const bool valid = lr < RPC && rl < a.Nc;
   const int64_t r = a.ray0 + rl;                          // global ray
-  const int64_t pl = rl * S + s, p = r * S + s;           // chunk-local / global point
+  const int64_t p = r * S + s;                            // global point
   const int rb = lr * S;                                  // first thread of my ray
   float* xc = XC + t;
   float x[3] = {0.f, 0.f, 0.f}, zv = 0.f, occ = 0.f;
+  // weight-gradient operands leave the kernel as bf16 hi/lo tile images: this CTA owns T rows = T/RS sub-tiles,
+  // each laid out [half][chunk][RS rows] (tc.cu: k_dw_img); rows of absent points are written as zeros
+  const bool stash = a.need_dparams != 0;
+  const int RS = a.RS, sub = t / RS, rr = t - sub * RS;
+  const int64_t img_row0 = ((int64_t)blockIdx.x * T + (int64_t)sub * RS) * 2;
+  auto img = [&](uint4* base, int K, int c) -> uint4* { return stash ? base + img_row0 * K + c * RS + rr : nullptr; };
 
   // ---- stage this point's row of X = [OneBlob(x) 48 | latent 32 | pixel feature 32] as bf16 hi/lo chunks
   if (valid) {
@@ -88,13 +94,8 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     for (int c = 0; c < 3; ++c) {
       float pe[16];
       oneblob16(x[c], pe);
-      put_chunk(X_hi, X_lo, 2 * c, cs, t, pe);
-      put_chunk(X_hi, X_lo, 2 * c + 1, cs, t, pe + 8);
-      if (a.need_dparams) {
-        float4* d4 = reinterpret_cast<float4*>(a.X2 + pl * kIn2 + 16 * c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d4[q] = make_float4(pe[4 * q], pe[4 * q + 1], pe[4 * q + 2], pe[4 * q + 3]);
-      }
+      put_chunk_img(X_hi, X_lo, 2 * c, cs, t, pe, img(a.X2img, 14, 2 * c), img(a.X2img, 14, 14 + 2 * c));
+      put_chunk_img(X_hi, X_lo, 2 * c + 1, cs, t, pe + 8, img(a.X2img, 14, 2 * c + 1), img(a.X2img, 14, 15 + 2 * c));
     }
     {
       float row[kOutP];
@@ -106,12 +107,8 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
       }
       occ = row[0];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) put_chunk(X_hi, X_lo, 6 + c, cs, t, row + 1 + 8 * c);
-      if (a.need_dparams) {
-        float4* d4 = reinterpret_cast<float4*>(a.X2 + pl * kIn2 + 48);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) d4[q] = make_float4(row[1 + 4 * q], row[2 + 4 * q], row[3 + 4 * q], row[4 + 4 * q]);
-      }
+      for (int c = 0; c < 4; ++c)
+        put_chunk_img(X_hi, X_lo, 6 + c, cs, t, row + 1 + 8 * c, img(a.X2img, 14, 6 + c), img(a.X2img, 14, 20 + c));
     }
     {
       float row[32];
@@ -127,12 +124,8 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
         for (int k = 0; k < 32; ++k) row[k] = 0.f;
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) put_chunk(X_hi, X_lo, 10 + c, cs, t, row + 8 * c);
-      if (a.need_dparams) {
-        float4* d4 = reinterpret_cast<float4*>(a.X2 + pl * kIn2 + 80);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) d4[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
-      }
+      for (int c = 0; c < 4; ++c)
+        put_chunk_img(X_hi, X_lo, 10 + c, cs, t, row + 8 * c, img(a.X2img, 14, 10 + c), img(a.X2img, 14, 24 + c));
     }
   } else {
     const uint4 z4 = make_uint4(0, 0, 0, 0);
@@ -140,6 +133,7 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     for (int c = 0; c < 14; ++c) {
       *reinterpret_cast<uint4*>(X_hi + c * cs + t * 16) = z4;
       *reinterpret_cast<uint4*>(X_lo + c * cs + t * 16) = z4;
+      if (stash) *img(a.X2img, 14, c) = *img(a.X2img, 14, 14 + c) = z4;
     }
   }
   fence_async_smem();
@@ -360,34 +354,32 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     float d_alpha = d_u * Ts - suf / b;
     d_occ = d_alpha * 10.f * alpha * (1.f - alpha);
   }
-  if (valid) {
-    const float* rg = RG + lr * 8;
-    const float* qv = QV + lr * 32;
-    float dp[4];
+  {
+    float dp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const float* rg = RG + lr * 8;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) dp[c] = w * rg[c] * rgb[c] * (1.f - rgb[c]);
-    dp[3] = 0.f;
-    if (a.need_dparams) {
-      float4* hp = reinterpret_cast<float4*>(a.Hcol + pl * 32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) hp[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-      *reinterpret_cast<float4*>(a.dpre + pl * 4) = make_float4(dp[0], dp[1], dp[2], 0.f);
+      for (int c = 0; c < 3; ++c) dp[c] = w * rg[c] * rgb[c] * (1.f - rgb[c]);
     }
+    if (stash) {   // colour hidden activations (zeros for absent points) and the pre-sigmoid colour gradient
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float4 wv = *reinterpret_cast<const float4*>(W2c + 4 * j);
-      h[j] = h[j] > 0.f ? dp[0] * wv.x + dp[1] * wv.y + dp[2] * wv.z : 0.f;
-      h[32 + j] = h[32 + j] > 0.f ? w * qv[j] : 0.f;
+      for (int c = 0; c < 4; ++c) store_chunk_img(h + 8 * c, img(a.Hcolimg, 4, c), img(a.Hcolimg, 4, 4 + c));
+      store_chunk_img(dp, img(a.dpreimg, 1, 0), img(a.dpreimg, 1, 1));
     }
-    if (a.need_dparams) {
-      float4* dp4 = reinterpret_cast<float4*>(a.dH2 + pl * 64);
+    if (valid) {
+      const float* qv = QV + lr * 32;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) dp4[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      for (int j = 0; j < 32; ++j) {
+        float4 wv = *reinterpret_cast<const float4*>(W2c + 4 * j);
+        h[j] = h[j] > 0.f ? dp[0] * wv.x + dp[1] * wv.y + dp[2] * wv.z : 0.f;
+        h[32 + j] = h[32 + j] > 0.f ? w * qv[j] : 0.f;
+      }
     }
   }
   // ---- backward GEMM: dX = dH . W1  (A = dH K-major over hidden; B = W1 MN-major: features contiguous)
 #pragma unroll
-  for (int c = 0; c < 8; ++c) put_chunk(D_hi, D_lo, c, cs, t, h + 8 * c);   // invalid threads hold zeros
+  for (int c = 0; c < 8; ++c)   // invalid threads hold zeros
+    put_chunk_img(D_hi, D_lo, c, cs, t, h + 8 * c, img(a.dH2img, 8, c), img(a.dH2img, 8, 8 + c));
   fence_async_smem();
   tc_fence_before();
   __syncthreads();

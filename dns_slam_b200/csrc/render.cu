@@ -832,17 +832,24 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.coarse36 = c.take<float>(map ? Pc * kOutP : 4);
   w.dfine36 = c.take<float>(Pc * kOutP);
   w.Jst = nullptr;   // (a per-level Jacobian stash was measured slower than re-gathering the corners)
+  // Stashes for the weight gradients.  SIMT path: fp32 rows.  tcgen05 path: the same regions hold bf16 hi/lo
+  // tile images (32 B per value pair = the fp32 footprint; dOut rows padded 36 -> 40, ray-side rows padded to
+  // whole CTAs of T rows).
   w.Xst = c.take<float>(w.Q * kIn1);
-  w.Hc = c.take<float>(w.Q * 32);
-  w.Hf = c.take<float>(map ? w.Q * 32 : 4);
+  w.Hc = c.take<float>(w.Q * 32 * (map ? 2 : 1));
+  w.Hf = w.Hc ? w.Hc + w.Q * 32 : nullptr;
   w.dHc = c.take<float>(w.Q * 64);   // [Q][64]: columns 0..31 coarse, 32..63 class expert
   w.dHf = w.dHc ? w.dHc + 32 : nullptr;
-  w.dOc = c.take<float>(w.Q * kOutP);
-  w.dOf = c.take<float>(map ? w.Q * kOutP : 4);
-  w.X2 = c.take<float>(Pc * kIn2);
-  w.dH2 = c.take<float>(Pc * 64);
-  w.Hcol = c.take<float>(Pc * 32);
-  w.dpre = c.take<float>(Pc * 4);
+  w.dOc = c.take<float>(w.Q * 40 * (map ? 2 : 1));
+  w.dOf = w.dOc ? w.dOc + w.Q * 40 : nullptr;
+  int Tt, Rt;
+  pick_ray_block_tc(S, Tt, Rt);
+  const int64_t img_rows = ((Nc + Rt - 1) / Rt) * Tt;
+  const int64_t rows2 = img_rows > Pc ? img_rows : Pc;
+  w.X2 = c.take<float>(rows2 * kIn2);
+  w.dH2 = c.take<float>(rows2 * 64);
+  w.Hcol = c.take<float>(rows2 * 32);
+  w.dpre = c.take<float>(rows2 * 8);
   w.dlogit = c.take<float>(Nc * C4);
   w.Hbar = c.take<float>(Nc * 32);
   return c.off + 256;
@@ -975,6 +982,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     // point-order buffers are indexed with GLOBAL point ids: shift the chunk-local base
     pa.fine36 = w.fine36 - p0 * kOutP; pa.coarse36 = w.coarse36 - p0 * kOutP; pa.dfine36 = w.dfine36 - p0 * kOutP;
     pa.Jst = w.Jst; pa.Xst = w.Xst; pa.Hc = w.Hc; pa.Hf = w.Hf; pa.dHc = w.dHc; pa.dHf = w.dHf; pa.dOc = w.dOc; pa.dOf = w.dOf;
+    pa.Ximg = (uint4*)w.Xst; pa.Himg = (uint4*)w.Hc; pa.dHimg = (uint4*)w.dHc; pa.dOimg = (uint4*)w.dOc;
     pa.lam_lt = a->lambda_lt; pa.lam_fs = a->lambda_fs; pa.lam_op = a->lambda_op;
     pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
@@ -1023,6 +1031,8 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.pred_logits = a->pred_logits; ra.raw = w.raw; ra.dfine36 = pa.dfine36; ra.d_features = a->d_features;
     ra.d_rays_o = a->d_rays_o; ra.d_rays_d = a->d_rays_d;
     ra.X2 = w.X2; ra.dH2 = w.dH2; ra.Hcol = w.Hcol; ra.dpre = w.dpre; ra.dlogit = w.dlogit; ra.Hbar = w.Hbar;
+    ra.X2img = (uint4*)w.X2; ra.dH2img = (uint4*)w.dH2; ra.Hcolimg = (uint4*)w.Hcol; ra.dpreimg = (uint4*)w.dpre;
+    ra.RS = T <= 96 ? T : T / 2;   // sub-tile rows of the ray-side images (multiple of 16; keeps >= 3 pipeline stages)
     ra.need_dparams = a->need_dparams; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d;
     ra.need_dfeat = a->need_dfeat && a->d_features;
     pa.need_drays = ra.need_drays;
@@ -1055,20 +1065,40 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       int e = 0;
       const int pt_tiles = (int)((Pc + kTile - 1) / kTile), ray_tiles = (int)((nc + kTile - 1) / kTile);
       if (use_tensor_cores()) {
-        // layer-1 weight gradients on tcgen05, the shared input operand read once:
-        //   X80^T [dHc | dHf] -> coarse W1 (+ class-expert W1);  X112^T [dH colour | dH logit] -> colour / logit W1
-        DwArgs g;
+        // tcgen05 path: every operand is a bf16 hi/lo tile image streamed by bulk copies (tc.cu: k_dw_img).
+        //   X80^T [dHc | dHf]            -> coarse W1 (+ class-expert W1), the shared input read once
+        //   dOut^T H  per net            -> coarse W2, class-expert W2
+        //   X112^T [dH colour | dH logit] -> colour / logit W1;   dpre^T H colour -> colour W2
+        const int hch = map ? 8 : 4, doch = map ? 10 : 5;
+        DwImgArgs g;
         memset(&g, 0, sizeof(g));
-        g.L = w.Xst; g.ldl = kIn1; g.nL = kIn1; g.Cc = w.dHc; g.ldcc = 64; g.nC = map ? 64 : 32;
-        g.n_rows = Qrows; g.n_tiles_dev = ntd; g.n_tiles_host = tiles_max; g.tile_class = map ? w.tile_class : nullptr;
+        g.L = DwImg{pa.Ximg, 10, 0, 10, kIn1}; g.Cc = DwImg{pa.dHimg, hch, 0, hch, map ? 64 : 32};
+        g.RS = kTile; g.subs_per_tile = 1; g.n_tiles_dev = ntd; g.n_tiles_host = tiles_max;
+        g.tile_class = map ? w.tile_class : nullptr;
         g.out0 = a->d_coarse; g.split = 32; g.sl0 = 1; g.sc0 = kIn1; g.cls0 = 0;
         g.out1 = map ? a->d_experts : nullptr; g.sl1 = 1; g.sc1 = kIn1; g.cls1 = 4096;
-        e |= launch_dw_gemm_tc2(g, st);
+        e |= launch_dw_img(g, st);
+        g.L = DwImg{pa.dOimg, doch, 0, 5, DNS_LATENT}; g.Cc = DwImg{pa.Himg, hch, 0, 4, 32};
+        g.tile_class = nullptr;
+        g.out0 = a->d_coarse + 2560; g.split = 32; g.sl0 = 32; g.sc0 = 1; g.cls0 = 0; g.out1 = nullptr;
+        e |= launch_dw_img(g, st);
+        if (map) {
+          g.L = DwImg{pa.dOimg, doch, 5, 5, DNS_LATENT}; g.Cc = DwImg{pa.Himg, hch, 4, 4, 32};
+          g.tile_class = w.tile_class;
+          g.out0 = a->d_experts + 2560; g.cls0 = 4096;
+          e |= launch_dw_img(g, st);
+        }
         memset(&g, 0, sizeof(g));
-        g.L = w.X2; g.ldl = kIn2; g.nL = kIn2; g.Cc = w.dH2; g.ldcc = 64; g.nC = 64;
-        g.n_rows = Pc; g.n_tiles_host = pt_tiles;
+        g.L = DwImg{ra.X2img, 14, 0, 14, kIn2}; g.Cc = DwImg{ra.dH2img, 8, 0, 8, 64};
+        g.RS = ra.RS; g.subs_per_tile = T / ra.RS; g.n_tiles_host = (int)((nc + RPC - 1) / RPC);
         g.out0 = a->d_color; g.split = 32; g.sl0 = 1; g.sc0 = kIn2; g.out1 = a->d_logit; g.sl1 = 1; g.sc1 = kIn2;
-        e |= launch_dw_gemm_tc2(g, st);
+        e |= launch_dw_img(g, st);
+        g.L = DwImg{ra.dpreimg, 1, 0, 1, 3}; g.Cc = DwImg{ra.Hcolimg, 4, 0, 4, 32};
+        g.out0 = a->d_color + 32 * kIn2; g.sl0 = 32; g.sc0 = 1; g.out1 = nullptr;
+        e |= launch_dw_img(g, st);
+        e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st);
+        if (e) return DNS_ERR_CUDA;
+        continue;
       } else {
         e |= launch_dw_gemm(w.dHc, 64, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, nullptr, a->d_coarse, kIn1, 0, st);
         if (map)
@@ -1109,7 +1139,7 @@ int dns_render_counts(const dns_render_args* a, int32_t* counts4, void* stream) 
 int64_t dns_tv_workspace_bytes(int n) {
   int64_t n3 = (int64_t)n * n * n;
   int64_t Q = ((n3 + kTile - 1) / kTile) * kTile;
-  return 4096 + 16384 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + kOutP)) + 10 * 256;
+  return 4096 + 16384 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + 40)) + 10 * 256;
 }
 
 int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
@@ -1133,7 +1163,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   float* Xst = c.take<float>(Q * kIn1);
   float* Hc = c.take<float>(Q * 32);
   float* dHc = c.take<float>(Q * 64);
-  float* dOc = c.take<float>(Q * kOutP);
+  float* dOc = c.take<float>(Q * 40);   // fp32 rows of 36, or the 5-chunk tile image of the tcgen05 path
   uint4* wc_tc = c.take<uint4>(1024);
   const bool tc = use_tensor_cores();
   static bool attr = false;
@@ -1156,6 +1186,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   pa.n = n; pa.voxel = a->voxel; pa.G = a->grid; pa.table = (const float2*)a->table;
   pa.n_tiles_host = tiles; pa.WTc = WTc; pa.occ = occ; pa.docc = docc;
   pa.Xst = Xst; pa.Hc = Hc; pa.dHc = dHc; pa.dOc = dOc;
+  pa.Ximg = (uint4*)Xst; pa.Himg = (uint4*)Hc; pa.dHimg = (uint4*)dHc; pa.dOimg = (uint4*)dOc;
   pa.d_table = (float2*)a->d_table; pa.need_dparams = a->need_dparams; pa.need_drays = 0;
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT);
   PhaseScope* pht = new PhaseScope(phTvFwd, st, 4);
@@ -1175,8 +1206,20 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
     else k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
     if (int e = check_launch("tv bwd")) return e;
     int e = 0;
-    e |= launch_dw_gemm(dHc, 64, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st);
-    e |= launch_dw_gemm(dOc, kOutP, 1, Hc, 32, 32, Q, nullptr, tiles, nullptr, a->d_coarse + 2560, 32, 0, st);
+    if (tc) {
+      DwImgArgs g;
+      memset(&g, 0, sizeof(g));
+      g.L = DwImg{pa.Ximg, 10, 0, 10, kIn1}; g.Cc = DwImg{pa.dHimg, 4, 0, 4, 32};
+      g.RS = kTile; g.subs_per_tile = 1; g.n_tiles_host = tiles;
+      g.out0 = a->d_coarse; g.split = 32; g.sl0 = 1; g.sc0 = kIn1;
+      e |= launch_dw_img(g, st);
+      g.L = DwImg{pa.dOimg, 5, 0, 5, 1}; g.Cc = DwImg{pa.Himg, 4, 0, 4, 32};
+      g.out0 = a->d_coarse + 2560; g.sl0 = 32; g.sc0 = 1;
+      e |= launch_dw_img(g, st);
+    } else {
+      e |= launch_dw_gemm(dHc, 64, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st);
+      e |= launch_dw_gemm(dOc, kOutP, 1, Hc, 32, 32, Q, nullptr, tiles, nullptr, a->d_coarse + 2560, 32, 0, st);
+    }
     if (e) return DNS_ERR_CUDA;
   }
   return DNS_OK;

@@ -45,6 +45,12 @@ struct RayArgs {
   float* dpre;   // [Pc][4]
   float* dlogit; // [Nc][C4]
   float* Hbar;   // [Nc][32]
+  // tcgen05 path: per-CTA bf16 hi/lo tile images [cta][sub][half][chunk][RS rows] over the fp32 regions above
+  uint4* X2img;    // 14 chunks
+  uint4* dH2img;   // 8 chunks: colour | logit hidden gradients
+  uint4* Hcolimg;  // 4 chunks
+  uint4* dpreimg;  // 2 chunks (3 used columns)
+  int RS;          // rows per sub-tile (T or T/2)
   int need_dparams, need_drays, need_dfeat;
 };
 
@@ -87,6 +93,12 @@ struct PointArgs {
   float* dHf;
   float* dOc;   // [Q][36]
   float* dOf;
+  // tcgen05 path: the same stashes as bf16 hi/lo tile images  [tile][half][chunk][128 slots][8 x bf16]
+  // (they overlay the fp32 regions above; chunks per half: X 10, H / dH 8 (4 without experts), dOut 10 (5))
+  uint4* Ximg;
+  uint4* Himg;
+  uint4* dHimg;
+  uint4* dOimg;
   // losses / gradients
   float lam_lt, lam_fs, lam_op, trunc, sigma;
   float* raw;

@@ -21,6 +21,8 @@
 //
 // One CTA owns a contiguous range of tiles, keeps the accumulator in TMEM across them and flushes it
 // with atomics once per range (or when the class of a class-grouped tile stream changes).
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -199,7 +201,10 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
     const int cls = a.tile_class ? a.tile_class[t] : 0;
     int te = t + 1;
     while (te < t1 && (a.tile_class ? a.tile_class[te] : 0) == cls) ++te;   // run of equal-class tiles [t, te)
-    if (cls >= 0) {
+    // tiles without an expert (class < 0) still feed class-independent outputs
+    float* const o0 = (cls >= 0 || a.cls0 == 0) ? a.out0 + (int64_t)(cls < 0 ? 0 : cls) * a.cls0 : nullptr;
+    float* const o1 = (a.out1 && (cls >= 0 || a.cls1 == 0)) ? a.out1 + (int64_t)(cls < 0 ? 0 : cls) * a.cls1 : nullptr;
+    if (o0 || o1) {
       if (tid == 0) {
         const int n = (te - t) * a.subs_per_tile;
         const int64_t sub0 = (int64_t)t * a.subs_per_tile;
@@ -244,8 +249,6 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
       __syncthreads();
       tc_fence_after();
       {
-        float* o0 = a.out0 + (int64_t)cls * a.cls0;
-        float* o1 = a.out1 ? a.out1 + (int64_t)cls * a.cls1 : nullptr;
         const int l = tid;
         for (int c0 = 0; c0 < nC16; c0 += 16) {
           float v[16];
@@ -255,8 +258,9 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
             for (int i = 0; i < 16; ++i) {
               const int c = c0 + i;
               if (c < a.Cc.n_valid && v[i] != 0.f) {
-                if (c < a.split) atomicAdd(o0 + (int64_t)l * a.sl0 + (int64_t)c * a.sc0, v[i]);
-                else if (o1) atomicAdd(o1 + (int64_t)l * a.sl1 + (int64_t)(c - a.split) * a.sc1, v[i]);
+                if (c < a.split) {
+                  if (o0) atomicAdd(o0 + (int64_t)l * a.sl0 + (int64_t)c * a.sc0, v[i]);
+                } else if (o1) atomicAdd(o1 + (int64_t)l * a.sl1 + (int64_t)(c - a.split) * a.sc1, v[i]);
               }
             }
           }
@@ -404,6 +408,22 @@ int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, 
   a.sl0 = N;   // lanes = m -> row stride N
   a.sc0 = 1;
   int e = launch_dw_img(a, st);
+  if (const char* reps = getenv("DNS_IMG_REPS")) {   // isolated timing of the pipeline (scratch measurements)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int n = atoi(reps);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < n; ++i) launch_dw_img(a, st);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double bytes = (double)n_sub * RS * 32.0 * (lch + cch);
+    printf("dw_img M %d N %d rows %lld RS %d: %.3f ms/launch, %.1f GB/s\n", M, N, (long long)rows, RS, ms / n, bytes / (ms / n) * 1e-6);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   cudaStreamSynchronize(st);
   cudaFree(li);
   cudaFree(ci);

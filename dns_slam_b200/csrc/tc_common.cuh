@@ -128,5 +128,25 @@ __device__ __forceinline__ void put_chunk(unsigned char* hi_tile, unsigned char*
   *reinterpret_cast<uint4*>(hi_tile + chunk * cs + point * 16) = h;
   *reinterpret_cast<uint4*>(lo_tile + chunk * cs + point * 16) = l;
 }
+// 8 values -> bf16 hi / lo chunks of a global tile image only
+__device__ __forceinline__ void store_chunk_img(const float* v8, uint4* g_hi, uint4* g_lo) {
+  uint4 h, l;
+  split8(make_float4(v8[0], v8[1], v8[2], v8[3]), make_float4(v8[4], v8[5], v8[6], v8[7]), h, l);
+  *g_hi = h;
+  *g_lo = l;
+}
+// same, plus a copy of both halves into a global tile image for the weight-gradient GEMMs (tc.cu: k_dw_img).
+// Within one chunk neighbouring rows are 16 B apart, so a warp writes 512 contiguous bytes per store.
+__device__ __forceinline__ void put_chunk_img(unsigned char* hi_tile, unsigned char* lo_tile, int chunk, int cs, int point,
+                                              const float* v8, uint4* g_hi, uint4* g_lo) {
+  uint4 h, l;
+  split8(make_float4(v8[0], v8[1], v8[2], v8[3]), make_float4(v8[4], v8[5], v8[6], v8[7]), h, l);
+  *reinterpret_cast<uint4*>(hi_tile + chunk * cs + point * 16) = h;
+  *reinterpret_cast<uint4*>(lo_tile + chunk * cs + point * 16) = l;
+  if (g_hi) {
+    *g_hi = h;
+    *g_lo = l;
+  }
+}
 
 }  // namespace dns
