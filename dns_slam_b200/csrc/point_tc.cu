@@ -14,11 +14,10 @@
 // Operand tiles use the no-swizzle canonical UMMA layout  [chunk of 8 features][row][16 B]; the same
 // shared-memory weight copy serves as K-major B operand in the forward and MN-major B operand in the
 // backward GEMMs (see ray_tc.cu).
-#include "tc_common.cuh"
+#include "point_tc.cuh"
 
 namespace dns {
 
-constexpr int kNetTc = 1024;  // uint4 per net: W1 hi [10][32] | W1 lo | W2 hi [4][48] | W2 lo
 
 // params [n][4096] (W1[32][80] | W2[48][32]) -> bf16 hi/lo chunk tiles
 __global__ void k_prep_net80_tc(const float* __restrict__ params, uint4* __restrict__ out) {
@@ -50,37 +49,6 @@ __global__ void k_prep_net80_tc(const float* __restrict__ params, uint4* __restr
       o[640 + (i - 320)] = h;
       o[832 + (i - 320)] = l;
     }
-  }
-}
-
-// shared-memory carve (bytes)
-constexpr int kXTile = 10 * 2048;       // one half of the X tile [10 chunks][128][16]
-constexpr int kW1Tile = 10 * 64 * 16;   // one half of the combined W1 tile [10 chunks][64 rows][16]
-constexpr int kW2Tile = 4 * 48 * 16;    // one half of a W2 tile [4 chunks][48 rows][16]
-constexpr int kDOTile = 6 * 2048;       // one half of a dOut tile [6 chunks][128][16]
-
-__device__ __forceinline__ void load_weights_tc(unsigned char* W1_hi, unsigned char* W1_lo, unsigned char* W2c_hi,
-                                                unsigned char* W2f_hi, const uint4* __restrict__ wc,
-                                                const uint4* __restrict__ we, bool fine) {
-  const uint4 z4 = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 640; i += kTile) {  // combined W1: rows 0..31 coarse, 32..63 expert
-    int c = i >> 6, j = i & 63;
-    uint4 h, l;
-    if (j < 32) {
-      h = wc[c * 32 + j];
-      l = wc[320 + c * 32 + j];
-    } else if (fine) {
-      h = we[c * 32 + j - 32];
-      l = we[320 + c * 32 + j - 32];
-    } else {
-      h = l = z4;
-    }
-    reinterpret_cast<uint4*>(W1_hi)[i] = h;
-    reinterpret_cast<uint4*>(W1_lo)[i] = l;
-  }
-  for (int i = threadIdx.x; i < 384; i += kTile) {  // W2 coarse hi|lo contiguous
-    reinterpret_cast<uint4*>(W2c_hi)[i] = wc[640 + i];
-    reinterpret_cast<uint4*>(W2f_hi)[i] = fine ? we[640 + i] : z4;
   }
 }
 
@@ -491,7 +459,18 @@ static void set_attrs() {
   done = true;
 }
 
+// DNS_PT1=1 selects the one-thread-per-slot kernels of this file (A/B measurements); default: point_tc2.cu
+static bool one_thread_per_slot() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DNS_PT1");
+    v = (e && atoi(e)) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
+  if (!one_thread_per_slot()) return launch_point_fwd_tc2(mode, pa, tiles, wc, we, st);
   set_attrs();
   const size_t smem = point_fwd_tc_smem();
   if (mode == kMap) k_point_fwd_tc<kMap><<<tiles, kTile, smem, st>>>(pa, wc, we);
@@ -500,6 +479,7 @@ int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* w
   return check_launch("point_fwd_tc");
 }
 int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
+  if (!one_thread_per_slot()) return launch_point_bwd_tc2(mode, pa, tiles, wc, we, st);
   set_attrs();
   const size_t smem = point_bwd_tc_smem();
   if (mode == kMap) k_point_bwd_tc<kMap><<<tiles, kTile, smem, st>>>(pa, wc, we);

@@ -121,6 +121,73 @@ __device__ __forceinline__ void hashgrid_bwd_regs(const dns_grid& G, const float
     }
   }
 }
+// Level ranges of the same, for kernels that split one point's levels over two threads.
+template <int L0, int L1>
+__device__ __forceinline__ void hashgrid_fwd_range(const dns_grid& G, const float2* __restrict__ table, const float x[3],
+                                                   float (&out)[2 * (L1 - L0)]) {
+#pragma unroll
+  for (int l = L0; l < L1; ++l) {
+    uint32_t g[3];
+    float w[3];
+    const float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      v[c] = __ldg(table + corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+      a0 += wt * v[c].x;
+      a1 += wt * v[c].y;
+    }
+    out[2 * (l - L0)] = a0;
+    out[2 * (l - L0) + 1] = a1;
+  }
+}
+template <int L0, int L1>
+__device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const float2* __restrict__ table, float2* d_table,
+                                                   const float x[3], const float (&dg)[2 * (L1 - L0)], bool want_dx,
+                                                   float dx[3]) {
+  dx[0] = dx[1] = dx[2] = 0.f;
+#pragma unroll
+  for (int l = L0; l < L1; ++l) {
+    const float g0 = dg[2 * (l - L0)], g1 = dg[2 * (l - L0) + 1];
+    if (g0 == 0.f && g1 == 0.f) continue;
+    uint32_t g[3];
+    float w[3];
+    const float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    uint32_t idx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      idx[c] = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+    if (d_table) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+        atomicAdd(d_table + idx[c], make_float2(wt * g0, wt * g1));
+      }
+    }
+    if (want_dx) {
+      float s[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float2 v = __ldg(table + idx[c]);
+        s[c] = v.x * g0 + v.y * g1;
+      }
+      const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
+      dx[0] += sc * (wy0 * wz0 * (s[1] - s[0]) + w[1] * wz0 * (s[3] - s[2]) + wy0 * w[2] * (s[5] - s[4]) + w[1] * w[2] * (s[7] - s[6]));
+      dx[1] += sc * (wx0 * wz0 * (s[2] - s[0]) + w[0] * wz0 * (s[3] - s[1]) + wx0 * w[2] * (s[6] - s[4]) + w[0] * w[2] * (s[7] - s[5]));
+      dx[2] += sc * (wx0 * wy0 * (s[4] - s[0]) + w[0] * wy0 * (s[5] - s[1]) + wx0 * w[1] * (s[6] - s[2]) + w[0] * w[1] * (s[7] - s[3]));
+    }
+  }
+}
 __device__ __forceinline__ void put_chunk(unsigned char* hi_tile, unsigned char* lo_tile, int chunk, int cs, int point,
                                           const float* v8) {
   uint4 h, l;
