@@ -59,15 +59,16 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
         put_chunk_img(X_hi, X_lo, 2 * c, 2048, row, pe, XIMG(2 * c));
         put_chunk_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, XIMG(2 * c + 1));
       }
-      float g[16];
-      hashgrid_fwd_range<0, 8>(a.G, a.table, x, g);
-      put_chunk_img(X_hi, X_lo, 6, 2048, row, g, XIMG(6));
-      put_chunk_img(X_hi, X_lo, 7, 2048, row, g + 8, XIMG(7));
+      hashgrid_fwd_to_tile<0, 8>(a.G, a.table, x, X_hi, X_lo, row);
     } else {
-      float g[16];
-      hashgrid_fwd_range<8, 16>(a.G, a.table, x, g);
-      put_chunk_img(X_hi, X_lo, 8, 2048, row, g, XIMG(8));
-      put_chunk_img(X_hi, X_lo, 9, 2048, row, g + 8, XIMG(9));
+      hashgrid_fwd_to_tile<8, 16>(a.G, a.table, x, X_hi, X_lo, row);
+    }
+    if (ximg) {   // the two grid chunks this thread has just written (its own row): tile -> global image
+#pragma unroll
+      for (int c = 6 + 2 * grp; c < 8 + 2 * grp; ++c) {
+        ximg[c * kTile] = *reinterpret_cast<const uint4*>(X_hi + c * 2048 + row * 16);
+        ximg[(10 + c) * kTile] = *reinterpret_cast<const uint4*>(X_lo + c * 2048 + row * 16);
+      }
     }
   } else {
     const uint4 z4 = make_uint4(0, 0, 0, 0);
@@ -225,12 +226,15 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kTile2, 3) k_point_bwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
+__global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
                                                              const uint4* __restrict__ we_all) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
-  unsigned char* DOc_hi = sm;                       // dOut tiles: coarse hi | lo | fine hi | lo
+  // dOut tiles coarse hi | lo | fine hi | lo, six chunks each.  (Packing them at five chunks would fit a third CTA
+  // per SM; measured SLOWER -- 9.6 vs 7.6 ms -- because the kernel is bound by the L2 atomic units, and more
+  // resident CTAs only deepen the queue in front of them.)
+  unsigned char* DOc_hi = sm;
   unsigned char* DOc_lo = sm + kDOTile;
   unsigned char* DOf_hi = sm + 2 * kDOTile;
   unsigned char* DOf_lo = sm + 3 * kDOTile;
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_bwd_tc2(PointArgs a, const 
 #pragma unroll
     for (int c3 = 0; c3 < 3; ++c3) {
       const int c = 3 * grp + c3;
-      const bool gi = stash && c < 5;
+      const bool gi = stash && c < 5;   // channels 40..47 are zeros: not part of the global image
       put_chunk_img(DOc_hi, DOc_lo, c, 2048, row, dc + 8 * c3, gi ? doimg + c * kTile : nullptr,
                     gi ? doimg + (DOCH + c) * kTile : nullptr);
       if (MODE == kMap)
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_bwd_tc2(PointArgs a, const 
   __syncthreads();   // every accumulator row has been read; the operand tiles are free (DXS aliases them)
   if (warp == 0) tmem_dealloc(tmem_d, 128);
   float dxg[3] = {0.f, 0.f, 0.f};
-  float2* dtab = (a.need_dparams && !(a.dbg & 4)) ? a.d_table : nullptr;
+  float2* dtab = (a.need_dparams && !(a.dbg & 4) && !(a.dbg & (grp ? 32 : 16))) ? a.d_table : nullptr;
   const bool want_dx = a.need_drays != 0 && !(a.dbg & 8);
   if (valid) {
     if (grp == 0) hashgrid_bwd_range<0, 8>(a.G, a.table, dtab, x, dg, want_dx, dxg);
@@ -441,10 +445,12 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_bwd_tc2(PointArgs a, const 
   }
 }
 
+static size_t point_bwd_tc2_smem() { return point_bwd_tc_smem(); }
+
 static void set_attrs2() {
   static bool done = false;
   if (done) return;
-  const int f = (int)point_fwd_tc_smem(), b = (int)point_bwd_tc_smem();
+  const int f = (int)point_fwd_tc_smem(), b = (int)point_bwd_tc2_smem();
   cudaFuncSetAttribute(k_point_fwd_tc2<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
   cudaFuncSetAttribute(k_point_fwd_tc2<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
   cudaFuncSetAttribute(k_point_fwd_tc2<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
@@ -464,7 +470,7 @@ int launch_point_fwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* 
 }
 int launch_point_bwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
   set_attrs2();
-  const size_t smem = point_bwd_tc_smem();
+  const size_t smem = point_bwd_tc2_smem();
   if (mode == kMap) k_point_bwd_tc2<kMap><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else if (mode == kTrack) k_point_bwd_tc2<kTrack><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else k_point_bwd_tc2<kTv><<<tiles, kTile2, smem, st>>>(pa, wc, we);

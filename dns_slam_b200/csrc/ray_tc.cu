@@ -84,7 +84,11 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   const bool stash = a.need_dparams != 0;
   const int RS = a.RS, sub = t / RS, rr = t - sub * RS;
   const int64_t img_row0 = ((int64_t)blockIdx.x * T + (int64_t)sub * RS) * 2;
-  auto img = [&](uint4* base, int K, int c) -> uint4* { return stash ? base + img_row0 * K + c * RS + rr : nullptr; };
+  uint4* const x2p = stash ? a.X2img + img_row0 * 14 + rr : nullptr;     // + chunk * RS (hi), + (K + chunk) * RS (lo)
+  uint4* const dh2p = stash ? a.dH2img + img_row0 * 8 + rr : nullptr;
+  uint4* const hcp = stash ? a.Hcolimg + img_row0 * 4 + rr : nullptr;
+  uint4* const dpp = stash ? a.dpreimg + img_row0 + rr : nullptr;
+#define IMG2(p, K, c) ((p) ? (p) + (c) * RS : nullptr), ((p) ? (p) + ((K) + (c)) * RS : nullptr)
 
   // ---- stage this point's row of X = [OneBlob(x) 48 | latent 32 | pixel feature 32] as bf16 hi/lo chunks
   if (valid) {
@@ -94,8 +98,8 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     for (int c = 0; c < 3; ++c) {
       float pe[16];
       oneblob16(x[c], pe);
-      put_chunk_img(X_hi, X_lo, 2 * c, cs, t, pe, img(a.X2img, 14, 2 * c), img(a.X2img, 14, 14 + 2 * c));
-      put_chunk_img(X_hi, X_lo, 2 * c + 1, cs, t, pe + 8, img(a.X2img, 14, 2 * c + 1), img(a.X2img, 14, 15 + 2 * c));
+      put_chunk_img(X_hi, X_lo, 2 * c, cs, t, pe, IMG2(x2p, 14, 2 * c));
+      put_chunk_img(X_hi, X_lo, 2 * c + 1, cs, t, pe + 8, IMG2(x2p, 14, 2 * c + 1));
     }
     {
       float row[kOutP];
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
       occ = row[0];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        put_chunk_img(X_hi, X_lo, 6 + c, cs, t, row + 1 + 8 * c, img(a.X2img, 14, 6 + c), img(a.X2img, 14, 20 + c));
+        put_chunk_img(X_hi, X_lo, 6 + c, cs, t, row + 1 + 8 * c, IMG2(x2p, 14, 6 + c));
     }
     {
       float row[32];
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        put_chunk_img(X_hi, X_lo, 10 + c, cs, t, row + 8 * c, img(a.X2img, 14, 10 + c), img(a.X2img, 14, 24 + c));
+        put_chunk_img(X_hi, X_lo, 10 + c, cs, t, row + 8 * c, IMG2(x2p, 14, 10 + c));
     }
   } else {
     const uint4 z4 = make_uint4(0, 0, 0, 0);
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     for (int c = 0; c < 14; ++c) {
       *reinterpret_cast<uint4*>(X_hi + c * cs + t * 16) = z4;
       *reinterpret_cast<uint4*>(X_lo + c * cs + t * 16) = z4;
-      if (stash) *img(a.X2img, 14, c) = *img(a.X2img, 14, 14 + c) = z4;
+      if (stash) x2p[c * RS] = x2p[(14 + c) * RS] = z4;
     }
   }
   fence_async_smem();
@@ -244,37 +248,48 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     }
   }
   __syncthreads();
-  if (valid && s == 0) {
+  // ---- per-ray losses and their gradients: one warp per ray, lanes over samples / classes
+  for (int l2 = warp; l2 < RPC; l2 += (T >> 5)) {
+    const int64_t rl2 = (int64_t)blockIdx.x * RPC + l2, r2 = a.ray0 + rl2;
+    if (rl2 >= a.Nc) break;   // uniform over the warp
+    const int lane = t & 31;
     float var = 0.f, swdz = 0.f;
-    for (int j = 0; j < S; ++j) {
-      var += bs[rb + j];
-      swdz += us[rb + j];
+    for (int j = lane; j < S; j += 32) {
+      var += bs[l2 * S + j];
+      swdz += us[l2 * S + j];
     }
-    float* ro = RO + lr * 8;
-    float* rg = RG + lr * 8;
-    float* lg = LG + lr * C4;
-    const float dhat = ro[3];
-    a.pred_color[3 * r] = ro[0];
-    a.pred_color[3 * r + 1] = ro[1];
-    a.pred_color[3 * r + 2] = ro[2];
-    a.pred_depth[r] = dhat;
-    a.pred_var[r] = var;
+    float* ro = RO + l2 * 8;
+    float* rg = RG + l2 * 8;
+    float* lg = LG + l2 * C4;
     float mx = -INFINITY;
-    for (int c = 0; c < C; ++c) {
-      a.pred_logits[r * C + c] = lg[c];
-      mx = fmaxf(mx, lg[c]);
+    for (int c = lane; c < C; c += 32) {
+      const float v = lg[c];
+      a.pred_logits[r2 * C + c] = v;
+      mx = fmaxf(mx, v);
     }
-    const float gd = a.gt_depth[r];
-    const int64_t lab = a.gt_label[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      var += __shfl_xor_sync(0xffffffffu, var, o);
+      swdz += __shfl_xor_sync(0xffffffffu, swdz, o);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += __expf(lg[c] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    // scalars of the ray: evaluated by every lane (same values), written by lane 0
+    const float dhat = ro[3];
+    const float gd = a.gt_depth[r2];
+    const int64_t lab = a.gt_label[r2];
     const bool track = a.mode == kTrack;
-    const bool m = track ? (a.mask ? a.mask[r] != 0 : true) : true;
+    const bool m = track ? (a.mask ? a.mask[r2] != 0 : true) : true;
     const float n_ray = track ? (float)a.counts[cMask] : (float)a.N_total;
     float lp = 0.f, ldp = 0.f, ll = 0.f;
-    float g_rgb[3] = {0.f, 0.f, 0.f}, g_d = 0.f, g_var = 0.f, g_ce = 0.f;
+    float g_rgb[3] = {0.f, 0.f, 0.f}, g_d = 0.f, g_var = 0.f, g_ce = 0.f, lse = 0.f;
     if (m) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float e = ro[c] - a.gt_color[3 * r + c];
+        float e = ro[c] - a.gt_color[3 * r2 + c];
         lp = fmaf(e, e, lp);
         g_rgb[c] = a.lam_p * 2.f * e / (3.f * n_ray);
       }
@@ -290,27 +305,31 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
         ldp = fabsf(diff);
         g_d = a.lam_d * sgn / (float)a.counts[cDpos];
       }
-      float se = 0.f;
-      for (int c = 0; c < C; ++c) se += __expf(lg[c] - mx);
-      float lse = logf(se) + mx;
+      lse = logf(se) + mx;
       ll = lse - lg[lab];
       g_ce = a.lam_l / n_ray;
-      for (int c = 0; c < C; ++c) lg[c] = g_ce * (__expf(lg[c] - lse) - (c == lab ? 1.f : 0.f));
-    } else {
-      for (int c = 0; c < C; ++c) lg[c] = 0.f;
     }
-    for (int c = C; c < C4; ++c) lg[c] = 0.f;
-    rg[0] = g_rgb[0];
-    rg[1] = g_rgb[1];
-    rg[2] = g_rgb[2];
-    rg[3] = g_d;
-    rg[4] = g_var;
-    atomicAdd(LS + 0, lp);
-    atomicAdd(LS + 1, ldp);
-    atomicAdd(LS + 2, ll);
-    if (a.need_dparams) {
-      for (int c = 0; c < C4; ++c) a.dlogit[rl * C4 + c] = lg[c];
-      for (int j = 0; j < 32; ++j) a.Hbar[rl * 32 + j] = HB[lr * 32 + j];
+    __syncwarp();   // lg[lab] has been read by every lane before any entry is overwritten
+    for (int c = lane; c < C4; c += 32) {
+      const float g = (m && c < C) ? g_ce * (__expf(lg[c] - lse) - (c == lab ? 1.f : 0.f)) : 0.f;
+      lg[c] = g;
+      if (a.need_dparams) a.dlogit[rl2 * C4 + c] = g;
+    }
+    if (a.need_dparams) a.Hbar[rl2 * 32 + lane] = HB[l2 * 32 + lane];
+    if (lane == 0) {
+      a.pred_color[3 * r2] = ro[0];
+      a.pred_color[3 * r2 + 1] = ro[1];
+      a.pred_color[3 * r2 + 2] = ro[2];
+      a.pred_depth[r2] = dhat;
+      a.pred_var[r2] = var;
+      rg[0] = g_rgb[0];
+      rg[1] = g_rgb[1];
+      rg[2] = g_rgb[2];
+      rg[3] = g_d;
+      rg[4] = g_var;
+      atomicAdd(LS + 0, lp);
+      atomicAdd(LS + 1, ldp);
+      atomicAdd(LS + 2, ll);
     }
   }
   __syncthreads();
@@ -363,8 +382,8 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     }
     if (stash) {   // colour hidden activations (zeros for absent points) and the pre-sigmoid colour gradient
 #pragma unroll
-      for (int c = 0; c < 4; ++c) store_chunk_img(h + 8 * c, img(a.Hcolimg, 4, c), img(a.Hcolimg, 4, 4 + c));
-      store_chunk_img(dp, img(a.dpreimg, 1, 0), img(a.dpreimg, 1, 1));
+      for (int c = 0; c < 4; ++c) store_chunk_img(h + 8 * c, hcp + c * RS, hcp + (4 + c) * RS);
+      store_chunk_img(dp, dpp, dpp + RS);
     }
     if (valid) {
       const float* qv = QV + lr * 32;
@@ -379,7 +398,8 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   // ---- backward GEMM: dX = dH . W1  (A = dH K-major over hidden; B = W1 MN-major: features contiguous)
 #pragma unroll
   for (int c = 0; c < 8; ++c)   // invalid threads hold zeros
-    put_chunk_img(D_hi, D_lo, c, cs, t, h + 8 * c, img(a.dH2img, 8, c), img(a.dH2img, 8, 8 + c));
+    put_chunk_img(D_hi, D_lo, c, cs, t, h + 8 * c, IMG2(dh2p, 8, c));
+#undef IMG2
   fence_async_smem();
   tc_fence_before();
   __syncthreads();

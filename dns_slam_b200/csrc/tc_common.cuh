@@ -148,6 +148,38 @@ __device__ __forceinline__ void hashgrid_fwd_range(const dns_grid& G, const floa
     out[2 * (l - L0) + 1] = a1;
   }
 }
+// Rolled variant for the forward tile: each level's feature pair goes straight into the bf16 hi / lo operand tile
+// (4 bytes at  chunk 6 + l/4, row, element pair l%4), so no per-thread feature array exists and the loop body is
+// emitted twice instead of eight times (the fully unrolled form showed instruction-fetch stalls in ncu).
+template <int L0, int L1>
+__device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const float2* __restrict__ table, const float x[3],
+                                                     unsigned char* X_hi, unsigned char* X_lo, int row) {
+#pragma unroll 2
+  for (int l = L0; l < L1; ++l) {
+    uint32_t g[3];
+    float w[3];
+    const float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      v[c] = __ldg(table + corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+      a0 += wt * v[c].x;
+      a1 += wt * v[c].y;
+    }
+    const uint32_t h = cvt_bf16x2(a0, a1);
+    const uint32_t lo = cvt_bf16x2(a0 - __uint_as_float(h << 16), a1 - __uint_as_float(h & 0xffff0000u));
+    const int off = (6 + (l >> 2)) * 2048 + row * 16 + (l & 3) * 4;
+    *reinterpret_cast<uint32_t*>(X_hi + off) = h;
+    *reinterpret_cast<uint32_t*>(X_lo + off) = lo;
+  }
+}
 template <int L0, int L1>
 __device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const float2* __restrict__ table, float2* d_table,
                                                    const float x[3], const float (&dg)[2 * (L1 - L0)], bool want_dx,
