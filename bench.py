@@ -388,14 +388,19 @@ def _iteration_timings(shape, n_class, dev):
     def track():
         slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, n_it, s["cam_lr"], lambda it: td[it])
     t_track = _time_cuda(track, 3, 1) / n_it
-    # marginal cost of a CUDA-graph-replayed iteration: (210 - 110 iterations) / 100, capture cost cancels out
-    def track_graph(n):
-        return lambda: slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, n, s["cam_lr"], lambda it: td[it % n_it],
-                                        use_graph=True)
-    track_graph(20)()
-    t_long = min(_time_cuda(track_graph(210), 1, 0) for _ in range(2))
-    t_short = min(_time_cuda(track_graph(110), 1, 0) for _ in range(2))
-    t_track_graph = (t_long - t_short) / 100.0
+    # device time of one CUDA-graph-replayed iteration: events around 100 replays (slam.graph_timing), best of 3
+    def graph_ms(fn):
+        best = None
+        for _ in range(3):
+            slam.graph_timing = {}
+            fn()
+            ms = slam.graph_timing.get("replay_ms_per_iteration")
+            slam.graph_timing = None
+            if ms is not None:
+                best = ms if best is None else min(best, ms)
+        return best
+    t_track_graph = graph_ms(lambda: slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, 103, s["cam_lr"],
+                                                      lambda it: td[it % n_it], use_graph=True))
     mp = slam.MapperCore(cam, dec, s["mapping_pixels"], 32, 15,
                          lambdas=dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0,
                                       fs=s["lambda_fs"], op=s["lambda_opacity"]),
@@ -410,15 +415,9 @@ def _iteration_timings(shape, n_class, dev):
         slam.map_optimize(mp, target, refer, sc["feats"], est_list, m_it, s["lr"], s["BA_cam_lr"], True, [],
                           lambda it: md[it], lambda it: tv[it])
     t_map = _time_cuda(mapit, 2, 1) / m_it
-    big, small = 64, 34
     mdg, tvg = bench_util.mapping_draws(sc, s["mapping_pixels"], 8)
-
-    def map_graph(n):
-        return lambda: slam.map_optimize(mp, target, refer, sc["feats"], est_list, n, s["lr"], s["BA_cam_lr"], True, [],
-                                         lambda it: mdg[it % 8], lambda it: tvg[it % 8], use_graph=True)
-    map_graph(6)()
-    t_map_graph = (min(_time_cuda(map_graph(big), 1, 0) for _ in range(2))
-                   - min(_time_cuda(map_graph(small), 1, 0) for _ in range(2))) / (big - small)
+    t_map_graph = graph_ms(lambda: slam.map_optimize(mp, target, refer, sc["feats"], est_list, 43, s["lr"], s["BA_cam_lr"], True, [],
+                                                     lambda it: mdg[it % 8], lambda it: tvg[it % 8], use_graph=True))
     return {"tracking_ms_per_iteration": t_track, "tracking_ms_per_iteration_cuda_graph": t_track_graph,
             "tracking_rays": s["tracking_pixels"],
             "mapping_ms_per_iteration": t_map, "mapping_ms_per_iteration_cuda_graph": t_map_graph,

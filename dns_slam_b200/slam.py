@@ -15,14 +15,64 @@ from . import _lib, fused
 BOTTOM = [0.0, 0.0, 0.0, 1.0]
 
 
-def quad2rotation(quad):
-    """utils/common.py:406-429 (device-safe)."""
+def _quad2rotation_formula(quad):
     qr, qi, qj, qk = quad[:, 0], quad[:, 1], quad[:, 2], quad[:, 3]
     two_s = 2.0 / (quad * quad).sum(-1)
     rows = [1 - two_s * (qj ** 2 + qk ** 2), two_s * (qi * qj - qk * qr), two_s * (qi * qk + qj * qr),
             two_s * (qi * qj + qk * qr), 1 - two_s * (qi ** 2 + qk ** 2), two_s * (qj * qk - qi * qr),
             two_s * (qi * qk - qj * qr), two_s * (qj * qk + qi * qr), 1 - two_s * (qi ** 2 + qj ** 2)]
     return torch.stack(rows, -1).reshape(quad.shape[0], 3, 3)
+
+
+_QUAD_HESS = {}
+
+
+def _quad_hessian(device):
+    """C[m,a,b,p] = d^2 A_ab / dq_m dq_p of the quadratic form A(q) with R = I + (2/|q|^2) A(q): a constant."""
+    key = str(device)
+    if key not in _QUAD_HESS:
+        def A(q):
+            r, i, j, k = q[0], q[1], q[2], q[3]
+            return torch.stack([-(j * j + k * k), i * j - k * r, i * k + j * r,
+                                i * j + k * r, -(i * i + k * k), j * k - i * r,
+                                i * k - j * r, j * k + i * r, -(i * i + j * j)]).reshape(3, 3)
+        q0 = torch.zeros(4, dtype=torch.float64)
+        H = torch.stack([torch.autograd.functional.hessian(lambda q, a=a, b=b: A(q)[a, b], q0)
+                         for a in range(3) for b in range(3)]).reshape(3, 3, 4, 4)       # [a,b,m,p]
+        _QUAD_HESS[key] = H.permute(2, 0, 1, 3).contiguous().to(torch.float32).to(device)
+    return _QUAD_HESS[key]
+
+
+class _Quad2Rot(torch.autograd.Function):
+    """Forward: the reference's element-wise formula, evaluated without a graph (same values).  Backward: the
+    closed form  dL/dq = s (G : dA/dq) - s^2 q (G : A),  s = 2/|q|^2, A = (R - I)/s, in three small tensor ops
+    instead of the ~150 scalar-sized autograd kernels the formula leaves behind (they dominated a graph-replayed
+    iteration)."""
+
+    @staticmethod
+    def forward(ctx, quad):
+        with torch.no_grad():
+            R = _quad2rotation_formula(quad)
+        ctx.save_for_backward(quad, R)
+        return R
+
+    @staticmethod
+    def backward(ctx, G):
+        quad, R = ctx.saved_tensors
+        C = _quad_hessian(quad.device)
+        s = 2.0 / (quad * quad).sum(-1)                                    # [B]
+        dA = torch.einsum("mabp,np->nmab", C, quad)                        # [B,4,3,3]
+        term1 = s[:, None] * (dA * G[:, None]).sum((-1, -2))               # [B,4]
+        eye = torch.eye(3, device=quad.device, dtype=quad.dtype)
+        GA = ((R - eye) * G).sum((-1, -2)) / s                             # G : A
+        return term1 - (s * s * GA)[:, None] * quad
+
+
+def quad2rotation(quad):
+    """utils/common.py:406-429 (device-safe)."""
+    if quad.requires_grad and torch.is_grad_enabled():
+        return _Quad2Rot.apply(quad)
+    return _quad2rotation_formula(quad)
 
 
 def get_rotation_from_quad(quad):
@@ -70,15 +120,27 @@ def class_balanced_indices(tables, n, draws):
     counts_h, starts_h = tables.counts_h, tables.starts_h
     n_class = len(counts_h)
     n_k = n // n_class
-    out, di = [], 0
-    for c in range(n_class):
-        m = n - n_k * (n_class - 1) if c == 0 else n_k
-        if counts_h[c] == 1:
-            out.append(order[starts_h[c]].reshape(1).repeat(m))
-        else:
-            out.append(order[starts_h[c] + draws[di].to(order.device)])
-            di += 1
-    return torch.cat(out, -1), di
+    # One gather for all classes: out[j] = order[start(class of slot j) + draw_j].  The slot -> start table is
+    # fixed per frame and n (cached on the tables object); a class with a single pixel takes offset 0.
+    cache = tables.__dict__.setdefault("_slot_cache", {})
+    if n not in cache:
+        base, keep = [], []
+        for c in range(n_class):
+            m = n - n_k * (n_class - 1) if c == 0 else n_k
+            base += [starts_h[c]] * m
+            keep += [counts_h[c] != 1] * m
+        base_t = torch.tensor(base, dtype=torch.int64, device=order.device)
+        pos = None if all(keep) else torch.nonzero(torch.tensor(keep, device=order.device)).reshape(-1)
+        cache[n] = (base_t, pos, sum(1 for c in counts_h if c != 1))
+    base_t, pos, n_used = cache[n]
+    flat = torch.cat([d.reshape(-1) for d in draws[:n_used]], 0).to(order.device) if n_used else None
+    if pos is None:
+        off = flat
+    else:
+        off = torch.zeros_like(base_t)
+        if flat is not None:
+            off[pos] = flat
+    return order[base_t + off], n_used
 
 
 class TrackerCore:
@@ -144,11 +206,16 @@ class MapperCore:
         window = (0, self.H, 0, self.W)
         acc = {k: [] for k in ("gt_color", "gt_depth", "gt_label", "rays_o", "rays_d", "z_vals", "mask", "features")}
         target_idx = target_frames["kf_idx"]
+        # all target poses in ONE evaluation of the quaternion formula (same per-element arithmetic)
+        R_all = quad2rotation(torch.stack(list(quad_list), 0))
+        T_all = torch.stack(list(T_list), 0)
+        c2w_all = torch.cat((torch.cat((R_all, T_all[:, :, None]), -1),
+                             fused.bottom_row(R_all.device)[None].expand(n_t, 1, 4)), 1)
         for i in range(n_t):
             fr = target_frames["frames"][i]
-            R = get_rotation_from_quad(quad_list[i])
+            R = R_all[i]
             T = T_list[i]
-            cur_c2w = c2w_from_quad_T(quad_list[i], T)
+            cur_c2w = c2w_all[i]
             dev = R.device
             idx1 = draws[i]["idx_uniform"].to(dev)
             idx2, _ = class_balanced_indices(target_frames["class_tables"][i], n_pixels // 3, draws[i]["class_draws"])
@@ -166,7 +233,7 @@ class MapperCore:
                     c2w = cur_c2w.detach()
                 elif rid in target_idx:
                     t = target_idx.index(rid)
-                    c2w = c2w_from_quad_T(quad_list[t], T_list[t]).detach()
+                    c2w = c2w_all[t].detach()
                 else:
                     c2w = refer_frames["est_c2w"][i][k].detach()
                 w2c.append(fused.rigid_inverse(c2w))
@@ -249,6 +316,25 @@ def uniq_class_indices(tables, n, class_list, draws):
     return torch.cat(out, -1), di
 
 
+# Benchmarks set this to a dict: the graph loops then bracket their replays with CUDA events and store
+# ``replay_ms_per_iteration`` (device time of one replayed iteration, draw uploads included).
+graph_timing = None
+
+
+def _timed_replays(n, body):
+    if graph_timing is None or n <= 0:
+        for it in range(n):
+            body(it)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(n):
+        body(it)
+    e1.record()
+    e1.synchronize()
+    graph_timing["replay_ms_per_iteration"] = e0.elapsed_time(e1) / n
+
+
 def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR=False,
                 use_graph=False):
     """The pose-optimisation loop of ``Tracker.run`` (slams/tracking.py:304-346): Adam over
@@ -291,8 +377,8 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
     T = est_c2w[:3, 3].detach().clone().to(dev).requires_grad_(True)
     opt = torch.optim.Adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
                             {"params": [quad], "lr": cam_lr}], capturable=True)
-    d0 = draws_fn(0)
-    static = {k: v.to(dev).clone() for k, v in d0.items()}
+    packed = _PackedStatic(draws_fn(0), dev)
+    static = packed.static
     best_loss = torch.full((), 1e10, device=dev)
     best = torch.cat((quad, T), 0).detach().clone()
     hist = torch.zeros(n_iters, device=dev)
@@ -319,20 +405,18 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for it in range(n_warm):
-            for k, v in draws_fn(it).items():
-                static[k].copy_(v)
+            packed.update(draws_fn(it))
             one()
     torch.cuda.current_stream().wait_stream(side)
     if n_iters > n_warm:
-        for k, v in draws_fn(n_warm).items():
-            static[k].copy_(v)
+        packed.update(draws_fn(n_warm))
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             one()
-        for it in range(n_warm, n_iters):          # capture only records: the captured iteration is replayed too
-            for k, v in draws_fn(it).items():
-                static[k].copy_(v, non_blocking=True)
+        def replay(j):                             # capture only records: the captured iteration is replayed too
+            packed.update(draws_fn(n_warm + j))
             graph.replay()
+        _timed_replays(n_iters - n_warm, replay)
     return best, best_loss, hist
 
 
@@ -417,23 +501,69 @@ def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, 
     return ld
 
 
-def _to_static(d, dev):
-    if isinstance(d, torch.Tensor):
-        return d.to(dev).clone()
-    if isinstance(d, dict):
-        return {k: _to_static(v, dev) for k, v in d.items()}
-    return [_to_static(v, dev) for v in d]
+class _PackedStatic:
+    """Static device copies of a nested draw structure (dict / list of host tensors) for graph replay.
+    All leaves live in ONE device buffer and are refreshed with ONE host-to-device copy per iteration from a
+    small ring of pinned staging buffers (a mapping iteration has ~170 draw tensors; one copy each was
+    1-2 ms of launch overhead per replayed iteration)."""
 
+    RING = 4
 
-def _copy_static(dst, src):
-    if isinstance(dst, torch.Tensor):
-        dst.copy_(src, non_blocking=True)
-    elif isinstance(dst, dict):
-        for k in dst:
-            _copy_static(dst[k], src[k])
-    else:
-        for a, b in zip(dst, src):
-            _copy_static(a, b)
+    def __init__(self, template, dev):
+        self.leaves = []                      # (offset, nbytes, dtype, shape)
+        off = 0
+
+        def plan(d):
+            nonlocal off
+            if isinstance(d, torch.Tensor):
+                n = d.numel() * d.element_size()
+                self.leaves.append((off, n, d.dtype, tuple(d.shape)))
+                off = (off + n + 15) & ~15
+                return len(self.leaves) - 1
+            if isinstance(d, dict):
+                return {k: plan(v) for k, v in d.items()}
+            return [plan(v) for v in d]
+
+        self.index = plan(template)
+        self.nbytes = max(off, 16)
+        self.dev_buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)
+        self.host = [torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory() for _ in range(self.RING)]
+        self.done = [None] * self.RING
+        self.turn = 0
+        self.static = self._views(self.dev_buf, self.index)
+        self.update(template)
+
+    def _leaf(self, buf, i):
+        off, n, dt, shape = self.leaves[i]
+        return buf[off:off + n].view(dt).view(shape)
+
+    def _views(self, buf, idx):
+        if isinstance(idx, int):
+            return self._leaf(buf, idx)
+        if isinstance(idx, dict):
+            return {k: self._views(buf, v) for k, v in idx.items()}
+        return [self._views(buf, v) for v in idx]
+
+    def _fill(self, buf, idx, src):
+        if isinstance(idx, int):
+            self._leaf(buf, idx).copy_(src)
+        elif isinstance(idx, dict):
+            for k, v in idx.items():
+                self._fill(buf, v, src[k])
+        else:
+            for v, s in zip(idx, src):
+                self._fill(buf, v, s)
+
+    def update(self, src):
+        k = self.turn
+        self.turn = (k + 1) % self.RING
+        if self.done[k] is not None:
+            self.done[k].synchronize()        # the copy that last read this staging buffer has finished
+        self._fill(self.host[k], self.index, src)
+        self.dev_buf.copy_(self.host[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.done[k] = ev
 
 
 def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,
@@ -459,8 +589,8 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
         groups += [{"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
                    {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}]
     opt = torch.optim.Adam(groups, capturable=True)
-    static_d = _to_static(draws_fn(0), dev)
-    static_tv = _to_static(list(tv_draws_fn(0)), dev)
+    packed = _PackedStatic([draws_fn(0), list(tv_draws_fn(0))], dev)
+    static_d, static_tv = packed.static
     mapper.inside_ok = None
     last = {}
 
@@ -479,19 +609,17 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for it in range(3):
-            _copy_static(static_d, draws_fn(it))
-            _copy_static(static_tv, list(tv_draws_fn(it)))
+            packed.update([draws_fn(it), list(tv_draws_fn(it))])
             one()
     torch.cuda.current_stream().wait_stream(side)
     graph = torch.cuda.CUDAGraph()
-    _copy_static(static_d, draws_fn(3))
-    _copy_static(static_tv, list(tv_draws_fn(3)))
+    packed.update([draws_fn(3), list(tv_draws_fn(3))])
     with torch.cuda.graph(graph):
         one()
-    for it in range(3, n_iters):
-        _copy_static(static_d, draws_fn(it))
-        _copy_static(static_tv, list(tv_draws_fn(it)))
+    def replay(j):
+        packed.update([draws_fn(3 + j), list(tv_draws_fn(3 + j))])
         graph.replay()
+    _timed_replays(n_iters - 3, replay)
     ok = bool(mapper.inside_ok)          # the single host read of the loop
     mapper.inside_ok = None
     mapper.last_graph_ok = ok

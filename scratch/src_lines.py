@@ -36,3 +36,7 @@ print(f"total warp instr {tot_i}, samples {tot_s}")
 print("--- by samples")
 for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{100*a[1]/max(tot_s,1):5.1f}% smp {100*a[0]/max(tot_i,1):5.1f}% ins  {f}:{l}  {a[2].strip()[:110]}")
+
+print("--- by instructions")
+for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    print(f"{100*a[0]/max(tot_i,1):5.1f}% ins {100*a[1]/max(tot_s,1):5.1f}% smp  {f}:{l}  {a[2].strip()[:110]}")
