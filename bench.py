@@ -365,7 +365,35 @@ def _extra_configs(args, dev):
     # T_iter: whole iterations incl. sampling, feature matching + Merge, TV, Adam
     for shape in ("replica", "scannet"):
         out["iteration_" + shape] = _iteration_timings(shape, args.n_class, dev)
+    out["inference_replica"] = _inference_timings("replica", args.n_class, dev)
     return out
+
+
+def _inference_timings(shape, n_class, dev):
+    """Inference path: one full-frame render (every pixel x 47 samples, frame_vis of
+    slams/mapping.py:636-690) and free-point queries at the mesh-extraction batch size (meshing.py:640-655)."""
+    from dns_slam_b200 import bench_util, inference, synthetic as syn
+    dec = bench_util.make_decoder(shape, n_class, dev, seed=1)
+    sc = bench_util.slam_scene(shape, n_class, dev, seed=2, n_target=1)
+    cam = sc["cam"]
+    g = torch.Generator().manual_seed(4)
+    ts, tz = torch.rand(15, generator=g), torch.rand(15, generator=g)
+    refer_w2c = torch.inverse(sc["poses"][0])
+
+    def frame():
+        inference.render_frame(cam, dec, sc["frames"][0], sc["poses"][1], refer_w2c, sc["feats"][0][:1].contiguous(),
+                               32, 15, ts, tz, n_pts_batch=131072)
+    t_frame = _time_cuda(frame, 3, 1)
+    P = 1 << 21
+    lo, hi = dec.bound[:, 0].float(), dec.bound[:, 1].float()
+    pts = lo + (hi - lo) * torch.rand(P, 3, generator=g).to(dev)
+    pix = (torch.randn(P, 32, generator=g) * 0.3).to(dev)
+    lab = torch.randint(0, n_class, (P,), generator=g).to(dev)
+    t_q = _time_cuda(lambda: inference.eval_points(dec, pts, pix, lab, "fine"), 5, 2)
+    return {"full_frame_render_ms": t_frame, "frame_pixels": cam["H"] * cam["W"], "n_samples": 47,
+            "frame_rays_per_s": cam["H"] * cam["W"] / (t_frame * 1e-3),
+            "eval_points_ms_per_2M": t_q, "eval_points_per_s": P / (t_q * 1e-3),
+            "grid_256^3_query_s_est": (256 ** 3 / P) * t_q * 1e-3}
 
 
 def _iteration_timings(shape, n_class, dev):

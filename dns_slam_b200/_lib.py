@@ -47,7 +47,7 @@ class RenderArgs(C.Structure):
                 ("d_experts", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("d_features", _P),
                 ("workspace", _P), ("workspace_bytes", C.c_int64),
                 ("n_rays_total", C.c_int64), ("ray_offset", C.c_int64), ("gt_label_all", _P),
-                ("global_counts", _P)]
+                ("global_counts", _P), ("forward_only", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class TvArgs(C.Structure):

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   float sumu = 0.f;
   if (valid)
     for (int j = 0; j < S; ++j) sumu += us[rb + j];
-  const float w = valid ? u / sumu : 0.f;
+  const float w = valid ? (a.fwd_only == 2 ? 1.f : u / sumu) : 0.f;   // 2: free-point query, no compositing
   __syncthreads();
   if (valid) {
 #pragma unroll
@@ -337,6 +337,12 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     atomicAdd(a.raw + rP, LS[0]);
     atomicAdd(a.raw + rD, LS[1]);
     atomicAdd(a.raw + rL, LS[2]);
+  }
+  if (a.fwd_only) {   // inference: predictions are out, nothing to differentiate (uniform over the CTA)
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+    return;
   }
   for (int e = t; e < RPC * 32; e += T) {
     int l2 = e >> 5, j = e & 31;

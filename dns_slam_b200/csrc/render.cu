@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(256) k_ray(RayArgs a) {
   float sumu = 0.f;
   if (valid)
     for (int j = 0; j < S; ++j) sumu += us[rb + j];
-  const float w = valid ? u / sumu : 0.f;
+  const float w = valid ? (a.fwd_only == 2 ? 1.f : u / sumu) : 0.f;   // 2: free-point query, no compositing
   __syncthreads();
   // stage w * {logit hidden (32), rgb (3), z} and reduce per ray
   if (valid) {
@@ -611,6 +611,7 @@ __global__ void __launch_bounds__(256) k_ray(RayArgs a) {
     atomicAdd(a.raw + rD, LS[1]);
     atomicAdd(a.raw + rL, LS[2]);
   }
+  if (a.fwd_only) return;   // inference (uniform over the CTA)
   // QV[ray][j] = sum_c d_logit[c] * W2l[c][j]
   for (int e = t; e < RPC * 32; e += T) {
     int l2 = e >> 5, j = e & 31;
@@ -986,7 +987,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.lam_lt = a->lambda_lt; pa.lam_fs = a->lambda_fs; pa.lam_op = a->lambda_op;
     pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
-    pa.need_dparams = a->need_dparams; pa.need_drays = a->need_drays;
+    pa.need_dparams = a->need_dparams && !a->forward_only; pa.need_drays = a->need_drays;
     { const char* e = getenv("DNS_DBG"); pa.dbg = e ? atoi(e) : 0; }
     if (map) {
       PhaseScope phc(phClassPrep, st, 5);
@@ -1033,8 +1034,10 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.X2 = w.X2; ra.dH2 = w.dH2; ra.Hcol = w.Hcol; ra.dpre = w.dpre; ra.dlogit = w.dlogit; ra.Hbar = w.Hbar;
     ra.X2img = (uint4*)w.X2; ra.dH2img = (uint4*)w.dH2; ra.Hcolimg = (uint4*)w.Hcol; ra.dpreimg = (uint4*)w.dpre;
     ra.RS = T <= 96 ? T : T / 2;   // sub-tile rows of the ray-side images (multiple of 16; keeps >= 3 pipeline stages)
-    ra.need_dparams = a->need_dparams; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d;
-    ra.need_dfeat = a->need_dfeat && a->d_features;
+    const bool fwd_only = a->forward_only != 0;
+    ra.fwd_only = a->forward_only;
+    ra.need_dparams = a->need_dparams && !fwd_only; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d && !fwd_only;
+    ra.need_dfeat = a->need_dfeat && a->d_features && !fwd_only;
     pa.need_drays = ra.need_drays;
     {
       PhaseScope phr(phRay, st, 1);
@@ -1045,7 +1048,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       }
     }
     if (int e = check_launch("ray")) return e;
-    {
+    if (!fwd_only) {
       PhaseScope phb(phPointBwd, st, 1);
       if (tc) {
         if (int e = launch_point_bwd_tc(map ? kMap : kTrack, pa, tiles_max, w.wc_tc, w.we_tc, st)) return e;
@@ -1058,7 +1061,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     if (map && a->coarse_out)
       k_unpad33<<<(int)((Pc * DNS_LATENT + 255) / 256), 256, 0, st>>>(w.coarse36, a->coarse_out + p0 * DNS_LATENT, Pc);
 
-    if (a->need_dparams) {
+    if (a->need_dparams && !fwd_only) {
       PhaseScope phg(phDwGemm, st, map ? 8 : 6);
       const int64_t Qrows = (int64_t)tiles_max * kTile;
       const int* ntd = map ? w.counts + cTiles : nullptr;

@@ -51,6 +51,7 @@ struct RayArgs {
   uint4* Hcolimg;  // 4 chunks
   uint4* dpreimg;  // 2 chunks (3 used columns)
   int RS;          // rows per sub-tile (T or T/2)
+  int fwd_only;    // inference: stop after the predictions
   int need_dparams, need_drays, need_dfeat;
 };
 

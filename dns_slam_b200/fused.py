@@ -163,7 +163,7 @@ def render_counts(cfg):
 
 
 def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, features, grads, need_drays,
-               need_dfeat):
+               need_dfeat, forward_only=0):
     """One ``dns_render_fwd_bwd`` call.  ``grads``: dict with optional device buffers
     ``table/coarse/color/logit/experts`` that are ACCUMULATED into (None => no parameter grads).
     Returns (losses[8], preds dict, d_rays_o, d_rays_d, d_features)."""
@@ -174,6 +174,7 @@ def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, featur
     mask8 = _fill_inputs(a, cfg)
     need_dparams = grads is not None
     a.need_dparams, a.need_drays, a.need_dfeat = int(need_dparams), int(need_drays), int(need_dfeat)
+    a.forward_only = int(forward_only)
     _lib.fill_bound(a.bound, cfg.bound)
     a.lambda_p, a.lambda_d, a.lambda_l = cfg.lam["p"], cfg.lam["d"], cfg.lam["l"]
     a.lambda_lt, a.lambda_fs, a.lambda_op = cfg.lam["lt"], cfg.lam["fs"], cfg.lam["op"]

@@ -147,6 +147,12 @@ typedef struct dns_render_args {
   int64_t ray_offset;
   const int64_t* gt_label_all;   /* [n_rays_total] labels of the whole batch */
   const int32_t* global_counts;  /* [4] all-reduced dns_render_counts output */
+  /* inference (slams/mapping.py:638-724 frame_vis, slams/meshing.py:461-498 eval_points): predictions and latents
+   * only -- no loss gradients, no backward kernels, gradient outputs untouched.
+   * 1: rays (compositing as in training); 2: free points (n_samples must be 1: rays_o holds the points, the
+   * colour / logits of the single sample are returned without the occupancy weight). */
+  int32_t forward_only;
+  int32_t reserved_;
 } dns_render_args;
 
 int64_t dns_render_workspace_bytes(int mode, int n_rays, int n_samples, int n_class, int n_class_ids);

@@ -541,3 +541,56 @@ def mapper_get_target_samples(cam, bound, decoder, frames, quad_list, T_list, re
     out = {k: v[m] for k, v in cat.items()}
     out["_inside"] = m
     return out
+
+
+# --------------------------------------------------------------------------------------
+# inference path: full-frame render and point queries
+# --------------------------------------------------------------------------------------
+def eval_points(decoder, experts, bound, pts, pixel_pts, gt_label_pts=None, stage="fine"):
+    """slams/meshing.py:461-498: occupancy / colour / label of free points.  Returns
+    (values [P,4] = rgb | occupancy with -100 outside the bound, labels [P] int64 with -1 outside, or None)."""
+    mask = ((pts[:, 0] < bound[0, 1]) & (pts[:, 0] > bound[0, 0]) & (pts[:, 1] < bound[1, 1]) & (pts[:, 1] > bound[1, 0])
+            & (pts[:, 2] < bound[2, 1]) & (pts[:, 2] > bound[2, 0]))
+    p = (pts.clone() - bound[:, 0]) / (bound[:, 1] - bound[:, 0])
+    pe, grid = decoder.pe_fn(p)
+    if stage == "coarse":
+        lat = decoder.coarse_fn(pe, features=grid)
+    else:
+        lat = fine_fn(experts, decoder.hidden_dim, pe, gt_label_pts, grid)
+    color, logits = decoder.out_fn(pe, torch.cat((lat[:, 1:], pixel_pts), -1))
+    values = torch.cat((color, lat[:, 0:1]), -1)
+    values[~mask, 3] = -100
+    if stage == "coarse":
+        return values, None
+    labels = torch.argmax(logits, -1)
+    labels[~mask] = -1
+    return values, labels
+
+
+def frame_vis_render(cam, bound, decoder, experts, frame, c2w, refer_w2c, feats, n_samples, n_surface, tape,
+                     n_pts_batch):
+    """slams/mapping.py:636-690 (frame_vis without the plotting): every pixel of the frame, rays from ``c2w``,
+    depth-guided samples, ONE reference view for the pixel features, the mapper renderer per chunk of
+    ``n_pts_batch`` rays (the class rule class(p) = label[p mod n] therefore runs per chunk).
+    refer_w2c [1,4,4], feats [1,64,h,w].  Returns (color [H,W,3], depth [H,W], label [H,W] int64)."""
+    H, W = cam["H"], cam["W"]
+    idx = torch.arange(H * W)
+    i, j = uv_from_flat(idx, 0, 0, W)
+    rays_o, rays_d = rays_from_uv(i, j, c2w[:3, :3], c2w[:3, 3], cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    gd = frame["depth"].flatten(0, 1)
+    gl = frame["label"].flatten(0, 1)
+    t = (bound.unsqueeze(0) - rays_o.detach().unsqueeze(-1)) / rays_d.detach().unsqueeze(-1)
+    far_bb = torch.min(torch.max(t, dim=2)[0], dim=1)[0].unsqueeze(-1) + 0.01
+    z = sample_along_rays(gd, n_samples, n_surface, far_bb, tape)
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
+    cols, deps, labs = [], [], []
+    for a in range(0, H * W, n_pts_batch):
+        b = min(a + n_pts_batch, H * W)
+        code, _, _ = feature_matching(H, W, cam["K"], pts[a:b].flatten(0, 1), refer_w2c, feats, decoder.merge)
+        smp = {"rays_o": rays_o[a:b].float(), "rays_d": rays_d[a:b].float(), "gt_label": gl[a:b].to(torch.int64),
+               "pts": pts[a:b].float(), "z_vals": z[a:b].float(), "features": code.reshape(b - a, z.shape[1], -1)}
+        rgb, depth, _, logits, _, _ = mapper_renderer(decoder, experts, bound, smp)
+        cols.append(rgb)
+        deps.append(depth)
+        labs.append(torch.argmax(logits, -1))
+    return torch.cat(cols, 0).reshape(H, W, 3), torch.cat(deps, 0).reshape(H, W), torch.cat(labs, 0).reshape(H, W)
