@@ -904,6 +904,10 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     set_error("render: the fused path is built for 16 levels x 2 features");
     return DNS_ERR_UNSUPPORTED;
   }
+  if (((uintptr_t)a->table & 15) || ((uintptr_t)a->d_table & 15)) {
+    set_error("render: table / d_table must be 16-byte aligned (paired corner accesses)");
+    return DNS_ERR_ARG;
+  }
   const bool map = mode == DNS_MODE_MAP;
   const int nci = map ? (a->n_class_ids < 1 ? 1 : a->n_class_ids) : 1;
   if (map && (!a->experts || !a->class_to_expert || a->n_experts < 1 || a->n_experts > nci)) {
@@ -1154,6 +1158,10 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   }
   if (!a->workspace || a->workspace_bytes < dns_tv_workspace_bytes(n)) {
     set_error("tv: workspace too small");
+    return DNS_ERR_ARG;
+  }
+  if (((uintptr_t)a->table & 15) || ((uintptr_t)a->d_table & 15)) {
+    set_error("tv: table / d_table must be 16-byte aligned (paired corner accesses)");
     return DNS_ERR_ARG;
   }
   const int64_t n3 = (int64_t)n * n * n;

@@ -121,6 +121,21 @@ __device__ __forceinline__ void hashgrid_bwd_regs(const dns_grid& G, const float
     }
   }
 }
+// Table entries of the x and x+1 corners of one cell edge.  They are neighbours in memory (dense levels: consecutive
+// indices; hashed levels: the x prime is 1, so an even x only flips bit 0); when they share an aligned 16-byte pair,
+// one 16-byte load fetches both (a quarter fewer L1 / L2 requests over the 8 corners).
+__device__ __forceinline__ void load_corner_pair(const float2* __restrict__ table, uint32_t i0, uint32_t i1, float2& v0,
+                                                 float2& v1) {
+  if ((i0 ^ i1) == 1u) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(table + (i0 & ~1u)));
+    const bool odd = i0 & 1u;
+    v0 = odd ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
+    v1 = odd ? make_float2(q.x, q.y) : make_float2(q.z, q.w);
+  } else {
+    v0 = __ldg(table + i0);
+    v1 = __ldg(table + i1);
+  }
+}
 // Level ranges of the same, for kernels that split one point's levels over two threads.
 template <int L0, int L1>
 __device__ __forceinline__ void hashgrid_fwd_range(const dns_grid& G, const float2* __restrict__ table, const float x[3],
@@ -164,8 +179,9 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
     grid_pos(x[2], sc, g[2], w[2]);
     float2 v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      v[c] = __ldg(table + corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
+    for (int c = 0; c < 8; c += 2)
+      load_corner_pair(table, corner_index(G, l, g[0], g[1] + ((c >> 1) & 1), g[2] + (c >> 2)),
+                       corner_index(G, l, g[0] + 1, g[1] + ((c >> 1) & 1), g[2] + (c >> 2)), v[c], v[c + 1]);
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -180,7 +196,7 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
     *reinterpret_cast<uint32_t*>(X_lo + off) = lo;
   }
 }
-template <int L0, int L1>
+template <int L0, int L1, bool PAIR = true>
 __device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const float2* __restrict__ table, float2* d_table,
                                                    const float x[3], const float (&dg)[2 * (L1 - L0)], bool want_dx,
                                                    float dx[3]) {
@@ -200,14 +216,26 @@ __device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const floa
     for (int c = 0; c < 8; ++c)
       idx[c] = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
     if (d_table) {
+      // The x and x+1 corners of a cell edge are neighbours in memory (dense levels: consecutive indices; hashed
+      // levels: the x prime is 1, so an even x only flips bit 0).  When they share an aligned 16-byte pair, ONE
+      // vector reduction carries both: a quarter fewer operations for the L2 atomic units that bound this kernel.
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
-        atomicAdd(d_table + idx[c], make_float2(wt * g0, wt * g1));
+      for (int c = 0; c < 8; c += 2) {
+        const float wyz = ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+        const float w0 = (1.f - w[0]) * wyz, w1 = w[0] * wyz;
+        const uint32_t i0 = idx[c], i1 = idx[c + 1];
+        if (PAIR && ((i0 ^ i1) == 1u)) {
+          const bool odd = i0 & 1u;
+          const float wa = odd ? w1 : w0, wb = odd ? w0 : w1;     // weights of entries (base, base + 1)
+          atomicAdd(reinterpret_cast<float4*>(d_table + (i0 & ~1u)), make_float4(wa * g0, wa * g1, wb * g0, wb * g1));
+        } else {
+          atomicAdd(d_table + i0, make_float2(w0 * g0, w0 * g1));
+          atomicAdd(d_table + i1, make_float2(w1 * g0, w1 * g1));
+        }
       }
     }
     if (want_dx) {
-      float s[8];
+      float s[8];   // (pairing these re-reads like the forward gathers was measured slower here: 6.9 -> 7.7 ms)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float2 v = __ldg(table + idx[c]);

@@ -155,6 +155,8 @@ typedef struct dns_render_args {
   int32_t reserved_;
 } dns_render_args;
 
+/* table and d_table must be 16-byte aligned (the kernels fetch / reduce the x, x+1 corner pair of a cell edge
+ * with one 16-byte access when both entries share an aligned pair). */
 int64_t dns_render_workspace_bytes(int mode, int n_rays, int n_samples, int n_class, int n_class_ids);
 int dns_render_fwd_bwd(const dns_render_args* a, void* stream);
 /* Local batch counts {n_mask, n_depth>0, n_front, n_band} (int32[4], device) that the loss
