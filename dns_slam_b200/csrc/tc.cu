@@ -205,45 +205,48 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
     float* const o0 = (cls >= 0 || a.cls0 == 0) ? a.out0 + (int64_t)(cls < 0 ? 0 : cls) * a.cls0 : nullptr;
     float* const o1 = (a.out1 && (cls >= 0 || a.cls1 == 0)) ? a.out1 + (int64_t)(cls < 0 ? 0 : cls) * a.cls1 : nullptr;
     if (o0 || o1) {
-      if (tid == 0) {
-        const int n = (te - t) * a.subs_per_tile;
+      const int n = (te - t) * a.subs_per_tile;   // sub-tiles of this run
+      if (tid == 32) {   // producer: bulk copies into the stage ring, as far ahead as the ring allows
         const int64_t sub0 = (int64_t)t * a.subs_per_tile;
-        int prod = 0, cons = 0;
-        while (cons < n) {
-          while (prod < n && prod - cons < n_stages) {
-            const uint32_t g = gi + prod, s = g % n_stages, ph = (g / n_stages) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            unsigned char* st = smem + (size_t)s * stage_bytes;
-            mbar_expect_tx(&full[s], 2 * (l_bytes + c_bytes));
-            const uint4* lsrc = a.L.ptr + (sub0 + prod) * l_sub + (int64_t)a.L.chunk0 * RS;
-            const uint4* csrc = a.Cc.ptr + (sub0 + prod) * c_sub + (int64_t)a.Cc.chunk0 * RS;
-            bulk_g2s(st, lsrc, l_bytes, &full[s]);                                             // L hi
-            bulk_g2s(st + l_bytes, lsrc + (int64_t)a.L.chunks_total * RS, l_bytes, &full[s]);  // L lo
-            bulk_g2s(st + 2 * l_bytes, csrc, c_bytes, &full[s]);                               // C hi
-            bulk_g2s(st + 2 * l_bytes + c_bytes, csrc + (int64_t)a.Cc.chunks_total * RS, c_bytes, &full[s]);
-            ++prod;
-          }
+        for (int prod = 0; prod < n; ++prod) {
+          const uint32_t g = gi + prod, s = g % n_stages, ph = (g / n_stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], 2 * (l_bytes + c_bytes));
+          const uint4* lsrc = a.L.ptr + (sub0 + prod) * l_sub + (int64_t)a.L.chunk0 * RS;
+          const uint4* csrc = a.Cc.ptr + (sub0 + prod) * c_sub + (int64_t)a.Cc.chunk0 * RS;
+          bulk_g2s(st, lsrc, l_bytes, &full[s]);                                             // L hi
+          bulk_g2s(st + l_bytes, lsrc + (int64_t)a.L.chunks_total * RS, l_bytes, &full[s]);  // L lo
+          bulk_g2s(st + 2 * l_bytes, csrc, c_bytes, &full[s]);                               // C hi
+          bulk_g2s(st + 2 * l_bytes + c_bytes, csrc + (int64_t)a.Cc.chunks_total * RS, c_bytes, &full[s]);
+        }
+      }
+      if (tid == 0) {    // MMA issuer: never waits for its own MMAs, only for data
+        for (int cons = 0; cons < n; ++cons) {
           const uint32_t g = gi + cons, s = g % n_stages, ph = (g / n_stages) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-#pragma unroll 1
-          for (int k = 0; k < RS / 16; ++k) {
-            const uint32_t koff = k * 256;
-            const uint64_t a_hi = umma_desc(base + koff, 128, cs), a_lo = umma_desc(base + l_bytes + koff, 128, cs);
-            const uint64_t b_hi = umma_desc(base + 2 * l_bytes + koff, 128, cs),
-                           b_lo = umma_desc(base + 2 * l_bytes + c_bytes + koff, 128, cs);
-            umma_bf16(tmem_d, a_hi, b_hi, idesc, (cons > 0 || k > 0) ? 1u : 0u);
+          // descriptors of the four operand halves at k = 0; a K step of 16 rows advances the start address by
+          // 256 B = 16 descriptor units (the issuing thread is the bottleneck of this kernel: keep its loop lean)
+          uint64_t a_hi = umma_desc(base, 128, cs), a_lo = umma_desc(base + l_bytes, 128, cs);
+          uint64_t b_hi = umma_desc(base + 2 * l_bytes, 128, cs), b_lo = umma_desc(base + 2 * l_bytes + c_bytes, 128, cs);
+          umma_bf16(tmem_d, a_hi, b_hi, idesc, cons > 0 ? 1u : 0u);
+          umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+          umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+#pragma unroll 4
+          for (int k = 1; k < RS / 16; ++k) {
+            a_hi += 16; a_lo += 16; b_hi += 16; b_lo += 16;
+            umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
             umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
             umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
           }
           umma_commit(&empty[s]);
-          ++cons;
         }
-        gi += n;
         umma_commit(&done);
         mbar_wait(&done, done_phase);
       }
+      gi += n;
       done_phase ^= 1;
       tc_fence_before();
       __syncthreads();
