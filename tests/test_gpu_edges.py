@@ -112,3 +112,34 @@ def test_tracking_all_masked_is_nan_like_reference():
     samples["mask"][5] = True
     ld, _ = fused.render_and_loss(dec, samples, _lib.MODE_TRACK, freeze_decoder=True)
     assert bool(torch.isfinite(ld["total"]))
+
+
+@pytest.mark.parametrize("N,S,C,mode", [(1, 47, 3, "map"), (131, 47, 40, "map"), (257, 33, 7, "map"), (100, 96, 5, "track"),
+                                        (37, 13, 4, "track")])
+def test_workspace_guard_bands_stay_intact(N, S, C, mode, monkeypatch):
+    """The kernels may only write inside [workspace, workspace + dns_render_workspace_bytes): the fused call runs on a
+    buffer of exactly that size cut out of a larger allocation whose borders carry a byte pattern."""
+    from dns_slam_b200 import _lib, bench_util, fused
+    dev = _dev()
+    dec, samples = bench_util.synthetic_batch("tiny", mode, N, S, C, dev, seed=3 * N + S, n_frames=1)
+    if mode == "map":
+        samples = {k: v for k, v in samples.items() if k != "mask"}
+    guard = 1 << 16
+    state = {}
+
+    def guarded(nbytes, device):
+        nbytes = int(nbytes)
+        big = torch.full((nbytes + 2 * guard + 512,), 0xCD, dtype=torch.uint8, device=device)
+        off = guard + (-(big.data_ptr() + guard)) % 256          # keep the 256-byte alignment of the carve
+        state["big"], state["off"], state["n"] = big, off, nbytes
+        return big[off:off + nbytes]
+
+    monkeypatch.setattr(fused, "workspace", guarded)
+    m = _lib.MODE_MAP if mode == "map" else _lib.MODE_TRACK
+    ld, _ = fused.render_and_loss(dec, samples, m, lambdas=LAM if mode == "map" else dict(p=5.0, d=5.0, l=0.1))
+    ld["total"].backward()
+    torch.cuda.synchronize()
+    big, off, n = state["big"], state["off"], state["n"]
+    assert bool((big[:off] == 0xCD).all()), "write below the workspace"
+    assert bool((big[off + n:] == 0xCD).all()), "write above the workspace"
+    assert torch.isfinite(ld["total"]).item()
