@@ -91,17 +91,30 @@ __global__ void k_counts(const float* __restrict__ gt_depth, const float* __rest
 // ---------------------------------------------------------------------------------------
 // class-homogeneous slot tiles (MAP): counting sort of the chunk's points by label[p mod N]
 // ---------------------------------------------------------------------------------------
-__global__ void k_class_hist(const int64_t* __restrict__ label, int64_t N, int64_t p0, int64_t Pc, int nci,
-                             int* hist, int* counts) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Pc; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t c = label[(p0 + i) % N];
-    if (c < 0 || c >= nci) {
-      counts[cErr] = 1;
-      c = 0;
+// Both passes aggregate per block in shared memory (kSortPer points per thread, classes kept in registers): one
+// global atomic per class and block instead of one per warp-level group of equal labels.
+constexpr int kSortPer = 8;
+__global__ void __launch_bounds__(256) k_class_hist(const int64_t* __restrict__ label, int64_t N, int64_t p0, int64_t Pc,
+                                                    int nci, int* hist, int* counts) {
+  extern __shared__ int sh[];   // [nci]
+  for (int c = threadIdx.x; c < nci; c += blockDim.x) sh[c] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (blockDim.x * kSortPer);
+#pragma unroll
+  for (int k = 0; k < kSortPer; ++k) {
+    const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
+    if (i < Pc) {
+      int64_t c = label[(p0 + i) % N];
+      if (c < 0 || c >= nci) {
+        counts[cErr] = 1;
+        c = 0;
+      }
+      atomicAdd(sh + (int)c, 1);
     }
-    unsigned m = __match_any_sync(__activemask(), (int)c);
-    if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(hist + c, __popc(m));
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < nci; c += blockDim.x)
+    if (sh[c]) atomicAdd(hist + c, sh[c]);
 }
 // one block: slot_start[c] (in slots), number of tiles, tile -> expert row
 __global__ void k_class_scan(const int* __restrict__ hist, int nci, const int* __restrict__ class_to_expert,
@@ -124,17 +137,37 @@ __global__ void k_class_scan(const int* __restrict__ hist, int nci, const int* _
     for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) tile_class[t] = e;
   }
 }
-__global__ void k_class_scatter(const int64_t* __restrict__ label, int64_t N, int64_t p0, int64_t Pc, int nci,
-                                const int* __restrict__ slot_start, int* cursor, int* perm) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Pc; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t c64 = label[(p0 + i) % N];
-    int c = (c64 < 0 || c64 >= nci) ? 0 : (int)c64;
-    unsigned m = __match_any_sync(__activemask(), c);
-    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(cursor + c, __popc(m));
-    base = __shfl_sync(m, base, leader);
-    perm[slot_start[c] + base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+__global__ void __launch_bounds__(256) k_class_scatter(const int64_t* __restrict__ label, int64_t N, int64_t p0, int64_t Pc,
+                                                       int nci, const int* __restrict__ slot_start, int* cursor, int* perm) {
+  extern __shared__ int sh[];   // [nci] block counts, then running ranks | [nci] block bases
+  int* cnt = sh;
+  int* bas = sh + nci;
+  for (int c = threadIdx.x; c < nci; c += blockDim.x) cnt[c] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * (blockDim.x * kSortPer);
+  int cls[kSortPer];
+#pragma unroll
+  for (int k = 0; k < kSortPer; ++k) {
+    const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
+    cls[k] = -1;
+    if (i < Pc) {
+      int64_t c64 = label[(p0 + i) % N];
+      cls[k] = (c64 < 0 || c64 >= nci) ? 0 : (int)c64;
+      atomicAdd(cnt + cls[k], 1);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < nci; c += blockDim.x) {
+    bas[c] = cnt[c] ? slot_start[c] + atomicAdd(cursor + c, cnt[c]) : 0;   // this block's range in the class region
+    cnt[c] = 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kSortPer; ++k) {
+    if (cls[k] >= 0) {
+      const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
+      perm[bas[cls[k]] + atomicAdd(cnt + cls[k], 1)] = (int)i;
+    }
   }
 }
 
@@ -910,6 +943,10 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   }
   const bool map = mode == DNS_MODE_MAP;
   const int nci = map ? (a->n_class_ids < 1 ? 1 : a->n_class_ids) : 1;
+  if (nci > 4096) {
+    set_error("render: at most 4096 class ids (got %d)", nci);
+    return DNS_ERR_UNSUPPORTED;
+  }
   if (map && (!a->experts || !a->class_to_expert || a->n_experts < 1 || a->n_experts > nci)) {
     set_error("render: MAP mode needs experts, class_to_expert and 1 <= n_experts <= n_class_ids");
     return DNS_ERR_ARG;
@@ -996,7 +1033,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     if (map) {
       PhaseScope phc(phClassPrep, st, 5);
       cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);
-      const bool whole = !sharded && ray0 == 0 && nc == N && (int64_t)N * S < 2147483647LL;
+      const bool whole = !sharded && ray0 == 0 && nc == N && (int64_t)N * S < 2147483647LL && !getenv("DNS_GENERIC_PREP");
       if (whole) {
         int rblocks = (int)((N + 255) / 256);
         rblocks = rblocks < 592 ? rblocks : 592;
@@ -1007,11 +1044,11 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
         k_perm_fill<<<tiles_max, kTile, 0, st>>>(w.slot_start, w.ray_start, w.hist, w.rays_sorted, nci, S, N, w.counts, w.perm);
       } else {
       cudaMemsetAsync(w.perm, 0xFF, (size_t)tiles_max * kTile * sizeof(int), st);
-      int64_t blocks = (Pc + 255) / 256;
-      int grid = (int)(blocks < 592 ? blocks : 592);
-      k_class_hist<<<grid, 256, 0, st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.hist, w.counts);
+      const int grid = (int)((Pc + 256 * kSortPer - 1) / (256 * kSortPer));
+      k_class_hist<<<grid, 256, nci * sizeof(int), st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.hist, w.counts);
       k_class_scan<<<1, 256, 0, st>>>(w.hist, nci, a->class_to_expert, w.slot_start, w.cursor, w.tile_class, w.counts);
-      k_class_scatter<<<grid, 256, 0, st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.slot_start, w.cursor, w.perm);
+      k_class_scatter<<<grid, 256, 2 * nci * sizeof(int), st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.slot_start, w.cursor,
+                                                                w.perm);
       }
       pa.perm = w.perm; pa.tile_class = w.tile_class;
     }

@@ -90,7 +90,8 @@ class ShardedMappingStep(MappingStep):
     def step_sharded(self, local_samples, n_total, need_drays=True, need_dfeat=True):
         lo, hi = shard_bounds(n_total, self.world_n, self.rank)
         assert local_samples["z_vals"].shape[0] == hi - lo, "local batch does not match the shard bounds"
-        labels_all = self.comm.all_gather(local_samples["gt_label"].contiguous())
+        sizes = [b - a for a, b in (shard_bounds(n_total, self.world_n, r) for r in range(self.world_n))]
+        labels_all = self.comm.all_gather(local_samples["gt_label"].contiguous(), sizes)
         cfg = self._config(local_samples)
         counts = self._local_counts(cfg)
         self.comm.all_reduce_sum(counts)
@@ -122,12 +123,18 @@ class TorchComm:
         torch.distributed.all_reduce(t, group=self.group)
         return t
 
-    def all_gather(self, t):
-        """Concatenation over ranks of possibly different-length 1-D tensors."""
+    def all_gather(self, t, sizes=None):
+        """Concatenation over ranks of possibly different-length 1-D tensors.  ``sizes`` (per-rank lengths known to the
+        caller, e.g. from shard_bounds) skips the size exchange and its device->host read."""
         world = torch.distributed.get_world_size(self.group)
-        n = torch.tensor([t.numel()], device=t.device)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        torch.distributed.all_gather(sizes, n, group=self.group)
+        if sizes is not None and len(set(sizes)) == 1:
+            out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+            torch.distributed.all_gather_into_tensor(out, t, group=self.group)
+            return out
+        if sizes is None:
+            n = torch.tensor([t.numel()], device=t.device)
+            sizes = [torch.zeros_like(n) for _ in range(world)]
+            torch.distributed.all_gather(sizes, n, group=self.group)
         mx = int(max(int(s) for s in sizes))
         pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
         pad[:t.numel()] = t
