@@ -1,47 +1,32 @@
-// Ray kernel with the two wide per-point GEMMs on tcgen05 (sm_100a).
+// Ray kernel on tcgen05, TWO threads per sample point (blockDim = 2 T, T a multiple of 128).
 //
-// Same mathematics as k_ray (render.cu; slams/tracking.py:188-214, slams/mapping.py:603-635,
-// utils/common.py:506-537): colour + logit layer 1 per point, colour head, logit layer 2 on the
-// composited hidden state, occupancy compositing, p/d/l losses and the full backward.  The difference is
-// WHERE the two 112x64 contractions per point run:
+// Same mathematics and the same two GEMMs as ray_tc.cu (slams/tracking.py:188-214, slams/mapping.py:603-635,
+// utils/common.py:506-537).  ncu shows k_ray_tc issue bound: ~6.5 k instructions per thread on 10 warps per SM
+// (176 registers, 104 KB of shared memory per CTA).  Here the threads t and t + T share point t (same TMEM lane
+// quarter because T % 128 == 0) and split its work:
 //
-//   forward   H[p][0..63]  = X[p][0..111] . W1^T      -> tcgen05.mma, M = 128 points, N = 64, K = 112
-//   backward  dX[p][0..111] = dH[p][0..63] . W1       -> tcgen05.mma, M = 128 points, N = 112, K = 64
+//   group 0 (t <  T)  OneBlob of the point -> X chunks 0..5; colour hidden units (accumulator columns 0..31),
+//                     colour head, colour gradients, dH chunks 0..3; OneBlob backward / ray gradients
+//   group 1 (t >= T)  latent + pixel-feature rows -> X chunks 6..13; occupancy compositing (transmittance scans),
+//                     logit hidden units (columns 32..63), depth / logit gradients, dH chunks 4..7,
+//                     d(latent) and d(feature) rows
 //
-// Operands are bf16 hi + lo halves (three products hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM), so
-// the results stay inside the 1e-3 parity bar.  Each thread owns one sample point = one TMEM lane: it
-// writes its row of X / dH as 16-byte feature chunks  [chunk][point][8 x bf16]  (K-major canonical UMMA
-// layout without swizzle: SBO = 128 B between 8-point groups, LBO = T*16 B between feature chunks) and
-// reads its accumulator row back with tcgen05.ld.32x32b.  The SAME shared-memory copy of W1
-// ([feature chunk][hidden row][8 features]) is the K-major B operand of the forward GEMM and the
-// MN-major B operand of the backward GEMM, so no transposed copy exists.
+// Per-ray work (column sums, logits, losses, QV) is spread over all 2 T threads.  T = 128 keeps two CTAs per SM
+// (16 warps), T = 256 one CTA of 16 warps with fewer idle rows; pick_ray_block_tc chooses by row efficiency.
 #include "tc_common.cuh"
 
 namespace dns {
 
-constexpr int kW1oBytes = 14 * 64 * 16;  // one bf16 half of the [64 x 112] colour|logit layer-1 weights
+constexpr int kW1oBytes2 = 14 * 64 * 16;  // one bf16 half of the [64 x 112] colour|logit layer-1 weights
 
-// colour | logit layer-1 weights -> bf16 hi / lo chunk tiles [14 feature chunks][64 hidden rows][8 features]
-__global__ void k_prep_w1o_tc(const float* __restrict__ color, const float* __restrict__ logit, uint4* __restrict__ hi,
-                              uint4* __restrict__ lo) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 14 * 64) return;
-  int c = i >> 6, j = i & 63;
-  const float* src = (j < 32 ? color + j * kIn2 : logit + (j - 32) * kIn2) + 8 * c;
-  float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-  uint4 h, l;
-  split8(a, b, h, l);
-  hi[i] = h;
-  lo[i] = l;
-}
-
-__global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restrict__ w1_hi, const uint4* __restrict__ w1_lo) {
+__global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restrict__ w1_hi, const uint4* __restrict__ w1_lo) {
   extern __shared__ __align__(1024) unsigned char smraw[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int T = a.T, S = a.S, RPC = a.RPC, C = a.C, C4 = a.C4, ld = T + 1;
+  const int NT = 2 * T;                        // threads
   const int cs = T * 16;                       // bytes between feature chunks of a point tile
-  const int MT = (T + 127) >> 7;               // 128-point MMA tiles
+  const int MT = T >> 7;                       // 128-point MMA tiles
   unsigned char* R = smraw;                    // aliased region: X tile -> staging -> dH tile -> staging
   unsigned char* X_hi = R;
   unsigned char* X_lo = R + 14 * cs;
@@ -49,40 +34,43 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   unsigned char* D_lo = R + 8 * cs;
   float* XC = reinterpret_cast<float*>(R);     // [36][T+1] staging for per-ray reductions
   unsigned char* W_hi = R + 28 * cs;
-  unsigned char* W_lo = W_hi + kW1oBytes;
-  float* W2c = reinterpret_cast<float*>(W_lo + kW1oBytes);  // [32][4]
+  unsigned char* W_lo = W_hi + kW1oBytes2;
+  float* W2c = reinterpret_cast<float*>(W_lo + kW1oBytes2);  // [32][4]
   float* bs = W2c + 128;                // [T]
   float* us = bs + T;                   // [T]
   float* ws = us + T;                   // [T]
-  float* HB = ws + T;                   // [RPC][32]
+  float* wsh = ws + T;                  // [T] compositing weight of the point (group 1 -> group 0)
+  float* tmp = wsh + T;                 // [T] colour part of d_w (group 0 -> group 1)
+  float* HB = tmp + T;                  // [RPC][32]
   float* QV = HB + RPC * 32;            // [RPC][32]
   float* RO = QV + RPC * 32;            // [RPC][8]
   float* RG = RO + RPC * 8;             // [RPC][8]
   float* LG = RG + RPC * 8;             // [RPC][C4]
   float* LS = LG + RPC * C4;            // [4]
   const int t = threadIdx.x, warp = t >> 5;
-  for (int i = t; i < kW1oBytes / 16; i += T) {
+  const int grp = t >= T ? 1 : 0, row = t - grp * T;
+  for (int i = t; i < kW1oBytes2 / 16; i += NT) {
     reinterpret_cast<uint4*>(W_hi)[i] = w1_hi[i];
     reinterpret_cast<uint4*>(W_lo)[i] = w1_lo[i];
   }
-  for (int i = t; i < 32; i += T) reinterpret_cast<float4*>(W2c)[i] = reinterpret_cast<const float4*>(a.W2cT)[i];
+  for (int i = t; i < 32; i += NT) reinterpret_cast<float4*>(W2c)[i] = reinterpret_cast<const float4*>(a.W2cT)[i];
   if (t < 4) LS[t] = 0.f;
   const uint32_t tmem_cols = MT == 1 ? 128 : 256;
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   if (t == 0) mbar_init(&bar, 1);
 
-  const int lr = t / S, s = t - lr * S;
+  const int lr = row / S, s = row - lr * S;
   const int64_t rl = (int64_t)blockIdx.x * RPC + lr;      // chunk-local ray
   const bool valid = lr < RPC && rl < a.Nc;
   const int64_t r = a.ray0 + rl;                          // global ray
   const int64_t p = r * S + s;                            // global point
-  const int rb = lr * S;                                  // first thread of my ray
-  float* xc = XC + t;
+  const int rb = lr * S;                                  // first row of my ray
+  float* xc = XC + row;
   float x[3] = {0.f, 0.f, 0.f}, zv = 0.f, occ = 0.f;
   // weight-gradient operands leave the kernel as bf16 hi/lo tile images: this CTA owns T rows = T/RS sub-tiles,
   // each laid out [half][chunk][RS rows] (tc.cu: k_dw_img); rows of absent points are written as zeros
   const bool stash = a.need_dparams != 0;
-  const int RS = a.RS, sub = t / RS, rr = t - sub * RS;
+  const int RS = a.RS, sub = row / RS, rr = row - sub * RS;
   const int64_t img_row0 = ((int64_t)blockIdx.x * T + (int64_t)sub * RS) * 2;
   uint4* const x2p = stash ? a.X2img + img_row0 * 14 + rr : nullptr;     // + chunk * RS (hi), + (K + chunk) * RS (lo)
   uint4* const dh2p = stash ? a.dH2img + img_row0 * 8 + rr : nullptr;
@@ -93,50 +81,53 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   // ---- stage this point's row of X = [OneBlob(x) 48 | latent 32 | pixel feature 32] as bf16 hi/lo chunks
   if (valid) {
     zv = a.z[p];
-    point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
+    if (grp == 0) {
+      point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float pe[16];
-      oneblob16(x[c], pe);
-      put_chunk_img(X_hi, X_lo, 2 * c, cs, t, pe, IMG2(x2p, 14, 2 * c));
-      put_chunk_img(X_hi, X_lo, 2 * c + 1, cs, t, pe + 8, IMG2(x2p, 14, 2 * c + 1));
-    }
-    {
-      float row[kOutP];
-      const float4* s4 = reinterpret_cast<const float4*>(a.fine36 + p * kOutP);
-#pragma unroll
-      for (int q = 0; q < kOutP / 4; ++q) {
-        float4 v = s4[q];
-        row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+      for (int c = 0; c < 3; ++c) {
+        float pe[16];
+        oneblob16(x[c], pe);
+        put_chunk_img(X_hi, X_lo, 2 * c, cs, row, pe, IMG2(x2p, 14, 2 * c));
+        put_chunk_img(X_hi, X_lo, 2 * c + 1, cs, row, pe + 8, IMG2(x2p, 14, 2 * c + 1));
       }
-      occ = row[0];
+    } else {
+      {
+        float lat[kOutP];
+        const float4* s4 = reinterpret_cast<const float4*>(a.fine36 + p * kOutP);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        put_chunk_img(X_hi, X_lo, 6 + c, cs, t, row + 1 + 8 * c, IMG2(x2p, 14, 6 + c));
-    }
-    {
-      float row[32];
-      if (a.features) {
-        const float4* s4 = reinterpret_cast<const float4*>(a.features + p * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < kOutP / 4; ++q) {
           float4 v = s4[q];
-          row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+          lat[4 * q] = v.x; lat[4 * q + 1] = v.y; lat[4 * q + 2] = v.z; lat[4 * q + 3] = v.w;
         }
-      } else {
+        occ = lat[0];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) row[k] = 0.f;
+        for (int c = 0; c < 4; ++c)
+          put_chunk_img(X_hi, X_lo, 6 + c, cs, row, lat + 1 + 8 * c, IMG2(x2p, 14, 6 + c));
       }
+      {
+        float ft[32];
+        if (a.features) {
+          const float4* s4 = reinterpret_cast<const float4*>(a.features + p * 32);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        put_chunk_img(X_hi, X_lo, 10 + c, cs, t, row + 8 * c, IMG2(x2p, 14, 10 + c));
+          for (int q = 0; q < 8; ++q) {
+            float4 v = s4[q];
+            ft[4 * q] = v.x; ft[4 * q + 1] = v.y; ft[4 * q + 2] = v.z; ft[4 * q + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) ft[k] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          put_chunk_img(X_hi, X_lo, 10 + c, cs, row, ft + 8 * c, IMG2(x2p, 14, 10 + c));
+      }
     }
   } else {
     const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int c = 0; c < 14; ++c) {
-      *reinterpret_cast<uint4*>(X_hi + c * cs + t * 16) = z4;
-      *reinterpret_cast<uint4*>(X_lo + c * cs + t * 16) = z4;
+    const int c0 = grp ? 6 : 0, c1 = grp ? 14 : 6;
+    for (int c = c0; c < c1; ++c) {
+      *reinterpret_cast<uint4*>(X_hi + c * cs + row * 16) = z4;
+      *reinterpret_cast<uint4*>(X_lo + c * cs + row * 16) = z4;
       if (stash) x2p[c * RS] = x2p[(14 + c) * RS] = z4;
     }
   }
@@ -164,22 +155,23 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   }
   mbar_wait(&bar, 0);
   tc_fence_after();
-  float h[64];
+  // this thread's half of the hidden row: group 0 colour units, group 1 logit units
+  const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((row >> 7) * 112);
+  float h[32];
   {
-    const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((t >> 7) * 112);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < 2; ++g) {
       float v[16];
-      tmem_ld16(taddr + 16 * g, v);
+      tmem_ld16(taddr + 32 * grp + 16 * g, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) h[16 * g + i] = valid ? fmaxf(v[i], 0.f) : 0.f;
     }
   }
   tc_fence_before();
-  __syncthreads();   // every thread has read its accumulator row: region R may be reused as staging
-  // colour head: 32 -> 3, sigmoid (decoder.py:123)
+  __syncthreads();   // every thread has read its accumulator half: region R may be reused as staging
   float rgb[3] = {0.f, 0.f, 0.f};
-  {
+  float alpha = 0.f, b = 1.f;
+  if (grp == 0) {    // colour head: 32 -> 3, sigmoid (decoder.py:123)
     float pre[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -190,32 +182,40 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) rgb[c] = sigmoidf_(pre[c]);
+  } else {           // occupancy compositing (common.py:524-532)
+    alpha = valid ? sigmoidf_(10.f * occ) : 0.f;
+    b = __fadd_rn(1.f - alpha, 1e-10f);
+    bs[row] = b;
   }
-  // occupancy compositing (common.py:524-532)
-  const float alpha = valid ? sigmoidf_(10.f * occ) : 0.f;
-  const float b = __fadd_rn(1.f - alpha, 1e-10f);
-  bs[t] = b;
   __syncthreads();
-  float Ts = 1.f;
-  if (valid)
-    for (int j = 0; j < s; ++j) Ts *= bs[rb + j];
-  const float u = alpha * Ts;
-  us[t] = u;
+  float Ts = 1.f, u = 0.f, sumu = 0.f, w = 0.f;
+  if (grp == 1) {
+    if (valid)
+      for (int j = 0; j < s; ++j) Ts *= bs[rb + j];
+    u = alpha * Ts;
+    us[row] = u;
+  }
   __syncthreads();
-  float sumu = 0.f;
-  if (valid)
-    for (int j = 0; j < S; ++j) sumu += us[rb + j];
-  const float w = valid ? (a.fwd_only == 2 ? 1.f : u / sumu) : 0.f;   // 2: free-point query, no compositing
+  if (grp == 1) {
+    if (valid)
+      for (int j = 0; j < S; ++j) sumu += us[rb + j];
+    w = valid ? (a.fwd_only == 2 ? 1.f : u / sumu) : 0.f;   // 2: free-point query, no compositing
+    wsh[row] = w;
+  }
   __syncthreads();
+  if (grp == 0) w = wsh[row];
   if (valid) {
+    if (grp == 1) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) xc[j * ld] = w * h[32 + j];
+      for (int j = 0; j < 32; ++j) xc[j * ld] = w * h[j];
+      xc[35 * ld] = w * zv;
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) xc[(32 + c) * ld] = w * rgb[c];
-    xc[35 * ld] = w * zv;
+      for (int c = 0; c < 3; ++c) xc[(32 + c) * ld] = w * rgb[c];
+    }
   }
   __syncthreads();
-  for (int e = t; e < RPC * 36; e += T) {
+  for (int e = t; e < RPC * 36; e += NT) {
     int l2 = e / 36, o = e - l2 * 36;
     if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
       const float* col = XC + o * ld + l2 * S;
@@ -226,11 +226,14 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     }
   }
   __syncthreads();
-  const float dz = valid ? zv - RO[lr * 8 + 3] : 0.f;
-  bs[t] = w * dz * dz;
-  us[t] = w * dz;
+  float dz = 0.f;
+  if (grp == 1) {
+    dz = valid ? zv - RO[lr * 8 + 3] : 0.f;
+    bs[row] = w * dz * dz;
+    us[row] = w * dz;
+  }
   const float* W2l = a.logit + 32 * kIn2;
-  for (int e = t; e < RPC * C; e += T) {
+  for (int e = t; e < RPC * C; e += NT) {
     int l2 = e / C, c = e - l2 * C;
     if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
       const float4* wr = reinterpret_cast<const float4*>(W2l + c * 32);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   }
   __syncthreads();
   // ---- per-ray losses and their gradients: one warp per ray, lanes over samples / classes
-  for (int l2 = warp; l2 < RPC; l2 += (T >> 5)) {
+  for (int l2 = warp; l2 < RPC; l2 += (NT >> 5)) {
     const int64_t rl2 = (int64_t)blockIdx.x * RPC + l2, r2 = a.ray0 + rl2;
     if (rl2 >= a.Nc) break;   // uniform over the warp
     const int lane = t & 31;
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
     return;
   }
-  for (int e = t; e < RPC * 32; e += T) {
+  for (int e = t; e < RPC * 32; e += NT) {
     int l2 = e >> 5, j = e & 31;
     if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
       const float* lg = LG + l2 * C4;
@@ -354,32 +357,50 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     }
   }
   __syncthreads();
-  // ---- per-point backward
-  float d_w = 0.f;
-  if (valid) {
-    const float* rg = RG + lr * 8;
-    const float* qv = QV + lr * 32;
-    d_w = rg[0] * rgb[0] + rg[1] * rgb[1] + rg[2] * rgb[2] + rg[3] * zv + rg[4] * dz * dz;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) d_w = fmaf(h[32 + j], qv[j], d_w);
+  // ---- per-point backward: d_w = dL/dw of the point, assembled from both groups
+  if (grp == 0) {
+    float part = 0.f;
+    if (valid) {
+      const float* rg = RG + lr * 8;
+      part = rg[0] * rgb[0] + rg[1] * rgb[1] + rg[2] * rgb[2];
+    }
+    tmp[row] = part;
   }
-  bs[t] = w * d_w;
-  ws[t] = b;
   __syncthreads();
-  float G = 0.f;
-  if (valid)
-    for (int j = 0; j < S; ++j) G += bs[rb + j];
-  const float d_u = valid ? (d_w - G) / sumu : 0.f;
-  us[t] = d_u * u;
+  float d_w = 0.f;
+  if (grp == 1) {
+    if (valid) {
+      const float* rg = RG + lr * 8;
+      const float* qv = QV + lr * 32;
+      d_w = tmp[row] + rg[3] * zv + rg[4] * dz * dz;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d_w = fmaf(h[j], qv[j], d_w);
+    }
+    bs[row] = w * d_w;
+    ws[row] = b;
+  }
+  __syncthreads();
+  float d_u = 0.f;
+  if (grp == 1) {
+    float G = 0.f;
+    if (valid)
+      for (int j = 0; j < S; ++j) G += bs[rb + j];
+    d_u = valid ? (d_w - G) / sumu : 0.f;
+    us[row] = d_u * u;
+  }
   __syncthreads();
   float d_occ = 0.f;
-  if (valid) {
-    float suf = 0.f;
-    for (int j = s + 1; j < S; ++j) suf += us[rb + j];
-    float d_alpha = d_u * Ts - suf / b;
-    d_occ = d_alpha * 10.f * alpha * (1.f - alpha);
-  }
-  {
+  if (grp == 1) {
+    if (valid) {
+      float suf = 0.f;
+      for (int j = s + 1; j < S; ++j) suf += us[rb + j];
+      float d_alpha = d_u * Ts - suf / b;
+      d_occ = d_alpha * 10.f * alpha * (1.f - alpha);
+      const float* qv = QV + lr * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = h[j] > 0.f ? w * qv[j] : 0.f;
+    }
+  } else {
     float dp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (valid) {
       const float* rg = RG + lr * 8;
@@ -392,19 +413,17 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
       store_chunk_img(dp, dpp, dpp + RS);
     }
     if (valid) {
-      const float* qv = QV + lr * 32;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float4 wv = *reinterpret_cast<const float4*>(W2c + 4 * j);
         h[j] = h[j] > 0.f ? dp[0] * wv.x + dp[1] * wv.y + dp[2] * wv.z : 0.f;
-        h[32 + j] = h[32 + j] > 0.f ? w * qv[j] : 0.f;
       }
     }
   }
   // ---- backward GEMM: dX = dH . W1  (A = dH K-major over hidden; B = W1 MN-major: features contiguous)
 #pragma unroll
-  for (int c = 0; c < 8; ++c)   // invalid threads hold zeros
-    put_chunk_img(D_hi, D_lo, c, cs, t, h + 8 * c, IMG2(dh2p, 8, c));
+  for (int c = 0; c < 4; ++c)   // invalid threads hold zeros
+    put_chunk_img(D_hi, D_lo, 4 * grp + c, cs, row, h + 8 * c, IMG2(dh2p, 8, 4 * grp + c));
 #undef IMG2
   fence_async_smem();
   tc_fence_before();
@@ -429,20 +448,26 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
   mbar_wait(&bar, 1);
   tc_fence_after();
   float g3[3] = {0.f, 0.f, 0.f};
-  {
-    const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((t >> 7) * 112);
-    float row[kOutP];
-    row[0] = d_occ;
-    row[33] = row[34] = row[35] = 0.f;
+  if (grp == 0) {   // dX columns 0..47: OneBlob backward -> d(ray)
+    if (a.need_drays) {
 #pragma unroll
-    for (int g = 0; g < 7; ++g) {
+      for (int g = 0; g < 3; ++g) {
+        float v[16];
+        tmem_ld16(taddr + 16 * g, v);
+        if (valid) g3[g] = oneblob16_bwd(x[g], v) / (float)a.B.ext[g];
+      }
+    }
+  } else {          // columns 48..79: d(latent) (with d_occ in channel 0); columns 80..111: d(pixel feature)
+    float lat[kOutP];
+    lat[0] = d_occ;
+    lat[33] = lat[34] = lat[35] = 0.f;
+#pragma unroll
+    for (int g = 3; g < 7; ++g) {
       float v[16];
-      tmem_ld16(taddr + 16 * g, v);
-      if (g < 3) {
-        if (a.need_drays && valid) g3[g] = oneblob16_bwd(x[g], v) / (float)a.B.ext[g];
-      } else if (g < 5) {
+      if (g < 5 || a.need_dfeat) tmem_ld16(taddr + 16 * g, v);
+      if (g < 5) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) row[1 + 16 * (g - 3) + i] = v[i];
+        for (int i = 0; i < 16; ++i) lat[1 + 16 * (g - 3) + i] = v[i];
       } else if (a.need_dfeat && valid) {
         float4* d4 = reinterpret_cast<float4*>(a.d_features + p * 32 + 16 * (g - 5));
 #pragma unroll
@@ -452,14 +477,14 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
     if (valid) {
       float4* d4 = reinterpret_cast<float4*>(a.dfine36 + p * kOutP);
 #pragma unroll
-      for (int q = 0; q < kOutP / 4; ++q) d4[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
+      for (int q = 0; q < kOutP / 4; ++q) d4[q] = make_float4(lat[4 * q], lat[4 * q + 1], lat[4 * q + 2], lat[4 * q + 3]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
   if (a.need_drays) {
-    if (valid) {
+    if (valid && grp == 0) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         xc[c * ld] = g3[c];
@@ -467,68 +492,62 @@ __global__ void __launch_bounds__(256) k_ray_tc(RayArgs a, const uint4* __restri
       }
     }
     __syncthreads();
-    for (int e = t; e < RPC * 6; e += T) {
+    for (int e = t; e < RPC * 6; e += NT) {
       int l2 = e / 6, o = e - l2 * 6;
-      int64_t rr = (int64_t)blockIdx.x * RPC + l2;
-      if (rr < a.Nc) {
+      int64_t rr2 = (int64_t)blockIdx.x * RPC + l2;
+      if (rr2 < a.Nc) {
         const float* col = XC + o * ld + l2 * S;
         float acc = 0.f;
         for (int j = 0; j < S; ++j) acc += col[j];
-        if (o < 3) a.d_rays_o[3 * (a.ray0 + rr) + o] = acc;
-        else a.d_rays_d[3 * (a.ray0 + rr) + o - 3] = acc;
+        if (o < 3) a.d_rays_o[3 * (a.ray0 + rr2) + o] = acc;
+        else a.d_rays_d[3 * (a.ray0 + rr2) + o - 3] = acc;
       }
     }
   }
 }
 
-bool ray_two_threads() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DNS_RAY1");
-    v = (e && atoi(e)) ? 0 : 1;
+// T in {128, 256}: the larger row efficiency wins (ties -> 128, two CTAs per SM); DNS_RAY_T overrides (measurements)
+void pick_ray_block_tc2(int S, int& T, int& RPC) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("DNS_RAY_T");
+    forced = e ? atoi(e) : 0;
   }
-  return v == 1;
-}
-void pick_ray_block_any(int S, int& T, int& RPC) {
-  if (ray_two_threads()) pick_ray_block_tc2(S, T, RPC);
-  else pick_ray_block_tc(S, T, RPC);
-}
-
-void pick_ray_block_tc(int S, int& T, int& RPC) {
-  // <= 160 threads keeps two CTAs per SM (shared memory); rays are never split across CTAs
-  int rmax = 160 / S;
-  if (rmax < 1) rmax = 1;
-  if (rmax > 16) rmax = 16;
-  int best_r = 1;
-  double best = 0.0;
-  for (int rr = 1; rr <= rmax; ++rr) {
-    int tt = (rr * S + 31) & ~31;
+  int best_t = 0;
+  double best = -1.0;
+  for (int tt = 128; tt <= 256; tt += 128) {
+    int rr = tt / S;
+    if (rr > 64) rr = 64;
+    if (rr < 1) continue;
     double eff = (double)(rr * S) / tt;
-    if (eff >= best - 1e-9) {
+    if (forced == tt) eff += 10.0;
+    if (eff > best + 1e-9) {
       best = eff;
-      best_r = rr;
+      best_t = tt;
     }
   }
-  RPC = best_r;
-  T = (RPC * S + 31) & ~31;
+  if (best_t == 0) {   // S > 256: rejected by dns_render_fwd_bwd; keep the workspace query well defined
+    T = 256;
+    RPC = 1;
+    return;
+  }
+  T = best_t;
+  RPC = T / S > 64 ? 64 : T / S;
 }
 
-size_t ray_tc_smem_bytes(int T, int RPC, int C4) {
-  return (size_t)28 * T * 16 + 2 * kW1oBytes + sizeof(float) * (128 + 3 * T + RPC * (32 + 32 + 8 + 8 + C4) + 8);
+size_t ray_tc2_smem_bytes(int T, int RPC, int C4) {
+  return (size_t)28 * T * 16 + 2 * kW1oBytes2 + sizeof(float) * (128 + 5 * T + RPC * (32 + 32 + 8 + 8 + C4) + 8);
 }
 
-int launch_ray_tc(const RayArgs& ra, const float* color, const float* logit, uint4* w1_hi, uint4* w1_lo, bool prep,
-                  int64_t n_rays_chunk, cudaStream_t st) {
+int launch_ray_tc2(const RayArgs& ra, uint4* w1_hi, uint4* w1_lo, int64_t n_rays_chunk, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_ray_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_ray_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  if (prep) k_prep_w1o_tc<<<(14 * 64 + 127) / 128, 128, 0, st>>>(color, logit, w1_hi, w1_lo);
-  if (ray_two_threads()) return launch_ray_tc2(ra, w1_hi, w1_lo, n_rays_chunk, st);
-  size_t smem = ray_tc_smem_bytes(ra.T, ra.RPC, ra.C4);
-  k_ray_tc<<<(int)((n_rays_chunk + ra.RPC - 1) / ra.RPC), ra.T, smem, st>>>(ra, w1_hi, w1_lo);
-  return check_launch("ray_tc");
+  size_t smem = ray_tc2_smem_bytes(ra.T, ra.RPC, ra.C4);
+  k_ray_tc2<<<(int)((n_rays_chunk + ra.RPC - 1) / ra.RPC), 2 * ra.T, smem, st>>>(ra, w1_hi, w1_lo);
+  return check_launch("ray_tc2");
 }
 
 }  // namespace dns

@@ -877,7 +877,7 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.dOc = c.take<float>(w.Q * 40 * (map ? 2 : 1));
   w.dOf = w.dOc ? w.dOc + w.Q * 40 : nullptr;
   int Tt, Rt;
-  pick_ray_block_tc(S, Tt, Rt);
+  pick_ray_block_any(S, Tt, Rt);
   const int64_t img_rows = ((Nc + Rt - 1) / Rt) * Tt;
   const int64_t rows2 = img_rows > Pc ? img_rows : Pc;
   w.X2 = c.take<float>(rows2 * kIn2);
@@ -1005,7 +1005,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   }
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT * (map ? 2 : 1));
   int T, RPC;
-  if (tc) pick_ray_block_tc(S, T, RPC);
+  if (tc) pick_ray_block_any(S, T, RPC);
   else pick_ray_block(S, T, RPC);
   const size_t smem_ray =
       sizeof(float) * (kIn2 * 64 + 128 + 48 * (T + 1) + 3 * T + RPC * (32 + 32 + 8 + 8 + C4) + 8);
@@ -1074,7 +1074,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.d_rays_o = a->d_rays_o; ra.d_rays_d = a->d_rays_d;
     ra.X2 = w.X2; ra.dH2 = w.dH2; ra.Hcol = w.Hcol; ra.dpre = w.dpre; ra.dlogit = w.dlogit; ra.Hbar = w.Hbar;
     ra.X2img = (uint4*)w.X2; ra.dH2img = (uint4*)w.dH2; ra.Hcolimg = (uint4*)w.Hcol; ra.dpreimg = (uint4*)w.dpre;
-    ra.RS = T <= 96 ? T : T / 2;   // sub-tile rows of the ray-side images (multiple of 16; keeps >= 3 pipeline stages)
+    ra.RS = T <= 96 ? T : (T == 160 ? 80 : 64);   // sub-tile rows of the ray-side images (multiple of 16, divides T)
     const bool fwd_only = a->forward_only != 0;
     ra.fwd_only = a->forward_only;
     ra.need_dparams = a->need_dparams && !fwd_only; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d && !fwd_only;
