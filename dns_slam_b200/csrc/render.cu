@@ -1074,7 +1074,8 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.d_rays_o = a->d_rays_o; ra.d_rays_d = a->d_rays_d;
     ra.X2 = w.X2; ra.dH2 = w.dH2; ra.Hcol = w.Hcol; ra.dpre = w.dpre; ra.dlogit = w.dlogit; ra.Hbar = w.Hbar;
     ra.X2img = (uint4*)w.X2; ra.dH2img = (uint4*)w.dH2; ra.Hcolimg = (uint4*)w.Hcol; ra.dpreimg = (uint4*)w.dpre;
-    ra.RS = T <= 96 ? T : (T == 160 ? 80 : 64);   // sub-tile rows of the ray-side images (multiple of 16, divides T)
+    ra.RS = T <= 96 ? T : (T == 160 ? 80 : (T == 256 ? 128 : 64));   // sub-tile rows of the ray-side images (divides T)
+    if (const char* e = getenv("DNS_RAY_RS")) ra.RS = atoi(e);
     const bool fwd_only = a->forward_only != 0;
     ra.fwd_only = a->forward_only;
     ra.need_dparams = a->need_dparams && !fwd_only; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d && !fwd_only;

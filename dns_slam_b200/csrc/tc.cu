@@ -281,8 +281,10 @@ int launch_dw_img(const DwImgArgs& a, cudaStream_t st) {
   if (a.n_tiles_host <= 0) return DNS_OK;
   const int cs = a.RS * 16;
   const int stage = 2 * (a.L.chunks_used + a.Cc.chunks_used) * cs;
-  // the MMA footprint of the lane operand spans 16 chunks from the start of each half: keep it inside the allocation
-  const int tail = 16 * cs;
+  // the MMA footprint of the lane operand spans 16 chunks from the start of each half (the lo half starts
+  // chunks_used chunks into the stage): pad the allocation by whatever reaches past the last stage
+  const int over = a.L.chunks_used + 16 - 2 * (a.L.chunks_used + a.Cc.chunks_used);
+  const int tail = over > 0 ? over * cs : 0;
   int ns = (200 * 1024 - tail) / stage;
   if (ns > kImgMaxStages) ns = kImgMaxStages;
   if (ns < 1 || (a.RS & 15) || a.L.chunks_used > 16 || ((a.Cc.n_valid + 15) & ~15) > a.Cc.chunks_used * 8) {
