@@ -76,7 +76,7 @@ SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_ena
            "dns_hashgrid_fwd", "dns_hashgrid_bwd", "dns_hashgrid_indices", "dns_mlp_fwd",
            "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd", "dns_render_counts",
            "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
-           "dns_adam_step"]
+           "dns_adam_step", "dns_merge_workspace_bytes", "dns_merge_fwd", "dns_merge_bwd"]
 
 
 def lib():
@@ -92,6 +92,7 @@ def lib():
     L.dns_last_error.restype = C.c_char_p
     L.dns_render_workspace_bytes.restype = C.c_int64
     L.dns_tv_workspace_bytes.restype = C.c_int64
+    L.dns_merge_workspace_bytes.restype = C.c_int64
     i64, i32, f32 = C.c_int64, C.c_int, C.c_float
     L.dns_struct_sizes.argtypes = [C.POINTER(C.c_int64)]
     L.dns_profile_enable.argtypes = [C.c_int]
@@ -114,6 +115,10 @@ def lib():
     L.dns_sample_rays.argtypes = [C.POINTER(SampleArgs), _P]
     L.dns_feature_gather.argtypes = [_P, i64, _P, i32, _P, i32, i32, _P, i32, i32, i32, _P, _P, _P, _P]
     L.dns_adam_step.argtypes = [_P, _P, _P, _P, i64, f32, f32, f32, f32, i32, _P]
+    bound_t = (C.c_double * 2) * 3
+    L.dns_merge_workspace_bytes.argtypes = [i64]
+    L.dns_merge_fwd.argtypes = [_P, _P, _P, i64, i32, bound_t, _P, i32, _P, i64, _P]
+    L.dns_merge_bwd.argtypes = [_P, _P, i64, i32, bound_t, _P, _P, _P, i64, _P]
     sizes = (C.c_int64 * 4)()
     L.dns_struct_sizes(sizes)
     mine = [C.sizeof(Grid), C.sizeof(RenderArgs), C.sizeof(TvArgs), C.sizeof(SampleArgs)]

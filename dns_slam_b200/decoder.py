@@ -15,6 +15,8 @@ into it), so that the fused Adam step and the multi-GPU gradient all-reduce are 
 operations.  The class-wise fine MLPs of ``Mapper.set_decoder``
 (``slams/mapping.py:727-761``) are rows of a pre-allocated expert bank.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -53,6 +55,11 @@ class Merge(nn.Module):
 
     def forward(self, p, o, features=None):
         n_refer, n_points, _ = features.shape
+        if (features.is_cuda and features.shape[-1] == 64 and self.decoder.n_output_dims == 32
+                and not os.environ.get("DNS_MERGE_OPS")):
+            # fused tcgen05 path: OneBlob + concat + MLP + mean over the views in one kernel each way
+            from . import fused
+            return fused.merge_fused(p, features, self.decoder.params, self.bound)
         p = (p - self.bound[:, 0]) / (self.bound[:, 1] - self.bound[:, 0])
         pe = self.pe_fn(p.flatten(0, 1))
         lat = self.decoder(torch.cat((pe, features.flatten(0, 1)), -1))

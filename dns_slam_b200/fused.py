@@ -414,6 +414,49 @@ def rigid_inverse(M):
     return torch.cat((top, bottom), -2)
 
 
+class _MergeFn(torch.autograd.Function):
+    """``Merge.forward`` (models/decoder.py:67-77) as two fused tcgen05 kernels (dns_merge_fwd / dns_merge_bwd):
+    gradients reach ``refer_p`` (and through it the points / poses) and the Merge weights; the gathered
+    features are constants (the reference rounds the pixel coordinates, utils/common.py:657)."""
+
+    @staticmethod
+    def forward(ctx, refer_p, code, params, bound):
+        R, P, _ = refer_p.shape
+        dev = refer_p.device
+        rp = refer_p.detach().to(torch.float32).contiguous()
+        cd = code.detach().to(torch.float32).contiguous()
+        L = _lib.lib()
+        keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[2])
+        # the activation images must survive until the backward: a buffer of their own, not the shared scratch
+        ws = torch.empty(int(L.dns_merge_workspace_bytes(R * P)), dtype=torch.uint8, device=dev)
+        out = torch.empty(P, 32, device=dev)
+        b = ((C.c_double * 2) * 3)()
+        _lib.fill_bound(b, bound)
+        _lib.check(L.dns_merge_fwd(_lib.ptr(rp), _lib.ptr(cd), _lib.ptr(params.detach(), torch.float32), P, R, b,
+                                   _lib.ptr(out), int(keep), ws.data_ptr(), ws.numel(), _lib.stream()))
+        ctx.save_for_backward(rp, ws, params)
+        ctx.bound, ctx.shape = bound, (R, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        rp, ws, params = ctx.saved_tensors
+        R, P = ctx.shape
+        d_rp = torch.empty_like(rp)
+        d_par = torch.zeros_like(params) if ctx.needs_input_grad[2] else None
+        b = ((C.c_double * 2) * 3)()
+        _lib.fill_bound(b, ctx.bound)
+        _lib.check(_lib.lib().dns_merge_bwd(_lib.ptr(rp), _lib.ptr(d_out.to(torch.float32).contiguous()), P, R, b,
+                                            _lib.ptr(d_rp), _lib.ptr(d_par, allow_none=True), ws.data_ptr(), ws.numel(),
+                                            _lib.stream()))
+        return (d_rp if ctx.needs_input_grad[0] else None), None, d_par, None
+
+
+def merge_fused(refer_p, code, params, bound):
+    """refer_p [R,P,3] (points minus the reference camera centres), code [R,P,64] -> [P,32]."""
+    return _MergeFn.apply(refer_p, code, params, bound)
+
+
 def feature_matching(H, W, K, pts_, refer_w2c, feats_cl, merge_fn):
     """utils.common.feature_matching with channels-last features (no 209 MB/view up-sample)."""
     code, _, _ = feature_gather(H, W, K, pts_, refer_w2c, feats_cl)

@@ -238,6 +238,19 @@ int dns_feature_gather(const float* pts, int64_t P, const float* w2c /*[R,4,4]*/
                        int C, int h, int w, float* code /*[R,P,C]*/, int64_t* uv /*[R,P,2] or NULL*/,
                        uint8_t* mask /*[R,P] or NULL*/, void* stream);
 
+/* Merge MLP of the pixel-feature branch, fused (models/decoder.py:67-77):
+ *   out[p] = mean_r  MLP_112->32->32( OneBlob((refer_p[r,p] - lo) / (hi - lo)) || code[r,p] )
+ * refer_p [R,P,3], code [R,P,64] (dns_feature_gather output), params = the tinycudann vector of Merge.decoder
+ * (W1[32][112] | W2[32][32]), out [P,32] overwritten.  With keep_for_backward the workspace keeps the activation
+ * images and the SAME workspace must be passed to dns_merge_bwd, which writes d_refer_p [R,P,3] and ACCUMULATES
+ * d_params (may be NULL).  The gathered features carry no gradient (utils/common.py:657 rounds the pixels). */
+int64_t dns_merge_workspace_bytes(int64_t n_rows /* R * P */);
+int dns_merge_fwd(const float* refer_p, const float* code, const float* params, int64_t P, int R,
+                  const double bound[3][2], float* out, int keep_for_backward, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+int dns_merge_bwd(const float* refer_p, const float* d_out, int64_t P, int R, const double bound[3][2],
+                  float* d_refer_p, float* d_params, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Adam == torch.optim.Adam defaults over a flat fp32 buffer
  * (slams/tracking.py:119-124,339; slams/mapping.py:464-466,910)

@@ -78,3 +78,31 @@ def test_dw_gemm_image_pipeline(M, N, rows, RS):
     want = A.double().t() @ B.double()
     err = float((C.double() - want).norm() / want.norm())
     assert err < 2e-5, f"relative error {err:.3e}"
+
+
+def test_fused_merge_matches_operator_chain(monkeypatch):
+    """dns_merge_fwd / dns_merge_bwd (one tcgen05 kernel each way) against the operator chain OneBlob -> concat ->
+    Network -> mean of the drop-in modules (models/decoder.py:67-77): values, d(refer_p), d(weights)."""
+    from dns_slam_b200 import decoder as D, synthetic as syn
+    dev = torch.device("cuda:0")
+    dec = D.Decoder(syn.model_cfg("tiny"), syn.load_bound(syn.SHAPES["tiny"]["bound"]), n_class=4, seed=3, device=dev)
+    g = torch.Generator().manual_seed(5)
+    R, P = 3, 1000 + 37
+    lo, hi = dec.bound[:, 0].float().cpu(), dec.bound[:, 1].float().cpu()
+    p0 = (lo + (hi - lo) * torch.rand(R, P, 3, generator=g)).to(dev)
+    code = (torch.randn(R, P, 64, generator=g) * (torch.rand(R, P, 1, generator=g) > 0.3)).to(dev)
+    o = torch.zeros(R, 3, device=dev)
+    w_out = torch.randn(P, 32, generator=g).to(dev)
+    res = {}
+    for mode in ("fused", "ops"):
+        if mode == "ops":
+            monkeypatch.setenv("DNS_MERGE_OPS", "1")
+        p = p0.clone().requires_grad_(True)
+        dec.zero_grad()
+        out = dec.merge(p, o, code)
+        (out * w_out).sum().backward()
+        res[mode] = (out.detach(), p.grad.clone(), dec.merge.decoder.params.grad.clone())
+    for k, name in enumerate(("out", "d_refer_p", "d_params")):
+        a, b = res["fused"][k].double(), res["ops"][k].double()
+        err = float((a - b).norm() / b.norm())
+        assert err < 1e-3, f"{name}: relative error {err:.3e}"
