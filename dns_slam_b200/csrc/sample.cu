@@ -37,65 +37,75 @@ __global__ void k_sample_gather(dns_sample_args a) {
   atomicMax(reinterpret_cast<int*>(a.scratch), __float_as_int(fmaxf(d, 0.f)));
 }
 
-__global__ void k_sample_z(dns_sample_args a) {
-  extern __shared__ float sm[];  // [S][blockDim.x]
-  const int r = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x, bd = blockDim.x;
-  if (r >= a.n) return;
+// kRaysZ rays per block, 128 threads: per-ray scalars by one thread each, then the S values, their ranks (S
+// comparisons per value) and the optional points spread over the whole block -- a single thread per ray made the
+// O(S^2) rank sort a 30 us latency chain at tracking-sized batches.
+constexpr int kRaysZ = 16;
+__global__ void __launch_bounds__(128) k_sample_z(dns_sample_args a) {
+  extern __shared__ float sm[];  // [S][kRaysZ] values
+  __shared__ double s_far[kRaysZ];
+  __shared__ float s_d[kRaysZ];
+  const int tid = threadIdx.x, r0 = blockIdx.x * kRaysZ;
   const int S = a.n_uniform + a.n_surface;
-  const float d = a.gt_depth[r];
+  const int nr = min(kRaysZ, a.n - r0);
   const float maxd = a.scratch[0];
-  // far plane in float64 (tracking.py:151-156)
-  double far_bb = INFINITY;
+  if (tid < nr) {
+    const int r = r0 + tid;
+    const float d = a.gt_depth[r];
+    // far plane in float64 (tracking.py:151-156)
+    double far_bb = INFINITY;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    double o = (double)a.rays_o[3 * r + c], dd = (double)a.rays_d[3 * r + c];
-    double t0 = (a.bound[c][0] - o) / dd, t1 = (a.bound[c][1] - o) / dd;
-    double m = fmax(t0, t1);
-    far_bb = fmin(far_bb, m);
-  }
-  a.inside[r] = far_bb >= (double)d ? 1 : 0;
-  far_bb += 0.01;
-  float* col = sm + tid;
-  // depth-guided samples
-  if (d > 0.f) {
-    float lo = __fmul_rn(0.95f, d), hi = __fmul_rn(1.05f, d);
-    for (int k = 0; k < a.n_surface; ++k) {
-      float t = a.t_surface[k];
-      col[(a.n_uniform + k) * bd] = __fadd_rn(__fmul_rn(lo, __fsub_rn(1.0f, t)), __fmul_rn(hi, t));
+    for (int c = 0; c < 3; ++c) {
+      double o = (double)a.rays_o[3 * r + c], dd = (double)a.rays_d[3 * r + c];
+      double t0 = (a.bound[c][0] - o) / dd, t1 = (a.bound[c][1] - o) / dd;
+      double m = fmax(t0, t1);
+      far_bb = fmin(far_bb, m);
     }
-  } else {
-    for (int k = 0; k < a.n_surface; ++k) {
-      float t = a.t_zero[k];
-      col[(a.n_uniform + k) * bd] = __fadd_rn(__fmul_rn(0.001f, __fsub_rn(1.0f, t)), __fmul_rn(maxd, t));
-    }
-  }
-  // uniform samples: near fp32, far fp64 (clamped), blended in fp64, rounded to fp32 at the end
-  {
-    float near = __fmul_rn(d, 0.001f);
+    a.inside[r] = far_bb >= (double)d ? 1 : 0;
+    far_bb += 0.01;
     double hi = (double)__fmul_rn(maxd, 1.2f);
-    double far = fmin(fmax(far_bb, 0.0), hi);
-    for (int k = 0; k < a.n_uniform; ++k) {
-      float t = a.t_lin[k];
-      double v = (double)__fmul_rn(near, __fsub_rn(1.0f, t)) + far * (double)t;
-      col[k * bd] = (float)v;
-    }
+    s_far[tid] = fmin(fmax(far_bb, 0.0), hi);
+    s_d[tid] = d;
   }
+  __syncthreads();
+  for (int e = tid; e < nr * S; e += blockDim.x) {
+    const int lr = e / S, k = e - lr * S;
+    const float d = s_d[lr];
+    float v;
+    if (k < a.n_uniform) {
+      // uniform samples: near fp32, far fp64 (clamped), blended in fp64, rounded to fp32 at the end
+      const float near = __fmul_rn(d, 0.001f), t = a.t_lin[k];
+      v = (float)((double)__fmul_rn(near, __fsub_rn(1.0f, t)) + s_far[lr] * (double)t);
+    } else if (d > 0.f) {   // depth-guided samples
+      const float lo = __fmul_rn(0.95f, d), hi = __fmul_rn(1.05f, d), t = a.t_surface[k - a.n_uniform];
+      v = __fadd_rn(__fmul_rn(lo, __fsub_rn(1.0f, t)), __fmul_rn(hi, t));
+    } else {
+      const float t = a.t_zero[k - a.n_uniform];
+      v = __fadd_rn(__fmul_rn(0.001f, __fsub_rn(1.0f, t)), __fmul_rn(maxd, t));
+    }
+    sm[k * kRaysZ + lr] = v;
+  }
+  __syncthreads();
   // ascending sort by rank (ties broken by position; equal values are interchangeable)
-  for (int i = 0; i < S; ++i) {
-    float v = col[i * bd];
+  for (int e = tid; e < nr * S; e += blockDim.x) {
+    const int lr = e / S, i = e - lr * S;
+    const float* col = sm + lr;
+    const float v = col[i * kRaysZ];
     int rank = 0;
     for (int j = 0; j < S; ++j) {
-      float u = col[j * bd];
+      float u = col[j * kRaysZ];
       rank += (u < v) || (u == v && j < i);
     }
-    a.z_vals[(int64_t)r * S + rank] = v;
+    a.z_vals[(int64_t)(r0 + lr) * S + rank] = v;
   }
   if (a.pts) {
-    for (int i = 0; i < S; ++i) {
-      float z = a.z_vals[(int64_t)r * S + i];
+    __syncthreads();   // the block's z values are complete (written by this block only)
+    for (int e = tid; e < nr * S; e += blockDim.x) {
+      const int lr = e / S;
+      const int64_t r = r0 + lr, q = (int64_t)r0 * S + e;
+      const float z = a.z_vals[q];
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        a.pts[((int64_t)r * S + i) * 3 + c] = __fadd_rn(a.rays_o[3 * r + c], __fmul_rn(a.rays_d[3 * r + c], z));
+      for (int c = 0; c < 3; ++c) a.pts[q * 3 + c] = __fadd_rn(a.rays_o[3 * r + c], __fmul_rn(a.rays_d[3 * r + c], z));
     }
   }
 }
@@ -168,14 +178,7 @@ int dns_sample_rays(const dns_sample_args* a, void* stream) {
   PhaseScope ph(phSample, st, 3);
   cudaMemsetAsync(a->scratch, 0, 2 * sizeof(float), st);
   k_sample_gather<<<(a->n + 127) / 128, 128, 0, st>>>(*a);
-  const int bd = 64;
-  size_t smem = sizeof(float) * S * bd;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_sample_z, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    attr = true;
-  }
-  k_sample_z<<<(a->n + bd - 1) / bd, bd, smem, st>>>(*a);
+  k_sample_z<<<(a->n + kRaysZ - 1) / kRaysZ, 128, sizeof(float) * S * kRaysZ, st>>>(*a);
   return check_launch("sample_rays");
 }
 
