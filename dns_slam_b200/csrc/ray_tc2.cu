@@ -21,7 +21,7 @@ constexpr int kW1oBytes2 = 14 * 64 * 16;  // one bf16 half of the [64 x 112] col
 
 __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restrict__ w1_hi, const uint4* __restrict__ w1_lo) {
   extern __shared__ __align__(1024) unsigned char smraw[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, wbar;
   __shared__ uint32_t tmem_base_s;
   const int T = a.T, S = a.S, RPC = a.RPC, C = a.C, C4 = a.C4, ld = T + 1;
   const int NT = 2 * T;                        // threads
@@ -49,15 +49,17 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   float* LS = LG + RPC * C4;            // [4]
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t >= T ? 1 : 0, row = t - grp * T;
-  for (int i = t; i < kW1oBytes2 / 16; i += NT) {
-    reinterpret_cast<uint4*>(W_hi)[i] = w1_hi[i];
-    reinterpret_cast<uint4*>(W_lo)[i] = w1_lo[i];
+  if (t == 0) {   // the 28 KB weight tile arrives by two bulk copies while the threads encode their rows
+    mbar_init(&bar, 1);
+    mbar_init(&wbar, 1);
+    mbar_expect_tx(&wbar, 2 * kW1oBytes2);
+    bulk_g2s(W_hi, w1_hi, kW1oBytes2, &wbar);
+    bulk_g2s(W_lo, w1_lo, kW1oBytes2, &wbar);
   }
   for (int i = t; i < 32; i += NT) reinterpret_cast<float4*>(W2c)[i] = reinterpret_cast<const float4*>(a.W2cT)[i];
   if (t < 4) LS[t] = 0.f;
   const uint32_t tmem_cols = MT == 1 ? 128 : 256;
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
-  if (t == 0) mbar_init(&bar, 1);
 
   const int lr = row / S, s = row - lr * S;
   const int64_t rl = (int64_t)blockIdx.x * RPC + lr;      // chunk-local ray
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   const uint32_t tmem_d = tmem_base_s;
   // ---- forward GEMM: H = X . W1^T  (A K-major: LBO = chunk stride, SBO = 128; B K-major: LBO = 1024, SBO = 128)
   if (t == 0) {
+    mbar_wait(&wbar, 0);   // weights landed
     const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
     for (int mt = 0; mt < MT; ++mt) {
       const uint32_t d = tmem_d + mt * 112;

@@ -971,11 +971,18 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     B.lo[c] = a->bound[c][0];
     B.ext[c] = a->bound[c][1] - a->bound[c][0];
   }
-  PhaseScope* ph = new PhaseScope(phPrep, st, map ? 6 : 5);
+  const bool tc = use_tensor_cores();
+  // weight preparation: bf16 hi/lo chunk tiles (tcgen05 path) or k-major fp32 copies (SIMT path)
+  PhaseScope* ph = new PhaseScope(phPrep, st, 1 + (a->global_counts ? 0 : 1) + (map ? 2 : 1));
   cudaMemsetAsync(w.counts, 0, 16 * sizeof(int), st);
   cudaMemsetAsync(w.raw, 0, 16 * sizeof(float), st);
-  k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, w.WTc);
-  if (map) k_transpose_net80<<<a->n_experts, 256, 0, st>>>(a->experts, w.WTe);
+  if (!tc) {
+    k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, w.WTc);
+    if (map) k_transpose_net80<<<a->n_experts, 256, 0, st>>>(a->experts, w.WTe);
+  } else if (int e = prep_nets_tc(a->coarse, map ? a->experts : nullptr, map ? a->n_experts : 0, w.wc_tc, w.we_tc, st)) {
+    delete ph;
+    return e;
+  }
   k_transpose_out<<<1, 256, 0, st>>>(a->color, a->logit, w.W1T2, w.W2cT);
   {
     if (a->global_counts) {
@@ -988,9 +995,6 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   }
   delete ph;
   if (int e = check_launch("render prep")) return e;
-  const bool tc = use_tensor_cores();
-  if (tc)
-    if (int e = prep_nets_tc(a->coarse, map ? a->experts : nullptr, map ? a->n_experts : 0, w.wc_tc, w.we_tc, st)) return e;
 
   static bool attr = false;
   if (!attr) {
@@ -1031,9 +1035,9 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.need_dparams = a->need_dparams && !a->forward_only; pa.need_drays = a->need_drays;
     { const char* e = getenv("DNS_DBG"); pa.dbg = e ? atoi(e) : 0; }
     if (map) {
-      PhaseScope phc(phClassPrep, st, 5);
-      cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);
       const bool whole = !sharded && ray0 == 0 && nc == N && (int64_t)N * S < 2147483647LL && !getenv("DNS_GENERIC_PREP");
+      PhaseScope phc(phClassPrep, st, whole ? 4 : 3);
+      cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);
       if (whole) {
         int rblocks = (int)((N + 255) / 256);
         rblocks = rblocks < 592 ? rblocks : 592;
@@ -1082,7 +1086,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.need_dfeat = a->need_dfeat && a->d_features && !fwd_only;
     pa.need_drays = ra.need_drays;
     {
-      PhaseScope phr(phRay, st, 1);
+      PhaseScope phr(phRay, st, 1 + ((tc && ray0 == 0) ? 1 : 0));
       if (tc) {
         if (int e = launch_ray_tc(ra, a->color, a->logit, w.W1o_hi, w.W1o_lo, ray0 == 0, nc, st)) return e;
       } else {
@@ -1104,7 +1108,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       k_unpad33<<<(int)((Pc * DNS_LATENT + 255) / 256), 256, 0, st>>>(w.coarse36, a->coarse_out + p0 * DNS_LATENT, Pc);
 
     if (a->need_dparams && !fwd_only) {
-      PhaseScope phg(phDwGemm, st, map ? 8 : 6);
+      PhaseScope phg(phDwGemm, st, tc ? (map ? 6 : 5) : (map ? 8 : 6));
       const int64_t Qrows = (int64_t)tiles_max * kTile;
       const int* ntd = map ? w.counts + cTiles : nullptr;
       int e = 0;
