@@ -457,6 +457,23 @@ static void set_attrs2() {
   cudaFuncSetAttribute(k_point_bwd_tc2<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
   cudaFuncSetAttribute(k_point_bwd_tc2<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
   cudaFuncSetAttribute(k_point_bwd_tc2<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+  {
+    // L1 beats occupancy for the forward gathers: the coarse hash-grid levels live in L1, and a carve-out that fits
+    // three CTAs (228 KB) leaves only 28 KB of it.  Measured at 131 072 rays x 47 (point_fwd ms): 86 % -> 4.93,
+    // 72 % -> 4.23, 58 % -> 4.15, 44 % -> 5.90.  The backward kernel is best at the driver's default (6.9 ms;
+    // 7.3 / 9.8 / 9.2 at 72 / 86 / 44 %).  DNS_FWD_CARVE / DNS_BWD_CARVE override (percent).
+    const char* e = getenv("DNS_FWD_CARVE");
+    const int pct = e ? atoi(e) : 58;
+    cudaFuncSetAttribute(k_point_fwd_tc2<kTrack>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_point_fwd_tc2<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_point_fwd_tc2<kTv>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
+  if (const char* e = getenv("DNS_BWD_CARVE")) {
+    const int pct = atoi(e);
+    cudaFuncSetAttribute(k_point_bwd_tc2<kTrack>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_point_bwd_tc2<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_point_bwd_tc2<kTv>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   done = true;
 }
 
