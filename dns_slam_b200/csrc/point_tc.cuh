@@ -37,6 +37,26 @@ __device__ __forceinline__ void load_weights_tc(unsigned char* W1_hi, unsigned c
   }
 }
 
+// combined layer-1 tile only (point_tc2.cu fetches the layer-2 tiles later, over this one)
+__device__ __forceinline__ void load_w1_tc(unsigned char* W1_hi, unsigned char* W1_lo, const uint4* __restrict__ wc,
+                                           const uint4* __restrict__ we, bool fine) {
+  const uint4 z4 = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 640; i += blockDim.x) {  // rows 0..31 coarse, 32..63 expert
+    int c = i >> 6, j = i & 63;
+    uint4 h, l;
+    if (j < 32) {
+      h = wc[c * 32 + j];
+      l = wc[320 + c * 32 + j];
+    } else if (fine) {
+      h = we[c * 32 + j - 32];
+      l = we[320 + c * 32 + j - 32];
+    } else {
+      h = l = z4;
+    }
+    reinterpret_cast<uint4*>(W1_hi)[i] = h;
+    reinterpret_cast<uint4*>(W1_lo)[i] = l;
+  }
+}
 
 size_t point_fwd_tc_smem();
 size_t point_bwd_tc_smem();

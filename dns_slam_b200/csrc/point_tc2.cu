@@ -23,16 +23,19 @@ template <int MODE>
 __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
                                                              const uint4* __restrict__ we_all) {
   extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, wbar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red[32];
+  // 60 KB: the operand region holds X, then H; the weight region holds W1, then (bulk-copied while the threads
+  // run the hidden-layer epilogue) the two W2 tiles.  Two CTAs fit a 132 KB carve-out, which leaves 124 KB of L1
+  // to the hash-table gathers.
   unsigned char* X_hi = sm;
   unsigned char* X_lo = sm + kXTile;
   unsigned char* H_hi = sm;                 // aliases the X tile once the first GEMM has completed
   unsigned char* H_lo = sm + 8 * 2048;
   unsigned char* W1_hi = sm + 2 * kXTile;
   unsigned char* W1_lo = W1_hi + kW1Tile;
-  unsigned char* W2c_hi = W1_lo + kW1Tile;  // hi | lo
+  unsigned char* W2c_hi = W1_hi;            // hi | lo; aliases W1 once the first GEMM has completed
   unsigned char* W2f_hi = W2c_hi + 2 * kW2Tile;
   const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, row = tid & (kTile - 1), grp = tid >> 7;
   const int n_tiles = a.perm ? a.counts[cTiles] : a.n_tiles_host;
@@ -40,9 +43,13 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
   int expert = -1;
   if (MODE == kMap) expert = a.tile_class[tile];
   const bool fine = MODE == kMap && expert >= 0;
-  load_weights_tc(W1_hi, W1_lo, W2c_hi, W2f_hi, wc_all, we_all + (int64_t)(fine ? expert : 0) * kNetTc, fine);
+  const uint4* we_net = we_all + (int64_t)(fine ? expert : 0) * kNetTc;
+  load_w1_tc(W1_hi, W1_lo, wc_all, we_net, fine);
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
-  if (tid == 0) mbar_init(&bar, 1);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&wbar, 1);
+  }
 
   const int64_t q = (int64_t)tile * kTile + row;
   int64_t i, r;
@@ -101,6 +108,11 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
   }
   mbar_wait(&bar, 0);
   tc_fence_after();
+  if (tid == 0) {   // W1 has been consumed: fetch the layer-2 weights over it (W2 hi | lo are contiguous per net)
+    mbar_expect_tx(&wbar, (fine ? 2u : 1u) * 2u * kW2Tile);
+    bulk_g2s(W2c_hi, wc_all + 640, 2 * kW2Tile, &wbar);
+    if (fine) bulk_g2s(W2f_hi, we_net + 640, 2 * kW2Tile, &wbar);
+  }
   const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
   {
     // hidden activations of this thread's share (NH/2 units): next A operand + global tile image (ReLU mask, dW2)
@@ -125,6 +137,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
   __syncthreads();   // accumulator rows read, H tile written: D columns and the X region are free again
   if (tid == 0) {    // O = H . W2^T per net
     tc_fence_after();
+    mbar_wait(&wbar, 0);
     const uint32_t idesc = umma_idesc_bf16(128, 48, 0, 0);
     for (int net = 0; net < (fine ? 2 : 1); ++net) {
       const unsigned char* Wh = net ? W2f_hi : W2c_hi;
@@ -446,11 +459,12 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
 }
 
 static size_t point_bwd_tc2_smem() { return point_bwd_tc_smem(); }
+static size_t point_fwd_tc2_smem() { return 2 * kXTile + 2 * kW1Tile; }
 
 static void set_attrs2() {
   static bool done = false;
   if (done) return;
-  const int f = (int)point_fwd_tc_smem(), b = (int)point_bwd_tc2_smem();
+  const int f = (int)point_fwd_tc2_smem(), b = (int)point_bwd_tc2_smem();
   cudaFuncSetAttribute(k_point_fwd_tc2<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
   cudaFuncSetAttribute(k_point_fwd_tc2<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
   cudaFuncSetAttribute(k_point_fwd_tc2<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
@@ -459,11 +473,12 @@ static void set_attrs2() {
   cudaFuncSetAttribute(k_point_bwd_tc2<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
   {
     // L1 beats occupancy for the forward gathers: the coarse hash-grid levels live in L1, and a carve-out that fits
-    // three CTAs (228 KB) leaves only 28 KB of it.  Measured at 131 072 rays x 47 (point_fwd ms): 86 % -> 4.93,
-    // 72 % -> 4.23, 58 % -> 4.15, 44 % -> 5.90.  The backward kernel is best at the driver's default (6.9 ms;
-    // 7.3 / 9.8 / 9.2 at 72 / 86 / 44 %).  DNS_FWD_CARVE / DNS_BWD_CARVE override (percent).
+    // three CTAs (228 KB) leaves only 28 KB of it.  Measured at 131 072 rays x 47 (point_fwd ms, 60 KB per CTA):
+    // 86 % -> 4.89, 72 % -> 3.80, 58 % -> 4.11 (with 74 KB per CTA: 4.93 / 4.23 / 4.15, 44 % -> 5.90).  The backward
+    // kernel is best at the driver's default (6.9 ms; 7.3 / 9.8 / 9.2 at 72 / 86 / 44 %).
+    // DNS_FWD_CARVE / DNS_BWD_CARVE override (percent).
     const char* e = getenv("DNS_FWD_CARVE");
-    const int pct = e ? atoi(e) : 58;
+    const int pct = e ? atoi(e) : 72;
     cudaFuncSetAttribute(k_point_fwd_tc2<kTrack>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_point_fwd_tc2<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_point_fwd_tc2<kTv>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -479,7 +494,7 @@ static void set_attrs2() {
 
 int launch_point_fwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
   set_attrs2();
-  const size_t smem = point_fwd_tc_smem();
+  const size_t smem = point_fwd_tc2_smem();
   if (mode == kMap) k_point_fwd_tc2<kMap><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else if (mode == kTrack) k_point_fwd_tc2<kTrack><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else k_point_fwd_tc2<kTv><<<tiles, kTile2, smem, st>>>(pa, wc, we);
