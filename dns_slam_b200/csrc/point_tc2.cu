@@ -244,18 +244,19 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
-  // dOut tiles coarse hi | lo | fine hi | lo, six chunks each.  (Packing them at five chunks would fit a third CTA
-  // per SM; measured SLOWER -- 9.6 vs 7.6 ms -- because the kernel is bound by the L2 atomic units, and more
-  // resident CTAs only deepen the queue in front of them.)
+  // 64 KB.  Phase 1: dOut tiles coarse hi | lo | fine hi | lo (six chunks each, 48 KB) and the W2 tiles.  Phase 2
+  // (after the first GEMM): the dH tile [8 chunks hi | lo, 32 KB] and the combined W1 tile (20 KB, prefetched into
+  // registers while the GEMM runs) take the place of the dOut tiles.  Two CTAs then fit a 132 KB carve-out and the
+  // corner re-reads get 124 KB of L1.  (More resident CTAs with a larger carve-out were measured slower.)
   unsigned char* DOc_hi = sm;
   unsigned char* DOc_lo = sm + kDOTile;
   unsigned char* DOf_hi = sm + 2 * kDOTile;
   unsigned char* DOf_lo = sm + 3 * kDOTile;
   unsigned char* DH_hi = sm;                        // dH tile [8 chunks] aliases the dOut tiles
   unsigned char* DH_lo = sm + 8 * 2048;
-  unsigned char* W1_hi = sm + 4 * kDOTile;
+  unsigned char* W1_hi = sm + 16 * 2048;            // behind the dH tile, still inside the (dead) dOut tiles
   unsigned char* W1_lo = W1_hi + kW1Tile;
-  unsigned char* W2c_hi = W1_lo + kW1Tile;
+  unsigned char* W2c_hi = sm + 16 * 2048 + 2 * kW1Tile;
   unsigned char* W2f_hi = W2c_hi + 2 * kW2Tile;
   float* DXS = reinterpret_cast<float*>(sm);        // [3][128] partial d/dx of group 1 (after the last GEMM)
   const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, row = tid & (kTile - 1), grp = tid >> 7;
@@ -264,7 +265,11 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   int expert = -1;
   if (MODE == kMap) expert = a.tile_class[tile];
   const bool fine = MODE == kMap && expert >= 0;
-  load_weights_tc(W1_hi, W1_lo, W2c_hi, W2f_hi, wc_all, we_all + (int64_t)(fine ? expert : 0) * kNetTc, fine);
+  const uint4* we_net = we_all + (int64_t)(fine ? expert : 0) * kNetTc;
+  for (int k = tid; k < 384; k += kTile2) {   // W2 coarse / expert, hi | lo contiguous per net
+    reinterpret_cast<uint4*>(W2c_hi)[k] = wc_all[640 + k];
+    reinterpret_cast<uint4*>(W2f_hi)[k] = fine ? we_net[640 + k] : make_uint4(0, 0, 0, 0);
+  }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
   if (tid == 0) mbar_init(&bar, 1);
 
@@ -368,8 +373,19 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
     }
     umma_commit(&bar);
   }
+  // combined W1 tile (rows 0..31 coarse, 32..63 expert per feature chunk; hi then lo): 1280 elements, five per
+  // thread, fetched while the GEMM runs and stored once the dOut tiles are dead
+  uint4 w1r[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int e = tid + k * kTile2, half = e >= 640 ? 1 : 0, idx = e - 640 * half, c = idx >> 6, j = idx & 63;
+    w1r[k] = j < 32 ? wc_all[320 * half + c * 32 + j]
+                    : (fine ? we_net[320 * half + c * 32 + j - 32] : make_uint4(0, 0, 0, 0));
+  }
   mbar_wait(&bar, 0);
   tc_fence_after();
+#pragma unroll
+  for (int k = 0; k < 5; ++k) reinterpret_cast<uint4*>(W1_hi)[tid + k * kTile2] = w1r[k];   // W1_lo follows W1_hi
   const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
   {
     // dH of this thread's share, masked by the ReLU: the bf16 hi half of the stashed activation is non-zero exactly
@@ -458,7 +474,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   }
 }
 
-static size_t point_bwd_tc2_smem() { return point_bwd_tc_smem(); }
+static size_t point_bwd_tc2_smem() { return 16 * 2048 + 2 * kW1Tile + 4 * kW2Tile; }
 static size_t point_fwd_tc2_smem() { return 2 * kXTile + 2 * kW1Tile; }
 
 static void set_attrs2() {
@@ -483,8 +499,9 @@ static void set_attrs2() {
     cudaFuncSetAttribute(k_point_fwd_tc2<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_point_fwd_tc2<kTv>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
-  if (const char* e = getenv("DNS_BWD_CARVE")) {
-    const int pct = atoi(e);
+  {
+    const char* e = getenv("DNS_BWD_CARVE");
+    const int pct = e ? atoi(e) : 58;
     cudaFuncSetAttribute(k_point_bwd_tc2<kTrack>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_point_bwd_tc2<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_point_bwd_tc2<kTv>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
