@@ -9,6 +9,6 @@ CMD="python bench.py --steps 2 --warmup 1 --rays-per-gpu 32768 --no-extra --cpu-
 $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'k_ray_tc|k_point_fwd_tc2|k_point_bwd_tc2|k_dw_img' -s 11 -c 10 -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_ray_tc2|k_point_fwd_tc2|k_point_bwd_tc2|k_dw_img' -s 10 -c 9 -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"
 ls -la $OUT
