@@ -13,6 +13,8 @@
 //             dH epilogue per net as above;  dX: group 0 OneBlob + levels 0..7, group 1 levels 8..15
 //
 // so 24 warps per SM are resident with the same shared-memory budget.
+#include <stdio.h>
+
 #include "point_tc.cuh"
 
 namespace dns {
@@ -487,31 +489,34 @@ static void set_attrs2() {
   cudaFuncSetAttribute(k_point_bwd_tc2<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
   cudaFuncSetAttribute(k_point_bwd_tc2<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
   cudaFuncSetAttribute(k_point_bwd_tc2<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-  {
-    // L1 beats occupancy for the forward gathers: the coarse hash-grid levels live in L1, and a carve-out that fits
-    // three CTAs (228 KB) leaves only 28 KB of it.  Measured at 131 072 rays x 47 (point_fwd ms, 60 KB per CTA):
-    // 86 % -> 4.89, 72 % -> 3.80, 58 % -> 4.11 (with 74 KB per CTA: 4.93 / 4.23 / 4.15, 44 % -> 5.90).  The backward
-    // kernel is best at the driver's default (6.9 ms; 7.3 / 9.8 / 9.2 at 72 / 86 / 44 %).
-    // DNS_FWD_CARVE / DNS_BWD_CARVE override (percent).
-    const char* e = getenv("DNS_FWD_CARVE");
-    const int pct = e ? atoi(e) : 72;
-    cudaFuncSetAttribute(k_point_fwd_tc2<kTrack>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(k_point_fwd_tc2<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(k_point_fwd_tc2<kTv>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  }
-  {
-    const char* e = getenv("DNS_BWD_CARVE");
-    const int pct = e ? atoi(e) : 58;
-    cudaFuncSetAttribute(k_point_bwd_tc2<kTrack>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(k_point_bwd_tc2<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(k_point_bwd_tc2<kTv>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  }
   done = true;
+}
+
+// L1 beats occupancy for the gathers: the coarse hash-grid levels live in L1, and a carve-out that fits three CTAs
+// (228 KB) leaves only 28 KB of it.  Measured at 131 072 rays x 47: point_fwd (60 KB per CTA) 86 % -> 4.89 ms,
+// 72 % -> 3.80, 58 % -> 4.11; point_bwd (64 KB per CTA) 58 % -> 6.79, 72 % -> 7.0, 86 % -> 9.9.  Changing the
+// carve-out between consecutive kernels costs a reconfiguration, which shows at SLAM-iteration sizes (mapping
+// iteration 2.37 -> 2.60 ms), so the preference is only set for large launches.  DNS_FWD_CARVE / DNS_BWD_CARVE
+// override the percentages.
+template <typename K>
+static void prefer_carveout(K kernel, int& last, int tiles, const char* env, int tuned) {
+  static const int kLargeTiles = 8192;
+  const char* e = getenv(env);
+  const int want = tiles >= kLargeTiles ? (e ? atoi(e) : tuned) : -1;   // -1: cudaSharedmemCarveoutDefault
+  if (want != last) {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, want);
+    if (getenv("DNS_CARVE_DEBUG")) fprintf(stderr, "carveout %s tiles %d -> %d (%s)\n", env, tiles, want, cudaGetErrorString(err));
+    last = want;
+  }
 }
 
 int launch_point_fwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
   set_attrs2();
   const size_t smem = point_fwd_tc2_smem();
+  static int last[3] = {-2, -2, -2};
+  if (mode == kMap) prefer_carveout(k_point_fwd_tc2<kMap>, last[0], tiles, "DNS_FWD_CARVE", 72);
+  else if (mode == kTrack) prefer_carveout(k_point_fwd_tc2<kTrack>, last[1], tiles, "DNS_FWD_CARVE", 72);
+  else prefer_carveout(k_point_fwd_tc2<kTv>, last[2], tiles, "DNS_FWD_CARVE", 72);
   if (mode == kMap) k_point_fwd_tc2<kMap><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else if (mode == kTrack) k_point_fwd_tc2<kTrack><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else k_point_fwd_tc2<kTv><<<tiles, kTile2, smem, st>>>(pa, wc, we);
@@ -520,6 +525,10 @@ int launch_point_fwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* 
 int launch_point_bwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
   set_attrs2();
   const size_t smem = point_bwd_tc2_smem();
+  static int last[3] = {-2, -2, -2};
+  if (mode == kMap) prefer_carveout(k_point_bwd_tc2<kMap>, last[0], tiles, "DNS_BWD_CARVE", 58);
+  else if (mode == kTrack) prefer_carveout(k_point_bwd_tc2<kTrack>, last[1], tiles, "DNS_BWD_CARVE", 58);
+  else prefer_carveout(k_point_bwd_tc2<kTv>, last[2], tiles, "DNS_BWD_CARVE", 58);
   if (mode == kMap) k_point_bwd_tc2<kMap><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else if (mode == kTrack) k_point_bwd_tc2<kTrack><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else k_point_bwd_tc2<kTv><<<tiles, kTile2, smem, st>>>(pa, wc, we);

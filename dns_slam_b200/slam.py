@@ -167,8 +167,11 @@ class TrackerCore:
         rays_o, rays_d = fused.attach_pose_grad(s["rays_o"], s["rays_d"], dirs, R, T)
         z = s["z_vals"]
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
+        merge = self.decoder.merge
+        if self.freeze_decoder and z.is_cuda:   # tracking never updates the Merge weights: skip their gradient GEMMs
+            merge = lambda p, o, f: fused.merge_fused(p, f, self.decoder.merge.decoder.params.detach(), self.decoder.merge.bound)  # noqa: E731
         code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), refer_frames["est_w2c"].detach(),
-                                      features_cl, self.decoder.merge)
+                                      features_cl, merge)
         code = code.reshape(pts.shape[0], pts.shape[1], -1) * trunc_mask(z, s["gt_depth"])[..., None]
         mask = (s["gt_depth"] > 0.01) * s["inside"]
         return {"gt_color": s["gt_color"], "gt_depth": s["gt_depth"], "gt_label": s["gt_label"],
