@@ -1,4 +1,4 @@
-// Shared pieces of the tcgen05 point kernels (point_tc.cu: one thread per slot; point_tc2.cu: two threads per slot).
+// Shared pieces of the tcgen05 point kernels (point_tc.cu: weight preparation; point_tc2.cu: the kernels).
 #pragma once
 #include "tc_common.cuh"
 
@@ -12,32 +12,7 @@ constexpr int kW1Tile = 10 * 64 * 16;   // one half of the combined W1 tile [10 
 constexpr int kW2Tile = 4 * 48 * 16;    // one half of a W2 tile [4 chunks][48 rows][16]
 constexpr int kDOTile = 6 * 2048;       // one half of a dOut tile [6 chunks][128][16]
 
-__device__ __forceinline__ void load_weights_tc(unsigned char* W1_hi, unsigned char* W1_lo, unsigned char* W2c_hi,
-                                                unsigned char* W2f_hi, const uint4* __restrict__ wc,
-                                                const uint4* __restrict__ we, bool fine) {
-  const uint4 z4 = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 640; i += blockDim.x) {  // combined W1: rows 0..31 coarse, 32..63 expert
-    int c = i >> 6, j = i & 63;
-    uint4 h, l;
-    if (j < 32) {
-      h = wc[c * 32 + j];
-      l = wc[320 + c * 32 + j];
-    } else if (fine) {
-      h = we[c * 32 + j - 32];
-      l = we[320 + c * 32 + j - 32];
-    } else {
-      h = l = z4;
-    }
-    reinterpret_cast<uint4*>(W1_hi)[i] = h;
-    reinterpret_cast<uint4*>(W1_lo)[i] = l;
-  }
-  for (int i = threadIdx.x; i < 384; i += blockDim.x) {  // W2 coarse hi|lo contiguous
-    reinterpret_cast<uint4*>(W2c_hi)[i] = wc[640 + i];
-    reinterpret_cast<uint4*>(W2f_hi)[i] = fine ? we[640 + i] : z4;
-  }
-}
-
-// combined layer-1 tile only (point_tc2.cu fetches the layer-2 tiles later, over this one)
+// combined layer-1 tile (the forward kernel fetches the layer-2 tiles later, over this one)
 __device__ __forceinline__ void load_w1_tc(unsigned char* W1_hi, unsigned char* W1_lo, const uint4* __restrict__ wc,
                                            const uint4* __restrict__ we, bool fine) {
   const uint4 z4 = make_uint4(0, 0, 0, 0);
@@ -58,9 +33,5 @@ __device__ __forceinline__ void load_w1_tc(unsigned char* W1_hi, unsigned char* 
   }
 }
 
-size_t point_fwd_tc_smem();
-size_t point_bwd_tc_smem();
-int launch_point_fwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
-int launch_point_bwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
 
 }  // namespace dns

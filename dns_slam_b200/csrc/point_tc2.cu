@@ -1,10 +1,19 @@
 // Point kernels on tcgen05, TWO threads per slot (256-thread CTAs, one 128-slot tile per CTA).
 //
-// Same mathematics and the same GEMMs as point_tc.cu; what changes is the occupancy.  The one-thread-per-slot
-// kernels are limited to 3 CTAs = 12 warps per SM by their operand tiles in shared memory, and ncu shows them
-// waiting on the 128 hash-table gathers (forward) / 128 vector atomics (backward) each thread issues.  Here the
-// two threads of a slot (tid and tid + 128: same TMEM lane quarter, so both may read the slot's accumulator
-// row) split that work:
+// Same mathematics as k_point_fwd / k_point_bwd (render.cu): OneBlob + hash-grid encode, the coarse MLP
+// 80 -> 32 -> 33 (models/decoder.py:80-94), the class-expert MLP of the tile (slams/mapping.py:590-601), the latent /
+// free-space / opacity loss terms (mapping.py:123-126, utils/common.py:769-802) and their backward down to the
+// hash-table scatter.  One CTA = one 128-slot tile = one 128-row MMA tile.  GEMMs (bf16 hi + lo halves, 3 products,
+// fp32 accumulation in TMEM):
+//
+//   fwd   H[128 x 64]    = X[128 x 80]  . [W1 coarse ; W1 expert]^T            K = 80
+//         Oc[128 x 48]   = Hc[128 x 32] . W2 coarse^T,  Of likewise            K = 32
+//   bwd   dHc[128 x 32]  = dOc[128 x 48] . W2 coarse,   dHf likewise           K = 48
+//         dX[128 x 80]   = [dHc | dHf][128 x 64] . [W1 coarse ; W1 expert]     K = 64  (sums both nets)
+//
+// A first version ran one thread per slot (12 warps per SM) and ncu showed it waiting on the 128 hash-table gathers
+// (forward) / 128 vector atomics (backward) each thread issues.  Here the two threads of a slot (tid and tid + 128:
+// same TMEM lane quarter, so both may read the slot's accumulator row) split that work:
 //
 //   forward   group 0: OneBlob of the 3 coordinates + hash-grid levels 0..7;   group 1: levels 8..15
 //             hidden epilogue: group g owns net g (coarse / class expert) or half of the single net
@@ -476,8 +485,8 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   }
 }
 
-static size_t point_bwd_tc2_smem() { return 16 * 2048 + 2 * kW1Tile + 4 * kW2Tile; }
-static size_t point_fwd_tc2_smem() { return 2 * kXTile + 2 * kW1Tile; }
+size_t point_bwd_tc2_smem() { return 16 * 2048 + 2 * kW1Tile + 4 * kW2Tile; }
+size_t point_fwd_tc2_smem() { return 2 * kXTile + 2 * kW1Tile; }
 
 static void set_attrs2() {
   static bool done = false;
@@ -510,7 +519,7 @@ static void prefer_carveout(K kernel, int& last, int tiles, const char* env, int
   }
 }
 
-int launch_point_fwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
+int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
   set_attrs2();
   const size_t smem = point_fwd_tc2_smem();
   static int last[3] = {-2, -2, -2};
@@ -522,7 +531,7 @@ int launch_point_fwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* 
   else k_point_fwd_tc2<kTv><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   return check_launch("point_fwd_tc2");
 }
-int launch_point_bwd_tc2(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
+int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
   set_attrs2();
   const size_t smem = point_bwd_tc2_smem();
   static int last[3] = {-2, -2, -2};

@@ -1,9 +1,18 @@
 // Ray kernel on tcgen05, TWO threads per sample point (blockDim = 2 T, T a multiple of 128).
 //
-// Same mathematics and the same two GEMMs as ray_tc.cu (slams/tracking.py:188-214, slams/mapping.py:603-635,
-// utils/common.py:506-537).  ncu shows k_ray_tc issue bound: ~6.5 k instructions per thread on 10 warps per SM
-// (176 registers, 104 KB of shared memory per CTA).  Here the threads t and t + T share point t (same TMEM lane
-// quarter because T % 128 == 0) and split its work:
+// Same mathematics as k_ray (render.cu; slams/tracking.py:188-214, slams/mapping.py:603-635,
+// utils/common.py:506-537): colour + logit layer 1 per point, colour head, logit layer 2 on the composited hidden
+// state, occupancy compositing, p/d/l losses and the full backward.  The two 112x64 contractions per point run on
+// tcgen05 (bf16 hi + lo halves, fp32 accumulation in TMEM):
+//
+//   forward   H[p][0..63]   = X[p][0..111] . W1^T     M = 128 points, N = 64, K = 112
+//   backward  dX[p][0..111] = dH[p][0..63] . W1       M = 128 points, N = 112, K = 64
+//
+// Operand rows are 16-byte feature chunks [chunk][point][8 x bf16] (canonical no-swizzle UMMA layout); the SAME
+// shared-memory copy of W1 ([feature chunk][hidden row][8 features]) is the K-major B operand of the forward GEMM
+// and the MN-major B operand of the backward GEMM.  A first version ran one thread per point and was issue bound
+// (~6.5 k instructions per thread on 10 warps per SM, 176 registers).  Here the threads t and t + T share point t
+// (same TMEM lane quarter because T % 128 == 0) and split its work:
 //
 //   group 0 (t <  T)  OneBlob of the point -> X chunks 0..5; colour hidden units (accumulator columns 0..31),
 //                     colour head, colour gradients, dH chunks 0..3; OneBlob backward / ray gradients
@@ -12,7 +21,7 @@
 //                     d(latent) and d(feature) rows
 //
 // Per-ray work (column sums, logits, losses, QV) is spread over all 2 T threads.  T = 128 keeps two CTAs per SM
-// (16 warps), T = 256 one CTA of 16 warps with fewer idle rows; pick_ray_block_tc chooses by row efficiency.
+// (16 warps), T = 256 one CTA of 16 warps with fewer idle rows; pick_ray_block_tc2 chooses by row efficiency.
 #include "tc_common.cuh"
 
 namespace dns {

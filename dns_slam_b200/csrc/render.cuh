@@ -198,14 +198,11 @@ int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* w
 int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
 
 // tcgen05 ray kernel (ray_tc.cu)
-void pick_ray_block_tc(int S, int& T, int& RPC);
-// two threads per point (ray_tc2.cu; default).  DNS_RAY1=1 selects the one-thread kernel of ray_tc.cu.
+// two threads per point (ray_tc2.cu)
 void pick_ray_block_tc2(int S, int& T, int& RPC);
 size_t ray_tc2_smem_bytes(int T, int RPC, int C4);
 int launch_ray_tc2(const RayArgs& ra, uint4* w1_hi, uint4* w1_lo, int64_t n_rays_chunk, cudaStream_t st);
-bool ray_two_threads();
 void pick_ray_block_any(int S, int& T, int& RPC);
-size_t ray_tc_smem_bytes(int T, int RPC, int C4);
 int launch_ray_tc(const RayArgs& ra, const float* color, const float* logit, uint4* w1_hi, uint4* w1_lo, bool prep,
                   int64_t n_rays_chunk, cudaStream_t st);
 
