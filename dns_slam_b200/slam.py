@@ -24,6 +24,31 @@ def _quad2rotation_formula(quad):
     return torch.stack(rows, -1).reshape(quad.shape[0], 3, 3)
 
 
+_QUAD_VEC = {}
+
+
+def _quad2rotation_vectorised(quad):
+    """The nine entries of ``_quad2rotation_formula`` evaluated as 9-vectors: R_flat = base + coef * two_s * (A*B + sgn*C*D)
+    with the SAME fp32 operations per entry (x**2 == x*x, a - b == a + (-1)*b, 1 - v == 1 + (-1)*v are exact
+    identities), so the result is bit-identical, in ~10 launches instead of ~45."""
+    key = str(quad.device)
+    if key not in _QUAD_VEC:
+        # entry:        00      01      02      10      11      12      20      21      22      (r,i,j,k = 0,1,2,3)
+        idx = torch.tensor([[2, 1, 1, 1, 1, 2, 1, 2, 1],      # A
+                            [2, 2, 3, 2, 1, 3, 3, 3, 1],      # B
+                            [3, 3, 2, 3, 3, 1, 2, 1, 2],      # C
+                            [3, 0, 0, 0, 3, 0, 0, 0, 2]])     # D
+        sgn = torch.tensor([1., -1., 1., 1., 1., -1., -1., 1., 1.])
+        coef = torch.tensor([-1., 1., 1., 1., -1., 1., 1., 1., -1.])
+        base = torch.tensor([1., 0., 0., 0., 1., 0., 0., 0., 1.])
+        _QUAD_VEC[key] = tuple(t.to(quad.device) for t in (idx.reshape(-1), sgn, coef, base))
+    idx, sgn, coef, base = _QUAD_VEC[key]
+    g = quad[:, idx].reshape(quad.shape[0], 4, 9)
+    two_s = 2.0 / (quad * quad).sum(-1)
+    inner = g[:, 0] * g[:, 1] + sgn * (g[:, 2] * g[:, 3])
+    return (base + coef * (two_s[:, None] * inner)).reshape(quad.shape[0], 3, 3)
+
+
 _QUAD_HESS = {}
 
 
@@ -52,7 +77,7 @@ class _Quad2Rot(torch.autograd.Function):
     @staticmethod
     def forward(ctx, quad):
         with torch.no_grad():
-            R = _quad2rotation_formula(quad)
+            R = _quad2rotation_vectorised(quad)
         ctx.save_for_backward(quad, R)
         return R
 

@@ -55,3 +55,11 @@ def test_quad2rotation_closed_form_backward():
     (R2 * G).sum().backward()
     assert torch.equal(R1, R2)
     assert torch.allclose(g1, q.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_vectorised_quad2rotation_is_bit_identical():
+    """The 9-vector evaluation used by the autograd wrapper against the element-wise formula of common.py:406-429."""
+    torch.manual_seed(1)
+    for _ in range(300):
+        q = torch.randn(4, 4) * (torch.rand(1) * 3 + 0.05)
+        assert torch.equal(slam._quad2rotation_vectorised(q), slam._quad2rotation_formula(q))
