@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTile) k_merge_fwd_tc(MergeArgs a) {
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 0);
+  mbar_wait_cta(&bar, 0);
   tc_fence_after();
   const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
   {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kTile) k_merge_fwd_tc(MergeArgs a) {
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 1);
+  mbar_wait_cta(&bar, 1);
   tc_fence_after();
   {
     const float inv_r = 1.f / (float)a.R;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kTile) k_merge_bwd_tc(MergeArgs a) {
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 0);
+  mbar_wait_cta(&bar, 0);
   tc_fence_after();
   const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
   {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kTile) k_merge_bwd_tc(MergeArgs a) {
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 1);
+  mbar_wait_cta(&bar, 1);
   tc_fence_after();
 #pragma unroll
   for (int c = 0; c < 3; ++c) {

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 0);
+  mbar_wait_cta(&bar, 0);
   tc_fence_after();
   if (tid == 0) {   // W1 has been consumed: fetch the layer-2 weights over it (W2 hi | lo are contiguous per net)
     mbar_expect_tx(&wbar, (fine ? 2u : 1u) * 2u * kW2Tile);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 1);
+  mbar_wait_cta(&bar, 1);
   tc_fence_after();
   float lt = 0.f, fs = 0.f, op = 0.f;
   if (MODE == kTv) {
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
     w1r[k] = j < 32 ? wc_all[320 * half + c * 32 + j]
                     : (fine ? we_net[320 * half + c * 32 + j - 32] : make_uint4(0, 0, 0, 0));
   }
-  mbar_wait(&bar, 0);
+  mbar_wait_cta(&bar, 0);
   tc_fence_after();
 #pragma unroll
   for (int k = 0; k < 5; ++k) reinterpret_cast<uint4*>(W1_hi)[tid + k * kTile2] = w1r[k];   // W1_lo follows W1_hi
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 1);
+  mbar_wait_cta(&bar, 1);
   tc_fence_after();
   // dX columns: 0..47 OneBlob (group 0), 48..63 levels 0..7 (group 0), 64..79 levels 8..15 (group 1)
   float dx[3] = {0.f, 0.f, 0.f}, dg[16];

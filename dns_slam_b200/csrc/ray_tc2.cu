@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 0);
+  mbar_wait_cta(&bar, 0);
   tc_fence_after();
   // this thread's half of the hidden row: group 0 colour units, group 1 logit units
   const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((row >> 7) * 112);
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
     umma_commit(&bar);
   }
-  mbar_wait(&bar, 1);
+  mbar_wait_cta(&bar, 1);
   tc_fence_after();
   float g3[3] = {0.f, 0.f, 0.f};
   if (grp == 0) {   // dX columns 0..47: OneBlob backward -> d(ray)
