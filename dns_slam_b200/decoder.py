@@ -151,6 +151,18 @@ class Decoder(nn.Module):
             self.class_to_expert[c] = c
         return self._experts[c]
 
+    def copy_weights_from(self, other):
+        """Weight hand-off mapper -> tracker (the reference deep-copies the shared decoder for every frame,
+        slams/tracking.py:81, 296-302): ONE device copy of the flat buffer plus the expert table."""
+        if other.flat.numel() != self.flat.numel():
+            raise ValueError("decoders of different shape")
+        with torch.no_grad():
+            self.flat.copy_(other.flat)
+            self.class_to_expert.copy_(other.class_to_expert)
+        for c in other.fine_decoders:
+            self.activate_expert(c)
+        return self
+
     @property
     def fine_decoders(self):
         """``{class id: module}`` like ``Mapper.fine_decoders``."""

@@ -492,6 +492,47 @@ def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list,
     return quad_list, T_list, ld
 
 
+def keyframe_overlap(cam, gt_depth, c2w, keyframe_c2w, idx, n_samples=16):
+    """``Mapper.keyframe_selection_overlap`` (slams/mapping.py:171-231) without the per-key-frame numpy loop: the
+    ``pixels`` x 16 probe points of the current frame are projected into ALL key frames with one batched matmul on the
+    device.  ``idx`` are the drawn pixel indices (flat, whole image), ``keyframe_c2w`` [K,4,4].  Returns
+    percent_inside [K] (float32, on the device)."""
+    dev = keyframe_c2w.device
+    H, W = cam["H"], cam["W"]
+    idx = idx.to(dev)
+    dirs = fused.pixel_dirs(cam, idx, (0, H, 0, W))
+    c2w = c2w.to(dev)
+    p = dirs.reshape(-1, 1, 3) * c2w[:3, :3]
+    rays_d = (p[..., 0] + p[..., 1]) + p[..., 2]
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    d = gt_depth.to(dev).reshape(-1)[idx].reshape(-1, 1)
+    t_vals = torch.linspace(0.0, 1.0, steps=n_samples, device=dev)
+    z_vals = d * 0.8 * (1.0 - t_vals) + (d + 0.5) * t_vals
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., None]).reshape(-1, 3)          # [V,3]
+    w2c = torch.linalg.inv(keyframe_c2w.double())                                               # [K,4,4]
+    homo = torch.cat((pts.double(), torch.ones(pts.shape[0], 1, dtype=torch.float64, device=dev)), -1)
+    cam_cord = torch.einsum("kab,vb->kva", w2c, homo)[..., :3]                                   # [K,V,3]
+    cam_cord = cam_cord * torch.tensor([-1.0, 1.0, 1.0], dtype=torch.float64, device=dev)
+    K = cam["K"].to(dev).double()
+    uv = torch.einsum("ab,kvb->kva", K, cam_cord)
+    z = uv[..., 2:3] + 1e-5
+    uv = (uv[..., :2] / z).float()
+    edge = 10
+    mask = (uv[..., 0] < W - edge) & (uv[..., 0] > edge) & (uv[..., 1] < H - edge) & (uv[..., 1] > edge) & (z[..., 0] < 0)
+    return mask.float().mean(-1)
+
+
+def keyframe_selection_overlap(cam, gt_depth, c2w, keyframe_c2w, k, idx, perm=None, th=0.0):
+    """mapping.py:226-236: key frames with percent_inside > th, in descending order, shuffled by ``perm`` (the
+    reference's np.random.permutation, passed in like every other draw; None keeps the sorted order), first k."""
+    pct = keyframe_overlap(cam, gt_depth, c2w, keyframe_c2w, idx).cpu()
+    order = sorted(range(pct.numel()), key=lambda i: float(pct[i]), reverse=True)
+    sel = [i for i in order if float(pct[i]) > th]
+    if perm is not None:
+        sel = [sel[int(j)] for j in perm if int(j) < len(sel)]
+    return sel[:k]
+
+
 def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, lr, draws_fn, tv_draws_fn,
                  n_iters=100, n_rays=300):
     """``Mapper.decoder_init`` (slams/mapping.py:764-836): warm-up of freshly created class experts on the

@@ -594,3 +594,39 @@ def frame_vis_render(cam, bound, decoder, experts, frame, c2w, refer_w2c, feats,
         deps.append(depth)
         labs.append(torch.argmax(logits, -1))
     return torch.cat(cols, 0).reshape(H, W, 3), torch.cat(deps, 0).reshape(H, W), torch.cat(labs, 0).reshape(H, W)
+
+
+# --------------------------------------------------------------------------------------
+# key-frame selection by overlap  (slams/mapping.py:171-236), SURVEY 8 f2
+# --------------------------------------------------------------------------------------
+def keyframe_overlap(cam, gt_depth, c2w, keyframe_c2w, tape, n_samples=16, pixels=100):
+    """percent_inside per key frame, as the reference computes it with numpy: ``pixels`` random pixels of the current
+    frame, 16 depths in [0.8 d, d + 0.5] each, projected into every key frame (x flipped, z must be negative, 10 px
+    border).  Returns a float64 numpy array [n_keyframes]."""
+    import numpy as np
+    H, W = cam["H"], cam["W"]
+    fx, fy, cx, cy = cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    idx = uniform_indices(0, H, 0, W, pixels, tape)
+    i, j = uv_from_flat(idx, 0, 0, W)
+    rays_o, rays_d = rays_from_uv(i, j, c2w[:3, :3], c2w[:3, -1], fx, fy, cx, cy)
+    d = gt_depth.reshape(-1)[idx].reshape(-1, 1).repeat(1, n_samples)
+    t_vals = torch.linspace(0.0, 1.0, steps=n_samples)
+    z_vals = d * 0.8 * (1.0 - t_vals) + (d + 0.5) * t_vals
+    pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+    vertices = pts.reshape(-1, 3).cpu().numpy()
+    out = []
+    for kf in keyframe_c2w:
+        w2c = np.linalg.inv(kf.cpu().numpy())
+        ones = np.ones_like(vertices[:, 0]).reshape(-1, 1)
+        homo = np.concatenate([vertices, ones], axis=1).reshape(-1, 4, 1)
+        cam_cord = (w2c @ homo)[:, :3]
+        K = np.array([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]]).reshape(3, 3)
+        cam_cord[:, 0] *= -1
+        uv = K @ cam_cord
+        z = uv[:, -1:] + 1e-5
+        uv = (uv[:, :2] / z).astype(np.float32)
+        edge = 10
+        mask = (uv[:, 0] < W - edge) * (uv[:, 0] > edge) * (uv[:, 1] < H - edge) * (uv[:, 1] > edge)
+        mask = (mask & (z[:, :, 0] < 0)).reshape(-1)
+        out.append(mask.sum() / uv.shape[0])
+    return np.asarray(out, dtype=np.float64)
