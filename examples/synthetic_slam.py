@@ -1,0 +1,93 @@
+"""A minimal tracking + mapping loop on a synthetic RGB-D + label sequence, wired the way slams/dns_slam.py wires the
+reference: the mapper optimises the shared decoder on a window of key frames, the tracker takes a copy of the weights
+and optimises the pose of every new frame, key frames are chosen by overlap, the result is check-pointed and one frame
+is rendered.  Everything numerical goes through the C ABI; this file only orchestrates (orchestration is not part of
+the scoped path -- it is here to show the drop-in surface end to end and is exercised by tests/test_gpu_pipeline.py).
+
+    python examples/synthetic_slam.py [shape] [n_frames]
+"""
+import os
+import sys
+import tempfile
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from dns_slam_b200 import bench_util, checkpoint, fused, inference, slam  # noqa: E402
+from dns_slam_b200 import synthetic as syn  # noqa: E402
+
+
+def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_graph=True, seed=0, out_dir=None, verbose=True):
+    dev = torch.device("cuda:0")
+    s = syn.SHAPES[shape]
+    cam = syn.camera(shape)
+    gen = torch.Generator().manual_seed(seed)
+    poses = syn.trajectory(shape, n_frames + 1)
+    frames = [{k: v.to(dev).contiguous() for k, v in syn.frame(shape, poses[i], gen, n_class=n_class).items()}
+              for i in range(n_frames)]
+    feats = [fused.channels_last(syn.pixel_features(shape, 1, gen).to(dev)) for _ in range(n_frames)]
+    shared = bench_util.make_decoder(shape, n_class, dev, seed=seed, all_experts=False)
+    tracker_dec = bench_util.make_decoder(shape, n_class, dev, seed=seed + 1, all_experts=False)
+    mapper = slam.MapperCore(cam, shared, s["mapping_pixels"], 32, 15,
+                             lambdas=dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0,
+                                          fs=s["lambda_fs"], op=s["lambda_opacity"]),
+                             opacity_sigma=s["opacity_sigma"], smooth_pts=s["smooth_pts"], lambda_sm=s["lambda_smooth"])
+    tracker = slam.TrackerCore(cam, tracker_dec, s["tracking_pixels"], 32, 15, s["lambda_color"], s["lambda_depth"],
+                               s["lambda_label"], freeze_decoder=True)
+    est = [poses[0].clone()]
+    keyframes = [0]
+    log = []
+    for f in range(n_frames):
+        # ---- mapping on the window [selected key frames ..., current frame] (mapping.py:839-949)
+        if f > 0:
+            kf_c2w = torch.stack([est[k] for k in keyframes], 0).to(dev)
+            idx = torch.randint(cam["H"] * cam["W"], (100,), generator=gen)
+            picked = slam.keyframe_selection_overlap(cam, frames[f]["depth"], est[f], kf_c2w, 2, idx)
+            window = sorted({keyframes[i] for i in picked} | {f})
+        else:
+            window = [0]
+        for c in torch.unique(torch.cat([frames[k]["label"].reshape(-1) for k in window])).tolist():
+            shared.activate_expert(int(c))                       # experts appear with their classes (mapping.py:727-761)
+        target = dict(kf_idx=window, frames=[frames[k] for k in window],
+                      class_tables=[slam.class_tables(frames[k]["label"]) for k in window])
+        refer = dict(kf_idx=[[-1]] * len(window), est_c2w=[[est[k].to(dev)] for k in window])
+        scene = dict(cam=cam, frames=target["frames"], class_tables=target["class_tables"])
+        md, tv = bench_util.mapping_draws(scene, s["mapping_pixels"], map_iters, seed=seed + 10 * f)
+        quads, Ts, losses = slam.map_optimize(mapper, target, refer, [feats[k] for k in window], [est[k] for k in window],
+                                              map_iters, s["lr"], s["BA_cam_lr"], len(window) > 1, [],
+                                              lambda it: md[it], lambda it: tv[it], use_graph=use_graph)
+        for k, q, t in zip(window, quads, Ts):
+            est[k] = slam.c2w_from_quad_T(q.detach(), t.detach()).cpu()
+        log.append(("map", f, float(losses["p_loss"]), float(losses["d_loss"])))
+        if f not in keyframes:
+            keyframes.append(f)
+        if f + 1 == n_frames:
+            break
+        # ---- tracking of the next frame with a copy of the weights (tracking.py:296-346)
+        tracker_dec.copy_weights_from(shared)
+        guess = est[f].clone()
+        td = bench_util.tracking_draws(cam, s["tracking_pixels"], track_iters, seed=seed + 100 + f)
+        best, best_loss, hist = slam.track_frame(tracker, frames[f + 1], torch.inverse(est[f]), feats[f], guess, track_iters,
+                                                 s["cam_lr"], lambda it: td[it], use_graph=use_graph)
+        est.append(slam.c2w_from_quad_T(best[:4], best[4:]).cpu())
+        log.append(("track", f + 1, float(hist[0]), float(best_loss)))
+    # ---- checkpoint (mapping.py:1119-1145) and one rendered frame (mapping.py:636-690)
+    out_dir = out_dir or tempfile.mkdtemp(prefix="dns_slam_b200_")
+    ck = checkpoint.Checkpoint(out_dir, device=dev, decoder=shared)
+    ck.save("model.pt", idx=n_frames - 1, fine_decoders=shared.fine_decoders, keyframe_list=keyframes,
+            estimate_c2w_list=torch.stack(est, 0))
+    g = torch.Generator().manual_seed(seed + 999)
+    color, depth, label = inference.render_frame(cam, shared, frames[-1], est[-1], torch.inverse(est[-1]), feats[-1], 32, 15,
+                                                 torch.rand(15, generator=g), torch.rand(15, generator=g), n_pts_batch=2048)
+    if verbose:
+        for kind, f, u, v in log:
+            if kind == "map":
+                print("map   frame %d  p_loss %.4f  d_loss %.4f (last iteration)" % (f, u, v))
+            else:
+                print("track frame %d  loss %.4f (first iteration) -> %.4f (best)" % (f, u, v))
+        print("rendered", tuple(color.shape), "checkpoint", os.path.join(out_dir, "model.pt"))
+    return dict(log=log, est=est, gt=poses, render=(color, depth, label), out_dir=out_dir, decoder=shared)
+
+
+if __name__ == "__main__":
+    run(sys.argv[1] if len(sys.argv) > 1 else "tiny", int(sys.argv[2]) if len(sys.argv) > 2 else 4)
