@@ -36,7 +36,7 @@ BYTES_RAY = dict(point_fwd=24, ray=228, point_bwd=0)              # per ray
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays-per-gpu", type=int, default=131072)
