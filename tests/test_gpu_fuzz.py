@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = [("map", 64, 5, 1), ("map", 700, 200, 101), ("map", 257, 128, 40), ("map", 1500, 1, 1), ("track", 100, 47, 2),
          ("map", 1500, 129, 101), ("track", 1171, 256, 9), ("track", 700, 2, 2), ("map", 700, 127, 5), ("map", 1, 256, 5),
-         ("track", 257, 1, 101), ("map", 1500, 33, 9), ("map", 2, 2, 1), ("track", 3, 13, 40)]
+         ("track", 257, 1, 101), ("map", 1500, 33, 9), ("map", 2, 2, 1), ("track", 3, 13, 40),
+         ("map", 300, 5, 128), ("track", 300, 6, 128), ("map", 40, 1, 128)]        # largest per-ray state of the ray kernel
 
 
 def _rel(a, b):
