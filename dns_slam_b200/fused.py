@@ -457,10 +457,11 @@ def merge_fused(refer_p, code, params, bound):
     return _MergeFn.apply(refer_p, code, params, bound)
 
 
-def feature_matching(H, W, K, pts_, refer_w2c, feats_cl, merge_fn):
-    """utils.common.feature_matching with channels-last features (no 209 MB/view up-sample)."""
-    code, _, _ = feature_gather(H, W, K, pts_, refer_w2c, feats_cl)
-    refer_o = rigid_inverse(refer_w2c)[:, :3, 3]
+def feature_matching(H, W, K, pts_, refer_w2c, feats_cl, merge_fn, refer_c2w=None):
+    """utils.common.feature_matching with channels-last features (no 209 MB/view up-sample).  ``refer_c2w``: the
+    poses ``refer_w2c`` was inverted from, when the caller has them (the reference inverts back, common.py:672)."""
+    code, _, _ = feature_gather(H, W, K, pts_, refer_w2c.contiguous(), feats_cl)
+    refer_o = (rigid_inverse(refer_w2c) if refer_c2w is None else refer_c2w)[:, :3, 3]
     refer_p = pts_[None, :, :] - refer_o[:, None, :]
     return merge_fn(refer_p, refer_o, code)
 

@@ -239,11 +239,24 @@ class MapperCore:
         T_all = torch.stack(list(T_list), 0)
         c2w_all = torch.cat((torch.cat((R_all, T_all[:, :, None]), -1),
                              fused.bottom_row(R_all.device)[None].expand(n_t, 1, 4)), 1)
+        # reference-view poses of every target frame, inverted in ONE batched call (mapping.py:534-551)
+        refer_c2w = []
+        for i in range(n_t):
+            for k, rid in enumerate(refer_frames["kf_idx"][i]):
+                if rid == -1:
+                    refer_c2w.append(c2w_all[i].detach())
+                elif rid in target_idx:
+                    refer_c2w.append(c2w_all[target_idx.index(rid)].detach())
+                else:
+                    refer_c2w.append(refer_frames["est_c2w"][i][k].detach().to(R_all.device))
+        n_ref = [len(refer_frames["kf_idx"][i]) for i in range(n_t)]
+        refer_c2w = torch.stack(refer_c2w, 0)
+        refer_w2c = fused.rigid_inverse(refer_c2w)
+        ref_at = [sum(n_ref[:i]) for i in range(n_t + 1)]
         for i in range(n_t):
             fr = target_frames["frames"][i]
             R = R_all[i]
             T = T_list[i]
-            cur_c2w = c2w_all[i]
             dev = R.device
             idx1 = draws[i]["idx_uniform"].to(dev)
             idx2, _ = class_balanced_indices(target_frames["class_tables"][i], n_pixels // 3, draws[i]["class_draws"])
@@ -255,18 +268,9 @@ class MapperCore:
             rays_o, rays_d = fused.attach_pose_grad(s["rays_o"], s["rays_d"], dirs, R, T)
             z = s["z_vals"]
             pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
-            w2c = []
-            for k, rid in enumerate(refer_frames["kf_idx"][i]):
-                if rid == -1:
-                    c2w = cur_c2w.detach()
-                elif rid in target_idx:
-                    t = target_idx.index(rid)
-                    c2w = c2w_all[t].detach()
-                else:
-                    c2w = refer_frames["est_c2w"][i][k].detach()
-                w2c.append(fused.rigid_inverse(c2w))
-            code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), torch.stack(w2c, 0),
-                                          features_cl[i], self.decoder.merge)
+            a, b = ref_at[i], ref_at[i + 1]
+            code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), refer_w2c[a:b],
+                                          features_cl[i], self.decoder.merge, refer_c2w=refer_c2w[a:b])
             code = code.reshape(pts.shape[0], pts.shape[1], -1) * trunc_mask(z, s["gt_depth"])[..., None]
             for k, v in (("gt_color", s["gt_color"]), ("gt_depth", s["gt_depth"]), ("gt_label", s["gt_label"]),
                          ("rays_o", rays_o), ("rays_d", rays_d), ("z_vals", z), ("mask", s["inside"]),
