@@ -253,6 +253,10 @@ class MapperCore:
         refer_c2w = torch.stack(refer_c2w, 0)
         refer_w2c = fused.rigid_inverse(refer_c2w)
         ref_at = [sum(n_ref[:i]) for i in range(n_t + 1)]
+        # with the same number of reference views everywhere, the Merge MLP (and the truncation mask) run ONCE over the
+        # points of all target frames instead of once per frame
+        batched = len(set(n_ref)) == 1
+        rp_all, code_all = [], []
         for i in range(n_t):
             fr = target_frames["frames"][i]
             R = R_all[i]
@@ -269,14 +273,27 @@ class MapperCore:
             z = s["z_vals"]
             pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
             a, b = ref_at[i], ref_at[i + 1]
-            code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), refer_w2c[a:b],
-                                          features_cl[i], self.decoder.merge, refer_c2w=refer_c2w[a:b])
-            code = code.reshape(pts.shape[0], pts.shape[1], -1) * trunc_mask(z, s["gt_depth"])[..., None]
+            if batched:
+                flat = pts.flatten(0, 1)
+                g, _, _ = fused.feature_gather(self.H, self.W, self.K, flat, refer_w2c[a:b].contiguous(), features_cl[i])
+                code_all.append(g)
+                rp_all.append(flat[None, :, :] - refer_c2w[a:b, :3, 3][:, None, :])
+                code = None
+            else:
+                code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), refer_w2c[a:b],
+                                              features_cl[i], self.decoder.merge, refer_c2w=refer_c2w[a:b])
+                code = code.reshape(pts.shape[0], pts.shape[1], -1) * trunc_mask(z, s["gt_depth"])[..., None]
             for k, v in (("gt_color", s["gt_color"]), ("gt_depth", s["gt_depth"]), ("gt_label", s["gt_label"]),
                          ("rays_o", rays_o), ("rays_d", rays_d), ("z_vals", z), ("mask", s["inside"]),
                          ("features", code)):
                 acc[k].append(v)
+        if batched:
+            acc.pop("features")
         cat = {k: torch.cat(v, 0) for k, v in acc.items()}
+        if batched:
+            merged = self.decoder.merge(torch.cat(rp_all, 1), refer_c2w[:n_ref[0], :3, 3], torch.cat(code_all, 1))
+            cat["features"] = merged.reshape(cat["z_vals"].shape[0], cat["z_vals"].shape[1], -1) \
+                * trunc_mask(cat["z_vals"], cat["gt_depth"])[..., None]
         m = cat.pop("mask")
         if assume_inside:          # graph replay: no compaction; the flag is checked once after the loop
             ok = m.all()
