@@ -257,21 +257,35 @@ class MapperCore:
         # points of all target frames instead of once per frame
         batched = len(set(n_ref)) == 1
         rp_all, code_all = [], []
+        # pass 1: pixel draws and the sampling kernel per frame (each frame has its own images)
+        dev = R_all.device
+        idx_l, s_l = [], []
         for i in range(n_t):
-            fr = target_frames["frames"][i]
-            R = R_all[i]
-            T = T_list[i]
-            dev = R.device
             idx1 = draws[i]["idx_uniform"].to(dev)
             idx2, _ = class_balanced_indices(target_frames["class_tables"][i], n_pixels // 3, draws[i]["class_draws"])
             idx = torch.cat((idx1, idx2), 0)
-            s = fused.sample_rays(self.cam, self.decoder.bound, fr, idx, window, R, T, self.n_samples_ray,
-                                  self.n_surface_ray, fused.fix_surface_draw(draws[i]["t_surface"], self.n_surface_ray),
-                                  draws[i]["t_zero"])
-            dirs = fused.pixel_dirs(self.cam, idx, window)
-            rays_o, rays_d = fused.attach_pose_grad(s["rays_o"], s["rays_d"], dirs, R, T)
-            z = s["z_vals"]
-            pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
+            idx_l.append(idx)
+            s_l.append(fused.sample_rays(self.cam, self.decoder.bound, target_frames["frames"][i], idx, window, R_all[i],
+                                         T_list[i], self.n_samples_ray, self.n_surface_ray,
+                                         fused.fix_surface_draw(draws[i]["t_surface"], self.n_surface_ray), draws[i]["t_zero"]))
+        # pose gradients and points for the rays of ALL frames at once (values stay the kernel's)
+        sizes = tuple(int(x.shape[0]) for x in idx_l)
+        fid = self.__dict__.setdefault("_frame_id_cache", {}).get((sizes, str(dev)))
+        if fid is None:
+            fid = torch.cat([torch.full((n,), i, dtype=torch.int64) for i, n in enumerate(sizes)]).to(dev)
+            self._frame_id_cache[(sizes, str(dev))] = fid
+        dirs_all = fused.pixel_dirs(self.cam, torch.cat(idx_l, 0), window)
+        e_d = torch.sum(dirs_all[:, None, :] * R_all[fid], -1)
+        e_o = T_all[fid]
+        rays_o_all = torch.cat([s["rays_o"] for s in s_l], 0) + (e_o - e_o.detach())
+        rays_d_all = torch.cat([s["rays_d"] for s in s_l], 0) + (e_d - e_d.detach())
+        z_all = torch.cat([s["z_vals"] for s in s_l], 0)
+        pts_all = rays_o_all[:, None, :] + rays_d_all[:, None, :] * z_all[:, :, None]
+        row_at = [sum(sizes[:i]) for i in range(n_t + 1)]
+        for i in range(n_t):
+            s = s_l[i]
+            r0, r1 = row_at[i], row_at[i + 1]
+            rays_o, rays_d, z, pts = rays_o_all[r0:r1], rays_d_all[r0:r1], z_all[r0:r1], pts_all[r0:r1]
             a, b = ref_at[i], ref_at[i + 1]
             if batched:
                 flat = pts.flatten(0, 1)
