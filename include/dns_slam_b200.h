@@ -252,6 +252,21 @@ int dns_merge_bwd(const float* refer_p, const float* d_out, int64_t P, int R, co
                   float* d_refer_p, float* d_params, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ResNet stem of the pixel-feature branch == models/encoder.py:9-17 over models/layers.py:52-114 (what is left of
+ * ResNet18 there): conv1 7x7 / stride 2 / pad 3, 3 -> 64, no bias -> bn1 -> ReLU, once per frame
+ * (slams/tracking.py:295-296, slams/mapping.py:666,768,846).  images [n,H,W,3] (the gt_color frames as the
+ * reference passes them), out [n,h,w,64] CHANNELS-LAST (the layout dns_feature_gather reads), h = (H-1)/2+1,
+ * w = (W-1)/2+1.  training = 1 (the reference never calls .eval()): bn1 normalises with the statistics of this
+ * batch of n views (biased variance) and, when the running_* pointers are given, updates them like
+ * torch.nn.BatchNorm2d (momentum, unbiased variance); training = 0: normalises with running_mean / running_var.
+ * conv_w [64,3,7,7]; bn_weight, bn_bias, running_mean, running_var [64].
+ * ------------------------------------------------------------------------------------- */
+int64_t dns_stem_workspace_bytes(void);
+int dns_stem_fwd(const float* images, int n, int H, int W, const float* conv_w, const float* bn_weight,
+                 const float* bn_bias, float eps, float momentum, int training, float* running_mean,
+                 float* running_var, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Adam == torch.optim.Adam defaults over a flat fp32 buffer
  * (slams/tracking.py:119-124,339; slams/mapping.py:464-466,910)
  * ------------------------------------------------------------------------------------- */

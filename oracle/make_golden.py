@@ -8,6 +8,7 @@ What is exercised from the reference, unmodified unless noted:
                     (quad2rotation source-patched P2: ``.to(quad.get_device())`` -> ``.to(quad.device)``)
   models/decoder.py Decoder / Pos_Encoding / Coarse / Out / Merge (on the tcnn stand-in)
   slams/tracking.py Tracker.get_target_samples, renderer, compute_*_loss
+  models/encoder.py ResNet (conv1 + bn1 + ReLU of models/layers.py:52-114; P4: un-pretrained constructor)
   slams/mapping.py  Mapper.get_target_samples, fine_fn, renderer, compute_*_loss, smoothness
                     (source-patched P1: ``reshape(pts_shape[:3], 1)`` -> ``reshape(*pts_shape[:3], 1)``)
 Stubbed modules: tinycudann (-> oracle.tcnn_standin), mathutils, matplotlib.pyplot, colorama.
@@ -282,12 +283,45 @@ def kernels_case(C):
                 sar_depth=depth, sar_far=far_bb, sar_tape=rec.items, sar_z=zv)
 
 
+def stem_case(seed=31):
+    """The reference's own models/encoder.py ResNet on seeded frames.  P4: ``ResNet18(pretrained=True)`` downloads the
+    torchvision weights, so the constructor it calls is replaced by the reference's un-pretrained one
+    (models/layers.py:52-72 initialisation) and bn1's affine parameters are randomised to make the vectors
+    sensitive to them.  Two training-mode calls (the mode the reference runs in) and one eval-mode call."""
+    import models.layers as L
+    import models.encoder as E
+    E.ResNet18 = lambda pretrained=False: L.ResNet(L.BasicBlock, [2, 2, 2, 2])
+    torch.manual_seed(seed)
+    enc = E.ResNet()
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        enc.conv_blocks.bn1.weight.copy_(torch.rand(64, generator=g) + 0.5)
+        enc.conv_blocks.bn1.bias.copy_(torch.randn(64, generator=g) * 0.3)
+    state0 = {k: v.clone() for k, v in enc.state_dict().items()}
+    frames1 = torch.rand(1, 3, 21, 30, 3, generator=g)     # odd / even sizes, ragged against the 4 x 64 tiles
+    frames2 = torch.rand(1, 1, 16, 135, 3, generator=g)    # more than one 64-pixel column tile
+    with torch.no_grad():
+        out1 = enc(frames1).clone()
+        state1 = {k: v.clone() for k, v in enc.state_dict().items()}
+        out2 = enc(frames2).clone()
+        state2 = {k: v.clone() for k, v in enc.state_dict().items()}
+        enc.eval()
+        out3 = enc(frames1).clone()
+    return dict(state0=state0, frames1=frames1, out1=out1, state1=state1, frames2=frames2, out2=out2,
+                state2=state2, out_eval=out3)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
     C, D, T, M = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if sys.argv[1:] == ["stem"]:     # only the stem vectors (the other files stay byte-identical)
+        torch.save(stem_case(), os.path.join(out_dir, "stem_tiny.pt"))
+        print("stem_tiny.pt", os.path.getsize(os.path.join(out_dir, "stem_tiny.pt")))
+        return
+    torch.save(stem_case(), os.path.join(out_dir, "stem_tiny.pt"))
     torch.save(kernels_case(C), os.path.join(out_dir, "kernels.pt"))
     torch.save(tracking_case(C, D, T), os.path.join(out_dir, "tracking_tiny.pt"))
     torch.save(mapping_case(C, D, M), os.path.join(out_dir, "mapping_tiny.pt"))

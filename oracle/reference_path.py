@@ -630,3 +630,21 @@ def keyframe_overlap(cam, gt_depth, c2w, keyframe_c2w, tape, n_samples=16, pixel
         mask = (mask & (z[:, :, 0] < 0)).reshape(-1)
         out.append(mask.sum() / uv.shape[0])
     return np.asarray(out, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------
+# ResNet stem of the pixel-feature branch
+# --------------------------------------------------------------------------------------
+def stem_forward(images, conv_w, bn_weight, bn_bias, running_mean=None, running_var=None, training=True,
+                 momentum=0.1, eps=1e-5):
+    """models/encoder.py:9-17 over models/layers.py:97-100: images [B,N,H,W,3] -> [B,N,64,h,w].
+    conv1 (7x7, stride 2, pad 3, no bias) -> bn1 -> ReLU.  The reference leaves the encoder in training mode
+    (slams/tracking.py:30, slams/mapping.py:33: no .eval()), so bn1 uses the statistics of this batch and updates
+    ``running_mean`` / ``running_var`` IN PLACE (torch semantics: momentum, unbiased variance)."""
+    B, N = images.shape[:2]
+    x = images.flatten(0, 1).permute(0, 3, 1, 2)
+    x = F.conv2d(x, conv_w, None, stride=2, padding=3)
+    x = F.batch_norm(x, running_mean, running_var, bn_weight, bn_bias, training, momentum, eps)
+    x = F.relu(x)
+    _, Cc, h, w = x.shape
+    return x.reshape(B, N, Cc, h, w)

@@ -85,3 +85,18 @@ def test_hash_tables_match_survey_appendix_b():
     assert t["n_entries"] == 853312 and list(t["hashed"]) == [0] * 4 + [1] * 12
     t = grid_level_tables(16, 16, np.exp2(np.log2(231 / 16) / 15), 20)
     assert t["n_entries"] == 7333944 and list(t["hashed"]) == [0] * 11 + [1] * 5
+
+
+def test_stem(golden_dir):
+    """oracle.stem_forward against the reference's own models/encoder.py ResNet (training-mode bn1, two calls,
+    then eval mode).
+    atol 1e-5 on the features: the convolution's summation order depends on the host thread count."""
+    g = load(golden_dir, "stem_tiny.pt")
+    s = {k: v.clone() for k, v in g["state0"].items()}
+    w, gam, bet = s["conv_blocks.conv1.weight"], s["conv_blocks.bn1.weight"], s["conv_blocks.bn1.bias"]
+    rm, rv = s["conv_blocks.bn1.running_mean"], s["conv_blocks.bn1.running_var"]
+    close(rp.stem_forward(g["frames1"], w, gam, bet, rm, rv, True), g["out1"], atol=1e-5)
+    close(rm, g["state1"]["conv_blocks.bn1.running_mean"]); close(rv, g["state1"]["conv_blocks.bn1.running_var"])
+    close(rp.stem_forward(g["frames2"], w, gam, bet, rm, rv, True), g["out2"], atol=1e-5)
+    close(rm, g["state2"]["conv_blocks.bn1.running_mean"]); close(rv, g["state2"]["conv_blocks.bn1.running_var"])
+    close(rp.stem_forward(g["frames1"], w, gam, bet, rm, rv, False), g["out_eval"], atol=1e-5)
