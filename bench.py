@@ -366,7 +366,27 @@ def _extra_configs(args, dev):
     for shape in ("replica", "scannet"):
         out["iteration_" + shape] = _iteration_timings(shape, args.n_class, dev)
     out["inference_replica"] = _inference_timings("replica", args.n_class, dev)
+    out["stem_replica"] = _stem_timings("replica", dev)
     return out
+
+
+def _stem_timings(shape, dev):
+    """ResNet stem (models/encoder.py:4-17): once per tracked frame (1 view) and once per mapping call
+    (the refer views of the window; 3 here).  Bytes: the frames in, the 64-channel half-resolution map written by the
+    convolution, read and written by the normalisation."""
+    from dns_slam_b200 import encoder, synthetic as syn
+    s = syn.SHAPES[shape]
+    H, W = s["H"], s["W"]
+    h, w = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    torch.manual_seed(0)
+    enc = encoder.ResNet().to(dev)
+    res = {"frame": [H, W]}
+    for n in (1, 3):
+        x = torch.rand(1, n, H, W, 3, device=dev)
+        t = _time_cuda(lambda: enc.forward_cl(x), 20, 3)
+        res[f"ms_{n}_view" + ("s" if n > 1 else "")] = t
+        res[f"gbs_{n}"] = n * (H * W * 3 + 3 * h * w * 64) * 4 / (t * 1e-3) / 1e9
+    return res
 
 
 def _inference_timings(shape, n_class, dev):

@@ -13,7 +13,7 @@ import tempfile
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from dns_slam_b200 import bench_util, checkpoint, fused, inference, slam  # noqa: E402
+from dns_slam_b200 import bench_util, checkpoint, encoder, inference, slam  # noqa: E402
 from dns_slam_b200 import synthetic as syn  # noqa: E402
 
 
@@ -25,7 +25,9 @@ def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_gra
     poses = syn.trajectory(shape, n_frames + 1)
     frames = [{k: v.to(dev).contiguous() for k, v in syn.frame(shape, poses[i], gen, n_class=n_class).items()}
               for i in range(n_frames)]
-    feats = [fused.channels_last(syn.pixel_features(shape, 1, gen).to(dev)) for _ in range(n_frames)]
+    torch.manual_seed(seed)
+    stem = encoder.ResNet().to(dev)     # random-initialised stem (no pretrained weights without a network), training-mode bn1
+    feats = [stem.forward_cl(fr["color"][None, None]) for fr in frames]      # [1, h, w, 64] channels-last per frame
     shared = bench_util.make_decoder(shape, n_class, dev, seed=seed, all_experts=False)
     tracker_dec = bench_util.make_decoder(shape, n_class, dev, seed=seed + 1, all_experts=False)
     mapper = slam.MapperCore(cam, shared, s["mapping_pixels"], 32, 15,
