@@ -56,20 +56,29 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.sm, self.max_sm, self.bits, self.stop, self.err = index, [], None, 0, False, None
-        self.th = threading.Thread(target=self.run, daemon=True)
-
-    def run(self):
+        self.nv = self.h = self.get_reasons = None
+        # NVML is initialised HERE, before the timed region: nvmlInit takes driver-wide locks for 100-200 ms, and
+        # inside a short timed loop that showed up as an idle GPU (262 144 rays x 10 steps: 51.7 instead of 34.6 ms)
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self.stop:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                self.bits |= int(get_reasons(h))
-                time.sleep(0.02)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) \
+                or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         except Exception as e:      # noqa: BLE001 - clocks are evidence, not a dependency of the measurement
+            self.err = repr(e)
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        if self.nv is None:
+            return
+        try:
+            while not self.stop:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.bits |= int(self.get_reasons(self.h))
+                time.sleep(0.02)
+        except Exception as e:      # noqa: BLE001
             self.err = repr(e)
 
     def __enter__(self):
@@ -139,7 +148,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     S, C, R = args.samples, args.n_class, args.rays_per_gpu
-    workload = f"{args.shape}_mapping_{R}rays_per_gpu_x{S}samples_{C}classes_hash2^16_plus_adam"
+    from dns_slam_b200 import synthetic as _syn
+    workload = (f"{args.shape}_mapping_{R}rays_per_gpu_x{S}samples_{C}classes_"
+                f"hash2^{_syn.SHAPES[args.shape]['hash_size']}_plus_adam")
     config = {"workload": workload, "rays_per_gpu": R, "n_samples": S, "n_class": C,
               "cache": "per-step inputs (~6.2 KB/ray) + activation stash exceed the 126 MB L2",
               "parallelism": f"rays sharded x{args.gpus}, flat-gradient all-reduce (NCCL)" if args.gpus > 1 else "single GPU"}
