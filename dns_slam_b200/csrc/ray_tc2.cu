@@ -142,6 +142,14 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       if (stash) x2p[c * RS] = x2p[(14 + c) * RS] = z4;
     }
   }
+  // occupancy compositing (common.py:524-532) depends on the latent row only: group 1 runs its scans while the
+  // forward GEMM is in flight (its own named barrier; group 0 issues / waits for the MMAs)
+  float alpha = 0.f, b = 1.f;
+  if (grp == 1) {
+    alpha = valid ? sigmoidf_(10.f * occ) : 0.f;
+    b = __fadd_rn(1.f - alpha, 1e-10f);
+    bs[row] = b;
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -165,6 +173,18 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
     umma_commit(&bar);
   }
+  float Ts = 1.f, u = 0.f, sumu = 0.f, w = 0.f;
+  if (grp == 1) {
+    if (valid)
+      for (int j = 0; j < s; ++j) Ts *= bs[rb + j];
+    u = alpha * Ts;
+    us[row] = u;
+    asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");   // group 1 only (T threads, whole warps)
+    if (valid)
+      for (int j = 0; j < S; ++j) sumu += us[rb + j];
+    w = valid ? (a.fwd_only == 2 ? 1.f : u / sumu) : 0.f;   // 2: free-point query, no compositing
+    wsh[row] = w;
+  }
   mbar_wait_cta(&bar, 0);
   tc_fence_after();
   // this thread's half of the hidden row: group 0 colour units, group 1 logit units
@@ -182,39 +202,18 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   tc_fence_before();
   __syncthreads();   // every thread has read its accumulator half: region R may be reused as staging
   float rgb[3] = {0.f, 0.f, 0.f};
-  float alpha = 0.f, b = 1.f;
   if (grp == 0) {    // colour head: 32 -> 3, sigmoid (decoder.py:123)
     float pre[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float4 w = *reinterpret_cast<const float4*>(W2c + 4 * j);
-      pre[0] = fmaf(h[j], w.x, pre[0]);
-      pre[1] = fmaf(h[j], w.y, pre[1]);
-      pre[2] = fmaf(h[j], w.z, pre[2]);
+      const float4 wv = *reinterpret_cast<const float4*>(W2c + 4 * j);
+      pre[0] = fmaf(h[j], wv.x, pre[0]);
+      pre[1] = fmaf(h[j], wv.y, pre[1]);
+      pre[2] = fmaf(h[j], wv.z, pre[2]);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) rgb[c] = sigmoidf_(pre[c]);
-  } else {           // occupancy compositing (common.py:524-532)
-    alpha = valid ? sigmoidf_(10.f * occ) : 0.f;
-    b = __fadd_rn(1.f - alpha, 1e-10f);
-    bs[row] = b;
   }
-  __syncthreads();
-  float Ts = 1.f, u = 0.f, sumu = 0.f, w = 0.f;
-  if (grp == 1) {
-    if (valid)
-      for (int j = 0; j < s; ++j) Ts *= bs[rb + j];
-    u = alpha * Ts;
-    us[row] = u;
-  }
-  __syncthreads();
-  if (grp == 1) {
-    if (valid)
-      for (int j = 0; j < S; ++j) sumu += us[rb + j];
-    w = valid ? (a.fwd_only == 2 ? 1.f : u / sumu) : 0.f;   // 2: free-point query, no compositing
-    wsh[row] = w;
-  }
-  __syncthreads();
   if (grp == 0) w = wsh[row];
   if (valid) {
     if (grp == 1) {
@@ -368,7 +367,6 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       QV[e] = acc;
     }
   }
-  __syncthreads();
   // ---- per-point backward: d_w = dL/dw of the point, assembled from both groups
   if (grp == 0) {
     float part = 0.f;
@@ -389,23 +387,23 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       for (int j = 0; j < 32; ++j) d_w = fmaf(h[j], qv[j], d_w);
     }
     bs[row] = w * d_w;
-    ws[row] = b;
   }
   __syncthreads();
-  float d_u = 0.f;
-  if (grp == 1) {
-    float G = 0.f;
-    if (valid)
-      for (int j = 0; j < S; ++j) G += bs[rb + j];
-    d_u = valid ? (d_w - G) / sumu : 0.f;
-    us[row] = d_u * u;
-  }
-  __syncthreads();
-  float d_occ = 0.f;
+  float d_u = 0.f, d_occ = 0.f;
   if (grp == 1) {
     if (valid) {
-      float suf = 0.f;
-      for (int j = s + 1; j < S; ++j) suf += us[rb + j];
+      // G = sum_j w_j d_w_j;  d_u_j = (d_w_j - G) / sumu;  suf = sum_{j>s} d_u_j u_j = sum_{j>s} w_j d_w_j - G sum_{j>s} w_j
+      float G = 0.f, sufB = 0.f, sufW = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const float bj = bs[rb + j];
+        G += bj;
+        if (j > s) {
+          sufB += bj;
+          sufW += wsh[rb + j];
+        }
+      }
+      d_u = (d_w - G) / sumu;
+      const float suf = sufB - G * sufW;
       float d_alpha = d_u * Ts - suf / b;
       d_occ = d_alpha * 10.f * alpha * (1.f - alpha);
       const float* qv = QV + lr * 32;
