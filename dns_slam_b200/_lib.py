@@ -77,7 +77,7 @@ SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_ena
            "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd", "dns_render_counts",
            "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
            "dns_adam_step", "dns_merge_workspace_bytes", "dns_merge_fwd", "dns_merge_bwd",
-           "dns_stem_workspace_bytes", "dns_stem_fwd"]
+           "dns_stem_workspace_bytes", "dns_stem_fwd", "dns_adam_multi"]
 
 
 def lib():
@@ -120,6 +120,7 @@ def lib():
     L.dns_merge_workspace_bytes.argtypes = [i64]
     L.dns_merge_fwd.argtypes = [_P, _P, _P, i64, i32, bound_t, _P, i32, _P, i64, _P]
     L.dns_merge_bwd.argtypes = [_P, _P, i64, i32, bound_t, _P, _P, _P, i64, _P]
+    L.dns_adam_multi.argtypes = [_P, i32, i64, _P, f32, f32, f32, _P]
     L.dns_stem_workspace_bytes.restype = C.c_int64
     L.dns_stem_workspace_bytes.argtypes = []
     L.dns_stem_fwd.argtypes = [_P, i32, i32, i32, _P, _P, _P, f32, f32, i32, _P, _P, _P, _P, i64, _P]

@@ -357,6 +357,28 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 
+// Several parameter segments (own learning rate each) in ONE launch, step counter on the device so that a captured
+// CUDA graph advances it on every replay (slams/tracking.py:119-124: translation / quaternion groups;
+// slams/mapping.py:464-466: decoder / quaternions / translations).
+__global__ void k_adam_tick(int* step) { *step += 1; }
+__global__ void k_adam_multi(const dns_adam_seg* __restrict__ segs, const int* __restrict__ step, float b1, float b2,
+                             float eps) {
+  const dns_adam_seg sg = segs[blockIdx.y];
+  const double t = (double)*step;
+  const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const float step_size = sg.lr / bc1;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < sg.n; i += stride) {
+    const float gi = sg.g[i];
+    const float mi = sg.m[i] + (1.f - b1) * (gi - sg.m[i]);
+    const float vi = b2 * sg.v[i] + (1.f - b2) * gi * gi;
+    sg.m[i] = mi;
+    sg.v[i] = vi;
+    sg.p[i] = sg.p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
 }  // namespace dns
 
 using namespace dns;
@@ -494,6 +516,21 @@ int dns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                  (float)bc1, (float)sqrt(bc2));
   return check_launch("adam");
+}
+
+int dns_adam_multi(const dns_adam_seg* segs_dev, int n_segs, int64_t max_n, int* step_dev, float beta1, float beta2,
+                   float eps, void* stream) {
+  if (n_segs <= 0 || max_n <= 0) return DNS_OK;
+  if (!segs_dev || !step_dev || n_segs > 65535) {
+    set_error("dns_adam_multi: bad arguments (%d segments)", n_segs);
+    return DNS_ERR_ARG;
+  }
+  int64_t blocks = (max_n + 255) / 256;
+  const int bx = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  PhaseScope ph(phAdam, (cudaStream_t)stream, 2);
+  k_adam_tick<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  k_adam_multi<<<dim3(bx, n_segs), 256, 0, (cudaStream_t)stream>>>(segs_dev, step_dev, beta1, beta2, eps);
+  return check_launch("adam_multi");
 }
 
 }  // extern "C"

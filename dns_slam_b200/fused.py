@@ -474,3 +474,74 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), 
     _lib.check(_lib.lib().dns_adam_step(_lib.ptr(params, torch.float32), _lib.ptr(grads, torch.float32),
                                         _lib.ptr(exp_avg, torch.float32), _lib.ptr(exp_avg_sq, torch.float32),
                                         params.numel(), lr, betas[0], betas[1], eps, step, _lib.stream()))
+
+
+class FusedAdam:
+    """``torch.optim.Adam`` (defaults) over parameter groups ``[{"params": [...], "lr": lr, "flat": buf?}, ...]`` in
+    ONE ``dns_adam_multi`` launch per step -- the groups of slams/tracking.py:119-124 and slams/mapping.py:464-466.
+
+    * Gradients live in buffers owned by the optimiser (``p.grad`` is set to a view once; ``zero_grad`` zeroes the
+      buffers), so every address is fixed: the segment table is uploaded once and a CUDA graph that captured
+      ``zero_grad`` / ``backward`` / ``step`` replays correctly; the step counter is a device integer.
+    * ``flat``: a contiguous buffer that the group's parameters tile exactly (``Decoder.flat``): the group becomes
+      one segment, its gradient one flat buffer (one memset per iteration).
+    * A parameter that receives no gradient in an iteration sees a zero gradient (torch would skip it); the loops
+      here give every optimised parameter a gradient in every iteration.
+    """
+
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
+        import numpy as np
+        self.betas, self.eps = betas, eps
+        self.groups = [g for g in groups if len(g["params"]) > 0]
+        dev = self.groups[0]["params"][0].device
+        segs, self._zero, self._keep = [], [], []
+        for g in self.groups:
+            ps, lr, flat = list(g["params"]), float(g["lr"]), g.get("flat")
+            for p in ps:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("FusedAdam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)")
+            covered = flat is not None and sum(p.numel() for p in ps) == flat.numel() and all(
+                0 <= p.data_ptr() - flat.data_ptr() <= 4 * (flat.numel() - p.numel()) for p in ps)
+            n = flat.numel() if covered else sum(p.numel() for p in ps)
+            gbuf, m, v = (torch.zeros(n, device=dev) for _ in range(3))
+            self._zero.append(gbuf)
+            self._keep += [m, v]
+            if covered:
+                for p in ps:
+                    off = (p.data_ptr() - flat.data_ptr()) // 4
+                    p.grad = gbuf[off:off + p.numel()].view_as(p)
+                segs.append((flat.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr))
+            else:
+                off = 0
+                for p in ps:
+                    k = p.numel()
+                    p.grad = gbuf[off:off + k].view_as(p)
+                    segs.append((p.data_ptr(), gbuf.data_ptr() + 4 * off, m.data_ptr() + 4 * off,
+                                 v.data_ptr() + 4 * off, k, lr))
+                    off += k
+        dt = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("lr", "<f4"), ("r", "<f4")])
+        tab = np.zeros(len(segs), dtype=dt)
+        for i, sg in enumerate(segs):
+            tab[i] = sg + (0.0,)
+        self.table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+        self.n_segs, self.max_n = len(segs), max(sg[4] for sg in segs)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def zero_grad(self, set_to_none=False):
+        for g in self._zero:
+            g.zero_()
+
+    def step(self):
+        _lib.check(_lib.lib().dns_adam_multi(_lib.ptr(self.table), self.n_segs, self.max_n,
+                                             _lib.ptr(self.step_dev, torch.int32), self.betas[0], self.betas[1],
+                                             self.eps, _lib.stream()))
+
+
+def make_adam(groups, capturable=False):
+    """The optimiser of the tracking / mapping loops: ``FusedAdam``; ``DNS_TORCH_ADAM=1`` selects
+    ``torch.optim.Adam`` (A/B reference)."""
+    import os
+    if os.environ.get("DNS_TORCH_ADAM") == "1":
+        gs = [{"params": g["params"], "lr": g["lr"]} for g in groups if len(g["params"]) > 0]
+        return torch.optim.Adam(gs, capturable=capturable)
+    return FusedAdam(groups)

@@ -415,8 +415,8 @@ def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr
     dev = tracker.decoder.bound.device
     quad = quad_from_matrix(est_c2w[:3, :3]).to(dev).requires_grad_(True)
     T = est_c2w[:3, 3].detach().clone().to(dev).requires_grad_(True)
-    opt = torch.optim.Adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
-                            {"params": [quad], "lr": cam_lr}])
+    opt = fused.make_adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
+                           {"params": [quad], "lr": cam_lr}])
     best_loss = torch.full((), 1e10, device=dev)
     best = torch.cat((quad, T), 0).detach().clone()
     cur = dict(frame, est_quad=quad, est_T=T)
@@ -441,8 +441,8 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
     dev = tracker.decoder.bound.device
     quad = quad_from_matrix(est_c2w[:3, :3]).to(dev).requires_grad_(True)
     T = est_c2w[:3, 3].detach().clone().to(dev).requires_grad_(True)
-    opt = torch.optim.Adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
-                            {"params": [quad], "lr": cam_lr}], capturable=True)
+    opt = fused.make_adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
+                           {"params": [quad], "lr": cam_lr}], capturable=True)
     packed = _PackedStatic(draws_fn(0), dev)
     static = packed.static
     best_loss = torch.full((), 1e10, device=dev)
@@ -516,9 +516,9 @@ def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list,
         T_list.append(t)
     net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
     cam_lr = BA_cam_lr * float(is_BA)
-    opt = torch.optim.Adam([{"params": net, "lr": lr},
-                            {"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
-                            {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}])
+    opt = fused.make_adam([{"params": net, "lr": lr, "flat": dec.flat},
+                           {"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
+                           {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}])
     ld = None
     for it in range(n_iters):
         opt.zero_grad()
@@ -581,7 +581,7 @@ def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, 
     for c in decoder_idx:
         dec.activate_expert(c)
     net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
-    opt = torch.optim.Adam([{"params": net, "lr": lr}])
+    opt = fused.make_adam([{"params": net, "lr": lr, "flat": dec.flat}])
     R, T = cur_c2w[:3, :3].to(dev), cur_c2w[:3, 3].to(dev)
     window = (0, mapper.H, 0, mapper.W)
     w2c = torch.inverse(cur_c2w.to(dev)).unsqueeze(0)
@@ -691,11 +691,11 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
         T_list.append(t)
     net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
     cam_lr = BA_cam_lr * float(is_BA)
-    groups = [{"params": net, "lr": lr}]
+    groups = [{"params": net, "lr": lr, "flat": dec.flat}]
     if any(q.requires_grad for q in quad_list):
         groups += [{"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
                    {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}]
-    opt = torch.optim.Adam(groups, capturable=True)
+    opt = fused.make_adam(groups, capturable=True)
     packed = _PackedStatic([draws_fn(0), list(tv_draws_fn(0))], dev)
     static_d, static_tv = packed.static
     mapper.inside_ok = None

@@ -273,6 +273,23 @@ int dns_stem_fwd(const float* images, int n, int H, int W, const float* conv_w, 
 int dns_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, void* stream);
 
+/* The same update over several segments in one launch, each with its own learning rate: the optimiser groups of
+ * slams/tracking.py:119-124 (translation, quaternion) and slams/mapping.py:464-466 (decoder, quaternions,
+ * translations).  segs_dev [n_segs] and step_dev live in DEVICE memory; the call first increments *step_dev and
+ * uses the new value for the bias corrections, so a captured CUDA graph advances the step on every replay.
+ * max_n = the longest segment (sizes the grid). */
+typedef struct {
+  float* p;        /* parameters, updated in place */
+  const float* g;  /* gradients */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  int64_t n;
+  float lr;
+  float reserved;
+} dns_adam_seg;
+int dns_adam_multi(const dns_adam_seg* segs_dev, int n_segs, int64_t max_n, int* step_dev, float beta1, float beta2,
+                   float eps, void* stream);
+
 /* 1 (default): MLP weight-gradient GEMMs run on tcgen05 tensor cores (bf16 hi+lo split, three
  * products, fp32 accumulation in TMEM); 0: fp32 SIMT path, kept for A/B comparison. */
 void dns_set_tensor_cores(int on);
