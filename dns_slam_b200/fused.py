@@ -379,7 +379,9 @@ def feature_gather(H, W, K, pts, refer_w2c, feats_cl):
     (the reference's ``torch.round`` cuts the gradient).  Returns code [R,P,C], uv [R,P,2], mask [R,P]."""
     dev = pts.device
     P, R = pts.shape[0], refer_w2c.shape[0]
-    _, h, w, Cc = feats_cl.shape
+    Rf, h, w, Cc = feats_cl.shape
+    if Rf != R:      # the C entry point only sees raw pointers: a short feature tensor would be read out of bounds
+        raise ValueError(f"feature_gather: {R} reference views but feature maps of {Rf} views")
     code = torch.empty(R, P, Cc, device=dev)
     uv = torch.empty(R, P, 2, dtype=torch.int64, device=dev)
     mask = torch.empty(R, P, dtype=torch.uint8, device=dev)
@@ -480,9 +482,11 @@ class FusedAdam:
     """``torch.optim.Adam`` (defaults) over parameter groups ``[{"params": [...], "lr": lr, "flat": buf?}, ...]`` in
     ONE ``dns_adam_multi`` launch per step -- the groups of slams/tracking.py:119-124 and slams/mapping.py:464-466.
 
-    * Gradients live in buffers owned by the optimiser (``p.grad`` is set to a view once; ``zero_grad`` zeroes the
-      buffers), so every address is fixed: the segment table is uploaded once and a CUDA graph that captured
-      ``zero_grad`` / ``backward`` / ``step`` replays correctly; the step counter is a device integer.
+    * Gradients are gathered into buffers owned by the optimiser (``step`` copies every ``p.grad`` into its slice
+      with one ``_foreach_copy_``; autograd itself sees ``p.grad = None`` after ``zero_grad``, exactly as with a torch
+      optimiser), so the segment table is uploaded once and a CUDA graph that captured ``zero_grad`` / ``backward`` /
+      ``step`` replays correctly; the step counter is a device integer.  ``DNS_ADAM_INPLACE=1`` pre-sets ``p.grad``
+      to views of the buffers instead (autograd accumulates in place, no copies).
     * ``flat``: a contiguous buffer that the group's parameters tile exactly (``Decoder.flat``): the group becomes
       one segment, its gradient one flat buffer (one memset per iteration).
     * A parameter that receives no gradient in an iteration sees a zero gradient (torch would skip it); the loops
@@ -491,7 +495,10 @@ class FusedAdam:
 
     def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
         import numpy as np
+        import os
         self.betas, self.eps = betas, eps
+        self.inplace = os.environ.get("DNS_ADAM_INPLACE") == "1"
+        self._views = []          # (parameter, its slice of the gradient buffer)
         self.groups = [g for g in groups if len(g["params"]) > 0]
         dev = self.groups[0]["params"][0].device
         segs, self._zero, self._keep = [], [], []
@@ -509,13 +516,13 @@ class FusedAdam:
             if covered:
                 for p in ps:
                     off = (p.data_ptr() - flat.data_ptr()) // 4
-                    p.grad = gbuf[off:off + p.numel()].view_as(p)
+                    self._views.append((p, gbuf[off:off + p.numel()].view_as(p)))
                 segs.append((flat.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr))
             else:
                 off = 0
                 for p in ps:
                     k = p.numel()
-                    p.grad = gbuf[off:off + k].view_as(p)
+                    self._views.append((p, gbuf[off:off + k].view_as(p)))
                     segs.append((p.data_ptr(), gbuf.data_ptr() + 4 * off, m.data_ptr() + 4 * off,
                                  v.data_ptr() + 4 * off, k, lr))
                     off += k
@@ -526,12 +533,29 @@ class FusedAdam:
         self.table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
         self.n_segs, self.max_n = len(segs), max(sg[4] for sg in segs)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.inplace:
+            for p, view in self._views:
+                p.grad = view
 
-    def zero_grad(self, set_to_none=False):
-        for g in self._zero:
-            g.zero_()
+    def zero_grad(self, set_to_none=True):
+        if self.inplace:
+            for g in self._zero:
+                g.zero_()
+        else:
+            for p, _ in self._views:
+                p.grad = None
 
     def step(self):
+        if not self.inplace:
+            dst, src = [], []
+            for p, view in self._views:
+                if p.grad is None:
+                    view.zero_()
+                else:
+                    dst.append(view)
+                    src.append(p.grad)
+            if dst:
+                torch._foreach_copy_(dst, src)
         _lib.check(_lib.lib().dns_adam_multi(_lib.ptr(self.table), self.n_segs, self.max_n,
                                              _lib.ptr(self.step_dev, torch.int32), self.betas[0], self.betas[1],
                                              self.eps, _lib.stream()))

@@ -527,7 +527,9 @@ def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list,
                                     tv_draws_fn(it), lambda_lt=lam_lt)
         ld["total"].backward()
         opt.step()
-    return quad_list, T_list, ld
+    # detached: a loss dictionary that still holds its autograd graph keeps the AccumulateGrad nodes of this (default)
+    # stream alive, and the next CUDA-graph capture of a loop then fails ("legacy stream depends on a capturing stream")
+    return quad_list, T_list, (None if ld is None else {k: v.detach() for k, v in ld.items()})
 
 
 def keyframe_overlap(cam, gt_depth, c2w, keyframe_c2w, idx, n_samples=16):
@@ -605,7 +607,7 @@ def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, 
         sm = fused.tv_loss(dec, mapper.smooth_pts, tv[0], tv[1])
         (ld["total"] + mapper.lambda_sm * sm).backward()
         opt.step()
-    return ld
+    return None if ld is None else {k: v.detach() for k, v in ld.items()}
 
 
 class _PackedStatic:

@@ -19,7 +19,7 @@ def test_synthetic_slam_runs_end_to_end(tmp_path, use_graph):
     assert torch.cuda.is_available()
     out = synthetic_slam.run("tiny", n_frames=3, track_iters=6, map_iters=6, use_graph=use_graph, out_dir=str(tmp_path),
                              verbose=False)
-    for kind, f, a, b in out["log"]:
+    for kind, f, a, b, *_ in out["log"]:
         assert a == a and b == b, (kind, f, a, b)
         if kind == "track":
             assert b <= a + 1e-6                       # the best loss of the pose loop is no worse than its first
