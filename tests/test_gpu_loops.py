@@ -188,3 +188,42 @@ def test_mapping_loop_cuda_graph_equals_eager():
         close(q1[i], q0[i], rtol=1e-3, atol=1e-5, name="quad")
         close(t1[i], t0[i], rtol=1e-3, atol=1e-5, name="T")
     assert rel_err(f1, f0) < 1e-3
+
+
+def test_graph_capture_after_an_eager_loop_on_the_same_decoder():
+    """Regression (found by the ScanNet-shaped sequence of examples/synthetic_slam.py): the eager loop used to return
+    its last loss dictionary with the autograd graph attached; held by the caller, it kept the AccumulateGrad nodes
+    of the default stream alive and the next capture failed with cudaErrorStreamCaptureImplicit."""
+    from dns_slam_b200 import bench_util, slam, synthetic as syn
+    dev = _dev()
+    s = syn.SHAPES["tiny"]
+    n_it = 6
+    sc = bench_util.slam_scene("tiny", 6, dev, seed=5, n_target=2)
+    md, tv = bench_util.mapping_draws(sc, s["mapping_pixels"], n_it, seed=6)
+    target = dict(kf_idx=sc["kf_idx"], frames=sc["frames"], class_tables=sc["class_tables"])
+    refer = dict(kf_idx=sc["refer_idx"], est_c2w=sc["refer_c2w"])
+    est = [sc["poses"][2 * f + 1].clone() for f in range(2)]
+    dec = bench_util.make_decoder("tiny", 6, dev, seed=2)
+    mp = slam.MapperCore(sc["cam"], dec, s["mapping_pixels"], 32, 15,
+                         lambdas=dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0), opacity_sigma=0.05,
+                         smooth_pts=s["smooth_pts"], lambda_sm=0.05)
+    args = (mp, target, refer, sc["feats"], est, n_it, 5e-3, 5e-4, True, [], lambda it: md[it], lambda it: tv[it])
+    _, _, kept = slam.map_optimize(*args, use_graph=False)          # the caller keeps this dictionary
+    assert all(v.grad_fn is None and not v.requires_grad for v in kept.values())
+    _, _, ld = slam.map_optimize(*args, use_graph=True)
+    assert getattr(mp, "last_graph_ok", False)
+    assert torch.isfinite(ld["total"]).all() and torch.isfinite(kept["total"]).all()
+
+
+def test_feature_gather_rejects_a_view_count_mismatch():
+    """The C entry point only sees raw pointers: a feature tensor with fewer views than poses would be read out of
+    bounds, so the wrapper refuses it."""
+    from dns_slam_b200 import fused
+    dev = _dev()
+    pts = torch.rand(10, 3, device=dev)
+    w2c = torch.eye(4, device=dev).repeat(2, 1, 1)
+    K = torch.tensor([[60.0, 0, 39.5], [0, 60.0, 29.5], [0, 0, 1]])
+    with pytest.raises(ValueError):
+        fused.feature_gather(60, 80, K, pts, w2c, torch.rand(1, 30, 40, 64, device=dev))
+    code, uv, mask = fused.feature_gather(60, 80, K, pts, w2c, torch.rand(2, 30, 40, 64, device=dev))
+    assert code.shape == (2, 10, 64)
