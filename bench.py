@@ -481,7 +481,7 @@ def _iteration_timings(shape, n_class, dev):
             "tracking_rays": s["tracking_pixels"],
             "mapping_ms_per_iteration": t_map, "mapping_ms_per_iteration_cuda_graph": t_map_graph,
             "mapping_graph_ok": bool(getattr(mp, "last_graph_ok", False)), "mapping_rays": s["mapping_pixels"], "tv_lattice": (s["smooth_pts"] - 1) ** 3,
-            "n_samples": 47, "note": "autograd drop-in path (render_and_loss + torch Adam), sampling + feature matching + TV included"}
+            "n_samples": 47, "note": "autograd drop-in path (render_and_loss + FusedAdam), sampling + feature matching + TV included"}
 
 
 if __name__ == "__main__":
