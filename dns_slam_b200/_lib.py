@@ -47,7 +47,7 @@ class RenderArgs(C.Structure):
                 ("d_experts", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("d_features", _P),
                 ("workspace", _P), ("workspace_bytes", C.c_int64),
                 ("n_rays_total", C.c_int64), ("ray_offset", C.c_int64), ("gt_label_all", _P),
-                ("global_counts", _P), ("forward_only", C.c_int32), ("reserved_", C.c_int32)]
+                ("global_counts", _P), ("forward_only", C.c_int32), ("use_simt", C.c_int32)]
 
 
 class TvArgs(C.Structure):
@@ -55,7 +55,8 @@ class TvArgs(C.Structure):
                 ("bound", (C.c_double * 2) * 3), ("offset", C.c_double * 3),
                 ("jitter", C.c_double * 3), ("lambda_sm", C.c_float), ("need_dparams", C.c_int32),
                 ("grid", Grid), ("table", _P), ("coarse", _P), ("loss", _P), ("d_table", _P),
-                ("d_coarse", _P), ("workspace", _P), ("workspace_bytes", C.c_int64), ("offset_jitter_dev", _P)]
+                ("d_coarse", _P), ("workspace", _P), ("workspace_bytes", C.c_int64), ("offset_jitter_dev", _P),
+                ("use_simt", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class SampleArgs(C.Structure):
@@ -66,18 +67,33 @@ class SampleArgs(C.Structure):
                 ("color", _P), ("depth", _P), ("label", _P), ("index", _P), ("R", _P), ("T", _P),
                 ("t_lin", _P), ("t_surface", _P), ("t_zero", _P),
                 ("gt_color", _P), ("gt_depth", _P), ("gt_label", _P), ("rays_o", _P),
-                ("rays_d", _P), ("z_vals", _P), ("pts", _P), ("inside", _P), ("scratch", _P)]
+                ("rays_d", _P), ("z_vals", _P), ("pts", _P), ("inside", _P), ("scratch", _P),
+                ("order", _P), ("slot_base", _P), ("n_direct", C.c_int32), ("phase", C.c_int32), ("pixel", _P)]
+
+
+MAX_FRAMES = 8
+
+
+class FeatMergeArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int32), ("n_samples", C.c_int32), ("n_frames", C.c_int32), ("n_views", C.c_int32),
+                ("ray_start", C.c_int32 * (MAX_FRAMES + 1)), ("H", C.c_int32), ("W", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("apply_trunc", C.c_int32), ("need_dparams", C.c_int32), ("need_drays", C.c_int32),
+                ("bound", (C.c_double * 2) * 3), ("K", _P), ("w2c", _P), ("cam_o", _P), ("feats", _P * MAX_FRAMES),
+                ("rays_o", _P), ("rays_d", _P), ("z_vals", _P), ("gt_depth", _P), ("params", _P), ("features", _P),
+                ("d_features", _P), ("d_params", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("workspace", _P),
+                ("workspace_bytes", C.c_int64)]
 
 
 _lib = None
 
 # every symbol include/dns_slam_b200.h declares
-SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_set_tensor_cores", "dns_debug_gemm_tc", "dns_debug_gemm_img", "dns_oneblob_fwd", "dns_oneblob_bwd",
+SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_debug_gemm_tc", "dns_debug_gemm_img", "dns_oneblob_fwd", "dns_oneblob_bwd",
            "dns_hashgrid_fwd", "dns_hashgrid_bwd", "dns_hashgrid_indices", "dns_mlp_fwd",
            "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd", "dns_render_counts",
            "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
            "dns_adam_step", "dns_merge_workspace_bytes", "dns_merge_fwd", "dns_merge_bwd",
-           "dns_stem_workspace_bytes", "dns_stem_fwd", "dns_adam_multi"]
+           "dns_stem_workspace_bytes", "dns_stem_fwd", "dns_adam_multi", "dns_featmerge_workspace_bytes",
+           "dns_featmerge_fwd", "dns_featmerge_bwd", "dns_pose_prepare", "dns_pose_grad"]
 
 
 def lib():
@@ -97,7 +113,6 @@ def lib():
     i64, i32, f32 = C.c_int64, C.c_int, C.c_float
     L.dns_struct_sizes.argtypes = [C.POINTER(C.c_int64)]
     L.dns_profile_enable.argtypes = [C.c_int]
-    L.dns_set_tensor_cores.argtypes = [C.c_int]
     L.dns_debug_gemm_tc.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int64, _P, _P]
     L.dns_debug_gemm_img.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]
     L.dns_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
@@ -124,9 +139,15 @@ def lib():
     L.dns_stem_workspace_bytes.restype = C.c_int64
     L.dns_stem_workspace_bytes.argtypes = []
     L.dns_stem_fwd.argtypes = [_P, i32, i32, i32, _P, _P, _P, f32, f32, i32, _P, _P, _P, _P, i64, _P]
-    sizes = (C.c_int64 * 4)()
+    L.dns_featmerge_workspace_bytes.restype = C.c_int64
+    L.dns_featmerge_workspace_bytes.argtypes = [i32, i32]
+    L.dns_featmerge_fwd.argtypes = [C.POINTER(FeatMergeArgs), _P]
+    L.dns_featmerge_bwd.argtypes = [C.POINTER(FeatMergeArgs), _P]
+    L.dns_pose_prepare.argtypes = [_P, _P, i32, _P, _P, _P, i32, _P, _P, _P, _P]
+    L.dns_pose_grad.argtypes = [_P, _P, _P, i32, C.POINTER(C.c_int32), i32, i32, i32, f32, f32, f32, f32, _P, _P, _P, _P, _P]
+    sizes = (C.c_int64 * 5)()
     L.dns_struct_sizes(sizes)
-    mine = [C.sizeof(Grid), C.sizeof(RenderArgs), C.sizeof(TvArgs), C.sizeof(SampleArgs)]
+    mine = [C.sizeof(Grid), C.sizeof(RenderArgs), C.sizeof(TvArgs), C.sizeof(SampleArgs), C.sizeof(FeatMergeArgs)]
     if list(sizes) != mine:
         raise RuntimeError(f"ctypes struct layout {mine} != C layout {list(sizes)}; rebuild the library")
     _lib = L

@@ -74,7 +74,29 @@ struct DwImgArgs {
   int64_t sl0, sc0, cls0, sl1, sc1, cls1;
 };
 int launch_dw_img(const DwImgArgs& a, cudaStream_t st);
-bool use_tensor_cores();
+
+// Function attributes (dynamic shared-memory limit, carve-out) are per DEVICE: a guard that is true the first time it
+// is asked on each device of the process (up to 64), so that a second GPU in the same process gets them too.
+inline bool first_call_on_device(unsigned long long& seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 15;
+}
+
+// Ablation switches exist only in -DDNS_ABLATE builds (scratch measurements); release kernels carry none.
+#ifdef DNS_ABLATE
+#define DNS_DBG(a) ((a).dbg)
+#else
+#define DNS_DBG(a) 0
+#endif
 
 // ---------------------------------------------------------------------------------------
 // OneBlob (16-bin periodic quartic kernel)

@@ -321,11 +321,10 @@ static void merge_carve(MergeArgs& m, void* workspace, int64_t n_rows) {
 }
 
 static void merge_attrs() {
-  static bool done = false;
-  if (done) return;
+  static unsigned long long seen = 0;
+  if (!first_call_on_device(seen)) return;
   cudaFuncSetAttribute(k_merge_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 28 * 2048 + kMergeW * 16);
   cudaFuncSetAttribute(k_merge_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 + kMergeW * 16);
-  done = true;
 }
 
 int dns_merge_fwd(const float* refer_p, const float* code, const float* params, int64_t P, int R, const double bound[3][2],

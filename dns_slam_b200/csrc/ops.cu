@@ -194,13 +194,12 @@ k_dw_gemm(const float* __restrict__ A, int lda, int M, const float* __restrict__
 int launch_dw_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows,
                       const int* n_tiles_dev, int n_tiles_host, const int* tile_class, float* C, int ldc,
                       int64_t c_stride, cudaStream_t st);
-bool use_tensor_cores();
 
 int launch_dw_gemm(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows,
                    const int* n_tiles_dev, int n_tiles_host, const int* tile_class, float* C, int ldc,
-                   int64_t c_stride, cudaStream_t st) {
+                   int64_t c_stride, cudaStream_t st, bool tensor_cores) {
   // the tcgen05 kernel stages rows with 16-byte loads: rows must be float4-aligned and padded
-  if (use_tensor_cores() && M <= 128 && N <= 128 && (lda & 3) == 0 && (ldb & 3) == 0 && ((M + 3) & ~3) <= lda &&
+  if (tensor_cores && M <= 128 && N <= 128 && (lda & 3) == 0 && (ldb & 3) == 0 && ((M + 3) & ~3) <= lda &&
       ((N + 3) & ~3) <= ldb && (((uintptr_t)A | (uintptr_t)B) & 15) == 0)
     return launch_dw_gemm_tc(A, lda, M, B, ldb, N, n_rows, n_tiles_dev, n_tiles_host, tile_class, C, ldc, c_stride, st);
   int Ms = (M + 3) & ~3, Ns = (N + 3) & ~3;
@@ -211,11 +210,8 @@ int launch_dw_gemm(const float* A, int lda, int M, const float* B, int ldb, int 
   if (n_tiles_host <= 0) return DNS_OK;
   size_t smem = (size_t)kGemmRows * (Ms + Ns) * sizeof(float);
   int grid = n_tiles_host < 592 ? n_tiles_host : 592;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_dw_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
-  }
+  static unsigned long long seen = 0;
+  if (first_call_on_device(seen)) cudaFuncSetAttribute(k_dw_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   k_dw_gemm<<<grid, 256, smem, st>>>(A, lda, M, B, ldb, N, n_rows, n_tiles_dev, n_tiles_host, tile_class, C, ldc,
                                      c_stride);
   return check_launch("dw_gemm");
@@ -413,11 +409,12 @@ int dns_profile_read(double* ms, long long* launches, int reset) {
 
 const char* dns_last_error(void) { return g_err; }
 int dns_version(void) { return 100; }
-void dns_struct_sizes(int64_t out[4]) {
+void dns_struct_sizes(int64_t out[5]) {
   out[0] = sizeof(dns_grid);
   out[1] = sizeof(dns_render_args);
   out[2] = sizeof(dns_tv_args);
   out[3] = sizeof(dns_sample_args);
+  out[4] = sizeof(dns_featmerge_args);
 }
 
 int dns_oneblob_fwd(const float* x, int64_t P, int D, int n_bins, float* out, void* stream) {
@@ -496,10 +493,10 @@ int dns_mlp_bwd(const float* x, const float* params, const float* hidden, const 
   if (int e = check_launch("mlp_bwd")) return e;
   if (d_params) {
     // dW1[j][k] = sum_p dH[p][j] X[p][k];  dW2[c][j] = sum_p dOut[p][c] H[p][j]
-    if (int e = launch_dw_gemm(d_hidden, 32, 32, x, n_in, n_in, P, nullptr, (int)tiles, nullptr, d_params, n_in, 0, st))
+    if (int e = launch_dw_gemm(d_hidden, 32, 32, x, n_in, n_in, P, nullptr, (int)tiles, nullptr, d_params, n_in, 0, st, true))
       return e;
     if (int e = launch_dw_gemm(d_out, n_out, n_out, hidden, 32, 32, P, nullptr, (int)tiles, nullptr,
-                               d_params + 32 * n_in, 32, 0, st))
+                               d_params + 32 * n_in, 32, 0, st, true))
       return e;
   }
   return DNS_OK;

@@ -24,7 +24,7 @@ namespace dns {
 
 int launch_dw_gemm(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_rows,
                    const int* n_tiles_dev, int n_tiles_host, const int* tile_class, float* C, int ldc,
-                   int64_t c_stride, cudaStream_t st);
+                   int64_t c_stride, cudaStream_t st, bool tensor_cores);
 
 
 // ---------------------------------------------------------------------------------------
@@ -590,7 +590,11 @@ __global__ void __launch_bounds__(256) k_ray(RayArgs a) {
       mx = fmaxf(mx, lg[c]);
     }
     const float gd = a.gt_depth[r];
-    const int64_t lab = a.gt_label[r];
+    int64_t lab = a.gt_label[r];
+    if (lab < 0 || lab >= C) {   // torch's cross_entropy raises here; the flag surfaces as losses[7] = -3
+      *a.err = 3;
+      lab = 0;
+    }
     const bool track = a.mode == kTrack;
     const bool m = track ? (a.mask ? a.mask[r] != 0 : true) : true;
     const float n_ray = track ? (float)a.counts[cMask] : (float)a.N_total;
@@ -971,7 +975,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     B.lo[c] = a->bound[c][0];
     B.ext[c] = a->bound[c][1] - a->bound[c][0];
   }
-  const bool tc = use_tensor_cores();
+  const bool tc = !a->use_simt;
   // weight preparation: bf16 hi/lo chunk tiles (tcgen05 path) or k-major fp32 copies (SIMT path)
   PhaseScope* ph = new PhaseScope(phPrep, st, 1 + (a->global_counts ? 0 : 1) + (map ? 2 : 1));
   cudaMemsetAsync(w.counts, 0, 16 * sizeof(int), st);
@@ -996,8 +1000,8 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   delete ph;
   if (int e = check_launch("render prep")) return e;
 
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long seen = 0;
+  if (first_call_on_device(seen)) {
     cudaFuncSetAttribute(k_point_fwd<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_point_fwd<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_point_fwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -1005,7 +1009,6 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     cudaFuncSetAttribute(k_point_bwd<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_point_bwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_ray, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr = true;
   }
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT * (map ? 2 : 1));
   int T, RPC;
@@ -1033,9 +1036,14 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
     pa.need_dparams = a->need_dparams && !a->forward_only; pa.need_drays = a->need_drays;
+#ifdef DNS_ABLATE
     { const char* e = getenv("DNS_DBG"); pa.dbg = e ? atoi(e) : 0; }
+#endif
     if (map) {
-      const bool whole = !sharded && ray0 == 0 && nc == N && (int64_t)N * S < 2147483647LL && !getenv("DNS_GENERIC_PREP");
+      bool whole = !sharded && ray0 == 0 && nc == N && (int64_t)N * S < 2147483647LL;
+#ifdef DNS_ABLATE
+      if (getenv("DNS_GENERIC_PREP")) whole = false;
+#endif
       PhaseScope phc(phClassPrep, st, whole ? 4 : 3);
       cudaMemsetAsync(w.hist, 0, (nci + 1) * sizeof(int), st);
       if (whole) {
@@ -1074,12 +1082,14 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.fine36 = pa.fine36; ra.W1T2 = w.W1T2; ra.W2cT = w.W2cT; ra.logit = a->logit; ra.counts = w.counts;
     ra.lam_p = a->lambda_p; ra.lam_d = a->lambda_d; ra.lam_l = a->lambda_l;
     ra.pred_color = a->pred_color; ra.pred_depth = a->pred_depth; ra.pred_var = a->pred_var;
-    ra.pred_logits = a->pred_logits; ra.raw = w.raw; ra.dfine36 = pa.dfine36; ra.d_features = a->d_features;
+    ra.pred_logits = a->pred_logits; ra.raw = w.raw; ra.err = w.counts + cErr; ra.dfine36 = pa.dfine36; ra.d_features = a->d_features;
     ra.d_rays_o = a->d_rays_o; ra.d_rays_d = a->d_rays_d;
     ra.X2 = w.X2; ra.dH2 = w.dH2; ra.Hcol = w.Hcol; ra.dpre = w.dpre; ra.dlogit = w.dlogit; ra.Hbar = w.Hbar;
     ra.X2img = (uint4*)w.X2; ra.dH2img = (uint4*)w.dH2; ra.Hcolimg = (uint4*)w.Hcol; ra.dpreimg = (uint4*)w.dpre;
     ra.RS = T <= 96 ? T : (T == 160 ? 80 : (T == 256 ? 128 : 64));   // sub-tile rows of the ray-side images (divides T)
+#ifdef DNS_ABLATE
     if (const char* e = getenv("DNS_RAY_RS")) ra.RS = atoi(e);
+#endif
     const bool fwd_only = a->forward_only != 0;
     ra.fwd_only = a->forward_only;
     ra.need_dparams = a->need_dparams && !fwd_only; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d && !fwd_only;
@@ -1113,7 +1123,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       const int* ntd = map ? w.counts + cTiles : nullptr;
       int e = 0;
       const int pt_tiles = (int)((Pc + kTile - 1) / kTile), ray_tiles = (int)((nc + kTile - 1) / kTile);
-      if (use_tensor_cores()) {
+      if (tc) {
         // tcgen05 path: every operand is a bf16 hi/lo tile image streamed by bulk copies (tc.cu: k_dw_img).
         //   X80^T [dHc | dHf]            -> coarse W1 (+ class-expert W1), the shared input read once
         //   dOut^T H  per net            -> coarse W2, class-expert W2
@@ -1145,22 +1155,22 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
         g.L = DwImg{ra.dpreimg, 1, 0, 1, 3}; g.Cc = DwImg{ra.Hcolimg, 4, 0, 4, 32};
         g.out0 = a->d_color + 32 * kIn2; g.sl0 = 32; g.sc0 = 1; g.out1 = nullptr;
         e |= launch_dw_img(g, st);
-        e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st);
+        e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st, tc);
         if (e) return DNS_ERR_CUDA;
         continue;
       } else {
-        e |= launch_dw_gemm(w.dHc, 64, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, nullptr, a->d_coarse, kIn1, 0, st);
+        e |= launch_dw_gemm(w.dHc, 64, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, nullptr, a->d_coarse, kIn1, 0, st, tc);
         if (map)
-          e |= launch_dw_gemm(w.dHf, 64, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, w.tile_class, a->d_experts, kIn1, 4096, st);
-        e |= launch_dw_gemm(w.dH2, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_color, kIn2, 0, st);
-        e |= launch_dw_gemm(w.dH2 + 32, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_logit, kIn2, 0, st);
+          e |= launch_dw_gemm(w.dHf, 64, 32, w.Xst, kIn1, kIn1, Qrows, ntd, tiles_max, w.tile_class, a->d_experts, kIn1, 4096, st, tc);
+        e |= launch_dw_gemm(w.dH2, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_color, kIn2, 0, st, tc);
+        e |= launch_dw_gemm(w.dH2 + 32, 64, 32, w.X2, kIn2, kIn2, Pc, nullptr, pt_tiles, nullptr, a->d_logit, kIn2, 0, st, tc);
       }
       // layer-2 weight gradients: dOut^T H
-      e |= launch_dw_gemm(w.dOc, kOutP, DNS_LATENT, w.Hc, 32, 32, Qrows, ntd, tiles_max, nullptr, a->d_coarse + 2560, 32, 0, st);
+      e |= launch_dw_gemm(w.dOc, kOutP, DNS_LATENT, w.Hc, 32, 32, Qrows, ntd, tiles_max, nullptr, a->d_coarse + 2560, 32, 0, st, tc);
       if (map)
-        e |= launch_dw_gemm(w.dOf, kOutP, DNS_LATENT, w.Hf, 32, 32, Qrows, ntd, tiles_max, w.tile_class, a->d_experts + 2560, 32, 4096, st);
-      e |= launch_dw_gemm(w.dpre, 4, 3, w.Hcol, 32, 32, Pc, nullptr, pt_tiles, nullptr, a->d_color + 32 * kIn2, 32, 0, st);
-      e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st);
+        e |= launch_dw_gemm(w.dOf, kOutP, DNS_LATENT, w.Hf, 32, 32, Qrows, ntd, tiles_max, w.tile_class, a->d_experts + 2560, 32, 4096, st, tc);
+      e |= launch_dw_gemm(w.dpre, 4, 3, w.Hcol, 32, 32, Pc, nullptr, pt_tiles, nullptr, a->d_color + 32 * kIn2, 32, 0, st, tc);
+      e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st, tc);
       if (e) return DNS_ERR_CUDA;
     }
   }
@@ -1218,12 +1228,11 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   float* dHc = c.take<float>(Q * 64);
   float* dOc = c.take<float>(Q * 40);   // fp32 rows of 36, or the 5-chunk tile image of the tcgen05 path
   uint4* wc_tc = c.take<uint4>(1024);
-  const bool tc = use_tensor_cores();
-  static bool attr = false;
-  if (!attr) {
+  const bool tc = !a->use_simt;
+  static unsigned long long seen = 0;
+  if (first_call_on_device(seen)) {
     cudaFuncSetAttribute(k_point_fwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_point_bwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
   }
   k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, WTc);
   cudaMemsetAsync(a->loss, 0, sizeof(float), st);
@@ -1270,8 +1279,8 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
       g.out0 = a->d_coarse + 2560; g.sl0 = 32; g.sc0 = 1;
       e |= launch_dw_img(g, st);
     } else {
-      e |= launch_dw_gemm(dHc, 64, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st);
-      e |= launch_dw_gemm(dOc, kOutP, 1, Hc, 32, 32, Q, nullptr, tiles, nullptr, a->d_coarse + 2560, 32, 0, st);
+      e |= launch_dw_gemm(dHc, 64, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st, tc);
+      e |= launch_dw_gemm(dOc, kOutP, 1, Hc, 32, 32, Q, nullptr, tiles, nullptr, a->d_coarse + 2560, 32, 0, st, tc);
     }
     if (e) return DNS_ERR_CUDA;
   }

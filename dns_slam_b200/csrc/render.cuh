@@ -1,4 +1,4 @@
-// Shared argument structs / enums of the fused render kernels (render.cu, ray_tc.cu).
+// Shared argument structs / enums of the fused render kernels (render.cu, point_tc.cu, ray_tc.cu).
 #pragma once
 #include "common.cuh"
 
@@ -28,6 +28,7 @@ struct RayArgs {
   const float* W2cT;
   const float* logit;  // tcnn layout; W2l = logit + 32*112, [Cpad][32]
   const int* counts;
+  int* err;       // counts[cErr]: 3 = label outside [0, n_class)
   float lam_p, lam_d, lam_l;
   float* pred_color;
   float* pred_depth;
@@ -107,7 +108,7 @@ struct PointArgs {
   float* d_rays_o;
   float* d_rays_d;
   int need_dparams, need_drays;
-  int dbg;   // experiment switches (DNS_DBG env): 1 no gather, 2 no stash stores, 4 no table atomics, 8 no regather
+  int dbg;   // -DDNS_ABLATE builds only (DNS_DBG env): 2 no stash stores, 4 no table atomics, 8 no regather
 };
 
 template <int MODE>
@@ -197,8 +198,7 @@ int prep_nets_tc(const float* coarse, const float* experts, int n_experts, uint4
 int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
 int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
 
-// tcgen05 ray kernel (ray_tc.cu)
-// two threads per point (ray_tc2.cu)
+// tcgen05 ray kernel, two threads per point (ray_tc.cu)
 void pick_ray_block_tc2(int S, int& T, int& RPC);
 size_t ray_tc2_smem_bytes(int T, int RPC, int C4);
 int launch_ray_tc2(const RayArgs& ra, uint4* w1_hi, uint4* w1_lo, int64_t n_rays_chunk, cudaStream_t st);

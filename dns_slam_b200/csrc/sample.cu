@@ -16,6 +16,9 @@ __global__ void k_sample_gather(dns_sample_args a) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.n) return;
   int64_t idx = a.index[r];
+  // class-balanced draws (utils/common.py:315-330): the draw is an offset into the pixels of the slot's class
+  if (a.order && r >= a.n_direct) idx = a.order[(int64_t)a.slot_base[r - a.n_direct] + idx];
+  if (a.pixel) a.pixel[r] = idx;
   int hh = a.H0 + (int)(idx / a.Ww), ww = a.W0 + (int)(idx % a.Ww);
   int64_t pix = (int64_t)hh * a.W + ww;
   float d = a.depth[pix];
@@ -61,7 +64,9 @@ __global__ void __launch_bounds__(128) k_sample_z(dns_sample_args a) {
       double m = fmax(t0, t1);
       far_bb = fmin(far_bb, m);
     }
-    a.inside[r] = far_bb >= (double)d ? 1 : 0;
+    const bool ins = far_bb >= (double)d;
+    a.inside[r] = ins ? 1 : 0;
+    if (!ins) atomicAdd(a.scratch + 1, 1.0f);   // rays that leave the bound before their depth (mapping.py:525 drops them)
     far_bb += 0.01;
     double hi = (double)__fmul_rn(maxd, 1.2f);
     s_far[tid] = fmin(fmax(far_bb, 0.0), hi);
@@ -175,10 +180,17 @@ int dns_sample_rays(const dns_sample_args* a, void* stream) {
     set_error("sample: need 1 <= n_uniform + n_surface <= 256");
     return DNS_ERR_UNSUPPORTED;
   }
+  if (a->order && (!a->slot_base || a->n_direct < 0 || a->n_direct > a->n)) {
+    set_error("sample: class-balanced draws need slot_base and 0 <= n_direct <= n");
+    return DNS_ERR_ARG;
+  }
   PhaseScope ph(phSample, st, 3);
-  cudaMemsetAsync(a->scratch, 0, 2 * sizeof(float), st);
-  k_sample_gather<<<(a->n + 127) / 128, 128, 0, st>>>(*a);
-  k_sample_z<<<(a->n + kRaysZ - 1) / kRaysZ, 128, sizeof(float) * S * kRaysZ, st>>>(*a);
+  if (a->phase != 2) {   // pixel gather, rays, batch max depth -> scratch[0]
+    cudaMemsetAsync(a->scratch, 0, 2 * sizeof(float), st);
+    k_sample_gather<<<(a->n + 127) / 128, 128, 0, st>>>(*a);
+  }
+  if (a->phase != 1)     // far plane, inside mask (outside count -> scratch[1]), z values
+    k_sample_z<<<(a->n + kRaysZ - 1) / kRaysZ, 128, sizeof(float) * S * kRaysZ, st>>>(*a);
   return check_launch("sample_rays");
 }
 

@@ -218,12 +218,9 @@ int dns_stem_fwd(const float* images, int n, int H, int W, const float* conv_w, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   StemWs* ws = (StemWs*)workspace;
-  static bool attr = false;
+  static unsigned long long seen = 0;
   const int smem = (kStemW + kStemIn) * (int)sizeof(float);
-  if (!attr) {
-    cudaFuncSetAttribute(k_stem_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (first_call_on_device(seen)) cudaFuncSetAttribute(k_stem_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   PhaseScope ph(phFeature, st, 4);
   k_stem_prep<<<(kStemW + 255) / 256, 256, 0, st>>>(conv_w, ws);
   dim3 grid((w + kSoC - 1) / kSoC, gy, n);

@@ -292,27 +292,18 @@ int launch_dw_img(const DwImgArgs& a, cudaStream_t st) {
     return DNS_ERR_UNSUPPORTED;
   }
   size_t smem = (size_t)ns * stage + tail;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_dw_img, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    attr = true;
-  }
+  static unsigned long long seen = 0;
+  if (first_call_on_device(seen)) cudaFuncSetAttribute(k_dw_img, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
   int grid = a.n_tiles_host < 148 ? a.n_tiles_host : 148;
   k_dw_img<<<grid, kTile, smem, st>>>(a, ns, stage);
   return check_launch("dw_img");
 }
 
-static bool g_use_tc = true;
-bool use_tensor_cores() { return g_use_tc; }
-
 template <int LQ, int CQ>
 static int launch_inst(const DwArgs& a, cudaStream_t st) {
   size_t smem = (size_t)(LQ + CQ + dw_pad_chunks<LQ, CQ>()) * 2048;   // 2 lane tiles + 2 column tiles + over-read pad
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_dw_gemm_tc<LQ, CQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  static unsigned long long seen = 0;
+  if (first_call_on_device(seen)) cudaFuncSetAttribute(k_dw_gemm_tc<LQ, CQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = a.n_tiles_host < 592 ? a.n_tiles_host : 592;
   k_dw_gemm_tc<LQ, CQ><<<grid, kTile, smem, st>>>(a);
   return check_launch("dw_gemm_tc");
@@ -413,6 +404,7 @@ int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, 
   a.sl0 = N;   // lanes = m -> row stride N
   a.sc0 = 1;
   int e = launch_dw_img(a, st);
+#ifdef DNS_ABLATE
   if (const char* reps = getenv("DNS_IMG_REPS")) {   // isolated timing of the pipeline (scratch measurements)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -429,14 +421,12 @@ int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
+#endif
   cudaStreamSynchronize(st);
   cudaFree(li);
   cudaFree(ci);
   return e;
 }
-// 1: weight-gradient GEMMs on tcgen05 (default); 0: fp32 SIMT path (A/B comparisons)
-void dns_set_tensor_cores(int on) { dns::g_use_tc = on != 0; }
-
 // debug / test entry: C[m][n] (ldc = N) += sum_p A[p][m] B[p][n] through the tcgen05 kernel
 int dns_debug_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows, float* C, void* stream) {
   int tiles = (int)((rows + dns::kTile - 1) / dns::kTile);

@@ -15,8 +15,6 @@ into it), so that the fused Adam step and the multi-GPU gradient all-reduce are 
 operations.  The class-wise fine MLPs of ``Mapper.set_decoder``
 (``slams/mapping.py:727-761``) are rows of a pre-allocated expert bank.
 """
-import os
-
 import torch
 from torch import nn
 
@@ -46,6 +44,10 @@ class Pos_Encoding(nn.Module):
 
 
 class Merge(nn.Module):
+    # True: the drop-in operator chain (OneBlob -> concat -> MLP -> mean) instead of the fused kernels; A/B hook of the
+    # parity tests
+    use_operator_chain = False
+
     def __init__(self, cfg, hidden_dim=32, feature_dim=64, bound=None, seed=0, device="cuda"):
         super().__init__()
         self.bound = bound
@@ -56,7 +58,7 @@ class Merge(nn.Module):
     def forward(self, p, o, features=None):
         n_refer, n_points, _ = features.shape
         if (features.is_cuda and features.shape[-1] == 64 and self.decoder.n_output_dims == 32
-                and not os.environ.get("DNS_MERGE_OPS")):
+                and not self.use_operator_chain):
             # fused tcgen05 path: OneBlob + concat + MLP + mean over the views in one kernel each way
             from . import fused
             return fused.merge_fused(p, features, self.decoder.params, self.bound)

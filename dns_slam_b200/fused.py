@@ -25,6 +25,31 @@ LOSS_KEYS = ("p_loss", "d_loss", "l_loss", "lt_loss", "fs_loss", "opacity_loss",
 
 _ws_cache = {}
 _tlin_cache = {}
+_use_simt = False
+
+
+class simt_path:
+    """``with fused.simt_path():`` -- the fused calls issued inside run the fp32 SIMT kernels (``use_simt`` of
+    dns_render_args / dns_tv_args) instead of the tcgen05 ones.  A/B reference of the parity tests; the library itself
+    holds no mode state."""
+
+    def __enter__(self):
+        global _use_simt
+        self.prev, _use_simt = _use_simt, True
+        return self
+
+    def __exit__(self, *exc):
+        global _use_simt
+        _use_simt = self.prev
+
+
+def raise_on_flag(losses):
+    """ONE device->host read of the fused call's error flag (losses[7] < 0): the reference raises on the spot
+    (slams/mapping.py:594-595 'Fine decoders does NOT have class'; torch's cross_entropy on a label outside the head)."""
+    flag = float(losses[7])
+    if flag < 0:
+        raise ValueError({-1: "label outside [0, n_class_ids)", -2: "Fine decoders does NOT have class",
+                          -3: "label outside [0, n_class) of the semantic head"}.get(int(flag), f"render error {flag}"))
 
 
 def workspace(nbytes, device):
@@ -47,10 +72,13 @@ def fix_surface_draw(t, n_surface):
 
 
 def sample_rays(cam, bound, frame, idx, window, R, T, n_samples, n_surface, t_surface, t_zero,
-                want_pts=False, t_lin=None):
+                want_pts=False, t_lin=None, class_order=None, slot_base=None, n_direct=None, want_pixel=False, out=None,
+                phase=0):
     """frame: dict(color [H,W,3] f32, depth [H,W] f32, label [H,W] i64) on the GPU; idx: flat
     window indices [n] int64 (the draws of common.py:274 / :327); window = (H0, H1, W0, W1).
-    Returns the ``samples`` fields of tracking.py:177-185 plus ``inside``."""
+    ``class_order`` / ``slot_base`` / ``n_direct``: rays >= n_direct are class-balanced draws resolved on the device
+    (``order[slot_base[j] + idx]``, common.py:315-330).  ``out``: pre-allocated output slices (dict) to write into.
+    Returns the ``samples`` fields of tracking.py:177-185 plus ``inside`` (and ``pixel`` with want_pixel)."""
     dev = frame["color"].device
     n = idx.numel()
     S = n_samples + n_surface
@@ -73,19 +101,33 @@ def sample_rays(cam, bound, frame, idx, window, R, T, n_samples, n_surface, t_su
     a.color, a.depth = _lib.ptr(keep[0], torch.float32), _lib.ptr(keep[1], torch.float32)
     a.label, a.index = _lib.ptr(keep[2], torch.int64), _lib.ptr(keep[3], torch.int64)
     a.R, a.T, a.t_lin, a.t_surface, a.t_zero = (_lib.ptr(k) for k in keep[4:])
-    out = dict(gt_color=torch.empty(n, 3, device=dev), gt_depth=torch.empty(n, device=dev),
-               gt_label=torch.empty(n, dtype=torch.int64, device=dev), rays_o=torch.empty(n, 3, device=dev),
-               rays_d=torch.empty(n, 3, device=dev), z_vals=torch.empty(n, S, device=dev),
-               inside=torch.empty(n, dtype=torch.uint8, device=dev))
-    if want_pts:
-        out["pts"] = torch.empty(n, S, 3, device=dev)
-    scratch = torch.empty(2, device=dev)
+    raw = out is not None
+    if out is None:
+        out = dict(gt_color=torch.empty(n, 3, device=dev), gt_depth=torch.empty(n, device=dev),
+                   gt_label=torch.empty(n, dtype=torch.int64, device=dev), rays_o=torch.empty(n, 3, device=dev),
+                   rays_d=torch.empty(n, 3, device=dev), z_vals=torch.empty(n, S, device=dev),
+                   inside=torch.empty(n, dtype=torch.uint8, device=dev))
+        if want_pts:
+            out["pts"] = torch.empty(n, S, 3, device=dev)
+        if want_pixel:
+            out["pixel"] = torch.empty(n, dtype=torch.int64, device=dev)
+        out["scratch"] = torch.empty(2, device=dev)
     for k in ("gt_color", "gt_depth", "gt_label", "rays_o", "rays_d", "z_vals", "inside"):
         setattr(a, k, _lib.ptr(out[k]))
     a.pts = _lib.ptr(out.get("pts"), allow_none=True)
-    a.scratch = _lib.ptr(scratch)
+    a.pixel = _lib.ptr(out.get("pixel"), torch.int64, allow_none=True)
+    a.scratch = _lib.ptr(out["scratch"])
+    if class_order is not None:
+        keep += [class_order, slot_base]
+        a.order, a.slot_base = _lib.ptr(class_order, torch.int64), _lib.ptr(slot_base, torch.int32)
+        a.n_direct = int(n_direct)
+    else:
+        a.n_direct = n
+    a.phase = int(phase)
     _lib.check(_lib.lib().dns_sample_rays(C.byref(a), _lib.stream()))
-    out["inside"] = out["inside"].bool()
+    if not raw:
+        out["inside"] = out["inside"].bool()
+        out.pop("scratch")
     return out
 
 
@@ -175,6 +217,7 @@ def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, featur
     need_dparams = grads is not None
     a.need_dparams, a.need_drays, a.need_dfeat = int(need_dparams), int(need_drays), int(need_dfeat)
     a.forward_only = int(forward_only)
+    a.use_simt = int(_use_simt)
     _lib.fill_bound(a.bound, cfg.bound)
     a.lambda_p, a.lambda_d, a.lambda_l = cfg.lam["p"], cfg.lam["d"], cfg.lam["l"]
     a.lambda_lt, a.lambda_fs, a.lambda_op = cfg.lam["lt"], cfg.lam["fs"], cfg.lam["op"]
@@ -282,9 +325,7 @@ def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_
     out = _RenderFn.apply(cfg, prm[0], prm[1], prm[2], prm[3], prm[4], samples["rays_o"], samples["rays_d"], feats)
     total, losses = out[0], out[1]
     if strict:   # one device->host read: the reference raises on the spot (mapping.py:594-595)
-        flag = float(losses[7])
-        if flag < 0:
-            raise ValueError("Fine decoders does NOT have class" if flag <= -2 else "label outside [0, n_class_ids)")
+        raise_on_flag(losses)
     ld = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
     ld["total"] = total
     preds = dict(color=out[2], depth=out[3], var=out[4], logits=out[5], fine=out[6], coarse=out[7])
@@ -326,6 +367,7 @@ def tv_raw(gstruct, bound, table, coarse, sample_points, offset, jitter, lambda_
             a.offset[k], a.jitter[k] = float(offset[k]), float(jitter[k])
     a.lambda_sm = lambda_sm
     a.need_dparams = int(d_table is not None)
+    a.use_simt = int(_use_simt)
     a.grid = gstruct
     a.table, a.coarse = _lib.ptr(table, torch.float32), _lib.ptr(coarse, torch.float32)
     loss = torch.empty(1, device=dev)
@@ -468,6 +510,174 @@ def feature_matching(H, W, K, pts_, refer_w2c, feats_cl, merge_fn, refer_c2w=Non
     return merge_fn(refer_p, refer_o, code)
 
 
+class Views:
+    """Reference views of a ray batch for the fused pixel-feature branch: rays [ray_start[f], ray_start[f+1]) belong to
+    target frame f, whose R views are rows f*R.. of ``w2c`` [F*R,4,4] / ``cam_o`` [F*R,3] and ``feats[f]``
+    ([R,h,w,64] channels-last, contiguous fp32 CUDA)."""
+
+    def __init__(self, w2c, cam_o, feats, ray_start):
+        self.w2c = w2c.detach().to(torch.float32).contiguous()
+        self.cam_o = cam_o.detach().to(torch.float32).contiguous()
+        self.feats = list(feats)
+        self.ray_start = [int(x) for x in ray_start]
+        self.F = len(self.feats)
+        self.R = self.w2c.shape[0] // self.F
+        for f in self.feats:
+            if f.shape[0] != self.R or f.shape[-1] != 64:
+                raise ValueError(f"feature maps must be [R={self.R},h,w,64] channels-last, got {tuple(f.shape)}")
+        if self.F > _lib.MAX_FRAMES or self.R > 8:
+            raise ValueError("at most 8 target frames and 8 views per frame in one fused call")
+
+
+def _featmerge_args(cam, bound, K, views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc, ws):
+    a = _lib.FeatMergeArgs()
+    N, S = z_vals.shape
+    a.n_rays, a.n_samples, a.n_frames, a.n_views = N, S, views.F, views.R
+    for f, r in enumerate(views.ray_start):
+        a.ray_start[f] = r
+    a.H, a.W = cam["H"], cam["W"]
+    a.h, a.w = views.feats[0].shape[1], views.feats[0].shape[2]
+    a.apply_trunc = int(apply_trunc)
+    _lib.fill_bound(a.bound, bound)
+    f32 = torch.float32
+    a.K, a.w2c, a.cam_o = _lib.ptr(K, f32), _lib.ptr(views.w2c, f32), _lib.ptr(views.cam_o, f32)
+    for f, t in enumerate(views.feats):
+        a.feats[f] = _lib.ptr(t, f32)
+    a.rays_o, a.rays_d = _lib.ptr(rays_o, f32), _lib.ptr(rays_d, f32)
+    a.z_vals, a.gt_depth = _lib.ptr(z_vals, f32), _lib.ptr(gt_depth, f32)
+    a.params = _lib.ptr(params, f32)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    return a
+
+
+_K_cache = {}
+
+
+def _K_dev(cam, dev):
+    key = (id(cam["K"]), dev.type, dev.index)
+    k = _K_cache.get(key)
+    if k is None:
+        k = _K_cache[key] = cam["K"].detach().to(dev, torch.float32).contiguous()
+    return k
+
+
+def featmerge_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc=True, ws=None, out=None):
+    """One ``dns_featmerge_fwd`` call.  Returns (features [N,S,32], workspace) -- the workspace holds the band row list
+    and must be handed to ``featmerge_bwd_raw``."""
+    dev = z_vals.device
+    N, S = z_vals.shape
+    L = _lib.lib()
+    if ws is None:
+        ws = torch.empty(int(L.dns_featmerge_workspace_bytes(N, S)), dtype=torch.uint8, device=dev)
+    a = _featmerge_args(cam, bound, _K_dev(cam, dev), views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc, ws)
+    if out is None:
+        out = torch.empty(N, S, 32, device=dev)
+    a.features = _lib.ptr(out, torch.float32)
+    _lib.check(L.dns_featmerge_fwd(C.byref(a), _lib.stream()))
+    return out, ws
+
+
+def featmerge_bwd_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, d_features, ws, d_params, d_rays_o,
+                      d_rays_d, apply_trunc=True):
+    """One ``dns_featmerge_bwd`` call: ACCUMULATES into d_params / d_rays_o / d_rays_d (None = not wanted)."""
+    a = _featmerge_args(cam, bound, _K_dev(cam, z_vals.device), views, rays_o, rays_d, z_vals, gt_depth, params,
+                        apply_trunc, ws)
+    a.d_features = _lib.ptr(d_features, torch.float32)
+    a.need_dparams, a.need_drays = int(d_params is not None), int(d_rays_o is not None)
+    a.d_params = _lib.ptr(d_params, torch.float32, allow_none=True)
+    a.d_rays_o, a.d_rays_d = _lib.ptr(d_rays_o, allow_none=True), _lib.ptr(d_rays_d, allow_none=True)
+    _lib.check(_lib.lib().dns_featmerge_bwd(C.byref(a), _lib.stream()))
+
+
+class _FeatMergeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, params, cam, bound, views, z_vals, gt_depth, apply_trunc):
+        ro, rd = rays_o.detach().contiguous(), rays_d.detach().contiguous()
+        pr = params.detach()
+        out, ws = featmerge_raw(cam, bound, views, ro, rd, z_vals, gt_depth, pr, apply_trunc)
+        ctx.save_for_backward(ro, rd, pr, z_vals, gt_depth, ws)
+        ctx.meta = (cam, bound, views, apply_trunc)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ro, rd, pr, z_vals, gt_depth, ws = ctx.saved_tensors
+        cam, bound, views, apply_trunc = ctx.meta
+        need = ctx.needs_input_grad
+        want_r = need[0] or need[1]
+        d_p = torch.zeros_like(pr) if need[2] else None
+        d_o = torch.zeros_like(ro) if want_r else None
+        d_d = torch.zeros_like(rd) if want_r else None
+        if want_r or need[2]:
+            featmerge_bwd_raw(cam, bound, views, ro, rd, z_vals, gt_depth, pr, d_out.to(torch.float32).contiguous(), ws,
+                              d_p, d_o, d_d, apply_trunc)
+        return (d_o if need[0] else None, d_d if need[1] else None, d_p, None, None, None, None, None, None)
+
+
+def feature_merge(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, merge_params, apply_trunc=True):
+    """``feature_matching`` + ``decoder.merge`` + truncation mask of the iteration bodies (tracking.py:163-171,
+    mapping.py:549-557) as ONE fused call each way: -> features [N,S,32], differentiable w.r.t. the rays (through the
+    OneBlob of the points) and the Merge weights."""
+    return _FeatMergeFn.apply(rays_o, rays_d, merge_params, cam, bound, views, z_vals.contiguous(),
+                              gt_depth.contiguous(), bool(apply_trunc))
+
+
+def pose_prepare(quats, trans, view_src=None, fixed_w2c=None, fixed_cam_o=None):
+    """``dns_pose_prepare``: R [F,3,3] of un-normalised quaternions (common.py:406-429) and, with ``view_src``, the
+    world-to-camera matrices / camera centres of the reference views (mapping.py:534-551)."""
+    dev = quats.device
+    F = quats.shape[0]
+    R = torch.empty(F, 3, 3, device=dev)
+    V = 0 if view_src is None else view_src.numel()
+    w2c = torch.empty(V, 4, 4, device=dev) if V else None
+    cam_o = torch.empty(V, 3, device=dev) if V else None
+    f32 = torch.float32
+    _lib.check(_lib.lib().dns_pose_prepare(
+        _lib.ptr(quats.detach().contiguous(), f32), _lib.ptr(trans.detach().contiguous(), f32), F,
+        _lib.ptr(view_src, torch.int32, allow_none=True), _lib.ptr(fixed_w2c, f32, allow_none=True),
+        _lib.ptr(fixed_cam_o, f32, allow_none=True), V, _lib.ptr(R), _lib.ptr(w2c, allow_none=True),
+        _lib.ptr(cam_o, allow_none=True), _lib.stream()))
+    return R, w2c, cam_o
+
+
+def pose_grad_raw(cam, window, d_rays_o, d_rays_d, pixel, ray_start, quats, d_quats, d_trans, scratch):
+    H0, H1, W0, W1 = window
+    rs = (C.c_int32 * len(ray_start))(*[int(x) for x in ray_start])
+    f32 = torch.float32
+    _lib.check(_lib.lib().dns_pose_grad(
+        _lib.ptr(d_rays_o, f32), _lib.ptr(d_rays_d, f32), _lib.ptr(pixel, torch.int64), len(ray_start) - 1, rs, H0, W0,
+        W1 - W0, cam["fx"], cam["fy"], cam["cx"], cam["cy"], _lib.ptr(quats, f32, allow_none=True),
+        _lib.ptr(d_quats, f32, allow_none=True), _lib.ptr(d_trans, f32, allow_none=True), _lib.ptr(scratch, f32),
+        _lib.stream()))
+
+
+class _PoseRaysFn(torch.autograd.Function):
+    """Identity on the sampler's rays in the forward pass (values stay the kernel's, bit exact); the backward is the
+    closed form of ``rays_d = R(q) dirs, rays_o = T`` (common.py:257-263, 406-429) in two small kernels
+    (``dns_pose_grad``) instead of the autograd chain of the quaternion formula."""
+
+    @staticmethod
+    def forward(ctx, quats, trans, rays_o, rays_d, pixel, ray_start, cam, window):
+        ctx.save_for_backward(quats.detach().contiguous(), pixel)
+        ctx.meta = (ray_start, cam, window)
+        return rays_o.view_as(rays_o), rays_d.view_as(rays_d)
+
+    @staticmethod
+    def backward(ctx, d_o, d_d):
+        quats, pixel = ctx.saved_tensors
+        ray_start, cam, window = ctx.meta
+        F = quats.shape[0]
+        dq, dt = torch.empty_like(quats), torch.empty(F, 3, device=quats.device)
+        pose_grad_raw(cam, window, d_o.contiguous(), d_d.contiguous(), pixel, ray_start, quats, dq, dt,
+                      torch.empty(12 * F, device=quats.device))
+        return dq, dt, None, None, None, None, None, None
+
+
+def pose_rays(quats, trans, rays_o, rays_d, pixel, ray_start, cam, window):
+    """Attach the pose gradient to sampled rays: quats [F,4] / trans [F,3] (stacked leaves), rays of F frames."""
+    return _PoseRaysFn.apply(quats, trans, rays_o, rays_d, pixel, list(ray_start), cam, window)
+
+
 # ----------------------------------------------------------------------------------------
 # Adam
 # ----------------------------------------------------------------------------------------
@@ -485,7 +695,7 @@ class FusedAdam:
     * Gradients are gathered into buffers owned by the optimiser (``step`` copies every ``p.grad`` into its slice
       with one ``_foreach_copy_``; autograd itself sees ``p.grad = None`` after ``zero_grad``, exactly as with a torch
       optimiser), so the segment table is uploaded once and a CUDA graph that captured ``zero_grad`` / ``backward`` /
-      ``step`` replays correctly; the step counter is a device integer.  ``DNS_ADAM_INPLACE=1`` pre-sets ``p.grad``
+      ``step`` replays correctly; the step counter is a device integer.  ``inplace=True`` pre-sets ``p.grad``
       to views of the buffers instead (autograd accumulates in place, no copies).
     * ``flat``: a contiguous buffer that the group's parameters tile exactly (``Decoder.flat``): the group becomes
       one segment, its gradient one flat buffer (one memset per iteration).
@@ -493,11 +703,10 @@ class FusedAdam:
       here give every optimised parameter a gradient in every iteration.
     """
 
-    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, inplace=False):
         import numpy as np
-        import os
         self.betas, self.eps = betas, eps
-        self.inplace = os.environ.get("DNS_ADAM_INPLACE") == "1"
+        self.inplace = bool(inplace)
         self._views = []          # (parameter, its slice of the gradient buffer)
         self.groups = [g for g in groups if len(g["params"]) > 0]
         dev = self.groups[0]["params"][0].device
@@ -561,11 +770,42 @@ class FusedAdam:
                                              self.eps, _lib.stream()))
 
 
+class AdamSegments:
+    """Raw-buffer Adam (torch defaults) over segments ``[(params, grads, lr), ...]`` of flat fp32 CUDA tensors in ONE
+    ``dns_adam_multi`` launch per step; owns the moments and a device-side step counter (fresh state per object, as
+    the reference builds a new optimiser per ``optimize()`` call, slams/mapping.py:438-468)."""
+
+    def __init__(self, segments, betas=(0.9, 0.999), eps=1e-8):
+        import numpy as np
+        self.betas, self.eps = betas, eps
+        self.segments = [(p, g, float(lr)) for p, g, lr in segments if p.numel() > 0]
+        dev = self.segments[0][0].device
+        dt = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("lr", "<f4"), ("r", "<f4")])
+        tab = np.zeros(len(self.segments), dtype=dt)
+        self._keep = []
+        for i, (p, g, lr) in enumerate(self.segments):
+            if not (p.is_cuda and g.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()):
+                raise RuntimeError("AdamSegments: contiguous fp32 CUDA tensors only (no CPU fallback)")
+            m, v = torch.zeros_like(p), torch.zeros_like(p)
+            self._keep += [m, v]
+            tab[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, 0.0)
+        self.table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+        self.n_segs, self.max_n = len(self.segments), max(p.numel() for p, _, _ in self.segments)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step(self):
+        _lib.check(_lib.lib().dns_adam_multi(_lib.ptr(self.table), self.n_segs, self.max_n,
+                                             _lib.ptr(self.step_dev, torch.int32), self.betas[0], self.betas[1],
+                                             self.eps, _lib.stream()))
+
+
+use_torch_adam = False      # A/B hook of tests / measurements: torch.optim.Adam instead of FusedAdam
+
+
 def make_adam(groups, capturable=False):
-    """The optimiser of the tracking / mapping loops: ``FusedAdam``; ``DNS_TORCH_ADAM=1`` selects
-    ``torch.optim.Adam`` (A/B reference)."""
-    import os
-    if os.environ.get("DNS_TORCH_ADAM") == "1":
+    """The optimiser of the tracking / mapping loops: ``FusedAdam`` (``fused.use_torch_adam = True`` selects
+    ``torch.optim.Adam``, the A/B reference)."""
+    if use_torch_adam:
         gs = [{"params": g["params"], "lr": g["lr"]} for g in groups if len(g["params"]) > 0]
         return torch.optim.Adam(gs, capturable=capturable)
     return FusedAdam(groups)

@@ -138,15 +138,15 @@ def class_tables(label_win):
     return ClassTables(classes, order, starts, counts)
 
 
-def class_balanced_indices(tables, n, draws):
-    """common.py:315-330 with the per-class randint draws supplied in order (a class with one
-    pixel consumes no draw)."""
+def class_balanced_offsets(tables, n, draws):
+    """common.py:315-330 with the per-class randint draws supplied in order (a class with one pixel consumes no
+    draw): returns (offsets [n] int64, slot_base [n] int32, draws used) such that slot j samples window pixel
+    ``order[slot_base[j] + offsets[j]]`` -- the lookup itself happens in the sampling kernel (``dns_sample_rays``)."""
     classes, order, starts, counts = tables
     counts_h, starts_h = tables.counts_h, tables.starts_h
     n_class = len(counts_h)
     n_k = n // n_class
-    # One gather for all classes: out[j] = order[start(class of slot j) + draw_j].  The slot -> start table is
-    # fixed per frame and n (cached on the tables object); a class with a single pixel takes offset 0.
+    # slot -> first pixel of its class: fixed per frame and n (cached on the tables object)
     cache = tables.__dict__.setdefault("_slot_cache", {})
     if n not in cache:
         base, keep = [], []
@@ -154,7 +154,7 @@ def class_balanced_indices(tables, n, draws):
             m = n - n_k * (n_class - 1) if c == 0 else n_k
             base += [starts_h[c]] * m
             keep += [counts_h[c] != 1] * m
-        base_t = torch.tensor(base, dtype=torch.int64, device=order.device)
+        base_t = torch.tensor(base, dtype=torch.int32, device=order.device)
         pos = None if all(keep) else torch.nonzero(torch.tensor(keep, device=order.device)).reshape(-1)
         cache[n] = (base_t, pos, sum(1 for c in counts_h if c != 1))
     base_t, pos, n_used = cache[n]
@@ -162,10 +162,16 @@ def class_balanced_indices(tables, n, draws):
     if pos is None:
         off = flat
     else:
-        off = torch.zeros_like(base_t)
+        off = torch.zeros(base_t.numel(), dtype=torch.int64, device=order.device)
         if flat is not None:
             off[pos] = flat
-    return order[base_t + off], n_used
+    return off, base_t, n_used
+
+
+def class_balanced_indices(tables, n, draws):
+    """The resolved window indices of ``class_balanced_offsets`` (host-side helper of tests / tools)."""
+    off, base_t, n_used = class_balanced_offsets(tables, n, draws)
+    return tables[1][base_t.long() + off], n_used
 
 
 class TrackerCore:
@@ -180,27 +186,33 @@ class TrackerCore:
         self.lambda_p, self.lambda_d, self.lambda_l = lambda_p, lambda_d, lambda_l
 
     def get_target_samples(self, cur_frames, refer_frames, features_cl, draws):
-        """draws = dict(idx [n] int64, t_surface [15], t_zero [15])."""
+        """draws = dict(idx [n] int64, t_surface [15], t_zero [15]).  ``refer_frames['est_w2c']`` [R,4,4]; optional
+        ``refer_frames['est_c2w']`` (the poses it was inverted from; the reference inverts back, common.py:672)."""
         quad, T = cur_frames["est_quad"], cur_frames["est_T"]
-        R = get_rotation_from_quad(quad)
+        R = get_rotation_from_quad(quad.detach())
         window = (20, self.H - 20, 20, self.W - 20)
         idx = draws["idx"].to(quad.device)
+        want_pose = quad.requires_grad or T.requires_grad
         s = fused.sample_rays(self.cam, self.decoder.bound, cur_frames, idx, window, R, T, self.n_samples_ray,
                               self.n_surface_ray, fused.fix_surface_draw(draws["t_surface"], self.n_surface_ray),
-                              draws["t_zero"])
-        dirs = fused.pixel_dirs(self.cam, idx, window)
-        rays_o, rays_d = fused.attach_pose_grad(s["rays_o"], s["rays_d"], dirs, R, T)
+                              draws["t_zero"], want_pixel=want_pose)
+        n = idx.numel()
+        rays_o, rays_d = s["rays_o"], s["rays_d"]
+        if want_pose:
+            rays_o, rays_d = fused.pose_rays(quad.reshape(1, 4), T.reshape(1, 3), rays_o, rays_d, s["pixel"], (0, n),
+                                             self.cam, window)
         z = s["z_vals"]
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
-        merge = self.decoder.merge
-        if self.freeze_decoder and z.is_cuda:   # tracking never updates the Merge weights: skip their gradient GEMMs
-            merge = lambda p, o, f: fused.merge_fused(p, f, self.decoder.merge.decoder.params.detach(), self.decoder.merge.bound)  # noqa: E731
-        code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), refer_frames["est_w2c"].detach(),
-                                      features_cl, merge)
-        code = code.reshape(pts.shape[0], pts.shape[1], -1) * trunc_mask(z, s["gt_depth"])[..., None]
+        w2c = refer_frames["est_w2c"].detach()
+        c2w = refer_frames.get("est_c2w")
+        cam_o = (fused.rigid_inverse(w2c) if c2w is None else c2w.detach())[:, :3, 3]
+        views = fused.Views(w2c, cam_o, [features_cl], (0, n))
+        mp = self.decoder.merge.decoder.params
+        if self.freeze_decoder:   # tracking never updates the Merge weights: skip their gradient GEMMs
+            mp = mp.detach()
+        code = fused.feature_merge(self.cam, self.decoder.merge.bound, views, rays_o, rays_d, z, s["gt_depth"], mp)
         mask = (s["gt_depth"] > 0.01) * s["inside"]
         return {"gt_color": s["gt_color"], "gt_depth": s["gt_depth"], "gt_label": s["gt_label"],
-                "rays_o": rays_o, "rays_d": rays_d, "pts": pts, "z_vals": z, "mask": mask, "features": code}
+                "rays_o": rays_o, "rays_d": rays_d, "z_vals": z, "mask": mask, "features": code}
 
     def iteration(self, cur_frames, refer_frames, features_cl, draws):
         """Body of tracking.py:322-329; returns (loss dict, preds, samples)."""
@@ -232,89 +244,72 @@ class MapperCore:
         n_t = len(target_frames["frames"])
         n_pixels = self.n_pixels // n_t
         window = (0, self.H, 0, self.W)
-        acc = {k: [] for k in ("gt_color", "gt_depth", "gt_label", "rays_o", "rays_d", "z_vals", "mask", "features")}
         target_idx = target_frames["kf_idx"]
-        # all target poses in ONE evaluation of the quaternion formula (same per-element arithmetic)
-        R_all = quad2rotation(torch.stack(list(quad_list), 0))
+        # all target poses in ONE evaluation of the quaternion formula (same per-element arithmetic, no graph: the
+        # backward is the closed form of fused.pose_rays)
+        quats = torch.stack(list(quad_list), 0)
         T_all = torch.stack(list(T_list), 0)
-        c2w_all = torch.cat((torch.cat((R_all, T_all[:, :, None]), -1),
-                             fused.bottom_row(R_all.device)[None].expand(n_t, 1, 4)), 1)
-        # reference-view poses of every target frame, inverted in ONE batched call (mapping.py:534-551)
-        refer_c2w = []
-        for i in range(n_t):
-            for k, rid in enumerate(refer_frames["kf_idx"][i]):
-                if rid == -1:
-                    refer_c2w.append(c2w_all[i].detach())
-                elif rid in target_idx:
-                    refer_c2w.append(c2w_all[target_idx.index(rid)].detach())
-                else:
-                    refer_c2w.append(refer_frames["est_c2w"][i][k].detach().to(R_all.device))
-        n_ref = [len(refer_frames["kf_idx"][i]) for i in range(n_t)]
-        refer_c2w = torch.stack(refer_c2w, 0)
-        refer_w2c = fused.rigid_inverse(refer_c2w)
+        dev = quats.device
+        with torch.no_grad():
+            R_all = _quad2rotation_formula(quats)
+            c2w_all = torch.cat((torch.cat((R_all, T_all[:, :, None]), -1),
+                                 fused.bottom_row(dev)[None].expand(n_t, 1, 4)), 1)
+            # reference-view poses of every target frame, inverted in ONE batched call (mapping.py:534-551)
+            refer_c2w = []
+            for i in range(n_t):
+                for k, rid in enumerate(refer_frames["kf_idx"][i]):
+                    if rid == -1:
+                        refer_c2w.append(c2w_all[i])
+                    elif rid in target_idx:
+                        refer_c2w.append(c2w_all[target_idx.index(rid)])
+                    else:
+                        refer_c2w.append(refer_frames["est_c2w"][i][k].detach().to(dev))
+            n_ref = [len(refer_frames["kf_idx"][i]) for i in range(n_t)]
+            refer_c2w = torch.stack(refer_c2w, 0)
+            refer_w2c = fused.rigid_inverse(refer_c2w)
         ref_at = [sum(n_ref[:i]) for i in range(n_t + 1)]
-        # with the same number of reference views everywhere, the Merge MLP (and the truncation mask) run ONCE over the
-        # points of all target frames instead of once per frame
-        batched = len(set(n_ref)) == 1
-        rp_all, code_all = [], []
-        # pass 1: pixel draws and the sampling kernel per frame (each frame has its own images)
-        dev = R_all.device
-        idx_l, s_l = [], []
+        # pixel draws and the sampling kernel per frame (each frame has its own images); the class-balanced third of
+        # the draws is resolved to pixels inside the kernel
+        want_pose = quats.requires_grad or T_all.requires_grad
+        s_l = []
         for i in range(n_t):
             idx1 = draws[i]["idx_uniform"].to(dev)
-            idx2, _ = class_balanced_indices(target_frames["class_tables"][i], n_pixels // 3, draws[i]["class_draws"])
-            idx = torch.cat((idx1, idx2), 0)
-            idx_l.append(idx)
-            s_l.append(fused.sample_rays(self.cam, self.decoder.bound, target_frames["frames"][i], idx, window, R_all[i],
-                                         T_list[i], self.n_samples_ray, self.n_surface_ray,
-                                         fused.fix_surface_draw(draws[i]["t_surface"], self.n_surface_ray), draws[i]["t_zero"]))
-        # pose gradients and points for the rays of ALL frames at once (values stay the kernel's)
-        sizes = tuple(int(x.shape[0]) for x in idx_l)
-        # ray -> frame as a one-hot matrix: the per-ray pose is a small matmul whose backward is a matmul too (the
-        # backward of an index gather with four distinct indices is a serialised scatter, 0.1 ms each)
-        hot = self.__dict__.setdefault("_frame_onehot_cache", {}).get((sizes, str(dev)))
-        if hot is None:
-            fid = torch.cat([torch.full((n,), i, dtype=torch.int64) for i, n in enumerate(sizes)])
-            hot = torch.nn.functional.one_hot(fid, n_t).to(torch.float32).to(dev)
-            self._frame_onehot_cache[(sizes, str(dev))] = hot
-        dirs_all = fused.pixel_dirs(self.cam, torch.cat(idx_l, 0), window)
-        e_d = torch.sum(dirs_all[:, None, :] * (hot @ R_all.reshape(n_t, 9)).reshape(-1, 3, 3), -1)
-        e_o = hot @ T_all
-        rays_o_all = torch.cat([s["rays_o"] for s in s_l], 0) + (e_o - e_o.detach())
-        rays_d_all = torch.cat([s["rays_d"] for s in s_l], 0) + (e_d - e_d.detach())
-        z_all = torch.cat([s["z_vals"] for s in s_l], 0)
-        pts_all = rays_o_all[:, None, :] + rays_d_all[:, None, :] * z_all[:, :, None]
+            tab = target_frames["class_tables"][i]
+            off, base, _ = class_balanced_offsets(tab, n_pixels // 3, draws[i]["class_draws"])
+            s_l.append(fused.sample_rays(self.cam, self.decoder.bound, target_frames["frames"][i], torch.cat((idx1, off), 0),
+                                         window, R_all[i], T_all[i].detach(), self.n_samples_ray, self.n_surface_ray,
+                                         fused.fix_surface_draw(draws[i]["t_surface"], self.n_surface_ray),
+                                         draws[i]["t_zero"], class_order=tab[1], slot_base=base,
+                                         n_direct=idx1.numel(), want_pixel=want_pose))
+        sizes = [int(x["z_vals"].shape[0]) for x in s_l]
         row_at = [sum(sizes[:i]) for i in range(n_t + 1)]
-        for i in range(n_t):
-            s = s_l[i]
-            r0, r1 = row_at[i], row_at[i + 1]
-            rays_o, rays_d, z, pts = rays_o_all[r0:r1], rays_d_all[r0:r1], z_all[r0:r1], pts_all[r0:r1]
-            a, b = ref_at[i], ref_at[i + 1]
-            if batched:
-                flat = pts.flatten(0, 1)
-                g, _, _ = fused.feature_gather(self.H, self.W, self.K, flat, refer_w2c[a:b].contiguous(), features_cl[i])
-                code_all.append(g)
-                rp_all.append(flat[None, :, :] - refer_c2w[a:b, :3, 3][:, None, :])
-                code = None
-            else:
-                code = fused.feature_matching(self.H, self.W, self.K, pts.flatten(0, 1), refer_w2c[a:b],
-                                              features_cl[i], self.decoder.merge, refer_c2w=refer_c2w[a:b])
-                code = code.reshape(pts.shape[0], pts.shape[1], -1) * trunc_mask(z, s["gt_depth"])[..., None]
-            for k, v in (("gt_color", s["gt_color"]), ("gt_depth", s["gt_depth"]), ("gt_label", s["gt_label"]),
-                         ("rays_o", rays_o), ("rays_d", rays_d), ("z_vals", z), ("mask", s["inside"]),
-                         ("features", code)):
-                acc[k].append(v)
-        if batched:
-            acc.pop("features")
-        cat = {k: torch.cat(v, 0) for k, v in acc.items()}
-        if batched:
-            merged = self.decoder.merge(torch.cat(rp_all, 1), refer_c2w[:n_ref[0], :3, 3], torch.cat(code_all, 1))
-            cat["features"] = merged.reshape(cat["z_vals"].shape[0], cat["z_vals"].shape[1], -1) \
-                * trunc_mask(cat["z_vals"], cat["gt_depth"])[..., None]
-        m = cat.pop("mask")
-        if assume_inside:          # graph replay: no compaction; the flag is checked once after the loop
-            ok = m.all()
-            self.inside_ok = ok if getattr(self, "inside_ok", None) is None else self.inside_ok & ok
+        cat = {k: torch.cat([x[k] for x in s_l], 0) for k in ("gt_color", "gt_depth", "gt_label", "rays_o", "rays_d",
+                                                               "z_vals", "inside")}
+        rays_o, rays_d = cat["rays_o"], cat["rays_d"]
+        if want_pose:   # pose gradients for the rays of ALL frames at once (values stay the kernel's)
+            rays_o, rays_d = fused.pose_rays(quats, T_all, rays_o, rays_d, torch.cat([x["pixel"] for x in s_l], 0), row_at,
+                                             self.cam, window)
+        mp = self.decoder.merge.decoder.params
+        bound = self.decoder.merge.bound
+        if len(set(n_ref)) == 1:
+            # the whole pixel-feature branch (projection, gather, Merge MLP, mean over the views, truncation mask) of
+            # all target frames in ONE fused call, band samples only
+            views = fused.Views(refer_w2c, refer_c2w[:, :3, 3], features_cl, row_at)
+            code = fused.feature_merge(self.cam, bound, views, rays_o, rays_d, cat["z_vals"], cat["gt_depth"], mp)
+        else:
+            parts = []
+            for i in range(n_t):
+                a, b, r0, r1 = ref_at[i], ref_at[i + 1], row_at[i], row_at[i + 1]
+                views = fused.Views(refer_w2c[a:b], refer_c2w[a:b, :3, 3], [features_cl[i]], (0, r1 - r0))
+                parts.append(fused.feature_merge(self.cam, bound, views, rays_o[r0:r1], rays_d[r0:r1],
+                                                 cat["z_vals"][r0:r1], cat["gt_depth"][r0:r1], mp))
+            code = torch.cat(parts, 0)
+        m = cat.pop("inside")
+        cat["rays_o"], cat["rays_d"], cat["features"] = rays_o, rays_d, code
+        if assume_inside:          # graph replay: no compaction; the flag accumulates IN PLACE in a persistent device
+            if getattr(self, "inside_ok", None) is None:   # bool (allocated before warm-up), read once after the loop
+                self.inside_ok = torch.ones((), dtype=torch.bool, device=dev)
+            self.inside_ok.logical_and_(m.all())
             return cat
         if bool(m.all()):          # one small D2H read; the reference syncs here too (mapping.py:576)
             return cat
@@ -432,8 +427,11 @@ def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr
             best_loss = torch.where(better, loss, best_loss)
             best = torch.where(better, torch.cat((quad, T), 0), best)
         history.append(loss.detach())
+        err = ld["n_valid"].detach() if it == 0 else torch.minimum(err, ld["n_valid"].detach())
         loss.backward()
         opt.step()
+    if n_iters > 0:   # ONE host read per frame: a label outside the semantic head raises (torch's cross_entropy would)
+        fused.raise_on_flag(torch.stack([err] * 8))
     return best, best_loss, torch.stack(history)
 
 
@@ -449,6 +447,7 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
     best = torch.cat((quad, T), 0).detach().clone()
     hist = torch.zeros(n_iters, device=dev)
     slot = torch.zeros((), dtype=torch.int64, device=dev)
+    err_flag = torch.zeros((), device=dev)
     refer = refer_w2c.to(dev)
     cur = dict(frame, est_quad=quad, est_T=T)
 
@@ -463,6 +462,7 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
             best_loss.copy_(torch.where(better, loss, best_loss))
             hist.index_copy_(0, slot.reshape(1), loss.detach().reshape(1))
             slot.add_(1)
+            err_flag.copy_(torch.minimum(err_flag, ld["n_valid"].detach()))
         loss.backward()
         opt.step()
 
@@ -471,7 +471,8 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for it in range(n_warm):
-            packed.update(draws_fn(it))
+            if it > 0:                             # draws_fn(0) is already in the static buffers (fetched ONCE: a
+                packed.update(draws_fn(it))        # stateful generator must see every iteration exactly once)
             one()
     torch.cuda.current_stream().wait_stream(side)
     if n_iters > n_warm:
@@ -483,6 +484,7 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
             packed.update(draws_fn(n_warm + j))
             graph.replay()
         _timed_replays(n_iters - n_warm, replay)
+    fused.raise_on_flag(torch.stack([err_flag] * 8))      # the single host read of the loop
     return best, best_loss, hist
 
 
@@ -520,6 +522,7 @@ def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list,
                            {"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
                            {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}])
     ld = None
+    err_flag = torch.zeros((), device=dev)
     for it in range(n_iters):
         opt.zero_grad()
         lam_lt = (10.0 if it > n_iters // 2 else 0.0) if len(new_decoders) > 0 else 10.0
@@ -527,6 +530,9 @@ def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list,
                                     tv_draws_fn(it), lambda_lt=lam_lt)
         ld["total"].backward()
         opt.step()
+        err_flag = torch.minimum(err_flag, ld["n_valid"].detach())
+    if n_iters > 0:   # ONE host read per optimize call: the reference raises inside the iteration (mapping.py:594-595)
+        fused.raise_on_flag(torch.stack([err_flag] * 8))
     # detached: a loss dictionary that still holds its autograd graph keeps the AccumulateGrad nodes of this (default)
     # stream alive, and the next CUDA-graph capture of a loop then fails ("legacy stream depends on a capturing stream")
     return quad_list, T_list, (None if ld is None else {k: v.detach() for k, v in ld.items()})
@@ -586,9 +592,10 @@ def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, 
     opt = fused.make_adam([{"params": net, "lr": lr, "flat": dec.flat}])
     R, T = cur_c2w[:3, :3].to(dev), cur_c2w[:3, 3].to(dev)
     window = (0, mapper.H, 0, mapper.W)
-    w2c = torch.inverse(cur_c2w.to(dev)).unsqueeze(0)
+    c2w = cur_c2w.to(dev).unsqueeze(0)
+    w2c = fused.rigid_inverse(c2w)
     lam = dict(mapper.lambdas, lt=0.0)
-    ld = None
+    ld, err = None, None
     for it in range(n_iters):
         opt.zero_grad()
         d = draws_fn(it)
@@ -596,17 +603,20 @@ def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, 
         s = fused.sample_rays(mapper.cam, dec.bound, frame, idx, window, R, T, mapper.n_samples_ray,
                               mapper.n_surface_ray, fused.fix_surface_draw(d["t_surface"], mapper.n_surface_ray),
                               d["t_zero"])
-        z = s["z_vals"]
-        pts = s["rays_o"][:, None, :] + s["rays_d"][:, None, :] * z[:, :, None]
-        code = fused.feature_matching(mapper.H, mapper.W, mapper.K, pts.flatten(0, 1), w2c, features_cl, dec.merge)
+        n = idx.numel()
+        views = fused.Views(w2c, c2w[:, :3, 3], [features_cl], (0, n))
+        code = fused.feature_merge(mapper.cam, dec.merge.bound, views, s["rays_o"], s["rays_d"], s["z_vals"], s["gt_depth"],
+                                   dec.merge.decoder.params, apply_trunc=False)   # no trunc mask here (mapping.py:807-809)
         samples = {"gt_color": s["gt_color"], "gt_depth": s["gt_depth"], "gt_label": s["gt_label"],
-                   "rays_o": s["rays_o"], "rays_d": s["rays_d"], "z_vals": z,
-                   "features": code.reshape(pts.shape[0], pts.shape[1], -1)}   # no trunc mask here (mapping.py:807-809)
+                   "rays_o": s["rays_o"], "rays_d": s["rays_d"], "z_vals": s["z_vals"], "features": code}
         ld, _ = fused.render_and_loss(dec, samples, _lib.MODE_MAP, lambdas=lam, opacity_sigma=mapper.opacity_sigma)
         tv = tv_draws_fn(it)
         sm = fused.tv_loss(dec, mapper.smooth_pts, tv[0], tv[1])
         (ld["total"] + mapper.lambda_sm * sm).backward()
         opt.step()
+        err = ld["n_valid"].detach() if err is None else torch.minimum(err, ld["n_valid"].detach())
+    if err is not None:   # ONE host read per call: 'Fine decoders does NOT have class' (mapping.py:594-595)
+        fused.raise_on_flag(torch.stack([err] * 8))
     return None if ld is None else {k: v.detach() for k, v in ld.items()}
 
 
@@ -700,7 +710,9 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
     opt = fused.make_adam(groups, capturable=True)
     packed = _PackedStatic([draws_fn(0), list(tv_draws_fn(0))], dev)
     static_d, static_tv = packed.static
-    mapper.inside_ok = None
+    # persistent device flags, updated IN PLACE by every (eager or replayed) iteration and read ONCE after the loop
+    mapper.inside_ok = torch.ones((), dtype=torch.bool, device=dev)
+    err_flag = torch.zeros((), device=dev)
     last = {}
 
     def one():
@@ -709,6 +721,7 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
                                     lambda_lt=10.0, assume_inside=True)
         ld["total"].backward()
         opt.step()
+        err_flag.copy_(torch.minimum(err_flag, ld["n_valid"].detach()))
         for k, v in ld.items():
             if k not in last:
                 last[k] = torch.zeros_like(v.detach())
@@ -718,7 +731,8 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for it in range(3):
-            packed.update([draws_fn(it), list(tv_draws_fn(it))])
+            if it > 0:
+                packed.update([draws_fn(it), list(tv_draws_fn(it))])
             one()
     torch.cuda.current_stream().wait_stream(side)
     graph = torch.cuda.CUDAGraph()
@@ -729,9 +743,14 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
         packed.update([draws_fn(3 + j), list(tv_draws_fn(3 + j))])
         graph.replay()
     _timed_replays(n_iters - 3, replay)
-    ok = bool(mapper.inside_ok)          # the single host read of the loop
+    flags = torch.stack((mapper.inside_ok.float(), err_flag)).tolist()   # the single host read of the loop
+    ok = flags[0] != 0.0
     mapper.inside_ok = None
     mapper.last_graph_ok = ok
+    if flags[1] < 0:                     # the reference raises inside the iteration (mapping.py:594-595)
+        with torch.no_grad():
+            dec.flat.copy_(saved)
+        fused.raise_on_flag(torch.tensor([0.0] * 7 + [flags[1]]))
     if not ok:                           # some ray left the bound: static shapes were wrong, redo eagerly
         with torch.no_grad():
             dec.flat.copy_(saved)

@@ -123,6 +123,10 @@ class TorchComm:
         torch.distributed.all_reduce(t, group=self.group)
         return t
 
+    def all_reduce_max(self, t):
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.group)
+        return t
+
     def all_gather(self, t, sizes=None):
         """Concatenation over ranks of possibly different-length 1-D tensors.  ``sizes`` (per-rank lengths known to the
         caller, e.g. from shard_bounds) skips the size exchange and its device->host read."""
@@ -202,3 +206,318 @@ class HostBatchPipeline:
             self.free[i].record(cur)
             self.result_host.copy_(out[0], non_blocking=True)
         return self.result_host
+
+
+class FrameBatchPlan:
+    """Ray bookkeeping and draw layout of a mapping batch over F target frames (host logic, device agnostic).
+
+    Per frame the GLOBAL slot list is ``[n_u uniform | n_c class balanced]`` with ``n_f = n_rays // F``,
+    ``n_u = n_f // 3 * 2``, ``n_c = n_f // 3`` (slams/mapping.py:504-508); rank r owns slice r of both parts.  The
+    iteration's draws travel as ONE byte buffer: per frame ``idx`` int64 [n_local] (uniform window indices, then the
+    class-balanced offsets into the pixels of each slot's class), ``t_surface`` / ``t_zero`` f32 [n_surface]
+    (common.py:572-573 already applied), then the TV ``offset | jitter`` f64 [6] (mapping.py:133-140)."""
+
+    def __init__(self, class_tables, n_rays, n_surface, window, bound, smooth_pts, rank=0, world=1):
+        self.tables, self.nf, self.window, self.bound, self.smooth_pts = class_tables, n_surface, window, bound, smooth_pts
+        self.rank, self.world = rank, world
+        F = self.F = len(class_tables)
+        n_f = n_rays // F
+        n_u, n_c = n_f // 3 * 2, n_f // 3
+        self.n_u, self.n_c = n_u, n_c
+        self.n_total = F * (n_u + n_c)
+        self.slices, self.ray_start = [], [0]
+        per_rank = [0] * world
+        for f in range(F):
+            for r in range(world):
+                (a, b), (c, d) = shard_bounds(n_u, world, r), shard_bounds(n_c, world, r)
+                per_rank[r] += (b - a) + (d - c)
+                if r == rank:
+                    self.slices.append(((a, b), (c, d)))
+                    self.ray_start.append(self.ray_start[-1] + (b - a) + (d - c))
+        self.n_local = self.ray_start[-1]
+        self.rank_sizes = per_rank
+        self.ray_offset = sum(per_rank[:rank])
+        # class-balanced slots: first pixel (in the label-sorted order) of the class each slot draws from
+        self.slot_base = []
+        for f in range(F):
+            _, (c, d) = self.slices[f]
+            base = []
+            for _, _, m, _, start in self.class_slot_ranges(f):
+                base += [start] * m
+            self.slot_base.append(torch.tensor(base[c:d], dtype=torch.int32))
+        self.draw_layout, off = {}, 0
+        for f in range(F):
+            n = self.ray_start[f + 1] - self.ray_start[f]
+            for name, nbytes in ((f"idx{f}", 8 * n), (f"ts{f}", 4 * n_surface), (f"tz{f}", 4 * n_surface)):
+                self.draw_layout[name] = (off, nbytes)
+                off = (off + nbytes + 15) & ~15
+        self.draw_layout["tv"] = (off, 48)
+        self.draw_bytes = off + 48
+
+    def class_slot_ranges(self, f):
+        """[(class position, first slot, slots, pixels of the class, first pixel)] of frame f's GLOBAL class-balanced slot
+        list (common.py:315-330: class 0 of the sorted list takes the remainder)."""
+        tab = self.tables[f]
+        counts, starts = tab.counts_h, tab.starts_h
+        n_class = len(counts)
+        n_k = self.n_c // n_class
+        out, s0 = [], 0
+        for c in range(n_class):
+            m = self.n_c - n_k * (n_class - 1) if c == 0 else n_k
+            out.append((c, s0, m, counts[c], starts[c]))
+            s0 += m
+        return out
+
+    def draw_view(self, buf, name, dtype):
+        off, n = self.draw_layout[name]
+        return buf[off:off + n].view(dtype)
+
+    def make_host_draws(self, gen, pinned=True, return_tape=False):
+        """Seeded host-side draws of one iteration in the reference's order: per frame one uniform
+        ``randint`` over the window, one ``randint`` per class with more than one pixel, ``rand(n_surface)`` twice; then
+        the two TV draws.  With ``return_tape`` also the raw draws as an oracle ``DrawTape`` item list (the reference's
+        call order; meaningful for a single rank)."""
+        from . import fused as _fused
+        buf = torch.zeros(self.draw_bytes, dtype=torch.uint8)
+        if pinned:
+            buf = buf.pin_memory()
+        tape = []
+        H0, H1, W0, W1 = self.window
+        n_win = (H1 - H0) * (W1 - W0)
+        for f in range(self.F):
+            (a, b), (c, d) = self.slices[f]
+            idx = self.draw_view(buf, f"idx{f}", torch.int64)
+            u = torch.randint(n_win, (b - a,), generator=gen)
+            idx[:b - a] = u
+            tape.append(("randint", u))
+            for _, s0, m, count, _ in self.class_slot_ranges(f):
+                lo, hi = max(s0, c), min(s0 + m, d)       # this rank's part of the class's slots
+                if count == 1:                            # a class with one pixel is repeated without a draw
+                    continue
+                if hi <= lo:
+                    if m == 0:                            # the reference still issues the (empty) randint
+                        tape.append(("randint", torch.zeros(0, dtype=torch.int64)))
+                    continue
+                dr = torch.randint(count, (hi - lo,), generator=gen)
+                idx[(b - a) + lo - c:(b - a) + hi - c] = dr
+                tape.append(("randint", dr))
+            ts = torch.rand(self.nf, generator=gen)
+            tz = torch.rand(self.nf, generator=gen)
+            tape += [("rand", ts.clone()), ("rand", tz.clone())]
+            if not bool((ts == 0.5).any()):
+                ts[self.nf // 2 + 1] = 0.5                                # common.py:572-573
+            self.draw_view(buf, f"ts{f}", torch.float32).copy_(ts)
+            self.draw_view(buf, f"tz{f}", torch.float32).copy_(tz)
+        r3, r113 = torch.rand(3, generator=gen), torch.rand(1, 1, 1, 3, generator=gen)
+        tape += [("rand", r3), ("rand", r113)]
+        off, jit = _fused.tv_offsets(self.bound, self.smooth_pts, r3, r113)
+        self.draw_view(buf, "tv", torch.float64).copy_(torch.cat((off, jit)))
+        return (buf, tape) if return_tape else buf
+
+
+class MappingFrameStep:
+    """One mapping iteration (``slams/mapping.py:884-910``) from what a SLAM host actually holds: key frames and their
+    feature maps resident on the device, camera poses, and the iteration's hoisted random draws (~8 B per ray).  No
+    autograd and no library kernels in the loop (torch only zeroes the gradient buffer and copies the 9-float loss
+    vector):
+
+        dns_pose_prepare -> dns_sample_rays per target frame (uniform + class-balanced draws resolved in the kernel)
+        -> dns_featmerge_fwd (feature matching + Merge + truncation mask, band samples only)
+        -> dns_render_fwd_bwd (all six losses, every gradient into ONE flat buffer) -> dns_featmerge_bwd
+        -> dns_tv_fwd_bwd (Mapper.smoothness) -> dns_pose_grad -> [NCCL all-reduce of the flat buffer] -> dns_adam_multi
+        over decoder + quaternions + translations (frame 0 frozen, mapping.py:457).
+
+    Ray sharding: rank r draws slice r of every frame's uniform and class-balanced slots; the global batch is
+    the rank-major concatenation (a fixed permutation of the reference's frame-major order: the draws are i.i.d.).
+    Batch-global scalars are exchanged first (max depth per frame, band / depth counts, labels for the class rule
+    ``class(p) = label[p mod N]``); losses and gradients of the ranks SUM to the single-GPU values.
+
+    ``draws``: one byte buffer (``draw_layout``): per frame ``idx`` int64 [n_f] (uniform window indices, then the
+    class-balanced offsets), ``t_surface`` / ``t_zero`` f32 [n_surface] each (common.py:572-573 already applied), and the
+    TV ``offset | jitter`` f64 [6] (mapping.py:133-140).  ``upload`` copies a pinned host image of it in ONE H2D copy.
+    """
+
+    def __init__(self, dec, cam, frames, class_tables, feats_cl, est_c2w, refer_idx, refer_c2w, kf_idx, n_rays,
+                 n_samples_ray=32, n_surface_ray=15, lr=5e-3, BA_cam_lr=5e-4, is_BA=True, lambdas=None, opacity_sigma=0.05,
+                 smooth_pts=64, lambda_sm=1e-5, with_tv=True, comm=None, rank=0, world=1):
+        from . import slam
+        self.dec, self.cam = dec, cam
+        dev = self.dev = dec.bound.device
+        self.frames, self.tables, self.feats = frames, class_tables, [f.contiguous() for f in feats_cl]
+        F = self.F = len(frames)
+        self.ns, self.nf = n_samples_ray, n_surface_ray
+        self.S = n_samples_ray + n_surface_ray
+        self.lambdas = dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0)
+        self.lambdas.update(lambdas or {})
+        self.opacity_sigma, self.smooth_pts, self.lambda_sm, self.with_tv = opacity_sigma, smooth_pts, lambda_sm, with_tv
+        self.comm, self.rank, self.world = comm, rank, world
+        H, W = cam["H"], cam["W"]
+        self.window = (0, H, 0, W)
+        plan = self.plan = FrameBatchPlan(class_tables, n_rays, n_surface_ray, self.window, dec.bound, smooth_pts, rank, world)
+        self.slices, self.ray_start, self.n_local, self.n_total = plan.slices, plan.ray_start, plan.n_local, plan.n_total
+        self.rank_sizes, self.ray_offset = plan.rank_sizes, plan.ray_offset
+        self.slot_base = [b.to(dev) for b in plan.slot_base]
+        N, S = self.n_local, self.S
+        # ---- poses: quaternion / translation device parameters; reference views
+        self.quats = torch.stack([slam.quad_from_matrix(c[:3, :3]) for c in est_c2w], 0).to(dev).contiguous()
+        self.trans = torch.stack([c[:3, 3].detach().clone().float() for c in est_c2w], 0).to(dev).contiguous()
+        n_ref = {len(x) for x in refer_idx}
+        if len(n_ref) != 1:
+            raise ValueError("MappingFrameStep needs the same number of reference views for every target frame")
+        self.R = n_ref.pop()
+        src, fixed = [], []
+        for i in range(F):
+            for k, rid in enumerate(refer_idx[i]):
+                if rid == -1:
+                    src.append(i)
+                elif rid in kf_idx:
+                    src.append(kf_idx.index(rid))
+                else:
+                    src.append(-1)
+                fixed.append(refer_c2w[i][k].detach().to(dev).float())
+        fixed = torch.stack(fixed, 0)
+        self.view_src = torch.tensor(src, dtype=torch.int32, device=dev)
+        self.fixed_w2c = fused.rigid_inverse(fixed).contiguous()
+        self.fixed_cam_o = fixed[:, :3, 3].contiguous()
+        V = F * self.R
+        self.R_all = torch.empty(F, 3, 3, device=dev)
+        self.w2c, self.cam_o = torch.empty(V, 4, 4, device=dev), torch.empty(V, 3, device=dev)
+        # ---- batch buffers
+        f32 = torch.float32
+        self.batch = dict(gt_color=torch.empty(N, 3, device=dev), gt_depth=torch.empty(N, device=dev),
+                          gt_label=torch.empty(N, dtype=torch.int64, device=dev), rays_o=torch.empty(N, 3, device=dev),
+                          rays_d=torch.empty(N, 3, device=dev), z_vals=torch.empty(N, S, device=dev),
+                          inside=torch.empty(N, dtype=torch.uint8, device=dev),
+                          pixel=torch.empty(N, dtype=torch.int64, device=dev))
+        self.scratch = torch.zeros(F, 2, device=dev)          # per frame: max depth, rays outside the bound
+        self.features = torch.empty(N, S, 32, device=dev)
+        self.fm_ws = torch.empty(int(_lib.lib().dns_featmerge_workspace_bytes(N, S)), dtype=torch.uint8, device=dev)
+        self.t_lin = torch.linspace(0.0, 1.0, steps=n_samples_ray).to(dev)
+        # ---- draws: ONE device buffer, refreshed with one H2D copy
+        self.draw_bytes = plan.draw_bytes
+        self.draws_dev = torch.zeros(self.draw_bytes, dtype=torch.uint8, device=dev)
+        # ---- gradients: [decoder flat | d_quats | d_trans | losses 8 | smooth 1 | pad], one all-reduce
+        nflat = dec.flat.numel()
+        self.packed = torch.zeros(nflat + 7 * F + 12, device=dev)
+        self.grad = self.packed[:nflat]
+        self.d_quats = self.packed[nflat:nflat + 4 * F].view(F, 4)
+        self.d_trans = self.packed[nflat + 4 * F:nflat + 7 * F].view(F, 3)
+        self.loss_vec = self.packed[nflat + 7 * F:nflat + 7 * F + 9]
+        self.pose_scratch = torch.empty(12 * F, device=dev)
+        self.d_features = torch.empty(N, S, 32, device=dev)
+        segs = [(dec.flat, self.grad, lr)]
+        self.opt_poses = bool(is_BA)
+        if self.opt_poses:
+            f0 = 0 if F == 1 else 1      # the oldest target frame stays fixed (mapping.py:457)
+            segs += [(self.quats[f0:].view(-1), self.d_quats[f0:].view(-1), BA_cam_lr),
+                     (self.trans[f0:].view(-1), self.d_trans[f0:].view(-1), BA_cam_lr)]
+        self.adam = fused.AdamSegments(segs)
+        self.result_host = torch.empty(9 + 2 * F, pin_memory=True)
+        self.result_dev = torch.empty(9 + 2 * F, device=dev)
+
+    def draw_view(self, buf, name, dtype):
+        return self.plan.draw_view(buf, name, dtype)
+
+    def make_host_draws(self, gen, pinned=True, return_tape=False):
+        return self.plan.make_host_draws(gen, pinned, return_tape)
+
+    def upload(self, host_buf, stream=None):
+        """ONE host-to-device copy of an iteration's draws (pinned ``host_buf`` -> asynchronous)."""
+        if stream is None:
+            self.draws_dev.copy_(host_buf, non_blocking=True)
+        else:
+            with torch.cuda.stream(stream):
+                self.draws_dev.copy_(host_buf, non_blocking=True)
+
+    # ------------------------------------------------------------------ stages
+    def _sample(self, phase, draws):
+        b = self.batch
+        for f in range(self.F):
+            r0, r1 = self.ray_start[f], self.ray_start[f + 1]
+            if r1 == r0:
+                continue
+            (a, bb), _ = self.slices[f]
+            out = {k: v[r0:r1] for k, v in b.items()}
+            out["scratch"] = self.scratch[f]
+            fused.sample_rays(self.cam, self.dec.bound, self.frames[f], self.draw_view(draws, f"idx{f}", torch.int64),
+                              self.window, self.R_all[f], self.trans[f], self.ns, self.nf,
+                              self.draw_view(draws, f"ts{f}", torch.float32), self.draw_view(draws, f"tz{f}", torch.float32),
+                              t_lin=self.t_lin, class_order=self.tables[f][1], slot_base=self.slot_base[f],
+                              n_direct=bb - a, out=out, phase=phase)
+
+    def _views(self):
+        return fused.Views(self.w2c, self.cam_o, self.feats, self.ray_start)
+
+    def _flat_views(self, buf):
+        lay = self.dec.layout
+        out = {k: buf[lay[k][0]:lay[k][0] + lay[k][1]] for k in ("table", "coarse", "color", "logit", "merge")}
+        a, n = lay["experts"]
+        out["experts"] = buf[a:a + n].view(-1, EXPERT_PARAMS)
+        return out
+
+    def step(self, draws=None):
+        """One iteration on the draws in ``self.draws_dev`` (or the given device byte buffer).  Returns the device vector
+        [p, d, l, lt, fs, op, total incl. smoothness, n_valid (< 0: error flag), smooth | per frame: max depth, rays outside]."""
+        draws = self.draws_dev if draws is None else draws
+        dec, b, F = self.dec, self.batch, self.F
+        L = _lib.lib()
+        f32 = torch.float32
+        _lib.check(L.dns_pose_prepare(_lib.ptr(self.quats, f32), _lib.ptr(self.trans, f32), F, _lib.ptr(self.view_src, torch.int32),
+                                      _lib.ptr(self.fixed_w2c, f32), _lib.ptr(self.fixed_cam_o, f32), F * self.R,
+                                      _lib.ptr(self.R_all), _lib.ptr(self.w2c), _lib.ptr(self.cam_o), _lib.stream()))
+        if self.world > 1:     # a frame's rays are spread over the ranks: its max depth is a batch-global scalar
+            self._sample(1, draws)
+            self.comm.all_reduce_max(self.scratch)
+            self._sample(2, draws)
+        else:
+            self._sample(0, draws)
+        self.packed.zero_()
+        views = self._views()
+        merge_p = dec.view("merge")
+        fused.featmerge_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
+                            True, ws=self.fm_ws, out=self.features)
+        cfg = fused.RenderConfig(_lib.MODE_MAP, dec.bound, dec.pe_fn.grid_fn.gstruct, b["z_vals"], b["gt_color"], b["gt_depth"],
+                                 b["gt_label"], None, dec.class_to_expert, dec.n_class, self.lambdas,
+                                 opacity_trunc=self.opacity_sigma)
+        if self.world > 1:
+            labels_all = self.comm.all_gather(b["gt_label"], self.rank_sizes)
+            counts = fused.render_counts(cfg)
+            self.comm.all_reduce_sum(counts)
+            cfg.shard(self.n_total, self.ray_offset, labels_all, counts)
+        p, g = self._flat_views(dec.flat), self._flat_views(self.grad)
+        losses, _, d_o, d_d, d_f = fused.render_raw(cfg, p["table"], p["coarse"], p["color"], p["logit"], p["experts"],
+                                                    b["rays_o"], b["rays_d"], self.features, g, True, True)
+        fused.featmerge_bwd_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
+                                d_f, self.fm_ws, g["merge"], d_o if self.opt_poses else None, d_d if self.opt_poses else None)
+        self.loss_vec[:8] = losses
+        if self.with_tv:       # parameter-only work, replicated: every rank contributes 1 / world of it
+            w = 1.0 / self.world
+            sm = fused.tv_raw(dec.pe_fn.grid_fn.gstruct, dec.bound, p["table"], p["coarse"], self.smooth_pts, None, None,
+                              self.lambda_sm * w, g["table"], g["coarse"], oj_dev=self.draw_view(draws, "tv", torch.float64))
+            self.loss_vec[8:9] = sm * w
+            self.loss_vec[6:7] += (self.lambda_sm * w) * sm
+        if self.opt_poses:
+            fused.pose_grad_raw(self.cam, self.window, d_o, d_d, b["pixel"], self.ray_start, self.quats, self.d_quats,
+                                self.d_trans, self.pose_scratch)
+        if self.world > 1:
+            self.comm.all_reduce_sum(self.packed)
+            self.loss_vec[7:8] /= self.world          # n_valid is a batch constant, not a partial sum
+        self.adam.step()
+        self.result_dev[:9] = self.loss_vec
+        self.result_dev[9:] = self.scratch.reshape(-1)
+        return self.result_dev
+
+    def read_result(self):
+        """Device -> pinned host read of the last step's result vector (asynchronous); ``check`` raises as the
+        reference would (mapping.py:594-595) once the copy has landed."""
+        self.result_host.copy_(self.result_dev, non_blocking=True)
+        return self.result_host
+
+    def check(self, host_vec=None):
+        v = self.result_host if host_vec is None else host_vec
+        if float(v[7]) < 0:
+            fused.raise_on_flag(v[:8])
+        outside = float(v[9:].reshape(self.F, 2)[:, 1].sum())
+        if outside > 0:
+            raise RuntimeError(f"{int(outside)} sampled rays leave the scene bound before their depth (mapping.py:525 "
+                               "drops them): static-shape step not applicable, use slam.map_optimize")

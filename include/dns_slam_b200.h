@@ -152,7 +152,10 @@ typedef struct dns_render_args {
    * 1: rays (compositing as in training); 2: free points (n_samples must be 1: rays_o holds the points, the
    * colour / logits of the single sample are returned without the occupancy weight). */
   int32_t forward_only;
-  int32_t reserved_;
+  /* 0 (default): every MLP contraction on tcgen05 tensor cores (bf16 hi+lo split, three products, fp32 accumulation in
+   * TMEM); 1: the fp32 SIMT kernels -- kept as the A/B reference of the parity tests.  Per call: the library holds
+   * no mode state. */
+  int32_t use_simt;
 } dns_render_args;
 
 /* table and d_table must be 16-byte aligned (the kernels fetch / reduce the x, x+1 corner pair of a cell edge
@@ -188,6 +191,8 @@ typedef struct dns_tv_args {
   /* optional: offset[3] | jitter[3] as float64 in DEVICE memory (overrides the by-value fields), so that a
    * captured CUDA graph can be replayed with new draws */
   const double* offset_jitter_dev;
+  int32_t use_simt;       /* as in dns_render_args */
+  int32_t reserved_;
 } dns_tv_args;
 
 int64_t dns_tv_workspace_bytes(int n);
@@ -222,7 +227,19 @@ typedef struct dns_sample_args {
   float* z_vals;          /* [n,S] ascending */
   float* pts;             /* [n,S,3] or NULL */
   uint8_t* inside;        /* [n] far_bb >= gt_depth */
-  float* scratch;         /* [2] device scratch: batch max depth */
+  float* scratch;         /* [2] device scratch: [0] batch max depth, [1] number of rays with inside == 0 */
+  /* class-balanced draws resolved on the device (utils/common.py:307-330, select_by_class): rays
+   * [n_direct, n) take the window index  order[slot_base[r - n_direct] + index[r]]  where `order` lists the window
+   * pixels sorted by label (stable) and slot_base[j] is the first entry of the class that slot j draws from; rays
+   * [0, n_direct) use index[r] directly (the uniform draws of common.py:274).  order == NULL: n_direct = n. */
+  const int64_t* order;
+  const int32_t* slot_base;
+  int32_t n_direct;
+  /* 0: the whole call.  A frame whose rays are split over several GPUs needs the max depth of ALL its rays
+   * (utils/common.py:581,591) between the two halves: 1 = pixel gather + rays only (scratch[0] = local max depth),
+   * then max-all-reduce scratch[0] across the ranks, then 2 = far plane + z values only. */
+  int32_t phase;
+  int64_t* pixel;         /* [n] resolved flat window index of every ray, or NULL */
 } dns_sample_args;
 
 int dns_sample_rays(const dns_sample_args* a, void* stream);
@@ -250,6 +267,67 @@ int dns_merge_fwd(const float* refer_p, const float* code, const float* params, 
                   int64_t workspace_bytes, void* stream);
 int dns_merge_bwd(const float* refer_p, const float* d_out, int64_t P, int R, const double bound[3][2],
                   float* d_refer_p, float* d_params, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The whole pixel-feature branch of one ray batch, fused == feature_matching + Merge + truncation mask as the
+ * iteration bodies use them (slams/tracking.py:163-171, slams/mapping.py:549-557 over utils/common.py:645-679 and
+ * models/decoder.py:67-77):
+ *   features[n,s,:] = trunc(n,s) * mean_v MLP_112->32->32( OneBlob((pt - cam_o[v] - lo) / (hi - lo)) || feat_v(pt) )
+ * with pt = rays_o[n] + rays_d[n] * z[n,s] rebuilt in the kernel, feat_v(pt) the 4-tap bilinear fetch of view v's
+ * half-resolution map at the ROUNDED projection of pt (zero when it falls outside the image or behind the camera) and
+ * trunc = 1 for samples within +-5 % of a positive gt depth.  Only those samples are evaluated (the reference
+ * evaluates all and multiplies two thirds by zero).  Rays [ray_start[f], ray_start[f+1]) belong to target frame f,
+ * whose n_views reference views are w2c / cam_o rows f*n_views .. and feats[f] ([n_views,h,w,64] channels-last).
+ * apply_trunc = 0 evaluates every sample (Mapper.decoder_init, slams/mapping.py:807-809, has no mask).
+ * dns_featmerge_bwd recomputes the activations (no stash): it ACCUMULATES d_params (Merge.decoder.params layout) and
+ * ADDS the gradient that reaches the points through OneBlob to d_rays_o / d_rays_d (the gathered features carry no
+ * gradient: common.py:657 rounds).  It must get the workspace of the matching forward call (band row list).
+ * ------------------------------------------------------------------------------------- */
+#define DNS_MAX_FRAMES 8
+typedef struct dns_featmerge_args {
+  int32_t n_rays, n_samples;
+  int32_t n_frames, n_views;
+  int32_t ray_start[DNS_MAX_FRAMES + 1];
+  int32_t H, W, h, w;       /* image size, feature-map size */
+  int32_t apply_trunc;
+  int32_t need_dparams, need_drays;   /* backward only */
+  double bound[3][2];
+  const float* K;           /* [3,3] */
+  const float* w2c;         /* [n_frames*n_views,4,4] */
+  const float* cam_o;       /* [n_frames*n_views,3] camera centres of the views (inverse(w2c)[:3,3], common.py:672-673) */
+  const float* feats[DNS_MAX_FRAMES];
+  const float* rays_o;      /* [N,3] */
+  const float* rays_d;      /* [N,3] */
+  const float* z_vals;      /* [N,S] */
+  const float* gt_depth;    /* [N] */
+  const float* params;      /* W1[32][112] | W2[32][32] */
+  float* features;          /* [N,S,32] overwritten (forward) */
+  const float* d_features;  /* [N,S,32] (backward) */
+  float* d_params;          /* += (backward), may be NULL */
+  float* d_rays_o;          /* [N,3] += (backward), may be NULL */
+  float* d_rays_d;
+  void* workspace;
+  int64_t workspace_bytes;
+} dns_featmerge_args;
+int64_t dns_featmerge_workspace_bytes(int n_rays, int n_samples);
+int dns_featmerge_fwd(const dns_featmerge_args* a, void* stream);
+int dns_featmerge_bwd(const dns_featmerge_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Camera poses of a mapping / tracking iteration on the device (utils/common.py:406-458 quad2rotation /
+ * get_camera_from_tensor; slams/mapping.py:534-551 reference-view poses; the pose part of autograd's backward).
+ * dns_pose_prepare: quats [F,4] (w,x,y,z, un-normalised), trans [F,3]  ->  R [F,3,3] (the sampler's input) and, for
+ * every view v < n_views_total, w2c[v] / cam_o[v]: view_src[v] >= 0 follows target frame view_src[v] (rigid inverse of
+ * its CURRENT pose, detached as in the reference), view_src[v] < 0 copies fixed_w2c[v] / fixed_cam_o[v].
+ * dns_pose_grad: d_rays_o / d_rays_d [N,3] of rays whose camera-frame directions follow from pixel[n] (flat window
+ * index as dns_sample_rays resolves it) -> d_quats [F,4], d_trans [F,3] (overwritten): the chain
+ * rays_d = R(q) dirs, rays_o = T (common.py:262-263) differentiated in closed form.  scratch: 12*F floats.
+ * ------------------------------------------------------------------------------------- */
+int dns_pose_prepare(const float* quats, const float* trans, int n_frames, const int32_t* view_src, const float* fixed_w2c,
+                     const float* fixed_cam_o, int n_views_total, float* R, float* w2c, float* cam_o, void* stream);
+int dns_pose_grad(const float* d_rays_o, const float* d_rays_d, const int64_t* pixel, int n_frames,
+                  const int32_t* ray_start /* host, [n_frames+1] */, int H0, int W0, int Ww, float fx, float fy, float cx,
+                  float cy, const float* quats, float* d_quats, float* d_trans, float* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * ResNet stem of the pixel-feature branch == models/encoder.py:9-17 over models/layers.py:52-114 (what is left of
@@ -290,9 +368,6 @@ typedef struct {
 int dns_adam_multi(const dns_adam_seg* segs_dev, int n_segs, int64_t max_n, int* step_dev, float beta1, float beta2,
                    float eps, void* stream);
 
-/* 1 (default): MLP weight-gradient GEMMs run on tcgen05 tensor cores (bf16 hi+lo split, three
- * products, fp32 accumulation in TMEM); 0: fp32 SIMT path, kept for A/B comparison. */
-void dns_set_tensor_cores(int on);
 /* Test entry of the tcgen05 GEMM: C[m][n] (row stride N) += sum_p A[p][m] * B[p][n]. */
 int dns_debug_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows,
                       float* C, void* stream);
@@ -309,9 +384,9 @@ int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, 
 void dns_profile_enable(int on);
 int dns_profile_read(double* ms /*[16]*/, long long* launches /*[16]*/, int reset);
 
-/* sizeof(dns_grid), sizeof(dns_render_args), sizeof(dns_tv_args), sizeof(dns_sample_args): lets a
- * foreign-language binding assert that its struct mirror matches this header. */
-void dns_struct_sizes(int64_t out[4]);
+/* sizeof(dns_grid), sizeof(dns_render_args), sizeof(dns_tv_args), sizeof(dns_sample_args),
+ * sizeof(dns_featmerge_args): lets a foreign-language binding assert that its struct mirror matches this header. */
+void dns_struct_sizes(int64_t out[5]);
 
 #ifdef __cplusplus
 }

@@ -20,23 +20,20 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("mode,N,S,C", CASES)
 def test_tensor_core_path_matches_simt_path(mode, N, S, C):
-    from dns_slam_b200 import _lib, bench_util, step as stepmod
+    import contextlib
+    from dns_slam_b200 import bench_util, fused, step as stepmod
     assert torch.cuda.is_available()
     dev = torch.device("cuda:0")
     dec, samples = bench_util.synthetic_batch("tiny", mode, N, S, C, dev, seed=N + 7 * S + C, n_frames=1)
-    L = _lib.lib()
     out = {}
-    try:
-        for tc in (0, 1):
-            L.dns_set_tensor_cores(tc)
+    for tc in (0, 1):
+        with (contextlib.nullcontext() if tc else fused.simt_path()):     # per-call switch (dns_render_args.use_simt)
             if mode == "map":
                 smp = {k: v for k, v in samples.items() if k != "mask"}
                 ms = stepmod.MappingStep(dec, 5e-3)
                 out[tc] = (ms.forward_backward(smp), ms.grad.clone())
             else:
                 out[tc] = (stepmod.TrackingStep(dec).forward_backward(samples), None)
-    finally:
-        L.dns_set_tensor_cores(1)
     (o0, g0), (o1, g1) = out[0], out[1]
     if not torch.isfinite(o0[0][:7]).all():          # e.g. a fully masked tracking batch: NaN like the reference, both paths
         assert not torch.isfinite(o1[0][:7]).all()

@@ -28,21 +28,16 @@ def test_dw_gemm_tc(M, lda, N, ldb, rows):
 
 def test_fused_gradients_same_with_and_without_tensor_cores():
     """The dW GEMMs of the fused path: tcgen05 vs the fp32 SIMT kernel on the same stash."""
-    from dns_slam_b200 import _lib, bench_util, step as stepmod
+    from dns_slam_b200 import bench_util, fused, step as stepmod
     dev = torch.device("cuda:0")
     dec, samples = bench_util.synthetic_batch("tiny", "map", 700, 47, 9, dev, seed=2, n_frames=2)
     samples = {k: v for k, v in samples.items() if k != "mask"}
     ms = stepmod.MappingStep(dec, 5e-3)
-    L = _lib.lib()
-    try:
-        L.dns_set_tensor_cores(0)
+    with fused.simt_path():               # per-call switch (dns_render_args.use_simt): fp32 SIMT kernels
         o0 = ms.forward_backward(samples)
         g0 = ms.grad.clone()
-        L.dns_set_tensor_cores(1)
-        o1 = ms.forward_backward(samples)
-        g1 = ms.grad.clone()
-    finally:
-        L.dns_set_tensor_cores(1)
+    o1 = ms.forward_backward(samples)
+    g1 = ms.grad.clone()
     torch.testing.assert_close(o1[0][:7], o0[0][:7], rtol=1e-4, atol=1e-7)            # losses
     for k in ("color", "depth", "var", "logits"):
         torch.testing.assert_close(o1[1][k], o0[1][k], rtol=1e-4, atol=1e-5)
@@ -95,8 +90,7 @@ def test_fused_merge_matches_operator_chain(monkeypatch):
     w_out = torch.randn(P, 32, generator=g).to(dev)
     res = {}
     for mode in ("fused", "ops"):
-        if mode == "ops":
-            monkeypatch.setenv("DNS_MERGE_OPS", "1")
+        monkeypatch.setattr(type(dec.merge), "use_operator_chain", mode == "ops")
         p = p0.clone().requires_grad_(True)
         dec.zero_grad()
         out = dec.merge(p, o, code)
