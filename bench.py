@@ -3,22 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A *step* is one pass of the mapping core over one Replica-shaped ray batch already resident in
-HBM: zero-grad -> fused encode + MLP + render + loss forward/backward (all six losses, hash-table,
-MLP, class-expert, ray and pixel-feature gradients) -> [NCCL all-reduce of the flat gradient when
-N > 1] -> fused Adam over the flat parameter buffer (``slams/mapping.py:888-910`` without the
-sampling stage).  Each rank owns ``--rays-per-gpu`` rays (weak scaling: 131072 x 8 = the 1M-ray
-mapping batch of BASELINE.json); ``value`` is whole-job rays/s.  ``e2e`` repeats the step with
-the ray batch coming from pinned HOST memory every step and the loss dictionary read back.
-``extra`` reports BASELINE configs 1 and 2 (tracking 1024 x 96, mapping 4096 x 47 + Adam) and the
-full iteration with sampling / feature matching / TV.  ``--impl reference`` times the oracle port
-of the reference's CPU path (the reference is Python on tinycudann, which is CUDA-only: the hash
-grid / MLPs run as the fp32 PyTorch stand-in) on the host cores.
+A *step* is ONE MAPPING ITERATION (``slams/mapping.py:884-910``) over a Replica-shaped ray batch drawn from four
+key frames that live on the device: ray / pixel sampling (uniform + class-balanced), far plane and depth-guided
+z values, feature matching + Merge + truncation mask for the band samples, fused encode + MLP + render + all six
+ray losses + TV smoothness, the backward down to hash table, every MLP, the class experts, Merge and the camera
+poses, [NCCL exchanges when N > 1] and Adam over decoder + poses.  What crosses the host boundary per step is what a
+SLAM host holds per iteration: its hoisted random draws (8 B per ray) in, the loss vector out.
+
+``value``  rays/s of whole-job steps with the step's draws already resident in HBM.
+``e2e``    the same steps through the public step API from HOST memory: the key frames (colour / depth / label), the
+           reference views' images, their upload, the ResNet stem and the per-frame class tables happen INSIDE the timed
+           region (once, as at the start of a mapping call), then every step uploads its draws from pinned memory and
+           reads the loss vector back.
+Each rank owns ``--rays-per-gpu`` rays of the global batch (weak scaling: 131072 x 8 = the 1M-ray mapping batch of
+BASELINE.json config 4).  ``extra`` holds BASELINE configs 0-3, the core-only step of round 1 and the inference / stem
+timings.  ``--impl reference`` times the oracle port of the SAME iteration on the host cores (the reference is Python
+on tinycudann, which is CUDA-only: hash grid / MLPs run as the fp32 PyTorch stand-in), on the same frames, poses,
+weights and draw generator, over a bounded number of rays per step.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -31,20 +36,24 @@ sys.path.insert(0, ROOT)
 METRIC = "rays/sec fused encode+MLP+render+loss fwd/bwd"
 BYTES_PT = dict(point_fwd=1024 + 4, ray=256, point_bwd=2048)      # SURVEY 8d, per sample point
 BYTES_RAY = dict(point_fwd=24, ray=228, point_bwd=0)              # per ray
+TV_BYTES_PT = 1024 + 2048 + 4                                     # SURVEY 8d, per lattice point (upper bound)
+FEAT_BYTES_ROW = 4 * 256                                          # 4 bilinear taps x 64 channels per (band sample, view)
+N_TARGET, N_REFER = 4, 3                                          # replica.yaml:41 (mapping window), refer views
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays-per-gpu", type=int, default=131072)
     ap.add_argument("--samples", type=int, default=47)
     ap.add_argument("--n-class", type=int, default=40)
     ap.add_argument("--shape", default="replica")
-    ap.add_argument("--cpu-rays", type=int, default=2048)
+    ap.add_argument("--cpu-rays", type=int, default=16384)
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
 
@@ -57,8 +66,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.sm, self.max_sm, self.bits, self.stop, self.err = index, [], None, 0, False, None
         self.nv = self.h = self.get_reasons = None
-        # NVML is initialised HERE, before the timed region: nvmlInit takes driver-wide locks for 100-200 ms, and
-        # inside a short timed loop that showed up as an idle GPU (262 144 rays x 10 steps: 51.7 instead of 34.6 ms)
+        # NVML is initialised HERE, before the timed region: nvmlInit takes driver-wide locks for 100-200 ms
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -91,7 +99,6 @@ class ClockSampler:
 
     def summary(self):
         sm = sorted(self.sm)
-        # NVML clocks-event-reason bits
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         reasons = sorted(n for b, n in names.items() if self.bits & b)
         out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
@@ -101,45 +108,137 @@ class ClockSampler:
         return out
 
 
-def cpu_reference(args, dec_state, samples_cpu, steps, warmup):
-    """The oracle port of mapping.py:888-910 (renderer + 6 losses + backward + torch Adam) on the
-    host cores.  Test-infrastructure code used here ONLY as the CPU baseline."""
-    from oracle import reference_path as rp
+# ----------------------------------------------------------------------------------------------------------------
+# the workload as the HOST holds it (CPU tensors, seeded): identical for the GPU arm and the CPU reference arm
+# ----------------------------------------------------------------------------------------------------------------
+def host_scene(shape, n_class, seed=100):
+    """Four target key frames, three reference views each (two neighbouring poses with their own images, and the frame
+    itself), poses, and every weight of the model -- all generated here with torch on the CPU."""
     from dns_slam_b200 import synthetic as syn
+    s = syn.SHAPES[shape]
+    gen = torch.Generator().manual_seed(seed)
+    poses = syn.trajectory(shape, 2 * N_TARGET + 2)
+    H, W = s["H"], s["W"]
+    frames, refer_img, refer_c2w, refer_idx = [], [], [], []
+    for f in range(N_TARGET):
+        fr = syn.frame(shape, poses[2 * f + 1], gen, n_class=n_class)
+        frames.append(fr)
+        refer_img.append(torch.stack((torch.rand(H, W, 3, generator=gen), torch.rand(H, W, 3, generator=gen), fr["color"]), 0))
+        refer_idx.append([100 + 2 * f, 101 + 2 * f, -1])
+        refer_c2w.append([poses[2 * f], poses[2 * f + 2], poses[2 * f + 1]])
+    est = [poses[2 * f + 1].clone() for f in range(N_TARGET)]
+
+    def uni(n, a):
+        return (torch.rand(n, generator=gen) * 2 - 1) * a
+
+    bound = syn.load_bound(s["bound"])
+    weights = {"table_scale": 0.1, "coarse": uni(4096, (6.0 / (80 + 32)) ** 0.5), "color": uni(32 * 112 + 16 * 32, 0.2),
+               "logit": uni(32 * 112 + ((n_class + 15) // 16 * 16) * 32, 0.2), "merge": uni(32 * 112 + 32 * 32, 0.2),
+               "experts": uni(n_class * 4096, (6.0 / (80 + 32)) ** 0.5).view(n_class, 4096),
+               "stem_conv": torch.randn(64, 3, 7, 7, generator=gen) * (2.0 / (7 * 7 * 64)) ** 0.5}
+    weights["table_seed"] = seed + 1
+    return dict(shape=shape, cam=syn.camera(shape), bound=bound, frames=frames, refer_img=refer_img, refer_c2w=refer_c2w,
+                refer_idx=refer_idx, est=est, kf_idx=list(range(N_TARGET)), weights=weights, s=s)
+
+
+def table_values(n, seed, scale):
+    return (torch.rand(n, generator=torch.Generator().manual_seed(seed)) * 2 - 1) * scale
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the same iteration
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference(args, scene, n_rays, steps, warmup, seed=1):
+    """mapping.py:884-910 through oracle/reference_path.py on the host cores: get_target_samples (incl. the 209 MB/view
+    up-sample of common.py:646), renderer, 7 losses, backward, torch Adam over decoder + experts + poses.  Test
+    infrastructure used here ONLY as the CPU baseline.  Returns (rays/s, s/step, steps timed)."""
+    from oracle import reference_path as rp
+    from dns_slam_b200 import slam, step as stepmod, synthetic as syn
     torch.set_num_threads(os.cpu_count())
-    bound = syn.load_bound(syn.SHAPES[args.shape]["bound"])
-    dec = rp.Decoder(syn.model_cfg(args.shape), bound, n_class=args.n_class)
+    s, cam, bound, w = scene["s"], scene["cam"], scene["bound"], scene["weights"]
+    C = args.n_class
+    dec = rp.Decoder(syn.model_cfg(scene["shape"]), bound, n_class=C)
     with torch.no_grad():
-        dec.pe_fn.grid_fn.params.copy_(dec_state["table"])
-        dec.coarse_fn.decoder.params.copy_(dec_state["coarse"])
-        dec.out_fn.color_decoder.params.copy_(dec_state["color"])
-        dec.out_fn.logit_decoder.params.copy_(dec_state["logit"])
+        dec.pe_fn.grid_fn.params.copy_(table_values(dec.pe_fn.grid_fn.params.numel(), w["table_seed"], w["table_scale"]))
+        dec.coarse_fn.decoder.params.copy_(w["coarse"])
+        dec.out_fn.color_decoder.params.copy_(w["color"])
+        dec.out_fn.logit_decoder.params.copy_(w["logit"])
+        dec.merge.decoder.params.copy_(w["merge"])
     experts = {}
-    for c in range(args.n_class):
+    for c in range(C):
         e = rp.new_expert(seed=c)
         with torch.no_grad():
-            e.params.copy_(dec_state["experts"][c])
+            e.params.copy_(w["experts"][c])
         experts[c] = e
-    s = syn.SHAPES[args.shape]
-    params = list(dec.parameters()) + [e.params for e in experts.values()]
-    opt = torch.optim.Adam(params, lr=s["lr"])
-    smp = dict(samples_cpu)
-    smp["pts"] = smp["rays_o"][:, None, :] + smp["rays_d"][:, None, :] * smp["z_vals"][:, :, None]
-    n = smp["z_vals"].shape[0]
+    # once per mapping call: the stem over the reference views of every target frame (mapping.py:846)
+    with torch.no_grad():
+        feats = [rp.stem_forward(img[None], w["stem_conv"], torch.ones(64), torch.zeros(64))[0] for img in scene["refer_img"]]
+    quad = [slam.quad_from_matrix(c[:3, :3]).requires_grad_(f != 0) for f, c in enumerate(scene["est"])]
+    T = [c[:3, 3].clone().requires_grad_(f != 0) for f, c in enumerate(scene["est"])]
+    opt = torch.optim.Adam([{"params": list(dec.parameters()) + [e.params for e in experts.values()], "lr": s["lr"]},
+                            {"params": quad[1:], "lr": s["BA_cam_lr"]}, {"params": T[1:], "lr": s["BA_cam_lr"]}])
+    tables = [slam.class_tables(f["label"]) for f in scene["frames"]]
+    plan = stepmod.FrameBatchPlan(tables, n_rays, 15, (0, cam["H"], 0, cam["W"]), bound, s["smooth_pts"])
+    gen = torch.Generator().manual_seed(seed)
     times = []
     for it in range(warmup + steps):
+        _, tape = plan.make_host_draws(gen, pinned=False, return_tape=True)
         t0 = time.perf_counter()
         opt.zero_grad()
+        tp = rp.DrawTape(tape)
+        smp = rp.mapper_get_target_samples(cam, bound, dec, scene["frames"], quad, T, scene["refer_idx"], scene["kf_idx"],
+                                           scene["refer_c2w"], feats, n_rays, 32, 15, tp)
         pc, pd, pv, pl, fine, coarse = rp.mapper_renderer(dec, experts, bound, smp)
         p, d, l, lt, fs, op = rp.mapping_losses(smp, pc, pd, pl, fine, coarse, s["opacity_sigma"])
+        sm = rp.smoothness(dec, bound, s["smooth_pts"], tp)
         loss = s["lambda_color"] * p + s["lambda_depth"] * d + s["lambda_label"] * l + 10 * lt \
-            + s["lambda_fs"] * fs + s["lambda_opacity"] * op
+            + s["lambda_fs"] * fs + s["lambda_opacity"] * op + s["lambda_smooth"] * sm
         loss.backward()
         opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return n / sec, sec
+    return plan.n_total / sec, sec, len(times)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def build_decoder(args, scene, dev):
+    """The product decoder carrying the scene's weights (all class experts active)."""
+    from dns_slam_b200 import bench_util
+    w = scene["weights"]
+    dec = bench_util.make_decoder(scene["shape"], args.n_class, dev, seed=0, table_scale=1.0)
+    with torch.no_grad():
+        dec.view("table").copy_(table_values(dec.view("table").numel(), w["table_seed"], w["table_scale"]))
+        for k in ("coarse", "color", "logit", "merge"):
+            dec.view(k).copy_(w[k])
+        dec.expert_params.copy_(w["experts"])
+    return dec
+
+
+def build_gpu_step(args, scene, dec, rank, world, comm, frames_dev, feats, tables):
+    """MappingFrameStep over key frames that are on the device (fresh Adam state, as per optimize() call)."""
+    from dns_slam_b200 import step as stepmod
+    s = scene["s"]
+    lam = dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0, fs=s["lambda_fs"], op=s["lambda_opacity"])
+    st = stepmod.MappingFrameStep(dec, scene["cam"], frames_dev, tables, feats, scene["est"], scene["refer_idx"],
+                                  scene["refer_c2w"], scene["kf_idx"], args.rays_per_gpu * world, 32, 15, lr=s["lr"],
+                                  BA_cam_lr=s["BA_cam_lr"], is_BA=True, lambdas=lam, opacity_sigma=s["opacity_sigma"],
+                                  smooth_pts=s["smooth_pts"], lambda_sm=s["lambda_smooth"], with_tv=True, comm=comm,
+                                  rank=rank, world=world)
+    return st
+
+
+def upload_scene(scene, host_pinned, dev, stem):
+    """What happens once per mapping call: key frames and reference images host -> device, the stem over the reference
+    views (mapping.py:846), the per-frame class tables (labels do not change between iterations)."""
+    from dns_slam_b200 import slam
+    frames_dev, feats, tables = [], [], []
+    for f in range(N_TARGET):
+        fr = {k: host_pinned["frames"][f][k].to(dev, non_blocking=True) for k in ("color", "depth", "label")}
+        frames_dev.append(fr)
+        feats.append(stem.forward_cl(host_pinned["refer_img"][f].to(dev, non_blocking=True)[None]))
+        tables.append(slam.class_tables(fr["label"]))
+    return frames_dev, feats, tables
 
 
 def main():
@@ -148,28 +247,34 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     S, C, R = args.samples, args.n_class, args.rays_per_gpu
-    from dns_slam_b200 import synthetic as _syn
-    workload = (f"{args.shape}_mapping_{R}rays_per_gpu_x{S}samples_{C}classes_"
-                f"hash2^{_syn.SHAPES[args.shape]['hash_size']}_plus_adam")
+    from dns_slam_b200 import synthetic as syn
+    workload = (f"{args.shape}_mapping_iteration_{R}rays_per_gpu_x{S}samples_{C}classes_"
+                f"hash2^{syn.SHAPES[args.shape]['hash_size']}_4keyframes_3views_sampling+featurematching+render+7losses+backward+adam")
     config = {"workload": workload, "rays_per_gpu": R, "n_samples": S, "n_class": C,
-              "cache": "per-step inputs (~6.2 KB/ray) + activation stash exceed the 126 MB L2",
-              "parallelism": f"rays sharded x{args.gpus}, flat-gradient all-reduce (NCCL)" if args.gpus > 1 else "single GPU"}
-
-    from dns_slam_b200 import bench_util, synthetic as syn
+              "boundary": "host holds key frames + poses + per-iteration draws; everything else on the device",
+              "cache": "key-frame feature maps (627 MB), per-step latents and activation stash exceed the 126 MB L2",
+              "parallelism": f"rays sharded x{args.gpus} (key frames and parameters replicated), max-depth / counts / label "
+                             f"exchange + ONE flat-gradient all-reduce (NCCL)" if args.gpus > 1 else "single GPU"}
+    if S != 47:
+        raise SystemExit("the benchmarked iteration uses the reference's 32 + 15 samples per ray")
+    scene = host_scene(args.shape, C)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # the reference's CPU path (oracle port) on a bounded sample of the same workload
-        dev = torch.device("cpu")
         n_cpu = min(args.cpu_rays, R)
-        dec_state, samples = _cpu_inputs(args, n_cpu)
-        rps, sec = cpu_reference(args, dec_state, samples, max(1, args.steps), max(1, min(args.warmup, 1)))
+        # bounded sample: one probe step sizes the rays per step so that K steps end within a few minutes
+        _, probe, _ = cpu_reference(args, scene, n_cpu, 1, 0)
+        while probe * (args.steps + 1) > 240.0 and n_cpu > 2048:
+            n_cpu //= 2
+            _, probe, _ = cpu_reference(args, scene, n_cpu, 1, 0)
+        rps, sec, k = cpu_reference(args, scene, n_cpu, max(1, args.steps), 1)
         line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                 "sample": f"{n_cpu} of {R} rays per step, full step (render+6 losses+backward+Adam)"},
+                                 "sample": f"{n_cpu} of {R} rays per step; the whole iteration (sampling, feature matching "
+                                           f"incl. up-sample, render, 7 losses, backward, Adam), {k} timed steps"},
                 "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -177,36 +282,40 @@ def main():
     assert torch.cuda.is_available(), "bench.py (ours) needs a GPU: dns_slam_b200 has no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    pg = None
+    comm = None
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
-        pg = torch.distributed.group.WORLD
-    from dns_slam_b200 import _lib, step as stepmod, fused
-
-    s = syn.SHAPES[args.shape]
-    dec = bench_util.make_decoder(args.shape, C, dev, seed=0)                       # identical on every rank
-    _, samples = bench_util.synthetic_batch(args.shape, "map", R, S, C, dev, seed=100 + rank, dec=dec)
-    lam = dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0, fs=s["lambda_fs"],
-               op=s["lambda_opacity"])
-    if world > 1:   # rays [rank*R, (rank+1)*R) of ONE global batch of R*world rays
-        sh = stepmod.ShardedMappingStep(dec, s["lr"], stepmod.TorchComm(pg), rank, world, lambdas=lam,
-                                        opacity_sigma=s["opacity_sigma"])
-
-        class _Ms:          # same .step(samples) surface as MappingStep
-            def step(self, smp):
-                return sh.step_sharded(smp, R * world)
-        ms = _Ms()
-    else:
-        ms = stepmod.MappingStep(dec, s["lr"], lam, s["opacity_sigma"])
+        from dns_slam_b200 import step as stepmod
+        comm = stepmod.TorchComm(torch.distributed.group.WORLD)
+    from dns_slam_b200 import _lib, encoder
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # host side of the boundary: pinned key frames / reference images, the stem's weights
+    host_pinned = {"frames": [{k: fr[k].contiguous().pin_memory() for k in ("color", "depth", "label")} for fr in scene["frames"]],
+                   "refer_img": [x.contiguous().pin_memory() for x in scene["refer_img"]]}
+    frame_bytes = sum(v.numel() * v.element_size() for fr in host_pinned["frames"] for v in fr.values()) \
+        + sum(x.numel() * x.element_size() for x in host_pinned["refer_img"])
+    stem = encoder.ResNet().to(dev)
+    with torch.no_grad():
+        stem.conv_blocks.conv1.weight.copy_(scene["weights"]["stem_conv"])
+
     # ---------------- device-resident timing
-    for _ in range(args.warmup):
-        ms.step(samples)
+    frames_dev, feats, tables = upload_scene(scene, host_pinned, dev, stem)
+    dec = build_decoder(args, scene, dev)
+    st = build_gpu_step(args, scene, dec, rank, world, comm, frames_dev, feats, tables)
+    gen = torch.Generator().manual_seed(1000 + rank)           # the rank's own pixel draws
+    shared_gen = torch.Generator().manual_seed(999) if world > 1 else None   # batch-level draws: same on every rank
+    n_bufs = max(args.steps, args.warmup)
+    host_draws = [st.make_host_draws(gen, shared_gen=shared_gen) for _ in range(min(n_bufs, 8))]
+    dev_draws = [h.to(dev) for h in host_draws]
+    for i in range(args.warmup):
+        st.step(dev_draws[i % len(dev_draws)])
+    res = st.step(dev_draws[0]).cpu()
+    st.check(res)                     # error flags / rays outside the bound would void the static-shape step
     barrier()
     _lib.profile_read(reset=True)
     _lib.profile_enable(True)
@@ -214,8 +323,8 @@ def main():
     with ClockSampler(local) as clk:
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            out = ms.step(samples)
+        for i in range(args.steps):
+            out = st.step(dev_draws[i % len(dev_draws)])
         e1.record()
         barrier()
     _lib.profile_enable(False)
@@ -225,22 +334,31 @@ def main():
         torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
     step_ms = float(t_ms) / args.steps
     value = R * world / (step_ms * 1e-3)
-    losses = out[0].cpu().tolist()
+    losses = out.cpu().tolist()
+    band_rows = int(st.fm_ws[:4].view(torch.int32)[0])
 
-    # ---------------- end to end: inputs from pinned host memory every step, losses read back
-    host = {k: v.detach().cpu().pin_memory() for k, v in samples.items() if k != "mask"}
-    pipe = stepmod.HostBatchPipeline(host, dev)
-    h2d = pipe.h2d_bytes
-    pipe.run([host] * max(2, args.warmup // 2), ms.step)
+    # ---------------- end to end: scene from HOST memory inside the timed region, draws from pinned memory every step,
+    # the loss vector read back every step
+    del st, dec, frames_dev, feats, tables
+    torch.cuda.empty_cache()
+    dec = build_decoder(args, scene, dev)          # weights are device state like in the reference (not per-call input)
     barrier()
     e0.record()
-    pipe.run([host] * args.steps, ms.step)       # every step: H2D of its inputs (overlapped with the previous
-    e1.record()                                  # step's kernels on a copy stream) + D2H of its loss vector
+    frames_dev, feats, tables = upload_scene(scene, host_pinned, dev, stem)
+    st = build_gpu_step(args, scene, dec, rank, world, comm, frames_dev, feats, tables)
+    for i in range(args.steps):
+        st.upload(host_draws[i % len(host_draws)])
+        st.step()
+        st.read_result()
+    e1.record()
     barrier()
+    st.check()
     t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
     e2e_val = R * world / (float(t2) / args.steps * 1e-3)
+    h2d = st.draw_bytes + frame_bytes / args.steps
+    d2h = st.result_host.numel() * 4
 
     if rank != 0:
         if world > 1:
@@ -253,85 +371,53 @@ def main():
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    kern = {k: phase_ms[k] / args.steps for k in ("point_fwd", "ray", "point_bwd", "dw_gemm", "adam", "class_prep", "prep")}
+    kern = {k: phase_ms.get(k, 0.0) / args.steps for k in ("point_fwd", "ray", "point_bwd", "dw_gemm", "feature", "sample",
+                                                           "tv_fwd", "tv_bwd", "adam", "class_prep", "prep", "finalize")}
     dom = max(("point_fwd", "ray", "point_bwd"), key=lambda k: kern[k])
     alg = R * (S * BYTES_PT[dom] + BYTES_RAY[dom])
     achieved = alg / (kern[dom] * 1e-3) / 1e9
-    traffic = None
-    tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tj):
-        bpp = json.load(open(tj)).get("bytes_per_point", {}).get(dom)   # ncu --set full, per sample point
-        traffic = bpp * R * S if bpp is not None else None
-    step_alg = R * (S * 3332 + 252)
-    roof = {"bound": "hbm", "kernel": {"point_fwd": "k_point_fwd", "ray": "k_ray", "point_bwd": "k_point_bwd"}[dom],
+    tv_pts = (scene["s"]["smooth_pts"] - 1) ** 3
+    step_alg = R * (S * 3332 + 252) + tv_pts * TV_BYTES_PT + band_rows * N_REFER * FEAT_BYTES_ROW
+    traffic, traffic_src = None, "no ncu capture in this run (profiles/ holds the per-round captures)"
+    roof = {"bound": "hbm", "kernel": {"point_fwd": "k_point_fwd_tc2", "ray": "k_ray_tc2", "point_bwd": "k_point_bwd_tc2"}[dom],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
             "algorithmic_bytes_per_launch": alg, "kernel_ms": kern[dom],
             "step": {"algorithmic_bytes": step_alg, "achieved": step_alg / (step_ms * 1e-3) / 1e9,
-                     "frac": step_alg / (step_ms * 1e-3) / 1e9 / peak},
+                     "frac": step_alg / (step_ms * 1e-3) / 1e9 / peak,
+                     "terms": {"rays": R * (S * 3332 + 252), "tv_lattice": tv_pts * TV_BYTES_PT,
+                               "feature_rows": band_rows * N_REFER * FEAT_BYTES_ROW}},
             "phase_ms_per_step": kern}
 
     extra = {}
-    if not args.no_extra:
-        extra = _extra_configs(args, dev)
+    if not args.no_extra and world == 1:
+        del st, dec, frames_dev, feats, tables
+        torch.cuda.empty_cache()
+        extra = _extra_configs(args, dev, scene)
 
     cpu = None
-    if world == 1:
+    if world == 1 and not args.no_cpu:
         n_cpu = min(args.cpu_rays, R)
-        dec_state = {"table": dec.view("table").cpu(), "coarse": dec.view("coarse").cpu(), "color": dec.view("color").cpu(),
-                     "logit": dec.view("logit").cpu(), "experts": dec.expert_params.detach().cpu()}
-        smp = {k: v[:n_cpu].detach().cpu() for k, v in samples.items()}
-        rps, sec = cpu_reference(args, dec_state, smp, 3, 1)
+        rps, sec, k = cpu_reference(args, scene, n_cpu, 2, 1)
         cpu = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{n_cpu} of {R} rays per step (same step: render + 6 losses + backward + Adam), "
-                         f"3 timed steps, {sec * 1e3:.0f} ms each"}
+               "sample": f"{n_cpu} of {R} rays per step on the same key frames / poses / weights / draw generator (the whole "
+                         f"iteration: sampling, feature matching incl. up-sample, render, 7 losses, backward, Adam), "
+                         f"{k} timed steps, {sec * 1e3:.0f} ms each"}
 
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
+            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": f"key frames + reference images ({frame_bytes} B) uploaded, stem and class tables run once "
+                            f"inside the timed region; {R * 8} B of draws per step"},
             "gpu_launches": int(sum(launches.values())), "launches_per_step": {k: v // args.steps for k, v in launches.items() if v},
-            "roofline": roof, "cpu_baseline": cpu, "losses_last_step": losses, "extra": extra}
+            "roofline": roof, "cpu_baseline": cpu, "losses_last_step": losses, "band_samples_per_ray": band_rows / R,
+            "extra": extra}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
-
-
-def _cpu_inputs(args, n_cpu):
-    """Inputs of the reference arm, generated on the CPU only (no GPU needed for --impl reference)."""
-    from oracle import reference_path as rp
-    from dns_slam_b200 import synthetic as syn, bench_util
-    S, C = args.samples, args.n_class
-    bound = syn.load_bound(syn.SHAPES[args.shape]["bound"])
-    odec = rp.Decoder(syn.model_cfg(args.shape), bound, n_class=C, seed=0)
-    with torch.no_grad():
-        odec.pe_fn.grid_fn.params.mul_(1000.0)
-    dec_state = {"table": odec.pe_fn.grid_fn.params.detach(), "coarse": odec.coarse_fn.decoder.params.detach(),
-                 "color": odec.out_fn.color_decoder.params.detach(), "logit": odec.out_fn.logit_decoder.params.detach(),
-                 "experts": torch.stack([rp.new_expert(seed=100 + c).params.detach() for c in range(C)])}
-    cam = syn.camera(args.shape)
-    gen = torch.Generator().manual_seed(100)
-    n_s, n_f = bench_util.split_samples(S)
-    poses = syn.trajectory(args.shape, 8)
-    parts = []
-    per = n_cpu // 4
-    for f in range(4):
-        c2w = poses[2 * f + 1]
-        fr = syn.frame(args.shape, c2w, gen, n_class=C)
-        img = torch.cat((fr["color"], fr["depth"].unsqueeze(-1), fr["label"].unsqueeze(-1)), -1)
-        tape = rp.DrawTape(seed=f)
-        idx = rp.uniform_indices(0, cam["H"], 0, cam["W"], per, tape)
-        i, j = rp.uv_from_flat(idx, 0, 0, cam["W"])
-        ro, rd = rp.rays_from_uv(i, j, c2w[:3, :3], c2w[:3, 3], cam["fx"], cam["fy"], cam["cx"], cam["cy"])
-        smp = rp.gather_window(img, 0, cam["H"], 0, cam["W"], idx)
-        far, inside = rp.far_plane(ro, rd, bound, smp[:, 3])
-        z = rp.sample_along_rays(smp[:, 3], n_s, n_f, far, tape)
-        parts.append(dict(gt_color=smp[:, :3].float(), gt_depth=smp[:, 3].float(), gt_label=smp[:, 4].long(),
-                          rays_o=ro.float(), rays_d=rd.float(), z_vals=z))
-    cat = {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
-    cat["features"] = torch.randn(cat["z_vals"].shape[0], S, 32, generator=gen) * 0.3 * rp.trunc_mask(cat["z_vals"], cat["gt_depth"])[..., None]
-    return dec_state, cat
 
 
 def _time_cuda(fn, steps, warmup):
@@ -347,11 +433,18 @@ def _time_cuda(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
-def _extra_configs(args, dev):
-    """BASELINE configs 1 and 2 on this GPU (device-resident, CUDA events)."""
+def _extra_configs(args, dev, scene):
+    """BASELINE configs 0-3 and the component timings of earlier rounds (device-resident, CUDA events)."""
     from dns_slam_b200 import bench_util, fused, step as stepmod, synthetic as syn
     s = syn.SHAPES[args.shape]
     out = {}
+    # the round-1 step: core only (features given), 131072 rays -- for continuity with BENCH_r01
+    dec, smp = bench_util.synthetic_batch(args.shape, "map", args.rays_per_gpu, 47, args.n_class, dev, seed=100)
+    ms = stepmod.MappingStep(dec, s["lr"], dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0), s["opacity_sigma"])
+    t = _time_cuda(lambda: ms.step(smp), 10, 3)
+    out["core_only_step_round1_definition"] = {"ms_per_step": t, "rays_per_s": args.rays_per_gpu / (t * 1e-3)}
+    del dec, smp, ms
+    torch.cuda.empty_cache()
     # config 2: mapping 4096 rays x 47, semantic head, hash-grid + MLP Adam step
     dec, smp = bench_util.synthetic_batch(args.shape, "map", 4096, 47, args.n_class, dev, seed=7)
     ms = stepmod.MappingStep(dec, s["lr"], dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0), s["opacity_sigma"])
@@ -373,18 +466,87 @@ def _extra_configs(args, dev):
     t1 = _time_cuda(lambda: ts.forward_backward(smp1), 50, 10)
     out["config1_tracking_1024x96"] = {"ms_per_iteration": t1, "rays_per_s": 1024 / (t1 * 1e-3),
                                        "ms_per_10_iterations": 10 * t1}
-    # T_iter: whole iterations incl. sampling, feature matching + Merge, TV, Adam
+    # the frames + draws step at the SLAM batch size (4 x 500 rays): whole iteration, eager launches and CUDA graph
+    out["iteration_native_step_replica_2000"] = _native_iteration(args, dev, scene, 2000)
+    # T_iter: whole iterations through the autograd drop-in host mirror
     for shape in ("replica", "scannet"):
         out["iteration_" + shape] = _iteration_timings(shape, args.n_class, dev)
     out["inference_replica"] = _inference_timings("replica", args.n_class, dev)
     out["stem_replica"] = _stem_timings("replica", dev)
+    # config 0: one full mapping iteration at 1200x680 with the reference's 2000 rays on the host cores (oracle port)
+    if not args.no_cpu:
+        rps, sec, k = cpu_reference(args, scene, 2000, 2, 1)
+        out["config0_cpu_full_iteration_1200x680_2000rays"] = {
+            "ms_per_iteration": sec * 1e3, "rays_per_s": rps, "cores": os.cpu_count(), "timed_iterations": k,
+            "gpu_ms_per_iteration": out["iteration_native_step_replica_2000"]["ms_per_iteration_cuda_graph"],
+            "note": "oracle port of slams/mapping.py:884-910 incl. get_target_samples, smoothness, backward, Adam"}
+    # config 3: ScanNet-shaped 200-frame tracking + mapping loop (examples/synthetic_slam.py)
+    out["config3_scannet_200"] = _config3(dev)
     return out
+
+
+def _native_iteration(args, dev, scene, n_rays):
+    """MappingFrameStep at the reference's mapping batch size: ms per iteration, eager and as a CUDA-graph replay."""
+    import copy
+    from dns_slam_b200 import encoder
+    a2 = copy.copy(args)
+    a2.rays_per_gpu = n_rays
+    stem = encoder.ResNet().to(dev)
+    hp = {"frames": scene["frames"], "refer_img": scene["refer_img"]}
+    frames_dev, feats, tables = upload_scene(scene, hp, dev, stem)
+    dec = build_decoder(a2, scene, dev)
+    st = build_gpu_step(a2, scene, dec, 0, 1, None, frames_dev, feats, tables)
+    gen = torch.Generator().manual_seed(5)
+    draws = [st.make_host_draws(gen).to(dev) for _ in range(4)]
+    it = [0]
+
+    def eager():
+        st.step(draws[it[0] % 4])
+        it[0] += 1
+    t_eager = _time_cuda(eager, 30, 5)
+    host = st.read_result()
+    torch.cuda.synchronize()
+    st.check(host)
+    # CUDA graph: one captured iteration, replayed with fresh draws copied into the static buffer
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        st.step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        st.step()
+
+    def replay():
+        st.draws_dev.copy_(draws[it[0] % 4], non_blocking=True)
+        graph.replay()
+        it[0] += 1
+    t_graph = _time_cuda(replay, 50, 5)
+    return {"rays": st.n_total, "ms_per_iteration": t_eager, "ms_per_iteration_cuda_graph": t_graph,
+            "rays_per_s_cuda_graph": st.n_total / (t_graph * 1e-3)}
+
+
+def _config3(dev):
+    """BASELINE config 3: 200 ScanNet-shaped frames, tracking every frame, mapping every 5th (scannet.yaml), through the
+    example loop; wall seconds include the host-side synthetic data generation."""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    try:
+        import synthetic_slam
+        t0 = time.perf_counter()
+        log = synthetic_slam.run("scannet", 200, n_class=40, track_iters=30, map_iters=100, use_graph=True, verbose=False, map_every=5)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        mp_ = [x for x in log["log"] if x[0] == "map"]
+        return {"wall_s": wall, "frames": 200, "timings": log["timings"],
+                "mapping_calls_replayed_as_cuda_graph": sum(1 for x in mp_ if x[4]), "mapping_calls": len(mp_),
+                "schedule": "scannet.yaml: 30 tracking iterations per frame, 100 mapping iterations every 5th frame"}
+    except Exception as e:      # noqa: BLE001 - a failing extra must not void the headline line
+        return {"error": repr(e)}
 
 
 def _stem_timings(shape, dev):
     """ResNet stem (models/encoder.py:4-17): once per tracked frame (1 view) and once per mapping call
-    (the refer views of the window; 3 here).  Bytes: the frames in, the 64-channel half-resolution map written by the
-    convolution, read and written by the normalisation."""
+    (the refer views of the window; 3 here)."""
     from dns_slam_b200 import encoder, synthetic as syn
     s = syn.SHAPES[shape]
     H, W = s["H"], s["W"]
@@ -403,7 +565,7 @@ def _stem_timings(shape, dev):
 def _inference_timings(shape, n_class, dev):
     """Inference path: one full-frame render (every pixel x 47 samples, frame_vis of
     slams/mapping.py:636-690) and free-point queries at the mesh-extraction batch size (meshing.py:640-655)."""
-    from dns_slam_b200 import bench_util, inference, synthetic as syn
+    from dns_slam_b200 import bench_util, inference
     dec = bench_util.make_decoder(shape, n_class, dev, seed=1)
     sc = bench_util.slam_scene(shape, n_class, dev, seed=2, n_target=1)
     cam = sc["cam"]
@@ -447,8 +609,8 @@ def _iteration_timings(shape, n_class, dev):
     def track():
         slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, n_it, s["cam_lr"], lambda it: td[it])
     t_track = _time_cuda(track, 3, 1) / n_it
-    # device time of one CUDA-graph-replayed iteration: events around 100 replays (slam.graph_timing), best of 3
-    def graph_ms(fn):
+
+    def graph_ms(fn):   # device time of one CUDA-graph-replayed iteration: events around the replays, best of 3
         best = None
         for _ in range(3):
             slam.graph_timing = {}

@@ -87,7 +87,7 @@ class FeatMergeArgs(C.Structure):
 _lib = None
 
 # every symbol include/dns_slam_b200.h declares
-SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_debug_gemm_tc", "dns_debug_gemm_img", "dns_oneblob_fwd", "dns_oneblob_bwd",
+SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_enable", "dns_profile_read", "dns_debug_gemm_tc", "dns_debug_gemm_fmt", "dns_debug_gemm_img", "dns_oneblob_fwd", "dns_oneblob_bwd",
            "dns_hashgrid_fwd", "dns_hashgrid_bwd", "dns_hashgrid_indices", "dns_mlp_fwd",
            "dns_mlp_bwd", "dns_render_workspace_bytes", "dns_render_fwd_bwd", "dns_render_counts",
            "dns_tv_workspace_bytes", "dns_tv_fwd_bwd", "dns_sample_rays", "dns_feature_gather",
@@ -114,6 +114,7 @@ def lib():
     L.dns_struct_sizes.argtypes = [C.POINTER(C.c_int64)]
     L.dns_profile_enable.argtypes = [C.c_int]
     L.dns_debug_gemm_tc.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int64, _P, _P]
+    L.dns_debug_gemm_fmt.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _P, _P]
     L.dns_debug_gemm_img.argtypes = [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]
     L.dns_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     L.dns_oneblob_fwd.argtypes = [_P, i64, i32, i32, _P, _P]

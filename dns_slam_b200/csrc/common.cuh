@@ -49,6 +49,7 @@ struct DwArgs {
   float* out1;
   int split;
   int64_t sl0, sc0, cls0, sl1, sc1, cls1;
+  int l_f16, c_f16;   // operand staged as fp16 hi/lo instead of bf16 hi/lo (test entry dns_debug_gemm_fmt)
 };
 int launch_dw_gemm_tc2(DwArgs a, cudaStream_t st);
 

@@ -56,6 +56,9 @@ __global__ void k_prep_net80_tc(const float* __restrict__ params, uint4* __restr
     if (i < 320) {
       o[i] = h;
       o[320 + i] = l;
+      split8_f16(a, b, h, l);      // the forward layer-1 GEMM runs on fp16 halves
+      o[kNetW1F16 + i] = h;
+      o[kNetW1F16 + 320 + i] = l;
     } else {
       o[640 + (i - 320)] = h;
       o[832 + (i - 320)] = l;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
   if (MODE == kMap) expert = a.tile_class[tile];
   const bool fine = MODE == kMap && expert >= 0;
   const uint4* we_net = we_all + (int64_t)(fine ? expert : 0) * kNetTc;
-  load_w1_tc(W1_hi, W1_lo, wc_all, we_net, fine);
+  load_w1_tc(W1_hi, W1_lo, wc_all + kNetW1F16, we_net + kNetW1F16, fine);   // fp16 halves
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -114,18 +117,19 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
       for (int c = 0; c < 3; ++c) {
         float pe[16];
         oneblob16(x[c], pe);
-        put_chunk_img(X_hi, X_lo, 2 * c, 2048, row, pe, XIMG(2 * c));
-        put_chunk_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, XIMG(2 * c + 1));
+        put_chunk_f16_img(X_hi, X_lo, 2 * c, 2048, row, pe, XIMG(2 * c));
+        put_chunk_f16_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, XIMG(2 * c + 1));
       }
       hashgrid_fwd_to_tile<0, 8>(a.G, a.table, x, X_hi, X_lo, row);
     } else {
       hashgrid_fwd_to_tile<8, 16>(a.G, a.table, x, X_hi, X_lo, row);
     }
-    if (ximg) {   // the two grid chunks this thread has just written (its own row): tile -> global image
+    if (ximg) {   // the two grid chunks this thread has just written (its own row): fp16 tile -> bf16 global image
 #pragma unroll
       for (int c = 6 + 2 * grp; c < 8 + 2 * grp; ++c) {
-        ximg[c * kTile] = *reinterpret_cast<const uint4*>(X_hi + c * 2048 + row * 16);
-        ximg[(10 + c) * kTile] = *reinterpret_cast<const uint4*>(X_lo + c * 2048 + row * 16);
+        float v[8];
+        f16_chunk_to_floats(X_hi, X_lo, c, 2048, row, v);
+        store_chunk_img(v, ximg + c * kTile, ximg + (10 + c) * kTile);
       }
     }
   } else {
@@ -144,8 +148,8 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
   constexpr int NH = MODE == kMap ? 64 : 32;  // hidden units computed per point
-  if (tid == 0) {  // H = X . W1^T
-    const uint32_t idesc = umma_idesc_bf16(128, NH, 0, 0);
+  if (tid == 0) {  // H = X . W1^T  (fp16 hi / lo halves)
+    const uint32_t idesc = umma_idesc_f16(128, NH, 0, 0, 0, 0);
 #pragma unroll 1
     for (int ks = 0; ks < 5; ++ks) {
       const uint32_t aoff = ks * 4096, boff = ks * 2048;

@@ -4,7 +4,6 @@
 
 namespace dns {
 
-constexpr int kNetTc = 1024;  // uint4 per net: W1 hi [10][32] | W1 lo | W2 hi [4][48] | W2 lo
 
 // shared-memory carve (bytes)
 constexpr int kXTile = 10 * 2048;       // one half of the X tile [10 chunks][128][16]

@@ -31,16 +31,19 @@ constexpr int kW1oBytes2 = 14 * 64 * 16;  // one bf16 half of the [64 x 112] col
 
 // colour | logit layer-1 weights -> bf16 hi / lo chunk tiles [14 feature chunks][64 hidden rows][8 features]
 __global__ void k_prep_w1o_tc(const float* __restrict__ color, const float* __restrict__ logit, uint4* __restrict__ hi,
-                              uint4* __restrict__ lo) {
+                              uint4* __restrict__ lo, uint4* __restrict__ hi16, uint4* __restrict__ lo16) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 14 * 64) return;
   int c = i >> 6, j = i & 63;
   const float* src = (j < 32 ? color + j * kIn2 : logit + (j - 32) * kIn2) + 8 * c;
   float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
   uint4 h, l;
-  split8(a, b, h, l);
+  split8(a, b, h, l);        // bf16 halves: backward GEMM (meets gradients)
   hi[i] = h;
   lo[i] = l;
+  split8_f16(a, b, h, l);    // fp16 halves: forward GEMM (decides the ReLU)
+  hi16[i] = h;
+  lo16[i] = l;
 }
 
 __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restrict__ w1_hi, const uint4* __restrict__ w1_lo) {
@@ -73,12 +76,12 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   float* LS = LG + RPC * C4;            // [4]
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t >= T ? 1 : 0, row = t - grp * T;
-  if (t == 0) {   // the 28 KB weight tile arrives by two bulk copies while the threads encode their rows
-    mbar_init(&bar, 1);
+  if (t == 0) {   // the 28 KB weight tile (fp16 halves for the forward GEMM) arrives by two bulk copies while the
+    mbar_init(&bar, 1);   // threads encode their rows; the bf16 halves replace it before the backward GEMM
     mbar_init(&wbar, 1);
     mbar_expect_tx(&wbar, 2 * kW1oBytes2);
-    bulk_g2s(W_hi, w1_hi, kW1oBytes2, &wbar);
-    bulk_g2s(W_lo, w1_lo, kW1oBytes2, &wbar);
+    bulk_g2s(W_hi, a.w16_hi, kW1oBytes2, &wbar);
+    bulk_g2s(W_lo, a.w16_lo, kW1oBytes2, &wbar);
   }
   for (int i = t; i < 32; i += NT) reinterpret_cast<float4*>(W2c)[i] = reinterpret_cast<const float4*>(a.W2cT)[i];
   if (t < 4) LS[t] = 0.f;
@@ -113,8 +116,8 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       for (int c = 0; c < 3; ++c) {
         float pe[16];
         oneblob16(x[c], pe);
-        put_chunk_img(X_hi, X_lo, 2 * c, cs, row, pe, IMG2(x2p, 14, 2 * c));
-        put_chunk_img(X_hi, X_lo, 2 * c + 1, cs, row, pe + 8, IMG2(x2p, 14, 2 * c + 1));
+        put_chunk_f16_img(X_hi, X_lo, 2 * c, cs, row, pe, IMG2(x2p, 14, 2 * c));
+        put_chunk_f16_img(X_hi, X_lo, 2 * c + 1, cs, row, pe + 8, IMG2(x2p, 14, 2 * c + 1));
       }
     } else {
       {
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
         occ = lat[0];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          put_chunk_img(X_hi, X_lo, 6 + c, cs, row, lat + 1 + 8 * c, IMG2(x2p, 14, 6 + c));
+          put_chunk_f16_img(X_hi, X_lo, 6 + c, cs, row, lat + 1 + 8 * c, IMG2(x2p, 14, 6 + c));
       }
       {
         float ft[32];
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          put_chunk_img(X_hi, X_lo, 10 + c, cs, row, ft + 8 * c, IMG2(x2p, 14, 10 + c));
+          put_chunk_f16_img(X_hi, X_lo, 10 + c, cs, row, ft + 8 * c, IMG2(x2p, 14, 10 + c));
       }
     }
   } else {
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   // ---- forward GEMM: H = X . W1^T  (A K-major: LBO = chunk stride, SBO = 128; B K-major: LBO = 1024, SBO = 128)
   if (t == 0) {
     mbar_wait(&wbar, 0);   // weights landed
-    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    const uint32_t idesc = umma_idesc_f16(128, 64, 0, 0, 0, 0);   // fp16 hi / lo halves
     for (int mt = 0; mt < MT; ++mt) {
       const uint32_t d = tmem_d + mt * 112;
 #pragma unroll 1
@@ -202,6 +205,11 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   }
   mbar_wait_cta(&bar, 0);
   tc_fence_after();
+  if (t == 0 && !a.fwd_only) {   // the forward GEMM has consumed the fp16 weight tile: fetch the bf16 halves over it
+    mbar_expect_tx(&wbar, 2 * kW1oBytes2);
+    bulk_g2s(W_hi, w1_hi, kW1oBytes2, &wbar);
+    bulk_g2s(W_lo, w1_lo, kW1oBytes2, &wbar);
+  }
   // this thread's half of the hidden row: group 0 colour units, group 1 logit units
   const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((row >> 7) * 112);
   float h[32];
@@ -459,6 +467,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   __syncthreads();
   if (t == 0) {
     tc_fence_after();
+    mbar_wait(&wbar, 1);   // bf16 weight halves landed
     const uint32_t idesc = umma_idesc_bf16(128, 112, 0, 1);
     for (int mt = 0; mt < MT; ++mt) {
       const uint32_t d = tmem_d + mt * 112;
@@ -579,7 +588,9 @@ void pick_ray_block_any(int S, int& T, int& RPC) { pick_ray_block_tc2(S, T, RPC)
 
 int launch_ray_tc(const RayArgs& ra, const float* color, const float* logit, uint4* w1_hi, uint4* w1_lo, bool prep,
                   int64_t n_rays_chunk, cudaStream_t st) {
-  if (prep) k_prep_w1o_tc<<<(14 * 64 + 127) / 128, 128, 0, st>>>(color, logit, w1_hi, w1_lo);
+  if (prep)
+    k_prep_w1o_tc<<<(14 * 64 + 127) / 128, 128, 0, st>>>(color, logit, w1_hi, w1_lo, const_cast<uint4*>(ra.w16_hi),
+                                                         const_cast<uint4*>(ra.w16_lo));
   return launch_ray_tc2(ra, w1_hi, w1_lo, n_rays_chunk, st);
 }
 

@@ -835,7 +835,8 @@ struct RenderWs {
   int *hist, *slot_start, *cursor, *ray_start, *rays_sorted;
   float *WTc, *WTe, *W1T2, *W2cT;
   uint4 *W1o_hi, *W1o_lo;   // bf16 hi / lo chunk tiles of the colour|logit layer-1 weights (tcgen05 path)
-  uint4 *wc_tc, *we_tc;     // bf16 hi / lo tiles of the coarse net and of every class expert (1024 uint4 each)
+  uint4 *W1o16_hi, *W1o16_lo;   // the same weights as fp16 halves (forward GEMM)
+  uint4 *wc_tc, *we_tc;     // prepared tiles of the coarse net and of every class expert (kNetTc uint4 each)
   int *perm, *tile_class;
   float *fine36, *coarse36, *dfine36;
   float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf, *Jst;
@@ -862,8 +863,10 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.W2cT = c.take<float>(128);
   w.W1o_hi = c.take<uint4>(14 * 64);
   w.W1o_lo = c.take<uint4>(14 * 64);
-  w.wc_tc = c.take<uint4>(1024);
-  w.we_tc = c.take<uint4>((int64_t)1024 * (map ? nci : 0) + 4);
+  w.W1o16_hi = c.take<uint4>(14 * 64);
+  w.W1o16_lo = c.take<uint4>(14 * 64);
+  w.wc_tc = c.take<uint4>(kNetTc);
+  w.we_tc = c.take<uint4>((int64_t)kNetTc * (map ? nci : 0) + 4);
   w.perm = c.take<int>(map ? w.Q : 4);
   w.tile_class = c.take<int>(w.tiles);
   w.fine36 = c.take<float>(Pc * kOutP);
@@ -1079,7 +1082,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.N_total = Ntot; ra.ray0 = ray0; ra.Nc = nc; ra.B = B;
     ra.rays_o = a->rays_o; ra.rays_d = a->rays_d; ra.z = a->z_vals; ra.gt_color = a->gt_color;
     ra.gt_depth = a->gt_depth; ra.gt_label = a->gt_label; ra.mask = map ? nullptr : a->mask; ra.features = a->features;
-    ra.fine36 = pa.fine36; ra.W1T2 = w.W1T2; ra.W2cT = w.W2cT; ra.logit = a->logit; ra.counts = w.counts;
+    ra.fine36 = pa.fine36; ra.w16_hi = w.W1o16_hi; ra.w16_lo = w.W1o16_lo; ra.W1T2 = w.W1T2; ra.W2cT = w.W2cT; ra.logit = a->logit; ra.counts = w.counts;
     ra.lam_p = a->lambda_p; ra.lam_d = a->lambda_d; ra.lam_l = a->lambda_l;
     ra.pred_color = a->pred_color; ra.pred_depth = a->pred_depth; ra.pred_var = a->pred_var;
     ra.pred_logits = a->pred_logits; ra.raw = w.raw; ra.err = w.counts + cErr; ra.dfine36 = pa.dfine36; ra.d_features = a->d_features;
@@ -1198,7 +1201,7 @@ int dns_render_counts(const dns_render_args* a, int32_t* counts4, void* stream) 
 int64_t dns_tv_workspace_bytes(int n) {
   int64_t n3 = (int64_t)n * n * n;
   int64_t Q = ((n3 + kTile - 1) / kTile) * kTile;
-  return 4096 + 16384 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + 40)) + 10 * 256;
+  return 4096 + 32768 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + 40)) + 10 * 256;
 }
 
 int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
@@ -1227,7 +1230,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   float* Hc = c.take<float>(Q * 32);
   float* dHc = c.take<float>(Q * 64);
   float* dOc = c.take<float>(Q * 40);   // fp32 rows of 36, or the 5-chunk tile image of the tcgen05 path
-  uint4* wc_tc = c.take<uint4>(1024);
+  uint4* wc_tc = c.take<uint4>(kNetTc);
   const bool tc = !a->use_simt;
   static unsigned long long seen = 0;
   if (first_call_on_device(seen)) {

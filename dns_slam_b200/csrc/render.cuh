@@ -27,6 +27,8 @@ struct RayArgs {
   const float* W1T2;
   const float* W2cT;
   const float* logit;  // tcnn layout; W2l = logit + 32*112, [Cpad][32]
+  const uint4* w16_hi; // fp16 hi / lo halves of the [64 x 112] colour|logit layer-1 weights (forward GEMM of the tcgen05 path)
+  const uint4* w16_lo;
   const int* counts;
   int* err;       // counts[cErr]: 3 = label outside [0, n_class)
   float lam_p, lam_d, lam_l;
@@ -193,7 +195,11 @@ __device__ __forceinline__ void opacity_masks(float zv, float d, float trunc, fl
 }
 
 
-// tcgen05 point kernels (point_tc.cu); wc / we: bf16 hi/lo weight tiles, 1024 uint4 per net
+// tcgen05 point kernels (point_tc.cu); wc / we: prepared weight tiles, kNetTc uint4 per net:
+//   W1 hi [10][32] | W1 lo | W2 hi [4][48] | W2 lo  as bf16 halves (backward GEMMs), then  W1 hi | W1 lo  as fp16 halves
+//   (the forward layer-1 GEMM, whose result decides the ReLU: tc_common.cuh put_chunk_f16_img)
+constexpr int kNetTc = 1664;
+constexpr int kNetW1F16 = 1024;
 int prep_nets_tc(const float* coarse, const float* experts, int n_experts, uint4* wc, uint4* we, cudaStream_t st);
 int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);
 int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st);

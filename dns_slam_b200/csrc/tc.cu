@@ -35,7 +35,7 @@ namespace dns {
 // unrolled load batch so that all loads of the row are in flight before the first conversion.
 template <int MAXQ>
 __device__ __forceinline__ void stage_row(const float* __restrict__ row, int quads, bool valid, unsigned char* hi_tile,
-                                          unsigned char* lo_tile, int point) {
+                                          unsigned char* lo_tile, int point, bool f16 = false) {
   float4 v[MAXQ];
   const float4* r4 = reinterpret_cast<const float4*>(row);
 #pragma unroll
@@ -44,7 +44,8 @@ __device__ __forceinline__ void stage_row(const float* __restrict__ row, int qua
   for (int c = 0; c < MAXQ / 2; ++c) {
     if (2 * c < quads) {
       uint4 hi, lo;
-      split8(v[2 * c], v[2 * c + 1], hi, lo);
+      if (f16) split8_f16(v[2 * c], v[2 * c + 1], hi, lo);
+      else split8(v[2 * c], v[2 * c + 1], hi, lo);
       *reinterpret_cast<uint4*>(hi_tile + c * 2048 + point * 16) = hi;
       *reinterpret_cast<uint4*>(lo_tile + c * 2048 + point * 16) = lo;
     }
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kTile) k_dw_gemm_tc(DwArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
-  const uint32_t idesc = umma_idesc_bf16(128, nC16, 1, 1);
+  const uint32_t idesc = umma_idesc_f16(128, nC16, 1, 1, a.l_f16 ? 0 : 1, a.c_f16 ? 0 : 1);
   const int lq = (a.nL + 3) >> 2, cq = (a.nC + 3) >> 2;
   uint32_t phase = 0;
   int cur_class = -1;
@@ -131,8 +132,8 @@ __global__ void __launch_bounds__(kTile) k_dw_gemm_tc(DwArgs a) {
     if (cls < 0) continue;
     const int64_t p = (int64_t)t * kTile + tid;
     const bool valid = p < a.n_rows;
-    stage_row<LQ>(a.L + p * a.ldl, lq, valid, L_hi, L_lo, tid);
-    stage_row<CQ>(a.Cc + p * a.ldcc, cq, valid, C_hi, C_lo, tid);
+    stage_row<LQ>(a.L + p * a.ldl, lq, valid, L_hi, L_lo, tid, a.l_f16 != 0);
+    stage_row<CQ>(a.Cc + p * a.ldcc, cq, valid, C_hi, C_lo, tid, a.c_f16 != 0);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -355,6 +356,7 @@ int launch_dw_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, i
   a.sc0 = a_on_lanes ? 1 : ldc;
   a.cls0 = c_stride;
   a.sl1 = a.sc1 = a.cls1 = 0;
+  a.l_f16 = a.c_f16 = 0;
   return launch_dw_gemm_tc2(a, st);
 }
 
@@ -427,6 +429,29 @@ int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, 
   cudaFree(ci);
   return e;
 }
+// test entry: the same product with fp16 hi/lo (22 mantissa bits) or bf16 hi/lo operand halves.  Both operands of one
+// tcgen05.mma kind::f16 must have the SAME element format: a mixed fp16 x bf16 descriptor traps with "illegal
+// instruction" on B200 (measured, round 2), so it is rejected here.  Needs M >= N (A goes to the TMEM lanes).
+int dns_debug_gemm_fmt(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows, int a_f16, int b_f16,
+                       float* C, void* stream) {
+  using namespace dns;
+  if (M < N) {
+    set_error("debug_gemm_fmt: needs M >= N");
+    return DNS_ERR_ARG;
+  }
+  if ((a_f16 != 0) != (b_f16 != 0)) {
+    set_error("debug_gemm_fmt: tcgen05.mma kind::f16 needs both operands in the same element format");
+    return DNS_ERR_UNSUPPORTED;
+  }
+  DwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = A; a.ldl = lda; a.nL = M; a.Cc = B; a.ldcc = ldb; a.nC = N; a.n_rows = rows;
+  a.n_tiles_host = (int)((rows + kTile - 1) / kTile);
+  a.out0 = C; a.split = N; a.sl0 = N; a.sc0 = 1;
+  a.l_f16 = a_f16; a.c_f16 = b_f16;
+  return launch_dw_gemm_tc2(a, (cudaStream_t)stream);
+}
+
 // debug / test entry: C[m][n] (ldc = N) += sum_p A[p][m] B[p][n] through the tcgen05 kernel
 int dns_debug_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows, float* C, void* stream) {
   int tiles = (int)((rows + dns::kTile - 1) / dns::kTile);

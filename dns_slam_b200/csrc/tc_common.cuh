@@ -189,11 +189,13 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
       a0 += wt * v[c].x;
       a1 += wt * v[c].y;
     }
-    const uint32_t h = cvt_bf16x2(a0, a1);
-    const uint32_t lo = cvt_bf16x2(a0 - __uint_as_float(h << 16), a1 - __uint_as_float(h & 0xffff0000u));
+    // fp16 hi / lo halves: the tile feeds the GEMM whose result decides the ReLU (22 mantissa bits, see put_chunk_f16_img)
+    const __half2 hh = __floats2half2_rn(a0, a1);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(a0 - back.x, a1 - back.y);
     const int off = (6 + (l >> 2)) * 2048 + row * 16 + (l & 3) * 4;
-    *reinterpret_cast<uint32_t*>(X_hi + off) = h;
-    *reinterpret_cast<uint32_t*>(X_lo + off) = lo;
+    *reinterpret_cast<__half2*>(X_hi + off) = hh;
+    *reinterpret_cast<__half2*>(X_lo + off) = ll;
   }
 }
 template <int L0, int L1, bool PAIR = true>
@@ -261,6 +263,40 @@ __device__ __forceinline__ void store_chunk_img(const float* v8, uint4* g_hi, ui
   split8(make_float4(v8[0], v8[1], v8[2], v8[3]), make_float4(v8[4], v8[5], v8[6], v8[7]), h, l);
   *g_hi = h;
   *g_lo = l;
+}
+// Layer-1 INPUT tiles (X of the point kernels, X of the ray kernel): the shared-memory operand is split into fp16 hi + lo
+// halves (11 + 11 mantissa bits) because the GEMM it feeds decides on which side of the ReLU a hidden unit lands -- with
+// bf16 halves (8 + 8 bits) about one pre-activation in 10^5 flipped against an fp32 evaluation, which is invisible in
+// the forward pass but switches that unit's sub-gradient (round-1 parity outliers).  The inputs are bounded (OneBlob in
+// [0,1], grid features, latents): fp16's range is enough, as it is for the reference's fp16 tinycudann networks.  The
+// global tile IMAGE of the same values stays bf16 hi + lo: it meets gradients (full fp32 range) in the weight-gradient
+// GEMM, and both operands of one tcgen05.mma must share the element format (a mixed descriptor traps on B200).
+__device__ __forceinline__ void put_chunk_f16_img(unsigned char* hi_tile, unsigned char* lo_tile, int chunk, int cs, int point,
+                                                  const float* v8, uint4* g_hi, uint4* g_lo) {
+  const float4 a = make_float4(v8[0], v8[1], v8[2], v8[3]), b = make_float4(v8[4], v8[5], v8[6], v8[7]);
+  uint4 h, l;
+  split8_f16(a, b, h, l);
+  *reinterpret_cast<uint4*>(hi_tile + chunk * cs + point * 16) = h;
+  *reinterpret_cast<uint4*>(lo_tile + chunk * cs + point * 16) = l;
+  if (g_hi) {
+    split8(a, b, h, l);
+    *g_hi = h;
+    *g_lo = l;
+  }
+}
+// one fp16 hi / lo chunk of a tile back to 8 floats (hi + lo is exact to 22 bits)
+__device__ __forceinline__ void f16_chunk_to_floats(const unsigned char* hi_tile, const unsigned char* lo_tile, int chunk, int cs,
+                                                    int point, float (&v)[8]) {
+  const uint4 h = *reinterpret_cast<const uint4*>(hi_tile + chunk * cs + point * 16);
+  const uint4 l = *reinterpret_cast<const uint4*>(lo_tile + chunk * cs + point * 16);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    v[2 * i] = a.x + b.x;
+    v[2 * i + 1] = a.y + b.y;
+  }
 }
 // same, plus a copy of both halves into a global tile image for the weight-gradient GEMMs (tc.cu: k_dw_img).
 // Within one chunk neighbouring rows are 16 B apart, so a warp writes 512 contiguous bytes per store.

@@ -2,6 +2,7 @@
 // shared-memory and instruction descriptors).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,6 +22,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with a per-operand element format: 0 = fp16, 1 = bf16 (bits [7,10) / [10,13) of the descriptor)
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int a_bf16, int b_bf16) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -94,6 +100,23 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
     const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);
     const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
     l[i] = cvt_bf16x2(r0, r1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// fp32 -> fp16 hi / lo halves: 11 + 11 mantissa bits, |x - hi - lo| <= max(2^-23 |x|, 2^-25) (lo may be subnormal).
+// Used for the operands that feed a ReLU decision (layer-1 inputs and weights: bounded values); gradients keep bf16 (range).
+__device__ __forceinline__ void split8_f16(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

@@ -272,11 +272,14 @@ class FrameBatchPlan:
         off, n = self.draw_layout[name]
         return buf[off:off + n].view(dtype)
 
-    def make_host_draws(self, gen, pinned=True, return_tape=False):
+    def make_host_draws(self, gen, pinned=True, return_tape=False, shared_gen=None):
         """Seeded host-side draws of one iteration in the reference's order: per frame one uniform
         ``randint`` over the window, one ``randint`` per class with more than one pixel, ``rand(n_surface)`` twice; then
         the two TV draws.  With ``return_tape`` also the raw draws as an oracle ``DrawTape`` item list (the reference's
-        call order; meaningful for a single rank)."""
+        call order; meaningful for a single rank).  ``shared_gen``: generator for the draws that belong to the whole
+        batch rather than to a ray (the per-frame surface offsets and the TV lattice): every rank of a sharded batch must
+        pass one with the SAME seed, ``gen`` then only feeds the rank's own pixel draws."""
+        sg = shared_gen if shared_gen is not None else gen
         from . import fused as _fused
         buf = torch.zeros(self.draw_bytes, dtype=torch.uint8)
         if pinned:
@@ -301,14 +304,14 @@ class FrameBatchPlan:
                 dr = torch.randint(count, (hi - lo,), generator=gen)
                 idx[(b - a) + lo - c:(b - a) + hi - c] = dr
                 tape.append(("randint", dr))
-            ts = torch.rand(self.nf, generator=gen)
-            tz = torch.rand(self.nf, generator=gen)
+            ts = torch.rand(self.nf, generator=sg)
+            tz = torch.rand(self.nf, generator=sg)
             tape += [("rand", ts.clone()), ("rand", tz.clone())]
             if not bool((ts == 0.5).any()):
                 ts[self.nf // 2 + 1] = 0.5                                # common.py:572-573
             self.draw_view(buf, f"ts{f}", torch.float32).copy_(ts)
             self.draw_view(buf, f"tz{f}", torch.float32).copy_(tz)
-        r3, r113 = torch.rand(3, generator=gen), torch.rand(1, 1, 1, 3, generator=gen)
+        r3, r113 = torch.rand(3, generator=sg), torch.rand(1, 1, 1, 3, generator=sg)
         tape += [("rand", r3), ("rand", r113)]
         off, jit = _fused.tv_offsets(self.bound, self.smooth_pts, r3, r113)
         self.draw_view(buf, "tv", torch.float64).copy_(torch.cat((off, jit)))
@@ -418,8 +421,8 @@ class MappingFrameStep:
     def draw_view(self, buf, name, dtype):
         return self.plan.draw_view(buf, name, dtype)
 
-    def make_host_draws(self, gen, pinned=True, return_tape=False):
-        return self.plan.make_host_draws(gen, pinned, return_tape)
+    def make_host_draws(self, gen, pinned=True, return_tape=False, shared_gen=None):
+        return self.plan.make_host_draws(gen, pinned, return_tape, shared_gen)
 
     def upload(self, host_buf, stream=None):
         """ONE host-to-device copy of an iteration's draws (pinned ``host_buf`` -> asynchronous)."""

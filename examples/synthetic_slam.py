@@ -48,12 +48,22 @@ def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_gra
     est = [poses[0].clone()]
     keyframes = [0]
     log = []
+    import time
+    spent = {"track": [], "map": []}        # wall seconds per tracked frame / mapping call (device work included)
+
+    def timed(kind, fn, *a, **kw):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn(*a, **kw)
+        torch.cuda.synchronize()
+        spent[kind].append(time.perf_counter() - t0)
+        return r
     for f in range(n_frames):
         if f % map_every != 0 and f + 1 < n_frames:      # tracked-only frame (mapping.every_frame)
             tracker_dec.copy_weights_from(shared)
             td = bench_util.tracking_draws(cam, s["tracking_pixels"], track_iters, seed=seed + 100 + f)
-            best, best_loss, hist = slam.track_frame(tracker, frames[f + 1], torch.inverse(est[f]), pair_feats(f), est[f].clone(),
-                                                     track_iters, s["cam_lr"], lambda it: td[it], use_graph=use_graph)
+            best, best_loss, hist = timed("track", slam.track_frame, tracker, frames[f + 1], torch.inverse(est[f]), pair_feats(f),
+                                          est[f].clone(), track_iters, s["cam_lr"], lambda it: td[it], use_graph=use_graph)
             est.append(slam.c2w_from_quad_T(best[:4], best[4:]).cpu())
             log.append(("track", f + 1, float(hist[0]), float(best_loss)))
             continue
@@ -72,9 +82,9 @@ def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_gra
         refer = dict(kf_idx=[[-1]] * len(window), est_c2w=[[est[k].to(dev)] for k in window])
         scene = dict(cam=cam, frames=target["frames"], class_tables=target["class_tables"])
         md, tv = bench_util.mapping_draws(scene, s["mapping_pixels"], map_iters, seed=seed + 10 * f)
-        quads, Ts, losses = slam.map_optimize(mapper, target, refer, [feats[k] for k in window], [est[k] for k in window],
-                                              map_iters, s["lr"], s["BA_cam_lr"], len(window) > 1, [],
-                                              lambda it: md[it], lambda it: tv[it], use_graph=use_graph)
+        quads, Ts, losses = timed("map", slam.map_optimize, mapper, target, refer, [feats[k] for k in window],
+                                  [est[k] for k in window], map_iters, s["lr"], s["BA_cam_lr"], len(window) > 1, [],
+                                  lambda it: md[it], lambda it: tv[it], use_graph=use_graph)
         for k, q, t in zip(window, quads, Ts):
             est[k] = slam.c2w_from_quad_T(q.detach(), t.detach()).cpu()
         log.append(("map", f, float(losses["p_loss"]), float(losses["d_loss"]),
@@ -87,8 +97,8 @@ def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_gra
         tracker_dec.copy_weights_from(shared)
         guess = est[f].clone()
         td = bench_util.tracking_draws(cam, s["tracking_pixels"], track_iters, seed=seed + 100 + f)
-        best, best_loss, hist = slam.track_frame(tracker, frames[f + 1], torch.inverse(est[f]), pair_feats(f), guess, track_iters,
-                                                 s["cam_lr"], lambda it: td[it], use_graph=use_graph)
+        best, best_loss, hist = timed("track", slam.track_frame, tracker, frames[f + 1], torch.inverse(est[f]), pair_feats(f), guess,
+                                      track_iters, s["cam_lr"], lambda it: td[it], use_graph=use_graph)
         est.append(slam.c2w_from_quad_T(best[:4], best[4:]).cpu())
         log.append(("track", f + 1, float(hist[0]), float(best_loss)))
     # ---- checkpoint (mapping.py:1119-1145) and one rendered frame (mapping.py:636-690)
@@ -106,7 +116,10 @@ def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_gra
             else:
                 print("track frame %d  loss %.4f (first iteration) -> %.4f (best)" % (f, u, v))
         print("rendered", tuple(color.shape), "checkpoint", os.path.join(out_dir, "model.pt"))
-    return dict(log=log, est=est, gt=poses, render=(color, depth, label), out_dir=out_dir, decoder=shared)
+    timings = {k: {"calls": len(v), "ms_per_call": 1e3 * sum(v) / max(len(v), 1)} for k, v in spent.items()}
+    timings["track"]["ms_per_iteration"] = timings["track"]["ms_per_call"] / max(track_iters, 1)
+    timings["map"]["ms_per_iteration"] = timings["map"]["ms_per_call"] / max(map_iters, 1)
+    return dict(log=log, est=est, gt=poses, render=(color, depth, label), out_dir=out_dir, decoder=shared, timings=timings)
 
 
 if __name__ == "__main__":

@@ -372,6 +372,12 @@ int dns_adam_multi(const dns_adam_seg* segs_dev, int n_segs, int64_t max_n, int*
 int dns_debug_gemm_tc(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows,
                       float* C, void* stream);
 
+/* Same with the operand halves as fp16 (1: 11 + 11 mantissa bits, for bounded values that feed a ReLU decision) or bf16
+ * (0: 8 + 8 bits, full fp32 range, for gradients).  a_f16 must equal b_f16: a mixed-format tcgen05.mma kind::f16 traps
+ * on B200 (DNS_ERR_UNSUPPORTED).  M >= N. */
+int dns_debug_gemm_fmt(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows, int a_f16, int b_f16,
+                       float* C, void* stream);
+
 /* Test entry of the tile-image GEMM pipeline (cp.async.bulk -> tcgen05.mma): same contract as
  * dns_debug_gemm_tc, operands converted to bf16 hi/lo tile images of RS rows first. */
 int dns_debug_gemm_img(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t rows,

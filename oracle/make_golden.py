@@ -311,12 +311,86 @@ def stem_case(seed=31):
                 state2=state2, out_eval=out3)
 
 
+def uniq_class_case(C, shape="tiny", n_class=6, seed=41):
+    """utils/common.py:364-403 (get_samples_by_uniq_class, used by Mapper.decoder_init): rays spread over a GIVEN class
+    list.  The image passed in carries the flat pixel index in channel 0, so the returned samples reveal the indices the
+    reference picked.  Cases: all classes present; a class with ONE pixel (repeated, no draw); an ABSENT class (skipped)."""
+    gen = torch.Generator().manual_seed(seed)
+    cam = syn.camera(shape)
+    H, W = cam["H"], cam["W"]
+    fr = syn.frame(shape, syn.trajectory(shape, 4)[1], gen, n_class=n_class)
+    label = fr["label"].clone()
+    label[3, 7] = n_class + 5                       # a class with exactly one pixel
+    img = torch.stack((torch.arange(H * W, dtype=torch.float64).reshape(H, W), fr["depth"].double(), label.double()), -1)
+    R, T = torch.eye(3), torch.zeros(3)
+    cases = []
+    for n, class_list in ((30, [0, 2, 5]), (31, [4, n_class + 5, 1]), (29, [3, 77, 0, 2])):
+        with Recorder() as rec:
+            _, _, smp = C.get_samples_by_uniq_class(0, H, 0, W, n, H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"], R, T,
+                                                    img, class_list, "cpu")
+        cases.append(dict(n=n, class_list=class_list, tape=rec.items, indices=smp[:, 0].to(torch.int64),
+                          labels=smp[:, 2].to(torch.int64)))
+    return dict(meta=dict(shape=shape, n_class=n_class, seed=seed, pose_index=1, single=(3, 7, n_class + 5)), cases=cases)
+
+
+def decoder_init_case(C, D, M, shape="tiny", n_class=6, seed=43, n_iters=3, decoder_idx=(1, 4)):
+    """slams/mapping.py:764-836 (Mapper.decoder_init) driven on the reference's own code for ``n_iters`` iterations
+    (the only source patch besides P1: ``range(100)`` -> ``range(n_iters)``): warm-up of freshly created class experts,
+    Adam over decoder + new experts.  Stored: the recorded draws, the pixel features the (stubbed) encoder returned and
+    every parameter after the last Adam step."""
+    s = syn.SHAPES[shape]
+    gen = torch.Generator().manual_seed(seed)
+    bound, odec, oexp = build_models(shape, n_class, seed, expert_classes=decoder_idx)
+    dec = D.Decoder(syn.model_cfg(shape), bound, n_class=n_class)
+    dec.load_state_dict(odec.state_dict())
+    cam = syn.camera(shape)
+    pose = syn.trajectory(shape, 6)[2]
+    fr = syn.frame(shape, pose, gen, n_class=n_class)
+    feat = syn.pixel_features(shape, 1, gen)                    # [1,64,h,w]
+    mp = object.__new__(M.Mapper)
+    mp.device = "cpu"
+    mp.bound = bound
+    for k in ("H", "W", "fx", "fy", "cx", "cy"):
+        setattr(mp, k, cam[k])
+    mp.K = cam["K"]
+    mp.n_samples_ray, mp.n_surface_ray = 32, 15
+    mp.decoder, mp.hidden_dim = dec, 32
+    mp.lr = s["lr"]
+    mp.lambda_p, mp.lambda_d, mp.lambda_l = s["lambda_color"], s["lambda_depth"], s["lambda_label"]
+    mp.lambda_fs, mp.lambda_opacity, mp.lambda_sm = s["lambda_fs"], s["lambda_opacity"], 0.05
+    mp.fine_decoders = {}
+    for c, net in oexp.items():
+        e = tcnn_standin.Network(80, 33, dict(rp._MLP_CFG))
+        e.load_state_dict(net.state_dict())
+        mp.fine_decoders[c] = e
+    mp.cfg = {"training": {"smooth_pts": s["smooth_pts"], "opacity_sigma": s["opacity_sigma"]}}
+    mp.encoder = lambda images: feat[None]                      # P4: the frozen ResNet is an input here
+    src = textwrap.dedent(inspect.getsource(M.Mapper.decoder_init)).replace("range(100)", "range(%d)" % n_iters)
+    assert "range(%d)" % n_iters in src
+    ns = {}
+    exec(src, M.__dict__, ns)
+    with Recorder() as rec:
+        ns["decoder_init"](mp, list(decoder_idx), fr["color"], fr["depth"], fr["label"], pose, pose)
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    table = sd.pop("pe_fn.grid_fn.params")
+    return dict(meta=dict(shape=shape, n_class=n_class, seed=seed, n_iters=n_iters, decoder_idx=list(decoder_idx),
+                          pose_index=2, lambda_sm=0.05, n_rays=300),
+                features=feat, tape=rec.items, params=sd, table=grad_summary(table), table_full_sum=table.double().sum(),
+                experts={c: e.params.detach().clone() for c, e in mp.fine_decoders.items()})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
     C, D, T, M = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if sys.argv[1:] == ["init"]:     # only the decoder_init / uniq-class vectors (round 2; the other files stay byte-identical)
+        torch.save(uniq_class_case(C), os.path.join(out_dir, "uniq_class_tiny.pt"))
+        torch.save(decoder_init_case(C, D, M), os.path.join(out_dir, "decoder_init_tiny.pt"))
+        for f in ("uniq_class_tiny.pt", "decoder_init_tiny.pt"):
+            print(f, os.path.getsize(os.path.join(out_dir, f)))
+        return
     if sys.argv[1:] == ["stem"]:     # only the stem vectors (the other files stay byte-identical)
         torch.save(stem_case(), os.path.join(out_dir, "stem_tiny.pt"))
         print("stem_tiny.pt", os.path.getsize(os.path.join(out_dir, "stem_tiny.pt")))
@@ -325,6 +399,8 @@ def main():
     torch.save(kernels_case(C), os.path.join(out_dir, "kernels.pt"))
     torch.save(tracking_case(C, D, T), os.path.join(out_dir, "tracking_tiny.pt"))
     torch.save(mapping_case(C, D, M), os.path.join(out_dir, "mapping_tiny.pt"))
+    torch.save(uniq_class_case(C), os.path.join(out_dir, "uniq_class_tiny.pt"))
+    torch.save(decoder_init_case(C, D, M), os.path.join(out_dir, "decoder_init_tiny.pt"))
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -100,3 +100,24 @@ def test_fused_merge_matches_operator_chain(monkeypatch):
         a, b = res["fused"][k].double(), res["ops"][k].double()
         err = float((a - b).norm() / b.norm())
         assert err < 1e-3, f"{name}: relative error {err:.3e}"
+
+
+@pytest.mark.parametrize("f16,tol", [(0, 2e-5), (1, 1e-6)])
+def test_dw_gemm_operand_formats(f16, tol):
+    """kind::f16 with bf16 hi + lo halves (gradient GEMMs: full fp32 range, ~2^-17) and with fp16 hi + lo halves (22
+    mantissa bits: operands that feed a ReLU decision), against float64 matmul.  A mixed fp16 x bf16 instruction traps
+    on B200 (measured in round 2), so the entry point refuses it."""
+    from dns_slam_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11 + f16)
+    rows, M, N = 1500, 112, 64
+    A = (torch.randn(rows, M, generator=g) * 0.7).to(dev)
+    B = (torch.randn(rows, N, generator=g) * (0.5 if f16 else 1e-6)).to(dev)    # bf16: gradient-sized values
+    C = torch.zeros(M, N, device=dev)
+    L = _lib.lib()
+    _lib.check(L.dns_debug_gemm_fmt(_lib.ptr(A), M, M, _lib.ptr(B), N, N, rows, f16, f16, _lib.ptr(C), _lib.stream()))
+    torch.cuda.synchronize()
+    want = A.double().t() @ B.double()
+    err = float((C.double() - want).norm() / want.norm())
+    assert err < tol, f"relative error {err:.3e}"
+    assert L.dns_debug_gemm_fmt(_lib.ptr(A), M, M, _lib.ptr(B), N, N, rows, 1, 0, _lib.ptr(C), _lib.stream()) != 0
