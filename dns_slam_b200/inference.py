@@ -108,3 +108,62 @@ def query_points(decoder, points, feature_fn, stage="fine", points_batch_size=50
         occ.append(v[:, 3])
         labs.append(l)
     return torch.cat(occ, 0), (torch.cat(labs, 0) if labs and labs[0] is not None else None)
+
+
+def get_2d_feature(cam, decoder, points, keyframes):
+    """``Mesher.get_2d_feature`` (slams/meshing.py:294-377): merged pixel features [P,32] and labels [P] of free points
+    from the key frames that see them -- the producer of ``eval_points``' ``pixel_pts`` / ``gt_label_pts`` in a mesh
+    extraction.  keyframes: list of dict(est_c2w [4,4], gt_label [H,W], gt_depth [H,W], features_cl [1,h,w,64] = the
+    channels-last stem output of the key frame's colour image, ``encoder.ResNet.forward_cl``).  Projection, masks, rounding
+    and the truncation test follow the reference line by line (fp32 torch ops on the device); the 209 MB/key-frame
+    up-sample of meshing.py:356 is replaced by the 4-tap bilinear fetch of the half-resolution map at the rounded pixel
+    (what ``dns_feature_gather`` does) and Merge runs as the fused kernel (``dns_merge_fwd``)."""
+    from . import fused
+    H, W = cam["H"], cam["W"]
+    dev = points.device
+    K = cam["K"].to(dev, torch.float32)
+    P = points.shape[0]
+    points = points.to(torch.float32)
+    pixel_pts = torch.zeros(P, 32, device=dev)
+    label_pts = torch.zeros(P, device=dev)
+    count_pts = torch.zeros(P, device=dev)
+    homo = torch.cat([points, torch.ones_like(points[:, :1])], dim=1).reshape(-1, 4, 1)
+    with torch.no_grad():
+        for kf in keyframes:
+            c2w = kf["est_c2w"].to(dev, torch.float32)
+            w2c = torch.inverse(c2w)
+            cam_cord = (w2c @ homo)[:, :3]
+            cam_cord[:, 0] *= -1
+            uv = K @ cam_cord
+            z = uv[:, -1:] + 1e-8
+            uv = uv[:, :2] / z
+            seen = (uv[:, 0] < W) & (uv[:, 0] > 0) & (uv[:, 1] < H) & (uv[:, 1] > 0)
+            seen = (seen & (z[:, :, 0] < 0)).reshape(-1)
+            uv_ = uv[seen, :, 0]
+            if uv_.numel() == 0:
+                continue
+            p = points[seen, :]
+            uv_ = torch.round(uv_).to(torch.int64)
+            ui, vi = uv_[:, 0].clamp(0, W - 1), uv_[:, 1].clamp(0, H - 1)
+            label_seen = kf["gt_label"].to(dev)[vi, ui]
+            depth_seen = kf["gt_depth"].to(dev)[vi, ui]
+            depth_proj = -z[seen].reshape(-1)
+            trunc = ((~(depth_proj < depth_seen * 0.95)) & (~(depth_proj > depth_seen * 1.05))).to(torch.float32)
+            # F.interpolate(..., bilinear, align_corners=True) at the integer pixel (vi, ui) of the half-resolution map
+            fm = kf["features_cl"][0]
+            h, w = fm.shape[0], fm.shape[1]
+            fy = vi.to(torch.float32) * (float(h - 1) / float(H - 1) if H > 1 else 0.0)
+            fx = ui.to(torch.float32) * (float(w - 1) / float(W - 1) if W > 1 else 0.0)
+            y0, x0 = fy.to(torch.int64), fx.to(torch.int64)
+            y1, x1 = y0 + (y0 < h - 1).to(torch.int64), x0 + (x0 < w - 1).to(torch.int64)
+            ly1, lx1 = (fy - y0.to(torch.float32))[:, None], (fx - x0.to(torch.float32))[:, None]
+            ly0, lx0 = 1.0 - ly1, 1.0 - lx1
+            ft = ly0 * (lx0 * fm[y0, x0] + lx1 * fm[y0, x1]) + ly1 * (lx0 * fm[y1, x0] + lx1 * fm[y1, x1])
+            refer_p = (p - c2w[:3, 3][None, :])[None].contiguous()
+            code = fused.merge_fused(refer_p, ft[None].contiguous(), decoder.merge.decoder.params.detach(), decoder.merge.bound)
+            count_pts[seen] += trunc
+            pixel_pts[seen, :] += code * trunc[:, None]
+            label_pts[seen] = label_seen.to(torch.float32)
+        ok = count_pts > 0
+        pixel_pts[ok, :] = pixel_pts[ok, :] / count_pts[ok, None]
+    return pixel_pts, label_pts

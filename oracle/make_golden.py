@@ -379,6 +379,46 @@ def decoder_init_case(C, D, M, shape="tiny", n_class=6, seed=43, n_iters=3, deco
                 experts={c: e.params.detach().clone() for c, e in mp.fine_decoders.items()})
 
 
+def get_2d_feature_case(D, shape="tiny", n_class=6, seed=47):
+    """slams/meshing.py:294-377 run on the reference's own Mesher.get_2d_feature (open3d / skimage / trimesh are absent and
+    unused by this method: stubbed at import).  Stored: inputs that cannot be regenerated from seeds (the encoder output
+    per key frame, P4) and the method's outputs."""
+    for name in ("open3d", "skimage", "skimage.measure", "trimesh"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    import slams.meshing as ME
+    gen = torch.Generator().manual_seed(seed)
+    bound, odec, _ = build_models(shape, n_class, seed)
+    dec = D.Decoder(syn.model_cfg(shape), bound, n_class=n_class)
+    dec.load_state_dict(odec.state_dict())
+    cam = syn.camera(shape)
+    poses = syn.trajectory(shape, 6)
+    kfs, feats = [], []
+    for i in (1, 3, 4):
+        fr = syn.frame(shape, poses[i], gen, n_class=n_class)
+        ft = syn.pixel_features(shape, 1, gen)
+        feats.append(ft)
+        kfs.append({"est_c2w": poses[i].clone(), "gt_color": fr["color"], "gt_label": fr["label"], "gt_depth": fr["depth"]})
+    lo, hi = bound[:, 0].float(), bound[:, 1].float()
+    pts = lo + (hi - lo) * torch.rand(4000, 3, generator=gen)
+    # half of the points on the observed surfaces (inside the truncation band of some key frame)
+    k0 = kfs[0]
+    jj = torch.randint(0, cam["H"], (2000,), generator=gen)
+    ii = torch.randint(0, cam["W"], (2000,), generator=gen)
+    d = k0["gt_depth"][jj, ii] * (1.0 + 0.04 * (torch.rand(2000, generator=gen) - 0.5))
+    dirs = torch.stack([(ii - cam["cx"]) / cam["fx"], -(jj - cam["cy"]) / cam["fy"], -torch.ones(2000)], -1)
+    pts[:2000] = (dirs * d[:, None]) @ k0["est_c2w"][:3, :3].t() + k0["est_c2w"][:3, 3]
+    me = object.__new__(ME.Mesher)
+    me.device = "cpu"
+    for k in ("H", "W", "fx", "fy", "cx", "cy"):
+        setattr(me, k, cam[k])
+    me.K, me.hidden_dim = cam["K"], 32
+    it = iter(feats)
+    with torch.no_grad():
+        pix, lab = me.get_2d_feature(pts, kfs, "cpu", None, encoder=lambda images: next(it)[None], decoders=dec)
+    return dict(meta=dict(shape=shape, n_class=n_class, seed=seed, kf_pose=[1, 3, 4]), points=pts, features=feats,
+                pixel_pts=pix, label_pts=lab)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -388,7 +428,8 @@ def main():
     if sys.argv[1:] == ["init"]:     # only the decoder_init / uniq-class vectors (round 2; the other files stay byte-identical)
         torch.save(uniq_class_case(C), os.path.join(out_dir, "uniq_class_tiny.pt"))
         torch.save(decoder_init_case(C, D, M), os.path.join(out_dir, "decoder_init_tiny.pt"))
-        for f in ("uniq_class_tiny.pt", "decoder_init_tiny.pt"):
+        torch.save(get_2d_feature_case(D), os.path.join(out_dir, "get_2d_feature_tiny.pt"))
+        for f in ("uniq_class_tiny.pt", "decoder_init_tiny.pt", "get_2d_feature_tiny.pt"):
             print(f, os.path.getsize(os.path.join(out_dir, f)))
         return
     if sys.argv[1:] == ["stem"]:     # only the stem vectors (the other files stay byte-identical)
@@ -401,6 +442,7 @@ def main():
     torch.save(mapping_case(C, D, M), os.path.join(out_dir, "mapping_tiny.pt"))
     torch.save(uniq_class_case(C), os.path.join(out_dir, "uniq_class_tiny.pt"))
     torch.save(decoder_init_case(C, D, M), os.path.join(out_dir, "decoder_init_tiny.pt"))
+    torch.save(get_2d_feature_case(D), os.path.join(out_dir, "get_2d_feature_tiny.pt"))
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

@@ -567,6 +567,55 @@ def eval_points(decoder, experts, bound, pts, pixel_pts, gt_label_pts=None, stag
     return values, labels
 
 
+def get_2d_feature(cam, decoder, points, keyframes, hidden_dim=32):
+    """slams/meshing.py:294-377 (Mesher.get_2d_feature): pixel features and labels of free points from the key frames
+    that see them.  keyframes: list of dict(est_c2w [4,4], gt_label [H,W], gt_depth [H,W], features [1,64,h,w] = the
+    encoder output of the key frame's colour image).  Per key frame: project (x flipped, z < 0 in front), mask to the
+    image, round + clamp, truncation mask against the key frame's depth, Merge over that ONE view; the codes are averaged
+    over the key frames whose truncation mask holds, the label is the one of the LAST key frame that sees the point."""
+    H, W = cam["H"], cam["W"]
+    K = cam["K"].float()
+    P = points.shape[0]
+    pixel_pts = torch.zeros(P, hidden_dim)
+    label_pts = torch.zeros(P)
+    count_pts = torch.zeros(P)
+    for kf in keyframes:
+        c2w = kf["est_c2w"]
+        w2c = torch.inverse(c2w).float()
+        homo = torch.cat([points, torch.ones_like(points[:, :1])], dim=1).reshape(-1, 4, 1).float()
+        cam_cord = (w2c @ homo)[:, :3]
+        cam_cord[:, 0] *= -1
+        uv = K @ cam_cord.float()
+        z = uv[:, -1:] + 1e-8
+        uv = (uv[:, :2] / z).float()
+        seen = (uv[:, 0] < W) & (uv[:, 0] > 0) & (uv[:, 1] < H) & (uv[:, 1] > 0)
+        seen = (seen & (z[:, :, 0] < 0)).reshape(-1)
+        uv_ = uv[seen, :, 0]
+        p = points[seen, :]
+        if uv_.numel() == 0:
+            continue
+        uv_ = torch.round(uv_).to(torch.int64)
+        uv_[:, 0] = uv_[:, 0].clamp(0, W - 1)
+        uv_[:, 1] = uv_[:, 1].clamp(0, H - 1)
+        label_seen = kf["gt_label"][uv_[:, 1], uv_[:, 0]]
+        depth_seen = kf["gt_depth"][uv_[:, 1], uv_[:, 0]]
+        depth_proj = -z[seen].squeeze()
+        front = torch.where(depth_proj < depth_seen * 0.95, torch.ones_like(depth_seen), torch.zeros_like(depth_seen))
+        back = torch.where(depth_proj > depth_seen * 1.05, torch.ones_like(depth_seen), torch.zeros_like(depth_seen))
+        trunc = (1.0 - front) * (1.0 - back)
+        feats = F.interpolate(kf["features"], size=[H, W], mode="bilinear", align_corners=True)
+        ft = feats[0, :, uv_[:, 1], uv_[:, 0]].permute(1, 0).unsqueeze(0)
+        refer_o = c2w[:3, 3].unsqueeze(0)
+        refer_p = p[None, :, :].clone() - refer_o[:, None, :]
+        code = decoder.merge(refer_p, refer_o, ft) * trunc[..., None]
+        count_pts[seen] += trunc
+        pixel_pts[seen, :] += code.float()
+        label_pts[seen] = label_seen.float()
+    ok = count_pts > 0
+    pixel_pts[ok, :] = pixel_pts[ok, :] / count_pts[ok, None]
+    return pixel_pts, label_pts
+
+
 def frame_vis_render(cam, bound, decoder, experts, frame, c2w, refer_w2c, feats, n_samples, n_surface, tape,
                      n_pts_batch):
     """slams/mapping.py:636-690 (frame_vis without the plotting): every pixel of the frame, rays from ``c2w``,

@@ -98,3 +98,35 @@ def test_eval_points_missing_expert_is_an_error():
     pts = torch.zeros(64, 3, device=dev)
     with pytest.raises(ValueError):
         inference.eval_points(dec, pts, torch.zeros(64, 32, device=dev), torch.full((64,), 2, device=dev), "fine")
+
+
+def test_get_2d_feature_vs_reference_golden(golden_dir):
+    """``inference.get_2d_feature`` (the producer of eval_points' pixel features in a mesh extraction) against the output
+    of the reference's own Mesher.get_2d_feature (slams/meshing.py:294-377, tests/golden/get_2d_feature_tiny.pt): labels
+    bit exact, merged features 1e-3."""
+    import os
+    from oracle.make_golden import build_models
+    from dns_slam_b200 import fused, inference, synthetic as syn
+    from gpu_util import product_decoder_from_oracle
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(golden_dir, "get_2d_feature_tiny.pt"), weights_only=False)
+    meta = g["meta"]
+    gen = torch.Generator().manual_seed(meta["seed"])
+    bound, odec, _ = build_models(meta["shape"], meta["n_class"], meta["seed"])
+    dec = product_decoder_from_oracle(meta["shape"], odec, n_class=meta["n_class"])
+    cam = syn.camera(meta["shape"])
+    poses = syn.trajectory(meta["shape"], 6)
+    kfs = []
+    for i, ft in zip(meta["kf_pose"], g["features"]):
+        fr = syn.frame(meta["shape"], poses[i], gen, n_class=meta["n_class"])
+        syn.pixel_features(meta["shape"], 1, gen)
+        kfs.append({"est_c2w": poses[i].clone(), "gt_label": fr["label"].to(dev), "gt_depth": fr["depth"].to(dev),
+                    "features_cl": fused.channels_last(ft.to(dev))})
+    pix, lab = inference.get_2d_feature(cam, dec, g["points"].to(dev), kfs)
+    same = lab.cpu() == g["label_pts"]
+    assert float(same.float().mean()) > 0.999          # a projected pixel on a rounding tie may fall either way
+    want = g["pixel_pts"]
+    rows = same & (((pix.cpu() != 0).any(-1)) == ((want != 0).any(-1)))
+    assert float(rows.float().mean()) > 0.998
+    err = (pix.cpu()[rows] - want[rows]).norm() / want[rows].norm()
+    assert float(err) < 1e-3, float(err)

@@ -227,3 +227,50 @@ def test_feature_gather_rejects_a_view_count_mismatch():
         fused.feature_gather(60, 80, K, pts, w2c, torch.rand(1, 30, 40, 64, device=dev))
     code, uv, mask = fused.feature_gather(60, 80, K, pts, w2c, torch.rand(2, 30, 40, 64, device=dev))
     assert code.shape == (2, 10, 64)
+
+
+def test_decoder_init_vs_reference_golden(golden_dir):
+    """``slam.decoder_init`` against ``Mapper.decoder_init`` of the reference itself (slams/mapping.py:764-836 run by
+    oracle/make_golden.py decoder_init_case for 3 iterations on the recorded draws): every parameter after the last
+    Adam step -- hash table, coarse / colour / logit / Merge nets and the freshly created class experts."""
+    import os
+    from oracle import make_golden as mg
+    from dns_slam_b200 import fused, slam, synthetic as syn
+    from gpu_util import frame_to, product_decoder_from_oracle, rel_err
+    dev = torch.device("cuda:0")
+    g = torch.load(os.path.join(golden_dir, "decoder_init_tiny.pt"), weights_only=False)
+    meta = g["meta"]
+    s = syn.SHAPES[meta["shape"]]
+    gen = torch.Generator().manual_seed(meta["seed"])
+    bound, odec, oexp = mg.build_models(meta["shape"], meta["n_class"], meta["seed"], expert_classes=meta["decoder_idx"])
+    dec = product_decoder_from_oracle(meta["shape"], odec, oexp, n_class=meta["n_class"])
+    cam = syn.camera(meta["shape"])
+    pose = syn.trajectory(meta["shape"], 6)[meta["pose_index"]]
+    fr = frame_to(syn.frame(meta["shape"], pose, gen, n_class=meta["n_class"]), dev)
+    feats = fused.channels_last(g["features"].to(dev))
+    mp = slam.MapperCore(cam, dec, s["mapping_pixels"], 32, 15,
+                         lambdas=dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=0.0, fs=s["lambda_fs"],
+                                      op=s["lambda_opacity"]),
+                         opacity_sigma=s["opacity_sigma"], smooth_pts=s["smooth_pts"], lambda_sm=meta["lambda_sm"])
+    # recorded draw order per iteration: one randint per class of decoder_idx with more than one pixel, rand x2
+    # (sample_along_rays), rand(3) + rand(1,1,1,3) (smoothness)
+    tape, per = g["tape"], len(g["tape"]) // meta["n_iters"]
+    its = []
+    for it in range(meta["n_iters"]):
+        chunk = tape[it * per:(it + 1) * per]
+        ints = [t for k, t in chunk if k == "randint"]
+        rands = [t for k, t in chunk if k == "rand"]
+        its.append((dict(class_draws=ints, t_surface=rands[0], t_zero=rands[1]), (rands[2], rands[3])))
+    table0 = dec.pe_fn.grid_fn.params.detach().clone()
+    slam.decoder_init(mp, meta["decoder_idx"], fr, slam.class_tables(fr["label"]), pose, feats, s["lr"],
+                      lambda it: its[it][0], lambda it: its[it][1], n_iters=meta["n_iters"], n_rays=meta["n_rays"])
+    sd = dec.state_dict()
+    for k, want in g["params"].items():
+        if k in sd and want.numel() == sd[k].numel():
+            assert rel_err(sd[k], want) < 2e-3, k
+    tab = dec.pe_fn.grid_fn.params.detach().cpu()
+    gt = g["table"]
+    moved = rel_err(tab[::int(gt["stride"])] - table0.cpu()[::int(gt["stride"])], gt["strided"] - table0.cpu()[::int(gt["stride"])])
+    assert moved < 5e-3, f"table update {moved:.2e}"
+    for c, want in g["experts"].items():
+        assert rel_err(dec.expert_params[c][:want.numel()], want) < 2e-3, f"expert {c}"

@@ -100,3 +100,28 @@ def test_stem(golden_dir):
     close(rp.stem_forward(g["frames2"], w, gam, bet, rm, rv, True), g["out2"], atol=1e-5)
     close(rm, g["state2"]["conv_blocks.bn1.running_mean"]); close(rv, g["state2"]["conv_blocks.bn1.running_var"])
     close(rp.stem_forward(g["frames1"], w, gam, bet, rm, rv, False), g["out_eval"], atol=1e-5)
+
+
+def test_get_2d_feature_restatement_matches_reference(golden_dir):
+    """oracle/reference_path.get_2d_feature against the output of the reference's own Mesher.get_2d_feature
+    (slams/meshing.py:294-377; oracle/make_golden.py get_2d_feature_case)."""
+    import os
+    import torch
+    from oracle import reference_path as rp
+    from oracle.make_golden import build_models
+    from dns_slam_b200 import synthetic as syn
+    g = torch.load(os.path.join(golden_dir, "get_2d_feature_tiny.pt"), weights_only=False)
+    meta = g["meta"]
+    gen = torch.Generator().manual_seed(meta["seed"])
+    bound, odec, _ = build_models(meta["shape"], meta["n_class"], meta["seed"])
+    cam = syn.camera(meta["shape"])
+    poses = syn.trajectory(meta["shape"], 6)
+    kfs = []
+    for i, ft in zip(meta["kf_pose"], g["features"]):
+        fr = syn.frame(meta["shape"], poses[i], gen, n_class=meta["n_class"])
+        syn.pixel_features(meta["shape"], 1, gen)        # keeps the generator in step with the golden script
+        kfs.append({"est_c2w": poses[i].clone(), "gt_label": fr["label"], "gt_depth": fr["depth"], "features": ft})
+    with torch.no_grad():
+        pix, lab = rp.get_2d_feature(cam, odec, g["points"], kfs)
+    assert torch.equal(lab, g["label_pts"])
+    torch.testing.assert_close(pix, g["pixel_pts"], rtol=1e-5, atol=1e-6)
