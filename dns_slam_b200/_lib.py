@@ -81,7 +81,7 @@ class FeatMergeArgs(C.Structure):
                 ("bound", (C.c_double * 2) * 3), ("K", _P), ("w2c", _P), ("cam_o", _P), ("feats", _P * MAX_FRAMES),
                 ("rays_o", _P), ("rays_d", _P), ("z_vals", _P), ("gt_depth", _P), ("params", _P), ("features", _P),
                 ("d_features", _P), ("d_params", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("workspace", _P),
-                ("workspace_bytes", C.c_int64)]
+                ("workspace_bytes", C.c_int64), ("stash", _P), ("stash_bytes", C.c_int64)]
 
 
 _lib = None

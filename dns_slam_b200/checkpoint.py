@@ -10,10 +10,15 @@ The decoder of this package has the reference's parameter names (``pe_fn.grid_fn
 ``coarse_fn.decoder.params``, ``out_fn.color_decoder.params``, ``out_fn.logit_decoder.params``,
 ``merge.decoder.params``: one flat fp32 ``params`` vector per tcnn module, weights row-major
 ``[out][in]`` with the output width padded to 16), so a reference ``decoder`` entry loads as is.
-The one difference is ``fine_decoders``: the reference pickles ``{class id: tcnn.Network}`` MODULE objects
-(unloadable without tinycudann); here the entry is ``{class id: {"params": fp32[4096]}}`` and the reader
-accepts either form (anything with ``state_dict()``, a ``params`` attribute, a dict with ``params`` or a bare
-tensor).  Parity of the tcnn layout itself is unpinned (no tinycudann in this build).
+``fine_decoders``: the reference pickles ``{class id: tcnn.Network}`` MODULE objects and its consumers CALL them
+(``extract_mesh.py:146-157``, ``eval_2d.py:385-386,143``).  The writer therefore stores ``{class id: Expert}`` --
+stand-alone ``dns_slam_b200.decoder.Expert`` modules (own copy of the 4096 weights, callable as
+``m(torch.cat((pe, grid), -1))`` and ``m(pe, features=grid)``, with ``parameters()`` / ``state_dict()['params']``), which
+a reference-side reader can use as is once this package is importable; ``as_modules=False`` stores plain
+``{"params": tensor}`` dicts.  The reader accepts every form (a module with ``state_dict()``, a ``params`` attribute, a
+dict with ``params`` or a bare tensor).  When ``save`` gets no ``fine_decoders`` argument it takes them from the registered
+decoder, so the activation state is never lost.  Parity of the tcnn layout itself is unpinned (no tinycudann in this
+build).
 """
 import os
 
@@ -32,11 +37,15 @@ class Checkpoint:
     def _path(self, filename):
         return filename if os.path.isabs(filename) else os.path.join(self.checkpoint_dir, filename)
 
-    def save(self, filename, **kwargs):
-        """checkpoint.py:21-35.  A ``fine_decoders`` argument holding modules is stored as tensors."""
+    def save(self, filename, as_modules=True, **kwargs):
+        """checkpoint.py:21-35."""
         out = dict(kwargs)
+        if "fine_decoders" not in out:
+            for v in self.module_dict.values():
+                if hasattr(v, "fine_decoders"):
+                    out["fine_decoders"] = v.fine_decoders
         if "fine_decoders" in out:
-            out["fine_decoders"] = fine_decoders_state(out["fine_decoders"])
+            out["fine_decoders"] = fine_decoders_state(out["fine_decoders"], as_modules)
         for k, v in self.module_dict.items():
             out[k] = v.state_dict()
         torch.save(out, self._path(filename))
@@ -48,7 +57,7 @@ class Checkpoint:
             if k not in state:
                 print(f'Warning: Could not find "{k}" in checkpoint!')
                 continue
-            own = mod.state_dict()
+            own = dict(mod.state_dict())
             for kk, vv in state[k].items():
                 if kk in own:
                     if tuple(own[kk].shape) != tuple(vv.shape):
@@ -73,9 +82,15 @@ def _expert_vector(obj):
     return obj.params
 
 
-def fine_decoders_state(fine_decoders):
-    """{class id: module | state | tensor} -> {class id: {"params": fp32 vector on the CPU}}."""
-    return {int(c): {"params": _expert_vector(m).detach().float().cpu().clone()} for c, m in fine_decoders.items()}
+def fine_decoders_state(fine_decoders, as_modules=True):
+    """{class id: module | state | tensor} -> {class id: stand-alone Expert module on the CPU} (or, with
+    ``as_modules=False``, {class id: {"params": fp32 vector}})."""
+    from .decoder import Expert
+    out = {}
+    for c, m in fine_decoders.items():
+        vec = _expert_vector(m).detach().float().cpu().clone()
+        out[int(c)] = Expert(vec) if as_modules else {"params": vec}
+    return out
 
 
 def load_fine_decoders(decoder, fine_decoders):

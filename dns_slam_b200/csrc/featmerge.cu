@@ -55,7 +55,10 @@ struct FmArgs {
   float* d_rays_o;            // [N][3] +=
   float* d_rays_d;
   int need_dparams, need_drays;
+  uint4* Ximg;                // optional stash: the X operand tiles of the forward pass, [tile][hi | lo][14 chunks][128 rows]
+  int64_t stash_bytes;
 };
+constexpr int kXImgBytes = 28 * 2048;   // one tile image = the shared-memory X tile, byte for byte
 
 // params = W1[32][112] | W2[32][32] (tinycudann layout) -> bf16 hi/lo chunk tiles
 __global__ void k_prep_featmerge(const float* __restrict__ params, uint4* __restrict__ out) {
@@ -140,6 +143,7 @@ struct RowGeom {
   float wy0, wy1, wx0, wx1;
 };
 
+template <bool PROJECT = true>
 __device__ __forceinline__ void row_geometry(const FmArgs& a, int64_t n_rows, int64_t tile, int row, const float* sK,
                                              const float* sW2c, const float* sCamO, RowGeom& g) {
   const int pslot = row / a.R, v = row - pslot * a.R;
@@ -160,6 +164,10 @@ __device__ __forceinline__ void row_geometry(const FmArgs& a, int64_t n_rows, in
   float pt[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) pt[c] = __fadd_rn(a.rays_o[3 * g.r + c], __fmul_rn(a.rays_d[3 * g.r + c], g.zv));
+  const float* co = sCamO + 3 * g.view;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) g.x[c] = (float)(((double)__fsub_rn(pt[c], co[c]) - a.B.lo[c]) / a.B.ext[c]);
+  if (!PROJECT) return;   // the backward with a stashed X tile needs the OneBlob argument only
   // projection (utils/common.py:648-660), the arithmetic of k_feature_gather (sample.cu)
   const float* M = sW2c + 16 * g.view;
   float cam[3];
@@ -190,20 +198,19 @@ __device__ __forceinline__ void row_geometry(const FmArgs& a, int64_t n_rows, in
     g.f10 = fm + ((int64_t)y1 * a.w + x0) * 64;
     g.f11 = fm + ((int64_t)y1 * a.w + x1) * 64;
   }
-  const float* co = sCamO + 3 * g.view;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) g.x[c] = (float)(((double)__fsub_rn(pt[c], co[c]) - a.B.lo[c]) / a.B.ext[c]);
 }
 
 // This thread's share of the row's X = [OneBlob 48 | feature 64]: group 0 the OneBlob chunks 0..5 and feature
 // chunks 6..8 (24 channels), group 1 feature chunks 9..13 (40 channels).
-__device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsigned char* X_hi, unsigned char* X_lo) {
+// ``img``: this row's slot in the tile image (NULL: no stash), chunk c hi at img[c * 128], lo at img[(14 + c) * 128].
+__device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsigned char* X_hi, unsigned char* X_lo, uint4* img) {
   const uint4 z4 = make_uint4(0, 0, 0, 0);
   const int c0 = grp ? 9 : 6, c1 = grp ? 14 : 9;
   if (!g.valid) {
     for (int c = grp ? 9 : 0; c < c1; ++c) {
       *reinterpret_cast<uint4*>(X_hi + c * 2048 + row * 16) = z4;
       *reinterpret_cast<uint4*>(X_lo + c * 2048 + row * 16) = z4;
+      if (img) img[c * kTile] = img[(14 + c) * kTile] = z4;
     }
     return;
   }
@@ -212,14 +219,16 @@ __device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsi
     for (int c = 0; c < 3; ++c) {
       float pe[16];
       oneblob16(g.x[c], pe);
-      put_chunk(X_hi, X_lo, 2 * c, 2048, row, pe);
-      put_chunk(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8);
+      put_chunk_img(X_hi, X_lo, 2 * c, 2048, row, pe, img ? img + (2 * c) * kTile : nullptr, img ? img + (14 + 2 * c) * kTile : nullptr);
+      put_chunk_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, img ? img + (2 * c + 1) * kTile : nullptr,
+                    img ? img + (15 + 2 * c) * kTile : nullptr);
     }
   }
   if (!g.vis) {   // code * mask (common.py:676): a hidden view contributes its OneBlob part only
     for (int c = c0; c < c1; ++c) {
       *reinterpret_cast<uint4*>(X_hi + c * 2048 + row * 16) = z4;
       *reinterpret_cast<uint4*>(X_lo + c * 2048 + row * 16) = z4;
+      if (img) img[c * kTile] = img[(14 + c) * kTile] = z4;
     }
     return;
   }
@@ -238,7 +247,7 @@ __device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsi
       f[4 * q + 2] = g.wy0 * (g.wx0 * a00.z + g.wx1 * a01.z) + g.wy1 * (g.wx0 * a10.z + g.wx1 * a11.z);
       f[4 * q + 3] = g.wy0 * (g.wx0 * a00.w + g.wx1 * a01.w) + g.wy1 * (g.wx0 * a10.w + g.wx1 * a11.w);
     }
-    put_chunk(X_hi, X_lo, c, 2048, row, f);
+    put_chunk_img(X_hi, X_lo, c, 2048, row, f, img ? img + c * kTile : nullptr, img ? img + (14 + c) * kTile : nullptr);
   }
 }
 
@@ -298,11 +307,13 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
   const float inv_r = 1.f / (float)a.R;
+  // the X tiles are kept for the backward when the caller's stash holds all of them (decided on the device: no host sync)
+  const bool use_img = a.Ximg != nullptr && n_tiles * (int64_t)kXImgBytes <= a.stash_bytes;
   uint32_t phase = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     RowGeom g;
     row_geometry(a, n_rows, tile, row, sK, sW2c, sCamO, g);
-    build_x(g, grp, row, X_hi, X_lo);
+    build_x(g, grp, row, X_hi, X_lo, use_img ? a.Ximg + tile * (kXImgBytes / 16) + row : nullptr);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
 
 __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
   extern __shared__ __align__(1024) unsigned char sm[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, xbar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float sK[9], sW2c[16 * kMaxViews], sCamO[3 * kMaxViews];
   __shared__ float DXS[kTile * 3];
@@ -397,7 +408,10 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
   for (int i = tid; i < kFW; i += kFT) reinterpret_cast<uint4*>(Wt)[i] = a.wts[i];
   load_views(a, sK, sW2c, sCamO);
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-  if (tid == 0) mbar_init(&bar, 1);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&xbar, 1);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -406,12 +420,22 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
   const float inv_r = 1.f / (float)a.R;
-  uint32_t phase = 0;
+  uint32_t phase = 0, xphase = 0;
   bool have_acc = false;
+  // X tiles stashed by the forward pass (same device-side rule): ONE bulk copy per tile instead of the gather + encode
+  const bool use_img = a.Ximg != nullptr && n_tiles * (int64_t)kXImgBytes <= a.stash_bytes;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     RowGeom g;
-    row_geometry(a, n_rows, tile, row, sK, sW2c, sCamO, g);
-    build_x(g, grp, row, X_hi, X_lo);
+    if (use_img) {
+      if (tid == 0) {   // the previous tile's MMAs have completed (end-of-loop barrier): the X region is free
+        mbar_expect_tx(&xbar, kXImgBytes);
+        bulk_g2s(X_hi, a.Ximg + tile * (kXImgBytes / 16), kXImgBytes, &xbar);
+      }
+      row_geometry<false>(a, n_rows, tile, row, sK, sW2c, sCamO, g);
+    } else {
+      row_geometry(a, n_rows, tile, row, sK, sW2c, sCamO, g);
+      build_x(g, grp, row, X_hi, X_lo, nullptr);
+    }
     {   // dO = d_features[sample] / R (the same for the R views of the sample): 16 channels per thread
       float f[16];
       if (g.valid) {
@@ -433,6 +457,10 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+      if (use_img) {
+        mbar_wait(&xbar, xphase);   // X tile landed
+        xphase ^= 1;
+      }
       mma_hidden(tmem_d, X_hi, X_lo, W1_hi, W1_lo);
       umma_commit(&bar);
     }
@@ -656,6 +684,10 @@ static int fm_fill(FmArgs& m, FmWs& w, const dns_featmerge_args* a, const char* 
   m.n_rows_dev = a->apply_trunc ? w.counter : nullptr;
   m.n_rows_host = N * S;
   m.wts = w.wts;
+  if (a->stash && a->stash_bytes >= kXImgBytes && ((uintptr_t)a->stash & 15) == 0) {
+    m.Ximg = (uint4*)a->stash;
+    m.stash_bytes = a->stash_bytes;
+  }
   return DNS_OK;
 }
 

@@ -98,7 +98,11 @@ class Expert(nn.Module):
         self.n_input_dims, self.n_output_dims = 80, 33
         self.params = nn.Parameter(params_view)
 
-    def forward(self, x):
+    def forward(self, x, features=None):
+        """``fine_decoders[c](torch.cat((pe, grid), -1))`` (slams/mapping.py:600) or ``fine_decoders[c](pe,
+        features=grid)`` (eval_2d.py:143)."""
+        if features is not None:
+            x = torch.cat((x, features), -1)
         return tcnn._MlpFn.apply(x.to(torch.float32).contiguous(), self.params, 80, 33)
 
 
@@ -139,9 +143,45 @@ class Decoder(nn.Module):
                 80, 48, 32, seed + 100 + c).to(device)
         self.flat = flat
         self.expert_params = nn.Parameter(flat[a:a + n].view(self.n_class_ids, EXPERT_PARAMS))
-        # class id -> expert row; -1 until the class is activated (mapping.py:736-749)
-        self.class_to_expert = torch.full((self.n_class_ids,), -1, dtype=torch.int32, device=device)
+        # class id -> expert row; -1 until the class is activated (mapping.py:736-749).  A persistent buffer: the
+        # activation state travels with state_dict(), load_state_dict() rebuilds the expert modules from it.
+        self.register_buffer("class_to_expert", torch.full((self.n_class_ids,), -1, dtype=torch.int32, device=device))
         self._experts = {}
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """Reference-shaped entries (no ``class_to_expert`` / ``expert_params`` keys) load too; the experts named by the
+        loaded ``class_to_expert`` are re-created (their modules are plain Python state)."""
+        own = self.state_dict()
+        merged = {k: state_dict.get(k, v) for k, v in own.items()}
+        extra = [k for k in state_dict if k not in own]
+        if strict and extra:
+            raise KeyError(f"unexpected keys in the decoder state: {extra}")
+        out = super().load_state_dict(merged, strict=True)
+        self._experts = {}
+        for c in torch.nonzero(self.class_to_expert >= 0).reshape(-1).tolist():
+            self._experts[c] = Expert(self.expert_params.detach()[c])
+        return out
+
+    def _apply(self, fn, recurse=True):
+        """``.to(device)`` / ``.cuda()``: the module Parameters must stay views of ONE flat buffer (fused Adam and the
+        gradient all-reduce run over it), so the buffer is moved and the views are rebuilt; dtype changes are refused."""
+        flat = fn(self.flat)
+        if flat.dtype != torch.float32:
+            raise RuntimeError("dns_slam_b200.Decoder keeps fp32 parameters (one flat buffer shared with the C ABI)")
+        if flat.data_ptr() == self.flat.data_ptr():
+            return self
+        self.flat = flat.detach()
+        for name, mod in (("table", self.pe_fn.grid_fn), ("coarse", self.coarse_fn.decoder), ("color", self.out_fn.color_decoder),
+                          ("logit", self.out_fn.logit_decoder), ("merge", self.merge.decoder)):
+            a, n = self.layout[name]
+            mod.params = nn.Parameter(self.flat[a:a + n], requires_grad=mod.params.requires_grad)
+        a, n = self.layout["experts"]
+        self.expert_params = nn.Parameter(self.flat[a:a + n].view(self.n_class_ids, EXPERT_PARAMS))
+        self.bound = fn(self.bound)
+        self.merge.bound = self.bound
+        self._buffers["class_to_expert"] = fn(self.class_to_expert)
+        self._experts = {c: Expert(self.expert_params.detach()[c]) for c in self._experts}
+        return self
 
     # ---- class-wise experts -------------------------------------------------------------
     def activate_expert(self, class_id):

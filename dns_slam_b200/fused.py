@@ -529,7 +529,18 @@ class Views:
             raise ValueError("at most 8 target frames and 8 views per frame in one fused call")
 
 
-def _featmerge_args(cam, bound, K, views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc, ws):
+FEATMERGE_TILE_BYTES = 57344      # one stashed operand tile (128 / R band samples x R views)
+
+
+def featmerge_stash(n_rays, n_samples, n_views, device, band_fraction=0.5):
+    """Stash for the operand tiles of ``dns_featmerge_fwd`` sized for ``band_fraction`` of the samples (the truncation
+    band holds about a third; a band that does not fit simply makes the backward recompute)."""
+    ppt = 128 // n_views
+    tiles = int(n_rays * n_samples * band_fraction) // ppt + 2
+    return torch.empty(tiles * FEATMERGE_TILE_BYTES, dtype=torch.uint8, device=device)
+
+
+def _featmerge_args(cam, bound, K, views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc, ws, stash=None):
     a = _lib.FeatMergeArgs()
     N, S = z_vals.shape
     a.n_rays, a.n_samples, a.n_frames, a.n_views = N, S, views.F, views.R
@@ -547,29 +558,31 @@ def _featmerge_args(cam, bound, K, views, rays_o, rays_d, z_vals, gt_depth, para
     a.z_vals, a.gt_depth = _lib.ptr(z_vals, f32), _lib.ptr(gt_depth, f32)
     a.params = _lib.ptr(params, f32)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    if stash is not None:
+        a.stash, a.stash_bytes = stash.data_ptr(), stash.numel()
     return a
 
 
-_K_cache = {}
-
-
 def _K_dev(cam, dev):
-    key = (id(cam["K"]), dev.type, dev.index)
-    k = _K_cache.get(key)
+    """Device copy of the intrinsics, cached ON the camera dict (a cache keyed by id() could alias a freed tensor)."""
+    cache = cam.setdefault("_K_dev", {})
+    key = (dev.type, dev.index)
+    k = cache.get(key)
     if k is None:
-        k = _K_cache[key] = cam["K"].detach().to(dev, torch.float32).contiguous()
+        k = cache[key] = cam["K"].detach().to(dev, torch.float32).contiguous()
     return k
 
 
-def featmerge_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc=True, ws=None, out=None):
+def featmerge_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc=True, ws=None, out=None,
+                  stash=None):
     """One ``dns_featmerge_fwd`` call.  Returns (features [N,S,32], workspace) -- the workspace holds the band row list
-    and must be handed to ``featmerge_bwd_raw``."""
+    and must be handed to ``featmerge_bwd_raw`` (like ``stash``, the optional operand-tile stash)."""
     dev = z_vals.device
     N, S = z_vals.shape
     L = _lib.lib()
     if ws is None:
         ws = torch.empty(int(L.dns_featmerge_workspace_bytes(N, S)), dtype=torch.uint8, device=dev)
-    a = _featmerge_args(cam, bound, _K_dev(cam, dev), views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc, ws)
+    a = _featmerge_args(cam, bound, _K_dev(cam, dev), views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc, ws, stash)
     if out is None:
         out = torch.empty(N, S, 32, device=dev)
     a.features = _lib.ptr(out, torch.float32)
@@ -578,10 +591,10 @@ def featmerge_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, a
 
 
 def featmerge_bwd_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, d_features, ws, d_params, d_rays_o,
-                      d_rays_d, apply_trunc=True):
+                      d_rays_d, apply_trunc=True, stash=None):
     """One ``dns_featmerge_bwd`` call: ACCUMULATES into d_params / d_rays_o / d_rays_d (None = not wanted)."""
     a = _featmerge_args(cam, bound, _K_dev(cam, z_vals.device), views, rays_o, rays_d, z_vals, gt_depth, params,
-                        apply_trunc, ws)
+                        apply_trunc, ws, stash)
     a.d_features = _lib.ptr(d_features, torch.float32)
     a.need_dparams, a.need_drays = int(d_params is not None), int(d_rays_o is not None)
     a.d_params = _lib.ptr(d_params, torch.float32, allow_none=True)
@@ -594,14 +607,18 @@ class _FeatMergeFn(torch.autograd.Function):
     def forward(ctx, rays_o, rays_d, params, cam, bound, views, z_vals, gt_depth, apply_trunc):
         ro, rd = rays_o.detach().contiguous(), rays_d.detach().contiguous()
         pr = params.detach()
-        out, ws = featmerge_raw(cam, bound, views, ro, rd, z_vals, gt_depth, pr, apply_trunc)
-        ctx.save_for_backward(ro, rd, pr, z_vals, gt_depth, ws)
+        N, S = z_vals.shape
+        stash = featmerge_stash(N, S, views.R, z_vals.device, 0.5 if apply_trunc else 1.0) if any(ctx.needs_input_grad[:3]) \
+            else torch.empty(0, dtype=torch.uint8, device=z_vals.device)
+        out, ws = featmerge_raw(cam, bound, views, ro, rd, z_vals, gt_depth, pr, apply_trunc,
+                                stash=stash if stash.numel() else None)
+        ctx.save_for_backward(ro, rd, pr, z_vals, gt_depth, ws, stash)
         ctx.meta = (cam, bound, views, apply_trunc)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        ro, rd, pr, z_vals, gt_depth, ws = ctx.saved_tensors
+        ro, rd, pr, z_vals, gt_depth, ws, stash = ctx.saved_tensors
         cam, bound, views, apply_trunc = ctx.meta
         need = ctx.needs_input_grad
         want_r = need[0] or need[1]
@@ -610,7 +627,7 @@ class _FeatMergeFn(torch.autograd.Function):
         d_d = torch.zeros_like(rd) if want_r else None
         if want_r or need[2]:
             featmerge_bwd_raw(cam, bound, views, ro, rd, z_vals, gt_depth, pr, d_out.to(torch.float32).contiguous(), ws,
-                              d_p, d_o, d_d, apply_trunc)
+                              d_p, d_o, d_d, apply_trunc, stash=stash if stash.numel() else None)
         return (d_o if need[0] else None, d_d if need[1] else None, d_p, None, None, None, None, None, None)
 
 

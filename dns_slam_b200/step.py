@@ -395,6 +395,7 @@ class MappingFrameStep:
         self.scratch = torch.zeros(F, 2, device=dev)          # per frame: max depth, rays outside the bound
         self.features = torch.empty(N, S, 32, device=dev)
         self.fm_ws = torch.empty(int(_lib.lib().dns_featmerge_workspace_bytes(N, S)), dtype=torch.uint8, device=dev)
+        self.fm_stash = fused.featmerge_stash(N, S, self.R, dev)      # forward operand tiles kept for the backward
         self.t_lin = torch.linspace(0.0, 1.0, steps=n_samples_ray).to(dev)
         # ---- draws: ONE device buffer, refreshed with one H2D copy
         self.draw_bytes = plan.draw_bytes
@@ -478,7 +479,7 @@ class MappingFrameStep:
         views = self._views()
         merge_p = dec.view("merge")
         fused.featmerge_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
-                            True, ws=self.fm_ws, out=self.features)
+                            True, ws=self.fm_ws, out=self.features, stash=self.fm_stash)
         cfg = fused.RenderConfig(_lib.MODE_MAP, dec.bound, dec.pe_fn.grid_fn.gstruct, b["z_vals"], b["gt_color"], b["gt_depth"],
                                  b["gt_label"], None, dec.class_to_expert, dec.n_class, self.lambdas,
                                  opacity_trunc=self.opacity_sigma)
@@ -491,7 +492,8 @@ class MappingFrameStep:
         losses, _, d_o, d_d, d_f = fused.render_raw(cfg, p["table"], p["coarse"], p["color"], p["logit"], p["experts"],
                                                     b["rays_o"], b["rays_d"], self.features, g, True, True)
         fused.featmerge_bwd_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
-                                d_f, self.fm_ws, g["merge"], d_o if self.opt_poses else None, d_d if self.opt_poses else None)
+                                d_f, self.fm_ws, g["merge"], d_o if self.opt_poses else None, d_d if self.opt_poses else None,
+                                stash=self.fm_stash)
         self.loss_vec[:8] = losses
         if self.with_tv:       # parameter-only work, replicated: every rank contributes 1 / world of it
             w = 1.0 / self.world

@@ -308,6 +308,11 @@ typedef struct dns_featmerge_args {
   float* d_rays_d;
   void* workspace;
   int64_t workspace_bytes;
+  /* optional: room for the operand tiles of the forward pass (57 344 B per 128 / n_views band samples).  When the band of
+   * the call fits (decided on the device), the backward pass bulk-copies them instead of gathering and encoding again;
+   * NULL, or a band that does not fit: the backward recomputes.  Must be the same buffer in both calls. */
+  void* stash;
+  int64_t stash_bytes;
 } dns_featmerge_args;
 int64_t dns_featmerge_workspace_bytes(int n_rays, int n_samples);
 int dns_featmerge_fwd(const dns_featmerge_args* a, void* stream);

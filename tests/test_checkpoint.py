@@ -31,6 +31,27 @@ def test_round_trip(tmp_path):
     assert b.class_to_expert.tolist() == a.class_to_expert.tolist()
     assert rest["scene"] == "room0" and int(rest["idx"]) == 7 and rest["keyframe_list"] == [0, 5]
     assert set(rest["fine_decoders"]) == {0, 3}
+    # what a reference-side consumer does with the entry (extract_mesh.py:146-157, eval_2d.py:143): module objects
+    m = rest["fine_decoders"][3]
+    assert torch.equal(m.state_dict()["params"], a.expert_params[3].detach()) and len(list(m.parameters())) == 1
+    assert callable(m)
+
+
+def test_activation_state_survives_without_the_kwarg(tmp_path):
+    """save() without fine_decoders= and a plain state_dict round trip keep the activated experts."""
+    a, b, c2 = _decoder(1), _decoder(2), _decoder(3)
+    a.activate_expert(4)
+    c = ck.Checkpoint(str(tmp_path), device="cpu", decoder=a)
+    c.save("m.pt", idx=1)
+    ck.Checkpoint(str(tmp_path), device="cpu", decoder=b).load("m.pt")
+    assert sorted(b.fine_decoders) == [4] and int(b.class_to_expert[4]) == 4
+    c2.load_state_dict(a.state_dict())
+    assert sorted(c2.fine_decoders) == [4] and torch.equal(c2.flat, a.flat)
+    # the module Parameters are still views of the flat buffer after a (no-op) .to()
+    c2.to("cpu")
+    with torch.no_grad():
+        c2.flat.add_(1.0)
+    assert torch.equal(c2.coarse_fn.decoder.params, c2.view("coarse"))
 
 
 def test_reads_reference_shaped_file(tmp_path):

@@ -134,3 +134,30 @@ def test_featmerge_matches_operator_chain_at_replica_size():
     assert rel_err(f1, f0) < 1e-5
     assert rel_err(g1, g0) < 1e-4
     assert rel_err(o1, o0) < 1e-4 and rel_err(d1, d0) < 1e-4
+
+
+def test_featmerge_backward_same_with_stash_and_recompute():
+    """The backward either bulk-copies the operand tiles the forward stashed or gathers + encodes again: same gradients;
+    a stash that is too small for the band falls back to recomputing (decided on the device)."""
+    from dns_slam_b200 import fused
+    c = _case("tiny", 2, 3, 400, seed=31)
+    dev, dec, cat = c["dev"], c["dec"], c["cat"]
+    w2c = torch.cat(c["w2c"], 0).to(dev)
+    cam_o = torch.inverse(torch.cat(c["w2c"], 0))[:, :3, 3].to(dev)
+    views = fused.Views(w2c, cam_o, [fused.channels_last(f.to(dev)) for f in c["feats"]], c["ray_start"])
+    mp = dec.merge.decoder.params.detach()
+    N, S = cat["z_vals"].shape
+    d_f = torch.randn(N, S, 32, generator=torch.Generator().manual_seed(3)).to(dev)
+    res = []
+    for stash in (None, fused.featmerge_stash(N, S, 3, dev), torch.empty(fused.FEATMERGE_TILE_BYTES, dtype=torch.uint8, device=dev)):
+        feat, ws = fused.featmerge_raw(c["cam"], dec.merge.bound, views, cat["rays_o"], cat["rays_d"], cat["z_vals"],
+                                       cat["gt_depth"], mp, stash=stash)
+        d_p, d_o, d_d = torch.zeros_like(mp), torch.zeros(N, 3, device=dev), torch.zeros(N, 3, device=dev)
+        fused.featmerge_bwd_raw(c["cam"], dec.merge.bound, views, cat["rays_o"], cat["rays_d"], cat["z_vals"], cat["gt_depth"],
+                                mp, d_f, ws, d_p, d_o, d_d, stash=stash)
+        res.append((feat, d_p, d_o, d_d))
+    assert int(ws[:4].view(torch.int32)[0]) > 42, "band too small to exercise more than one tile"
+    for other in res[1:]:
+        assert torch.equal(other[0], res[0][0])
+        for a, b in zip(other[1:], res[0][1:]):
+            assert rel_err(a, b) < 1e-5
