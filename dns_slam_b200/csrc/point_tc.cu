@@ -231,8 +231,14 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
       if (valid) d4[4] = make_float4(v[0], v[1], v[2], v[3]);
     }
   } else {
-    // group 0: coarse row + latent loss;  group 1: fine row + free-space / opacity terms
-    float* dst = valid ? (grp ? a.fine36 : a.coarse36) + (a.p0 + i) * kOutP : nullptr;
+    // group 0: coarse row + latent loss;  group 1: fine row + free-space / opacity terms.  With the slot-order hand-over
+    // group 0 stores  coarse - fine  in the row of its SLOT (what the backward needs of both) instead of the coarse row
+    float* dst = nullptr;
+    if (valid) {
+      if (grp) dst = a.fine36 + (a.p0 + i) * kOutP;
+      else if (a.want_coarse_pt) dst = a.coarse36 + (a.p0 + i) * kOutP;
+    }
+    float* dslot = (valid && grp == 0 && a.diff36s) ? a.diff36s + q * kOutP : nullptr;
     float fo32 = 0.f;
 #pragma unroll
     for (int g4 = 0; g4 < 3; ++g4) {
@@ -246,19 +252,30 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
       }
       if (valid) {
         const int n4 = g4 < 2 ? 4 : 1;                          // 36 = 16 + 16 + 4 floats
-        float4* d4 = reinterpret_cast<float4*>(dst + 16 * g4);
         if (grp == 0) {
+          if (dst) {
+            float4* d4 = reinterpret_cast<float4*>(dst + 16 * g4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < n4) d4[k] = make_float4(vc[4 * k], vc[4 * k + 1], vc[4 * k + 2], vc[4 * k + 3]);
+            for (int k = 0; k < 4; ++k)
+              if (k < n4) d4[k] = make_float4(vc[4 * k], vc[4 * k + 1], vc[4 * k + 2], vc[4 * k + 3]);
+          }
+          float dv[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            if (16 * g4 + k < DNS_LATENT) {
-              const float d = vc[k] - vf[k];
-              lt = fmaf(d, d, lt);
+            dv[k] = vc[k] - vf[k];
+            if (16 * g4 + k < DNS_LATENT) lt = fmaf(dv[k], dv[k], lt);
+          }
+          if (dslot) {
+            if (g4 < 2) {
+              float4* d4 = reinterpret_cast<float4*>(dslot + 16 * g4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) d4[k] = make_float4(dv[4 * k], dv[4 * k + 1], dv[4 * k + 2], dv[4 * k + 3]);
+            } else {
+              dslot[32] = dv[0];                                 // slot 33 belongs to group 1 (fine channel 32)
             }
           }
         } else {
+          float4* d4 = reinterpret_cast<float4*>(dst + 16 * g4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (k < n4) d4[k] = make_float4(vf[4 * k], vf[4 * k + 1], vf[4 * k + 2], vf[4 * k + 3]);
@@ -266,6 +283,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
         }
       }
     }
+    if (valid && grp == 1 && a.diff36s) a.diff36s[q * kOutP + 33] = fo32;
     if (valid && grp == 1) {
       float front, band, vd, d = a.gt_depth[r];
       opacity_masks(zv, d, a.trunc, front, band, vd);
@@ -357,11 +375,34 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
       }
     } else if (valid) {
       const float g_lt = 2.f * a.lam_lt / (33.f * (float)a.P_total);
+      float fo32 = 0.f;
+      if (a.dfine36s) {
+        // slot-order rows (written by the ray kernel and the forward kernel): unit stride, no permutation chase
+        const float4* sd = reinterpret_cast<const float4*>(a.dfine36s + q * kOutP + ch0);
+        const float4* sx = reinterpret_cast<const float4*>(a.diff36s + q * kOutP + ch0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          if (ch0 + 4 * k < kOutP) {
+            const float4 d = sd[k], x = sx[k];
+            const float dd[4] = {d.x, d.y, d.z, d.w}, xx[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int ch = ch0 + 4 * k + e;
+              if (ch < DNS_LATENT) {
+                const float gl = g_lt * xx[e];
+                dc[4 * k + e] = gl;            // coarse net: only the latent loss reaches it in mapping
+                df[4 * k + e] = dd[e] - gl;
+              } else if (ch == 33) {
+                fo32 = xx[e];
+              }
+            }
+          }
+        }
+      } else {
       const int64_t p = a.p0 + i;
       const float4* sd = reinterpret_cast<const float4*>(a.dfine36 + p * kOutP + ch0);
       const float4* sc = reinterpret_cast<const float4*>(a.coarse36 + p * kOutP + ch0);
       const float4* sf = reinterpret_cast<const float4*>(a.fine36 + p * kOutP + ch0);
-      float fo32 = 0.f;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         if (ch0 + 4 * k < kOutP) {
@@ -378,6 +419,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
             }
           }
         }
+      }
       }
       if (grp == 1 && a.counts[cFront] > 0 && a.counts[cBand] > 0) {
         float front, band, vd, d = a.gt_depth[r];

@@ -138,7 +138,8 @@ __global__ void k_class_scan(const int* __restrict__ hist, int nci, const int* _
   }
 }
 __global__ void __launch_bounds__(256) k_class_scatter(const int64_t* __restrict__ label, int64_t N, int64_t p0, int64_t Pc,
-                                                       int nci, const int* __restrict__ slot_start, int* cursor, int* perm) {
+                                                       int nci, const int* __restrict__ slot_start, int* cursor, int* perm,
+                                                       int* inv) {
   extern __shared__ int sh[];   // [nci] block counts, then running ranks | [nci] block bases
   int* cnt = sh;
   int* bas = sh + nci;
@@ -166,7 +167,9 @@ __global__ void __launch_bounds__(256) k_class_scatter(const int64_t* __restrict
   for (int k = 0; k < kSortPer; ++k) {
     if (cls[k] >= 0) {
       const int64_t i = base + (int64_t)k * blockDim.x + threadIdx.x;
-      perm[bas[cls[k]] + atomicAdd(cnt + cls[k], 1)] = (int)i;
+      const int slot = bas[cls[k]] + atomicAdd(cnt + cls[k], 1);
+      perm[slot] = (int)i;
+      if (inv) inv[i] = slot;
     }
   }
 }
@@ -224,7 +227,8 @@ __global__ void k_ray_scatter(const int64_t* __restrict__ label, int64_t N, int 
 // one CTA per tile: slot q -> point r + k N of the tile's class, -1 for the padding tail of the class
 __global__ void __launch_bounds__(kTile) k_perm_fill(const int* __restrict__ slot_start, const int* __restrict__ ray_start,
                                                      const int* __restrict__ ray_cnt, const int* __restrict__ rays_sorted,
-                                                     int nci, int S, int64_t N, const int* __restrict__ counts, int* perm) {
+                                                     int nci, int S, int64_t N, const int* __restrict__ counts, int* perm,
+                                                     int* inv) {
   __shared__ int cls;
   const int tile = blockIdx.x;
   if (tile >= counts[cTiles]) return;
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(kTile) k_perm_fill(const int* __restrict__ slo
   int p = -1;
   if (nc > 0 && t < (int64_t)nc * S) p = (int)(rays_sorted[ray_start[c] + (int)(t % nc)] + (t / nc) * N);
   perm[q0 + threadIdx.x] = p;
+  if (inv && p >= 0) inv[p] = q0 + threadIdx.x;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -837,8 +842,8 @@ struct RenderWs {
   uint4 *W1o_hi, *W1o_lo;   // bf16 hi / lo chunk tiles of the colour|logit layer-1 weights (tcgen05 path)
   uint4 *W1o16_hi, *W1o16_lo;   // the same weights as fp16 halves (forward GEMM)
   uint4 *wc_tc, *we_tc;     // prepared tiles of the coarse net and of every class expert (kNetTc uint4 each)
-  int *perm, *tile_class;
-  float *fine36, *coarse36, *dfine36;
+  int *perm, *inv, *tile_class;
+  float *fine36, *coarse36, *dfine36, *diff36s, *dfine36s;
   float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf, *Jst;
   float *X2, *dH2, *Hcol, *dpre, *dlogit, *Hbar;
   int64_t Q, tiles;
@@ -868,6 +873,9 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.wc_tc = c.take<uint4>(kNetTc);
   w.we_tc = c.take<uint4>((int64_t)kNetTc * (map ? nci : 0) + 4);
   w.perm = c.take<int>(map ? w.Q : 4);
+  w.inv = c.take<int>(map ? Pc : 4);
+  w.diff36s = c.take<float>(map ? w.Q * kOutP : 4);
+  w.dfine36s = c.take<float>(map ? w.Q * kOutP : 4);
   w.tile_class = c.take<int>(w.tiles);
   w.fine36 = c.take<float>(Pc * kOutP);
   w.coarse36 = c.take<float>(map ? Pc * kOutP : 4);
@@ -1056,16 +1064,21 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
         k_class_scan_rays<<<1, 256, 0, st>>>(w.hist, nci, S, a->class_to_expert, w.slot_start, w.ray_start, w.cursor,
                                             w.tile_class, w.counts);
         k_ray_scatter<<<rblocks, 256, 0, st>>>(a->gt_label, N, nci, w.ray_start, w.cursor, w.rays_sorted);
-        k_perm_fill<<<tiles_max, kTile, 0, st>>>(w.slot_start, w.ray_start, w.hist, w.rays_sorted, nci, S, N, w.counts, w.perm);
+        k_perm_fill<<<tiles_max, kTile, 0, st>>>(w.slot_start, w.ray_start, w.hist, w.rays_sorted, nci, S, N, w.counts, w.perm, w.inv);
       } else {
       cudaMemsetAsync(w.perm, 0xFF, (size_t)tiles_max * kTile * sizeof(int), st);
       const int grid = (int)((Pc + 256 * kSortPer - 1) / (256 * kSortPer));
       k_class_hist<<<grid, 256, nci * sizeof(int), st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.hist, w.counts);
       k_class_scan<<<1, 256, 0, st>>>(w.hist, nci, a->class_to_expert, w.slot_start, w.cursor, w.tile_class, w.counts);
       k_class_scatter<<<grid, 256, 2 * nci * sizeof(int), st>>>(lab_all, Ntot, goff + p0, Pc, nci, w.slot_start, w.cursor,
-                                                                w.perm);
+                                                                w.perm, w.inv);
       }
       pa.perm = w.perm; pa.tile_class = w.tile_class;
+      if (tc && !a->forward_only) {   // slot-order hand-over of the latent rows between the three kernels
+        pa.diff36s = w.diff36s;
+        pa.dfine36s = w.dfine36s;
+      }
+      pa.want_coarse_pt = a->coarse_out != nullptr || !pa.diff36s;
     }
     {
       PhaseScope php(phPointFwd, st, 1);
@@ -1087,6 +1100,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.pred_color = a->pred_color; ra.pred_depth = a->pred_depth; ra.pred_var = a->pred_var;
     ra.pred_logits = a->pred_logits; ra.raw = w.raw; ra.err = w.counts + cErr; ra.dfine36 = pa.dfine36; ra.d_features = a->d_features;
     ra.d_rays_o = a->d_rays_o; ra.d_rays_d = a->d_rays_d;
+    if (pa.dfine36s) { ra.inv = w.inv; ra.dfine36s = w.dfine36s; }
     ra.X2 = w.X2; ra.dH2 = w.dH2; ra.Hcol = w.Hcol; ra.dpre = w.dpre; ra.dlogit = w.dlogit; ra.Hbar = w.Hbar;
     ra.X2img = (uint4*)w.X2; ra.dH2img = (uint4*)w.dH2; ra.Hcolimg = (uint4*)w.Hcol; ra.dpreimg = (uint4*)w.dpre;
     ra.RS = T <= 96 ? T : (T == 160 ? 80 : (T == 256 ? 128 : 64));   // sub-tile rows of the ray-side images (divides T)

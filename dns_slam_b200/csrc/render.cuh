@@ -38,6 +38,10 @@ struct RayArgs {
   float* pred_logits;
   float* raw;
   float* dfine36;
+  // tcgen05 MAP path: d(latent) rows leave the kernel in SLOT order (row inv[point - ray0*S] of dfine36s), so that the
+  // point backward kernel streams them instead of chasing the class permutation
+  const int* inv;
+  float* dfine36s;
   float* d_features;
   float* d_rays_o;
   float* d_rays_d;
@@ -86,6 +90,11 @@ struct PointArgs {
   float* fine36;
   float* coarse36;
   float* dfine36;
+  // tcgen05 MAP path, SLOT order [Q][36]: diff36s = coarse - fine (channels 0..32) | fine[32] (slot 33), written by the
+  // forward kernel; dfine36s written by the ray kernel.  The backward reads both with unit stride.
+  float* diff36s;
+  float* dfine36s;
+  int want_coarse_pt;   // also store the coarse latents in point order (coarse_out requested)
   float* occ;   // TV: [n^3]
   float* docc;  // TV
   // stashes in slot order

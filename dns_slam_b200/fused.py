@@ -763,6 +763,13 @@ class FusedAdam:
             for p, view in self._views:
                 p.grad = view
 
+    def reset_state(self):
+        """Fresh moments and step counter (a new optimiser object per frame / per optimize() call in the reference),
+        in place: a CUDA graph that captured ``step`` keeps replaying on the same buffers."""
+        for t in self._keep:
+            t.zero_()
+        self.step_dev.zero_()
+
     def zero_grad(self, set_to_none=True):
         if self.inplace:
             for g in self._zero:

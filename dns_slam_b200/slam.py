@@ -435,57 +435,107 @@ def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr
     return best, best_loss, torch.stack(history)
 
 
-def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR):
-    dev = tracker.decoder.bound.device
-    quad = quad_from_matrix(est_c2w[:3, :3]).to(dev).requires_grad_(True)
-    T = est_c2w[:3, 3].detach().clone().to(dev).requires_grad_(True)
-    opt = fused.make_adam([{"params": [T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
-                           {"params": [quad], "lr": cam_lr}], capturable=True)
-    packed = _PackedStatic(draws_fn(0), dev)
-    static = packed.static
-    best_loss = torch.full((), 1e10, device=dev)
-    best = torch.cat((quad, T), 0).detach().clone()
-    hist = torch.zeros(n_iters, device=dev)
-    slot = torch.zeros((), dtype=torch.int64, device=dev)
-    err_flag = torch.zeros((), device=dev)
-    refer = refer_w2c.to(dev)
-    cur = dict(frame, est_quad=quad, est_T=T)
+class TrackLoop:
+    """The pose loop of one frame (slams/tracking.py:304-346) as ONE captured CUDA graph that is REUSED for every later
+    frame: frame images, reference pose, feature maps, pose leaves, Adam moments, best pose and loss history live in
+    static device buffers that are refreshed per frame (a few device copies), so a new frame costs no capture, no
+    warm-up and no allocation -- tracking is launch bound (hundreds of tiny launches per iteration), not GPU bound.
+    Cached on the tracker per (frame size, feature size, iteration count, learning rates)."""
 
-    def one():
-        opt.zero_grad(set_to_none=True)
-        est_w2c = torch.stack((refer, fused.rigid_inverse(c2w_from_quad_T(quad, T))), 0)
-        ld, _, _ = tracker.iteration(cur, {"est_w2c": est_w2c}, features_cl, static)
+    def __init__(self, tracker, frame, refer_w2c, features_cl, n_iters, cam_lr, seperate_LR, draws0):
+        dev = tracker.decoder.bound.device
+        self.tracker, self.n_iters, self.dev = tracker, n_iters, dev
+        self.frame = {k: torch.empty_like(v) for k, v in frame.items() if isinstance(v, torch.Tensor)}
+        self.refer = torch.empty(4, 4, device=dev)
+        self.feats = torch.empty_like(features_cl)
+        self.quad = torch.zeros(4, device=dev, requires_grad=True)
+        self.T = torch.zeros(3, device=dev, requires_grad=True)
+        self.opt = fused.make_adam([{"params": [self.T], "lr": cam_lr * (0.2 if seperate_LR else 1.0)},
+                                    {"params": [self.quad], "lr": cam_lr}], capturable=True)
+        self.packed = _PackedStatic(draws0, dev)
+        self.best_loss = torch.full((), 1e10, device=dev)
+        self.best = torch.zeros(7, device=dev)
+        self.hist = torch.zeros(n_iters, device=dev)
+        self.slot = torch.zeros((), dtype=torch.int64, device=dev)
+        self.err_flag = torch.zeros((), device=dev)
+        self.cur = dict(self.frame, est_quad=self.quad, est_T=self.T)
+        self.graph = None
+        self._draws0_loaded = True           # _PackedStatic has consumed draws0: do not fetch draws_fn(0) twice
+
+    def _one(self):
+        self.opt.zero_grad(set_to_none=True)
+        quad, T = self.quad, self.T
+        est_w2c = torch.stack((self.refer, fused.rigid_inverse(c2w_from_quad_T(quad, T))), 0)
+        ld, _, _ = self.tracker.iteration(self.cur, {"est_w2c": est_w2c}, self.feats, self.packed.static)
         loss = ld["total"]
         with torch.no_grad():
-            better = loss < best_loss
-            best.copy_(torch.where(better, torch.cat((quad, T), 0), best))
-            best_loss.copy_(torch.where(better, loss, best_loss))
-            hist.index_copy_(0, slot.reshape(1), loss.detach().reshape(1))
-            slot.add_(1)
-            err_flag.copy_(torch.minimum(err_flag, ld["n_valid"].detach()))
+            better = loss < self.best_loss
+            self.best.copy_(torch.where(better, torch.cat((quad, T), 0), self.best))
+            self.best_loss.copy_(torch.where(better, loss, self.best_loss))
+            self.hist.index_copy_(0, self.slot.reshape(1), loss.detach().reshape(1))
+            self.slot.add_(1)
+            self.err_flag.copy_(torch.minimum(self.err_flag, ld["n_valid"].detach()))
         loss.backward()
-        opt.step()
+        self.opt.step()
 
-    n_warm = min(3, n_iters)
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for it in range(n_warm):
-            if it > 0:                             # draws_fn(0) is already in the static buffers (fetched ONCE: a
-                packed.update(draws_fn(it))        # stateful generator must see every iteration exactly once)
-            one()
-    torch.cuda.current_stream().wait_stream(side)
-    if n_iters > n_warm:
-        packed.update(draws_fn(n_warm))
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            one()
-        def replay(j):                             # capture only records: the captured iteration is replayed too
-            packed.update(draws_fn(n_warm + j))
-            graph.replay()
-        _timed_replays(n_iters - n_warm, replay)
-    fused.raise_on_flag(torch.stack([err_flag] * 8))      # the single host read of the loop
-    return best, best_loss, hist
+    def _reset(self, frame, refer_w2c, features_cl, est_c2w):
+        with torch.no_grad():
+            for k, v in self.frame.items():
+                v.copy_(frame[k], non_blocking=True)
+            self.refer.copy_(refer_w2c, non_blocking=True)
+            self.feats.copy_(features_cl, non_blocking=True)
+            self.quad.copy_(quad_from_matrix(est_c2w[:3, :3]), non_blocking=True)
+            self.T.copy_(est_c2w[:3, 3].detach(), non_blocking=True)
+            self.best.copy_(torch.cat((self.quad, self.T), 0))
+            self.best_loss.fill_(1e10)
+            self.hist.zero_()
+            self.slot.zero_()
+            self.err_flag.zero_()
+        if hasattr(self.opt, "reset_state"):
+            self.opt.reset_state()           # fresh optimiser per frame (tracking.py:119-124)
+
+    def run(self, frame, refer_w2c, features_cl, est_c2w, draws_fn):
+        self._reset(frame, refer_w2c, features_cl, est_c2w)
+        n_iters = self.n_iters
+        start = 0
+        if self.graph is None:               # first frame: three eager iterations (they count), then the capture
+            n_warm = min(3, n_iters)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for it in range(n_warm):
+                    if it > 0 or not self._draws0_loaded:
+                        self.packed.update(draws_fn(it))
+                    self._one()
+            self._draws0_loaded = False
+            torch.cuda.current_stream().wait_stream(side)
+            start = n_warm
+            if n_iters > n_warm:
+                self.packed.update(draws_fn(n_warm))
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._one()
+
+        def replay(j):                       # capture only records: the captured iteration is replayed too
+            self.packed.update(draws_fn(start + j))
+            self.graph.replay()
+        if self.graph is not None:
+            _timed_replays(n_iters - start, replay)
+        fused.raise_on_flag(torch.stack([self.err_flag] * 8))      # the single host read of the loop
+        return self.best.clone(), self.best_loss.clone(), self.hist.clone()
+
+
+def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR):
+    dev = tracker.decoder.bound.device
+    key = (tuple(frame["color"].shape), tuple(features_cl.shape), int(n_iters), float(cam_lr), bool(seperate_LR),
+           tracker.n_pixels)
+    cache = tracker.__dict__.setdefault("_track_loops", {})
+    loop = cache.get(key)
+    if loop is None:
+        if len(cache) >= 2:                  # a captured graph pins its buffers: keep the cache small
+            cache.clear()
+        loop = cache[key] = TrackLoop(tracker, frame, refer_w2c.to(dev), features_cl, n_iters, cam_lr, seperate_LR, draws_fn(0))
+    return loop.run(frame, refer_w2c.to(dev), features_cl, est_c2w, draws_fn)
 
 
 def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,

@@ -144,4 +144,4 @@ if __name__ == "__main__":
               f"iterations); translation drift vs the synthetic trajectory (random-colour frames, not an accuracy "
               f"figure): mean {float(err.mean()):.4f} m, max {float(err.max()):.4f} m; last map p_loss {mp_[-1][2]:.4f} d_loss {mp_[-1][3]:.4f}; "
               f"{sum(1 for e in mp_ if e[4])} of {len(mp_)} mapping calls replayed as CUDA graphs (the others had rays "
-              f"leaving the bound and ran the eager loop)")
+              f"leaving the bound and ran the eager loop); per call: {out['timings']}")

@@ -72,6 +72,20 @@ def test_tracking_loop_vs_oracle():
     b_g, l_g, h_g = slam.track_frame(trk2, fr, refer_w2c, fcl, est, n2, lr, lambda it: draws2[it], use_graph=True)
     close(h_g, h_e, rtol=1e-4, atol=1e-6, name="graph vs eager loss trajectory")
     close(b_g, b_e, rtol=1e-5, atol=1e-6, name="graph vs eager best pose")
+    # the captured loop is REUSED for the next frame (new images, new start pose, fresh Adam state): no new capture
+    loops = trk2._track_loops
+    graph_before = next(iter(loops.values())).graph
+    fr2 = dict(fr)
+    fr2["color"] = (fr["color"] * 0.7 + 0.1).contiguous()
+    fr2["depth"] = (fr["depth"] * 1.03).contiguous()
+    est2 = est.clone()
+    est2[:3, 3] += torch.tensor([-0.01, 0.02, 0.0])
+    b_e2, l_e2, h_e2 = slam.track_frame(trk2, fr2, refer_w2c, fcl, est2, n2, lr, lambda it: draws2[it])
+    b_g2, l_g2, h_g2 = slam.track_frame(trk2, fr2, refer_w2c, fcl, est2, n2, lr, lambda it: draws2[it], use_graph=True)
+    assert len(loops) == 1 and next(iter(loops.values())).graph is graph_before
+    close(h_g2, h_e2, rtol=1e-4, atol=1e-6, name="reused graph vs eager loss trajectory")
+    close(b_g2, b_e2, rtol=1e-5, atol=1e-6, name="reused graph vs eager best pose")
+    assert not torch.equal(h_g2, h_g)
 
 
 def test_mapping_loop_vs_oracle():
