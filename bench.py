@@ -228,7 +228,7 @@ def build_gpu_step(args, scene, dec, rank, world, comm, frames_dev, feats, table
     return st
 
 
-def upload_scene(scene, host_pinned, dev, stem):
+def upload_scene(scene, host_pinned, dev, stem, n_class=None):
     """What happens once per mapping call: key frames and reference images host -> device, the stem over the reference
     views (mapping.py:846), the per-frame class tables (labels do not change between iterations)."""
     from dns_slam_b200 import slam
@@ -237,7 +237,7 @@ def upload_scene(scene, host_pinned, dev, stem):
         fr = {k: host_pinned["frames"][f][k].to(dev, non_blocking=True) for k in ("color", "depth", "label")}
         frames_dev.append(fr)
         feats.append(stem.forward_cl(host_pinned["refer_img"][f].to(dev, non_blocking=True)[None]))
-        tables.append(slam.class_tables(fr["label"]))
+        tables.append(slam.class_tables(fr["label"], n_ids=n_class))
     return frames_dev, feats, tables
 
 
@@ -304,7 +304,7 @@ def main():
         stem.conv_blocks.conv1.weight.copy_(scene["weights"]["stem_conv"])
 
     # ---------------- device-resident timing
-    frames_dev, feats, tables = upload_scene(scene, host_pinned, dev, stem)
+    frames_dev, feats, tables = upload_scene(scene, host_pinned, dev, stem, args.n_class)
     dec = build_decoder(args, scene, dev)
     st = build_gpu_step(args, scene, dec, rank, world, comm, frames_dev, feats, tables)
     gen = torch.Generator().manual_seed(1000 + rank)           # the rank's own pixel draws
@@ -343,7 +343,7 @@ def main():
     dec = build_decoder(args, scene, dev)          # weights are device state like in the reference (not per-call input)
     barrier()
     e0.record()
-    frames_dev, feats, tables = upload_scene(scene, host_pinned, dev, stem)
+    frames_dev, feats, tables = upload_scene(scene, host_pinned, dev, stem, args.n_class)
     st = build_gpu_step(args, scene, dec, rank, world, comm, frames_dev, feats, tables)
     for i in range(args.steps):
         st.upload(host_draws[i % len(host_draws)])
@@ -492,7 +492,7 @@ def _native_iteration(args, dev, scene, n_rays):
     a2.rays_per_gpu = n_rays
     stem = encoder.ResNet().to(dev)
     hp = {"frames": scene["frames"], "refer_img": scene["refer_img"]}
-    frames_dev, feats, tables = upload_scene(scene, hp, dev, stem)
+    frames_dev, feats, tables = upload_scene(scene, hp, dev, stem, args.n_class)
     dec = build_decoder(a2, scene, dev)
     st = build_gpu_step(a2, scene, dec, 0, 1, None, frames_dev, feats, tables)
     gen = torch.Generator().manual_seed(5)

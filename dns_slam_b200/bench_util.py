@@ -76,7 +76,7 @@ def slam_scene(shape, n_class, device, seed=0, n_target=4, n_refer=3):
         feats.append(fused.channels_last(syn.pixel_features(shape, n_refer, gen).to(device)))
         refer_idx.append([100 + 2 * f, 101 + 2 * f, -1][:n_refer])          # ids that are not target frames
         refer_c2w.append([poses[2 * f].to(device), poses[2 * f + 2].to(device), poses[2 * f + 1].to(device)][:n_refer])
-    tables = [slam.class_tables(fr["label"]) for fr in frames]
+    tables = [slam.class_tables(fr["label"], n_ids=n_class if fr["label"].is_cuda else None) for fr in frames]
     return dict(cam=cam, poses=poses, frames=frames, feats=feats, refer_idx=refer_idx, refer_c2w=refer_c2w,
                 class_tables=tables, kf_idx=list(range(n_target)))
 

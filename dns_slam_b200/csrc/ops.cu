@@ -360,6 +360,35 @@ __global__ void k_adam_tick(int* step) { *step += 1; }
 __global__ void k_adam_multi(const dns_adam_seg* __restrict__ segs, const int* __restrict__ step, float b1, float b2,
                              float eps) {
   const dns_adam_seg sg = segs[blockIdx.y];
+  if (sg.row_len > 0) {
+    // independent tensors per row: a row without gradient is skipped like a parameter whose .grad is None, the others
+    // advance their OWN step count (torch.optim.Adam keeps `step` per parameter tensor)
+    __shared__ int s_step;
+    const int64_t rows = sg.n / sg.row_len;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int64_t base = row * sg.row_len;
+      int any = 0;
+      for (int i = threadIdx.x; i < sg.row_len; i += blockDim.x) any |= sg.g[base + i] != 0.f;
+      any = __syncthreads_or(any);
+      if (!any) continue;                    // uniform over the block
+      if (threadIdx.x == 0) s_step = ++sg.row_steps[row];
+      __syncthreads();
+      const double tr = (double)s_step;
+      const float bc1 = (float)(1.0 - pow((double)b1, tr)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, tr));
+      const float step_size = sg.lr / bc1;
+      for (int i = threadIdx.x; i < sg.row_len; i += blockDim.x) {
+        const int64_t k = base + i;
+        const float gi = sg.g[k];
+        const float mi = sg.m[k] + (1.f - b1) * (gi - sg.m[k]);
+        const float vi = b2 * sg.v[k] + (1.f - b2) * gi * gi;
+        sg.m[k] = mi;
+        sg.v[k] = vi;
+        sg.p[k] = sg.p[k] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      }
+      __syncthreads();                       // s_step is rewritten for the next row
+    }
+    return;
+  }
   const double t = (double)*step;
   const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
   const float step_size = sg.lr / bc1;

@@ -206,3 +206,108 @@ int dns_feature_gather(const float* pts, int64_t P, const float* w2c, int R, con
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Per-frame class tables of the class-balanced draw (utils/common.py:312-322: unique(label) + nonzero per class): a
+// STABLE counting sort of the window pixels by label.  One warp owns kClsChunk consecutive pixels and walks them 32 at
+// a time in order (lanes = consecutive pixels, __match_any_sync groups equal labels), so the pixel order inside a class
+// is ascending exactly like torch.nonzero.
+// ---------------------------------------------------------------------------------------
+namespace dns {
+constexpr int kClsChunk = 4096;
+
+__global__ void __launch_bounds__(32) k_cls_hist(const int64_t* __restrict__ label, int64_t n, int n_ids, int* __restrict__ hist,
+                                                 int* __restrict__ err) {
+  extern __shared__ int cnt[];   // [n_ids]
+  const int lane = threadIdx.x;
+  for (int c = lane; c < n_ids; c += 32) cnt[c] = 0;
+  __syncwarp();
+  const int64_t base = (int64_t)blockIdx.x * kClsChunk;
+  for (int k = 0; k < kClsChunk; k += 32) {
+    const int64_t i = base + k + lane;
+    int64_t c = i < n ? label[i] : -1;
+    if (i < n && (c < 0 || c >= n_ids)) {
+      *err = 1;
+      c = 0;
+    }
+    const unsigned m = __match_any_sync(0xffffffffu, c);
+    if (c >= 0 && lane == __ffs(m) - 1) cnt[c] += __popc(m);
+    __syncwarp();
+  }
+  for (int c = lane; c < n_ids; c += 32) hist[(int64_t)blockIdx.x * n_ids + c] = cnt[c];
+}
+
+// counts[c], starts[c] and the per-chunk offsets (in place over hist): one block, ids spread over the threads
+__global__ void k_cls_scan(int* __restrict__ hist, int n_blocks, int n_ids, int* __restrict__ counts, int* __restrict__ starts) {
+  for (int c = threadIdx.x; c < n_ids; c += blockDim.x) {
+    int run = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+      const int v = hist[(int64_t)b * n_ids + c];
+      hist[(int64_t)b * n_ids + c] = run;
+      run += v;
+    }
+    counts[c] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int c = 0; c < n_ids; ++c) {
+      starts[c] = run;
+      run += counts[c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) k_cls_scatter(const int64_t* __restrict__ label, int64_t n, int n_ids,
+                                                    const int* __restrict__ offs, const int* __restrict__ starts,
+                                                    int64_t* __restrict__ order) {
+  extern __shared__ int cur[];   // [n_ids] next free position of the class for this chunk
+  const int lane = threadIdx.x;
+  for (int c = lane; c < n_ids; c += 32) cur[c] = starts[c] + offs[(int64_t)blockIdx.x * n_ids + c];
+  __syncwarp();
+  const int64_t base = (int64_t)blockIdx.x * kClsChunk;
+  for (int k = 0; k < kClsChunk; k += 32) {
+    const int64_t i = base + k + lane;
+    int64_t c = i < n ? label[i] : -1;
+    if (i < n && (c < 0 || c >= n_ids)) c = 0;
+    const unsigned m = __match_any_sync(0xffffffffu, c);
+    int pos = -1;
+    if (c >= 0) pos = cur[c] + __popc(m & ((1u << lane) - 1u));
+    __syncwarp();
+    if (c >= 0 && lane == __ffs(m) - 1) cur[c] += __popc(m);
+    __syncwarp();
+    if (pos >= 0) order[pos] = i;
+  }
+}
+}  // namespace dns
+
+extern "C" {
+
+int64_t dns_class_tables_workspace_bytes(int64_t n_pixels, int n_ids) {
+  const int64_t blocks = (n_pixels + dns::kClsChunk - 1) / dns::kClsChunk;
+  return blocks * (int64_t)n_ids * 4 + 256;
+}
+
+int dns_class_tables(const int64_t* label, int64_t n_pixels, int n_ids, int64_t* order, int32_t* counts, int32_t* starts,
+                     int32_t* err, void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace dns;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_pixels <= 0 || n_ids <= 0 || n_ids > 8192 || !label || !order || !counts || !starts || !err) {
+    set_error("class_tables: bad arguments (1 <= n_ids <= 8192)");
+    return DNS_ERR_ARG;
+  }
+  if (!workspace || workspace_bytes < dns_class_tables_workspace_bytes(n_pixels, n_ids)) {
+    set_error("class_tables: workspace too small");
+    return DNS_ERR_ARG;
+  }
+  const int blocks = (int)((n_pixels + kClsChunk - 1) / kClsChunk);
+  int* hist = (int*)workspace;
+  PhaseScope ph(phSample, st, 4);
+  cudaMemsetAsync(err, 0, sizeof(int), st);
+  k_cls_hist<<<blocks, 32, n_ids * sizeof(int), st>>>(label, n_pixels, n_ids, hist, err);
+  k_cls_scan<<<1, 256, 0, st>>>(hist, blocks, n_ids, counts, starts);
+  k_cls_scatter<<<blocks, 32, n_ids * sizeof(int), st>>>(label, n_pixels, n_ids, hist, starts, order);
+  return check_launch("class_tables");
+}
+
+}  // extern "C"

@@ -213,3 +213,8 @@ class Decoder(nn.Module):
     def view(self, name):
         a, n = self.layout[name]
         return self.flat[a:a + n]
+
+    def expert_rows(self):
+        """(offset, rows, row length) of the class-expert bank inside ``flat``: independent parameter tensors for Adam."""
+        a, n = self.layout["experts"]
+        return a, self.n_class_ids, EXPERT_PARAMS

@@ -716,8 +716,10 @@ class FusedAdam:
       to views of the buffers instead (autograd accumulates in place, no copies).
     * ``flat``: a contiguous buffer that the group's parameters tile exactly (``Decoder.flat``): the group becomes
       one segment, its gradient one flat buffer (one memset per iteration).
-    * A parameter that receives no gradient in an iteration sees a zero gradient (torch would skip it); the loops
-      here give every optimised parameter a gradient in every iteration.
+    * ``rows`` = ``Decoder.expert_rows()``: the class-expert bank at the tail of ``flat`` is a stack of independent
+      parameter tensors in the reference; a row that receives no gradient in an iteration (no sample of that class) is
+      skipped -- no moment decay, no step count -- exactly as ``torch.optim.Adam`` skips a parameter whose ``.grad`` is
+      None, and every row has its own step count.  Other parameters always get a gradient in the loops here.
     """
 
     def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, inplace=False):
@@ -743,19 +745,27 @@ class FusedAdam:
                 for p in ps:
                     off = (p.data_ptr() - flat.data_ptr()) // 4
                     self._views.append((p, gbuf[off:off + p.numel()].view_as(p)))
-                segs.append((flat.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr))
+                rows = g.get("rows")      # (offset, n_rows, row_len): the class-expert bank, independent tensors per row
+                if rows is not None and rows[0] + rows[1] * rows[2] == n:
+                    a = rows[0]
+                    steps = torch.zeros(rows[1], dtype=torch.int32, device=dev)
+                    self._keep.append(steps)
+                    segs.append((flat.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), a, lr, 0, 0))
+                    segs.append((flat.data_ptr() + 4 * a, gbuf.data_ptr() + 4 * a, m.data_ptr() + 4 * a, v.data_ptr() + 4 * a,
+                                 n - a, lr, rows[2], steps.data_ptr()))
+                else:
+                    segs.append((flat.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, 0, 0))
             else:
                 off = 0
                 for p in ps:
                     k = p.numel()
                     self._views.append((p, gbuf[off:off + k].view_as(p)))
                     segs.append((p.data_ptr(), gbuf.data_ptr() + 4 * off, m.data_ptr() + 4 * off,
-                                 v.data_ptr() + 4 * off, k, lr))
+                                 v.data_ptr() + 4 * off, k, lr, 0, 0))
                     off += k
-        dt = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("lr", "<f4"), ("r", "<f4")])
-        tab = np.zeros(len(segs), dtype=dt)
+        tab = np.zeros(len(segs), dtype=ADAM_SEG_DTYPE)
         for i, sg in enumerate(segs):
-            tab[i] = sg + (0.0,)
+            tab[i] = sg
         self.table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
         self.n_segs, self.max_n = len(segs), max(sg[4] for sg in segs)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -794,6 +804,25 @@ class FusedAdam:
                                              self.eps, _lib.stream()))
 
 
+def _adam_seg_dtype():
+    import numpy as np
+    return np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("lr", "<f4"), ("row_len", "<i4"),
+                     ("row_steps", "<u8")])
+
+
+ADAM_SEG_DTYPE = _adam_seg_dtype()      # mirror of dns_adam_seg (56 bytes)
+
+
+def split_expert_rows(flat, grad, lr, rows):
+    """One flat (params, grads, lr) segment -> [plain part, expert rows]: ``rows`` = (offset, n_rows, row_len) of the class
+    expert bank inside the flat buffer (``Decoder.expert_rows()``).  The experts are independent parameter tensors in the
+    reference (slams/mapping.py:445-446), so Adam treats each row on its own (``dns_adam_seg.row_len``)."""
+    off, n_rows, row_len = rows
+    if off + n_rows * row_len != flat.numel():
+        raise ValueError("the expert bank must be the tail of the flat buffer")
+    return [(flat[:off], grad[:off], lr, 0), (flat[off:], grad[off:], lr, row_len)]
+
+
 class AdamSegments:
     """Raw-buffer Adam (torch defaults) over segments ``[(params, grads, lr), ...]`` of flat fp32 CUDA tensors in ONE
     ``dns_adam_multi`` launch per step; owns the moments and a device-side step counter (fresh state per object, as
@@ -802,19 +831,20 @@ class AdamSegments:
     def __init__(self, segments, betas=(0.9, 0.999), eps=1e-8):
         import numpy as np
         self.betas, self.eps = betas, eps
-        self.segments = [(p, g, float(lr)) for p, g, lr in segments if p.numel() > 0]
+        self.segments = [(sg[0], sg[1], float(sg[2]), int(sg[3]) if len(sg) > 3 else 0) for sg in segments if sg[0].numel() > 0]
         dev = self.segments[0][0].device
-        dt = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"), ("lr", "<f4"), ("r", "<f4")])
-        tab = np.zeros(len(self.segments), dtype=dt)
+        tab = np.zeros(len(self.segments), dtype=ADAM_SEG_DTYPE)
         self._keep = []
-        for i, (p, g, lr) in enumerate(self.segments):
+        for i, (p, g, lr, row_len) in enumerate(self.segments):
             if not (p.is_cuda and g.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()):
                 raise RuntimeError("AdamSegments: contiguous fp32 CUDA tensors only (no CPU fallback)")
             m, v = torch.zeros_like(p), torch.zeros_like(p)
-            self._keep += [m, v]
-            tab[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, 0.0)
+            steps = torch.zeros(p.numel() // row_len, dtype=torch.int32, device=dev) if row_len else None
+            self._keep += [m, v, steps]
+            tab[i] = (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, row_len,
+                      steps.data_ptr() if row_len else 0)
         self.table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
-        self.n_segs, self.max_n = len(self.segments), max(p.numel() for p, _, _ in self.segments)
+        self.n_segs, self.max_n = len(self.segments), max(sg[0].numel() for sg in self.segments)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def step(self):

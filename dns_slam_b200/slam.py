@@ -121,17 +121,38 @@ class ClassTables(tuple):
     """(classes, order, starts, counts) with host copies of the small per-class lists made ONCE per frame,
     so that the per-iteration index draw needs no device->host read."""
 
-    def __new__(cls, classes, order, starts, counts):
+    def __new__(cls, classes, order, starts, counts, host=None):
         self = super().__new__(cls, (classes, order, starts, counts))
-        self.classes_h, self.starts_h, self.counts_h = classes.tolist(), starts.tolist(), counts.tolist()
+        self.classes_h, self.starts_h, self.counts_h = host or (classes.tolist(), starts.tolist(), counts.tolist())
         return self
 
 
-def class_tables(label_win):
+def class_tables(label_win, n_ids=None):
     """Per-frame tables for the class-balanced draw (common.py:312-322): labels do not change
     between iterations, so ``unique`` / ``nonzero`` are done once per frame, not per iteration.
-    Returns (classes ascending, sorted pixel indices, start offsets, counts)."""
+    Returns (classes ascending, sorted pixel indices, start offsets, counts).  On the device with ``n_ids`` (the
+    decoder's number of class ids) the tables come from ``dns_class_tables`` (a stable counting sort, three small
+    kernels); host tensors (tests, tools) take the torch formulation."""
     flat = label_win.reshape(-1)
+    if flat.is_cuda and n_ids is not None:
+        import ctypes as C
+        flat = flat.contiguous()
+        dev, n = flat.device, flat.numel()
+        L = _lib.lib()
+        order = torch.empty(n, dtype=torch.int64, device=dev)
+        cs = torch.empty(2, n_ids, dtype=torch.int32, device=dev)
+        err = torch.empty(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(int(L.dns_class_tables_workspace_bytes(n, n_ids)), dtype=torch.uint8, device=dev)
+        _lib.check(L.dns_class_tables(_lib.ptr(flat, torch.int64), n, n_ids, _lib.ptr(order), cs[0].data_ptr(),
+                                      cs[1].data_ptr(), _lib.ptr(err), ws.data_ptr(), ws.numel(), _lib.stream()))
+        host = torch.cat((cs.reshape(-1), err)).tolist()          # ONE small read per frame (the host lists below)
+        if host[-1]:
+            raise ValueError("label outside [0, n_class_ids)")
+        counts_all, starts_all = host[:n_ids], host[n_ids:2 * n_ids]
+        present = [c for c in range(n_ids) if counts_all[c] > 0]
+        idx = torch.tensor(present, dtype=torch.int64, device=dev)
+        return ClassTables(idx, order, cs[1].long()[idx], cs[0].long()[idx],
+                           host=(present, [starts_all[c] for c in present], [counts_all[c] for c in present]))
     order = torch.sort(flat, stable=True)[1]
     classes, counts = torch.unique_consecutive(flat[order], return_counts=True)
     starts = torch.cumsum(counts, 0) - counts
@@ -568,7 +589,7 @@ def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list,
         T_list.append(t)
     net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
     cam_lr = BA_cam_lr * float(is_BA)
-    opt = fused.make_adam([{"params": net, "lr": lr, "flat": dec.flat},
+    opt = fused.make_adam([{"params": net, "lr": lr, "flat": dec.flat, "rows": dec.expert_rows()},
                            {"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
                            {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}])
     ld = None
@@ -639,7 +660,7 @@ def decoder_init(mapper, decoder_idx, frame, class_table, cur_c2w, features_cl, 
     for c in decoder_idx:
         dec.activate_expert(c)
     net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
-    opt = fused.make_adam([{"params": net, "lr": lr, "flat": dec.flat}])
+    opt = fused.make_adam([{"params": net, "lr": lr, "flat": dec.flat, "rows": dec.expert_rows()}])
     R, T = cur_c2w[:3, :3].to(dev), cur_c2w[:3, 3].to(dev)
     window = (0, mapper.H, 0, mapper.W)
     c2w = cur_c2w.to(dev).unsqueeze(0)
@@ -753,7 +774,7 @@ def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2
         T_list.append(t)
     net = [p for p in dec.parameters() if p.requires_grad and p.numel() > 0]
     cam_lr = BA_cam_lr * float(is_BA)
-    groups = [{"params": net, "lr": lr, "flat": dec.flat}]
+    groups = [{"params": net, "lr": lr, "flat": dec.flat, "rows": dec.expert_rows()}]
     if any(q.requires_grad for q in quad_list):
         groups += [{"params": [q for q in quad_list if q.requires_grad], "lr": cam_lr},
                    {"params": [t for t in T_list if t.requires_grad], "lr": cam_lr}]

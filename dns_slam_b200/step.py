@@ -26,9 +26,13 @@ class MappingStep:
 
     def reset(self):
         """Fresh Adam state (the reference builds a new optimiser for every optimize() call)."""
-        self.m = torch.zeros_like(self.dec.flat)
-        self.v = torch.zeros_like(self.dec.flat)
+        self.adam = None
         self.t = 0
+
+    def _adam(self):
+        if self.adam is None:     # class experts are independent tensors: rows without gradient are skipped (fused.FusedAdam)
+            self.adam = fused.AdamSegments(fused.split_expert_rows(self.dec.flat, self.grad, self.lr, self.dec.expert_rows()))
+        self.adam.step()
 
     def _views(self, buf):
         lay = self.dec.layout
@@ -58,7 +62,7 @@ class MappingStep:
         if self.world > 1:
             torch.distributed.all_reduce(self.grad, group=self.pg)
         self.t += 1
-        fused.adam_step(self.dec.flat, self.grad, self.m, self.v, self.lr, self.t)
+        self._adam()
         return out
 
 
@@ -109,8 +113,6 @@ class ShardedMappingStep(MappingStep):
     def _local_counts(self, cfg):
         return fused.render_counts(cfg)
 
-    def _adam(self):
-        fused.adam_step(self.dec.flat, self.grad, self.m, self.v, self.lr, self.t)
 
 
 class TorchComm:
@@ -409,7 +411,7 @@ class MappingFrameStep:
         self.loss_vec = self.packed[nflat + 7 * F:nflat + 7 * F + 9]
         self.pose_scratch = torch.empty(12 * F, device=dev)
         self.d_features = torch.empty(N, S, 32, device=dev)
-        segs = [(dec.flat, self.grad, lr)]
+        segs = fused.split_expert_rows(dec.flat, self.grad, lr, dec.expert_rows())
         self.opt_poses = bool(is_BA)
         if self.opt_poses:
             f0 = 0 if F == 1 else 1      # the oldest target frame stays fixed (mapping.py:457)

@@ -78,7 +78,7 @@ def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_gra
         for c in torch.unique(torch.cat([frames[k]["label"].reshape(-1) for k in window])).tolist():
             shared.activate_expert(int(c))                       # experts appear with their classes (mapping.py:727-761)
         target = dict(kf_idx=window, frames=[frames[k] for k in window],
-                      class_tables=[slam.class_tables(frames[k]["label"]) for k in window])
+                      class_tables=[slam.class_tables(frames[k]["label"], n_ids=n_class) for k in window])
         refer = dict(kf_idx=[[-1]] * len(window), est_c2w=[[est[k].to(dev)] for k in window])
         scene = dict(cam=cam, frames=target["frames"], class_tables=target["class_tables"])
         md, tv = bench_util.mapping_draws(scene, s["mapping_pixels"], map_iters, seed=seed + 10 * f)

@@ -244,6 +244,15 @@ typedef struct dns_sample_args {
 
 int dns_sample_rays(const dns_sample_args* a, void* stream);
 
+/* Per-frame tables of the class-balanced draw (utils/common.py:312-322: torch.unique(label) + torch.nonzero per
+ * class): a STABLE counting sort of the window pixels by label.  label [n_pixels] int64 with ids in [0, n_ids);
+ * order [n_pixels]: pixel indices grouped by ascending label, ascending inside a label (== nonzero); counts / starts
+ * [n_ids] int32: pixels of every id and the first position of its group in `order`; *err = 1 if a label is out of
+ * range.  dns_sample_rays resolves a class-balanced draw as order[slot_base + offset] (see dns_sample_args). */
+int64_t dns_class_tables_workspace_bytes(int64_t n_pixels, int n_ids);
+int dns_class_tables(const int64_t* label, int64_t n_pixels, int n_ids, int64_t* order, int32_t* counts, int32_t* starts,
+                     int32_t* err, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Pixel-feature branch == utils/common.py:645-679 without the 209 MB/view upsample:
  * project P points into R views, round, mask, 4-tap bilinear fetch of the half-res feature
@@ -368,7 +377,13 @@ typedef struct {
   float* v;        /* exp_avg_sq */
   int64_t n;
   float lr;
-  float reserved;
+  /* row_len > 0: the segment is n / row_len independent parameter tensors (the class experts of slams/mapping.py:445-446,
+   * one tinycudann network each).  torch.optim.Adam skips a tensor whose gradient is None -- no moment decay, no step
+   * count -- which is what happens to the expert of a class that no sample of the iteration belongs to: a row whose
+   * gradient is all zero is skipped the same way, and every row keeps its own step count in row_steps[row] (int32,
+   * device, zero-initialised by the caller) for the bias corrections. */
+  int32_t row_len;
+  int32_t* row_steps;
 } dns_adam_seg;
 int dns_adam_multi(const dns_adam_seg* segs_dev, int n_segs, int64_t max_n, int* step_dev, float beta1, float beta2,
                    float eps, void* stream);

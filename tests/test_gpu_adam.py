@@ -78,3 +78,38 @@ def test_fused_adam_graph_replay_advances_the_step():
     assert int(ours.step_dev) == n
     for u, v in ((flat1, flat2), (q1, q2), (t1, t2)):
         torch.testing.assert_close(u.detach(), v.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_expert_rows_follow_torch_per_tensor_semantics():
+    """the class experts are independent parameter tensors in the reference (slams/mapping.py:445-446); an
+    expert whose class is absent from an iteration has ``.grad = None`` there and torch.optim.Adam skips it (no moment
+    decay, no step count).  ``dns_adam_seg.row_len`` reproduces that per row of the expert bank."""
+    from dns_slam_b200 import fused
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    n_rows, row_len, head = 5, 64, 100
+    flat = torch.randn(head + n_rows * row_len, generator=g).to(dev)
+    grad = torch.zeros_like(flat)
+    ref_head = flat[:head].clone().requires_grad_(True)
+    ref_rows = [flat[head + r * row_len:head + (r + 1) * row_len].clone().requires_grad_(True) for r in range(n_rows)]
+    ref = torch.optim.Adam([ref_head] + ref_rows, lr=5e-3)
+    ours = fused.AdamSegments(fused.split_expert_rows(flat, grad, 5e-3, (head, n_rows, row_len)))
+    present = [[0, 1, 2, 3, 4], [0, 2], [], [1, 2, 4], [3], [0, 1, 2, 3, 4], [2]]      # classes seen per iteration
+    for it, rows in enumerate(present):
+        grad.zero_()
+        gh = torch.randn(head, generator=g).to(dev)
+        grad[:head] = gh
+        ref_head.grad = gh.clone()
+        for r in range(n_rows):
+            if r in rows:
+                gr = (torch.randn(row_len, generator=g) * (10.0 if it % 2 else 0.1)).to(dev)
+                grad[head + r * row_len:head + (r + 1) * row_len] = gr
+                ref_rows[r].grad = gr.clone()
+            else:
+                ref_rows[r].grad = None
+        ref.step()
+        ours.step()
+    torch.testing.assert_close(flat[:head], ref_head.detach(), rtol=1e-5, atol=1e-6)
+    for r in range(n_rows):
+        torch.testing.assert_close(flat[head + r * row_len:head + (r + 1) * row_len], ref_rows[r].detach(), rtol=1e-5, atol=1e-6,
+                                   msg=lambda m, r=r: f"expert row {r}: {m}")

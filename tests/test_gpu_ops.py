@@ -196,3 +196,36 @@ def test_feature_gather(golden_dir):
     assert float(same.float().mean()) > 0.999
     sel = same.unsqueeze(-1).expand_as(captured["code"])
     close(code.cpu()[sel], captured["code"][sel], rtol=1e-4, atol=1e-5, name="feature code")
+
+
+@pytest.mark.parametrize("shape,n_ids", [((37, 53), 7), ((680, 1200), 40), ((1, 1), 3), ((64, 129), 300)])
+def test_class_tables_kernel_is_the_stable_sort(shape, n_ids):
+    """a2 (utils/common.py:312-322: torch.unique(label) + torch.nonzero per class) on the device: ``dns_class_tables`` is a
+    stable counting sort, bit identical to the torch formulation (ascending classes, ascending pixels inside a class),
+    including absent ids, a single-pixel class and more ids than a warp."""
+    from dns_slam_b200 import slam
+    dev = _dev()
+    g = torch.Generator().manual_seed(shape[0] * 1000 + n_ids)
+    present = torch.randperm(n_ids, generator=g)[:max(1, (2 * n_ids) // 3)]
+    label = present[torch.randint(len(present), shape, generator=g)]
+    if label.numel() > 10:
+        lone = [c for c in range(n_ids) if c not in present.tolist()]
+        if lone:
+            label[shape[0] // 2, shape[1] // 3] = lone[0]          # a class with exactly one pixel
+    want = slam.class_tables(label)                                # torch formulation on the host
+    got = slam.class_tables(label.to(dev), n_ids=n_ids)
+    for w, g_, name in zip(want, got, ("classes", "order", "starts", "counts")):
+        assert torch.equal(w, g_.cpu()), name
+    assert got.classes_h == want.classes_h and got.starts_h == want.starts_h and got.counts_h == want.counts_h
+
+
+def test_class_tables_kernel_rejects_out_of_range_labels():
+    from dns_slam_b200 import slam
+    dev = _dev()
+    label = torch.randint(5, (16, 16)).to(dev)
+    label[3, 3] = 5
+    with pytest.raises(ValueError):
+        slam.class_tables(label, n_ids=5)
+    label[3, 3] = -1
+    with pytest.raises(ValueError):
+        slam.class_tables(label, n_ids=5)
