@@ -620,7 +620,10 @@ def _iteration_timings(shape, n_class, dev):
                 best = ms if best is None else min(best, ms)
         return best
     t_track_graph = graph_ms(lambda: slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, 103, s["cam_lr"],
-                                                      lambda it: td[it % n_it], use_graph=True))
+                                                      lambda it: td[it % n_it], use_graph=True, native=False))
+    n_nat = s["tracking_iters"]           # whole calls of the native loop (per-frame reset and the final host read included)
+    t_track_native = _time_cuda(lambda: slam.track_frame(trk, sc["frames"][1], refer_w2c, feats2, est, n_nat, s["cam_lr"],
+                                                         lambda it: td[it % n_it], native=True), 3, 1) / n_nat
     mp = slam.MapperCore(cam, dec, s["mapping_pixels"], 32, 15,
                          lambdas=dict(p=s["lambda_color"], d=s["lambda_depth"], l=s["lambda_label"], lt=10.0,
                                       fs=s["lambda_fs"], op=s["lambda_opacity"]),
@@ -637,12 +640,21 @@ def _iteration_timings(shape, n_class, dev):
     t_map = _time_cuda(mapit, 2, 1) / m_it
     mdg, tvg = bench_util.mapping_draws(sc, s["mapping_pixels"], 8)
     t_map_graph = graph_ms(lambda: slam.map_optimize(mp, target, refer, sc["feats"], est_list, 43, s["lr"], s["BA_cam_lr"], True, [],
-                                                     lambda it: mdg[it % 8], lambda it: tvg[it % 8], use_graph=True))
+                                                     lambda it: mdg[it % 8], lambda it: tvg[it % 8], use_graph=True, native=False))
+    graph_ok = bool(getattr(mp, "last_graph_ok", False))
+    m_nat = s["mapping_iters"]            # whole calls of the native loop (step construction and the final host read included)
+    t_map_native = _time_cuda(lambda: slam.map_optimize(mp, target, refer, sc["feats"], est_list, m_nat, s["lr"], s["BA_cam_lr"],
+                                                        True, [], lambda it: mdg[it % 8], lambda it: tvg[it % 8], native=True),
+                              2, 1) / m_nat
+    native_ok = mp.last_path == "native"
     return {"tracking_ms_per_iteration": t_track, "tracking_ms_per_iteration_cuda_graph": t_track_graph,
-            "tracking_rays": s["tracking_pixels"],
+            "tracking_ms_per_iteration_native": t_track_native, "tracking_rays": s["tracking_pixels"],
             "mapping_ms_per_iteration": t_map, "mapping_ms_per_iteration_cuda_graph": t_map_graph,
-            "mapping_graph_ok": bool(getattr(mp, "last_graph_ok", False)), "mapping_rays": s["mapping_pixels"], "tv_lattice": (s["smooth_pts"] - 1) ** 3,
-            "n_samples": 47, "note": "autograd drop-in path (render_and_loss + FusedAdam), sampling + feature matching + TV included"}
+            "mapping_ms_per_iteration_native": t_map_native, "mapping_graph_ok": graph_ok, "mapping_native_ok": native_ok,
+            "mapping_rays": s["mapping_pixels"], "tv_lattice": (s["smooth_pts"] - 1) ** 3, "n_samples": 47,
+            "note": "slam.track_frame / slam.map_optimize incl. sampling + feature matching + TV + Adam: the autograd drop-in "
+                    "loop eager and as CUDA-graph replays (events around the replays), and the native loops "
+                    "(step.TrackingFrameStep / step.MappingFrameStep, the default fast path; whole calls / iterations)"}
 
 
 if __name__ == "__main__":

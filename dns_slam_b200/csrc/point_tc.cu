@@ -551,8 +551,10 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   float2* dtab = (a.need_dparams && !(DNS_DBG(a) & 4) && !(DNS_DBG(a) & (grp ? 32 : 16))) ? a.d_table : nullptr;
   const bool want_dx = a.need_drays != 0 && !(DNS_DBG(a) & 8);
   if (valid) {
-    if (grp == 0) hashgrid_bwd_range<0, 8>(a.G, a.table, dtab, x, dg, want_dx, dxg);
-    else hashgrid_bwd_range<8, 16>(a.G, a.table, dtab, x, dg, want_dx, dxg);
+    float2* dpriv = a.d_priv ? a.d_priv + (size_t)(blockIdx.x % a.priv_copies) * a.priv_end : nullptr;
+    const int pl = a.d_priv ? a.priv_levels : 0;
+    if (grp == 0) hashgrid_bwd_range<0, 8>(a.G, a.table, dtab, x, dg, want_dx, dxg, dpriv, pl);
+    else hashgrid_bwd_range<8, 16>(a.G, a.table, dtab, x, dg, want_dx, dxg, dpriv, pl);
   }
   if (a.need_drays && MODE != kTv) {
     if (grp == 1) {

@@ -114,6 +114,24 @@ __global__ void k_pose_finish(const float* __restrict__ sums, const float* __res
   for (int m = 0; m < 4; ++m) d_quats[4 * f + m] = s * dq[m] - s * s * q[m] * GA;
 }
 
+
+// best-pose bookkeeping of the tracking loop (slams/tracking.py:331-338), one thread: the reference compares the loss
+// on the host every iteration; here the comparison, the copy of the current pose, the loss history and the running
+// error flag stay on the device
+__global__ void k_track_best(const float* __restrict__ losses, const float* __restrict__ quat, const float* __restrict__ trans,
+                             float* best7, float* best_loss, float* hist, int* slot, int hist_len, float* err_min) {
+  const float l = losses[6];
+  if (l < *best_loss) {
+    *best_loss = l;
+    for (int k = 0; k < 4; ++k) best7[k] = quat[k];
+    for (int k = 0; k < 3; ++k) best7[4 + k] = trans[k];
+  }
+  const int s = *slot;
+  if (hist && s < hist_len) hist[s] = l;
+  *slot = s + 1;
+  if (losses[7] < *err_min) *err_min = losses[7];
+}
+
 }  // namespace dns
 
 using namespace dns;
@@ -156,6 +174,17 @@ int dns_pose_grad(const float* d_rays_o, const float* d_rays_d, const int64_t* p
   }
   k_pose_finish<<<(n_frames + 31) / 32, 32, 0, st>>>(scratch, quats, n_frames, d_quats, d_trans);
   return check_launch("pose_grad");
+}
+
+int dns_track_best(const float* losses, const float* quat, const float* trans, float* best7, float* best_loss, float* hist,
+                   int32_t* slot, int hist_len, float* err_min, void* stream) {
+  if (!losses || !quat || !trans || !best7 || !best_loss || !slot || !err_min) {
+    set_error("track_best: bad arguments");
+    return DNS_ERR_ARG;
+  }
+  PhaseScope ph(phFinalize, (cudaStream_t)stream, 1);
+  k_track_best<<<1, 1, 0, (cudaStream_t)stream>>>(losses, quat, trans, best7, best_loss, hist, slot, hist_len, err_min);
+  return check_launch("track_best");
 }
 
 }  // extern "C"

@@ -846,8 +846,44 @@ struct RenderWs {
   float *fine36, *coarse36, *dfine36, *diff36s, *dfine36s;
   float *Xst, *Hc, *Hf, *dHc, *dHf, *dOc, *dOf, *Jst;
   float *X2, *dH2, *Hcol, *dpre, *dlogit, *Hbar;
+  float2* dpriv;   // privatised gradient copies of the small hash-grid levels (kPrivBytes)
   int64_t Q, tiles;
 };
+// Privatised copies of the small leading levels of the gradient table (PointArgs::d_priv): levels of fewer than 2^16
+// entries, at most kPrivLevelBytes together, as many copies (<= kPrivCopies) as fit kPrivBytes.
+constexpr int64_t kPrivBytes = 8 << 20, kPrivLevelBytes = 2 << 20;
+constexpr int kPrivCopies = 8;
+static void priv_plan(const dns_grid& G, int& levels, uint32_t& end, int& copies) {
+  levels = 0;
+  end = 0;
+  while (levels < G.n_levels && G.size[levels] < 65536u && (int64_t)(G.offset[levels + 1]) * 8 <= kPrivLevelBytes) {
+    ++levels;
+    end = G.offset[levels];
+  }
+  copies = 0;
+  if (levels > 0) {
+    int64_t k = kPrivBytes / ((int64_t)end * 8);
+    copies = (int)(k < kPrivCopies ? k : kPrivCopies);
+    if (copies < 2) levels = copies = 0, end = 0;
+  }
+}
+// d_table[i] += sum_k d_priv[k][i]; the copies are cleared for the next call
+__global__ void k_priv_reduce(float2* __restrict__ d_table, float2* __restrict__ d_priv, uint32_t n, int copies) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float sx = 0.f, sy = 0.f;
+  for (int k = 0; k < copies; ++k) {
+    const float2 v = d_priv[(size_t)k * n + i];
+    sx += v.x;
+    sy += v.y;
+  }
+  if (sx != 0.f || sy != 0.f) {
+    float2 t = d_table[i];
+    t.x += sx;
+    t.y += sy;
+    d_table[i] = t;
+  }
+}
 static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C, int nci) {
   Carver c{base, 0};
   const int64_t Pc = Nc * S;
@@ -901,6 +937,7 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.dpre = c.take<float>(rows2 * 8);
   w.dlogit = c.take<float>(Nc * C4);
   w.Hbar = c.take<float>(Nc * 32);
+  w.dpriv = c.take<float2>(kPrivBytes / 8);
   return c.off + 256;
 }
 constexpr int64_t kMaxChunkRays = 1 << 17;
@@ -1047,8 +1084,15 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
     pa.need_dparams = a->need_dparams && !a->forward_only; pa.need_drays = a->need_drays;
+    if (tc && pa.need_dparams && a->d_table) {
+      priv_plan(a->grid, pa.priv_levels, pa.priv_end, pa.priv_copies);
+      pa.d_priv = pa.priv_copies ? w.dpriv : nullptr;
+    }
 #ifdef DNS_ABLATE
     { const char* e = getenv("DNS_DBG"); pa.dbg = e ? atoi(e) : 0; }
+    if (getenv("DNS_NO_PRIV")) pa.d_priv = nullptr;
+    if (const char* e = getenv("DNS_PRIV_COPIES")) { if (pa.d_priv && atoi(e) >= 1 && atoi(e) <= pa.priv_copies) pa.priv_copies = atoi(e); }
+    if (const char* e = getenv("DNS_PRIV_LEVELS")) { if (pa.d_priv && atoi(e) >= 1 && atoi(e) <= pa.priv_levels) { pa.priv_levels = atoi(e); pa.priv_end = a->grid.offset[pa.priv_levels]; } }
 #endif
     if (map) {
       bool whole = !sharded && ray0 == 0 && nc == N && (int64_t)N * S < 2147483647LL;
@@ -1122,11 +1166,14 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     }
     if (int e = check_launch("ray")) return e;
     if (!fwd_only) {
-      PhaseScope phb(phPointBwd, st, 1);
+      PhaseScope phb(phPointBwd, st, pa.d_priv ? 2 : 1);
+      if (pa.d_priv) cudaMemsetAsync(pa.d_priv, 0, (size_t)pa.priv_copies * pa.priv_end * sizeof(float2), st);
       if (tc) {
         if (int e = launch_point_bwd_tc(map ? kMap : kTrack, pa, tiles_max, w.wc_tc, w.we_tc, st)) return e;
       } else if (map) k_point_bwd<kMap><<<tiles_max, kTile, smem_pt, st>>>(pa);
       else k_point_bwd<kTrack><<<tiles_max, kTile, smem_pt, st>>>(pa);
+      if (pa.d_priv)
+        k_priv_reduce<<<(pa.priv_end + 255) / 256, 256, 0, st>>>((float2*)a->d_table, pa.d_priv, pa.priv_end, pa.priv_copies);
     }
     if (int e = check_launch("point_bwd")) return e;
 

@@ -116,6 +116,14 @@ struct PointArgs {
   float lam_lt, lam_fs, lam_op, trunc, sigma;
   float* raw;
   float2* d_table;
+  // Privatised gradient copies of the SMALL leading levels (tcgen05 backward): levels 0 .. priv_levels-1 (entries
+  // [0, priv_end)) are reduced into copy (blockIdx.x % priv_copies) of d_priv [priv_copies][priv_end] instead of d_table;
+  // k_priv_reduce folds the copies back.  Every level receives the same number of reductions, so the 32 KB of level 0
+  // would otherwise take 1/16 of them on 256 cache lines -- ncu showed the busiest L2 slice at 94 % of its tag rate while
+  // the average slice sat at 59 % (profiles/r02m_ncu_summary.md).
+  float2* d_priv;
+  uint32_t priv_end;
+  int priv_levels, priv_copies;
   float* d_rays_o;
   float* d_rays_d;
   int need_dparams, need_drays;

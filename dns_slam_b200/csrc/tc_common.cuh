@@ -199,12 +199,13 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
   }
 }
 template <int L0, int L1, bool PAIR = true>
-__device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const float2* __restrict__ table, float2* d_table,
+__device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const float2* __restrict__ table, float2* d_table_all,
                                                    const float x[3], const float (&dg)[2 * (L1 - L0)], bool want_dx,
-                                                   float dx[3]) {
+                                                   float dx[3], float2* d_priv = nullptr, int priv_levels = 0) {
   dx[0] = dx[1] = dx[2] = 0.f;
 #pragma unroll
   for (int l = L0; l < L1; ++l) {
+    float2* d_table = (d_table_all && l < priv_levels) ? d_priv : d_table_all;   // this CTA's private copy of a small level
     const float g0 = dg[2 * (l - L0)], g1 = dg[2 * (l - L0) + 1];
     if (g0 == 0.f && g1 == 0.f) continue;
     uint32_t g[3];

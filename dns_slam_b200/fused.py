@@ -852,6 +852,13 @@ class AdamSegments:
                                              _lib.ptr(self.step_dev, torch.int32), self.betas[0], self.betas[1],
                                              self.eps, _lib.stream()))
 
+    def reset_state(self):
+        """Fresh moments and step counts (a new optimiser per frame / per optimize() call in the reference)."""
+        for t in self._keep:
+            if t is not None:
+                t.zero_()
+        self.step_dev.zero_()
+
 
 use_torch_adam = False      # A/B hook of tests / measurements: torch.optim.Adam instead of FusedAdam
 

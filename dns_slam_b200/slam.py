@@ -418,14 +418,23 @@ def _timed_replays(n, body):
 
 
 def track_frame(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR=False,
-                use_graph=False):
+                use_graph=False, native=None):
     """The pose-optimisation loop of ``Tracker.run`` (slams/tracking.py:304-346): Adam over
     (translation, quaternion), the best-loss pose is kept.  The ``loss < current_min_loss`` test that
     costs the reference a host sync per iteration (tracking.py:331) stays on the device.
     ``draws_fn(it)`` -> dict(idx, t_surface, t_zero).  Returns (best [quad|T] 7-vector, best loss, losses).
     ``use_graph``: capture ONE iteration (sampling, feature matching, fused render + backward, Adam, best
     pose) in a CUDA graph after three eager warm-up iterations and replay it -- the loop is launch bound
-    (hundreds of tiny launches per iteration), not GPU bound."""
+    (hundreds of tiny launches per iteration), not GPU bound.
+    ``native`` (default: = ``use_graph`` for a tracker with a frozen decoder, i.e. the fast path): the loop runs through
+    ``step.TrackingFrameStep`` -- no autograd, no PyTorch kernels on the data path, about 25 launches of this library per
+    iteration, nothing to capture or warm up; one step object is cached on the tracker and serves every frame."""
+    if native is None:
+        native = use_graph and tracker.freeze_decoder
+    if native:
+        if not tracker.freeze_decoder:
+            raise ValueError("the native tracking loop moves the pose only (TrackerCore(freeze_decoder=True), tracking.py:108-126)")
+        return _track_frame_native(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR)
     if use_graph:
         return _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR)
     dev = tracker.decoder.bound.device
@@ -546,6 +555,20 @@ class TrackLoop:
         return self.best.clone(), self.best_loss.clone(), self.hist.clone()
 
 
+def _track_frame_native(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR):
+    from . import step as stepmod
+    key = (int(n_iters), float(cam_lr), bool(seperate_LR), tracker.n_pixels)
+    cache = tracker.__dict__.setdefault("_track_steps", {})
+    st = cache.get(key)
+    if st is None:
+        if len(cache) >= 2:
+            cache.clear()
+        st = cache[key] = stepmod.TrackingFrameStep(
+            tracker.decoder, tracker.cam, tracker.n_pixels, n_iters, tracker.n_samples_ray, tracker.n_surface_ray,
+            dict(p=tracker.lambda_p, d=tracker.lambda_d, l=tracker.lambda_l), cam_lr, seperate_LR)
+    return st.run(frame, refer_w2c, features_cl, est_c2w, draws_fn)
+
+
 def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters, cam_lr, draws_fn, seperate_LR):
     dev = tracker.decoder.bound.device
     key = (tuple(frame["color"].shape), tuple(features_cl.shape), int(n_iters), float(cam_lr), bool(seperate_LR),
@@ -560,7 +583,7 @@ def _track_frame_graph(tracker, frame, refer_w2c, features_cl, est_c2w, n_iters,
 
 
 def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,
-                 new_decoders, draws_fn, tv_draws_fn, use_graph=False):
+                 new_decoders, draws_fn, tv_draws_fn, use_graph=False, native=None, history=None):
     """The optimisation loop of ``Mapper.optimize`` (slams/mapping.py:868-910): one Adam over the decoder
     (hash grid + MLPs), the class experts present and -- when ``is_BA`` -- quaternion / translation of every
     target frame but the oldest (mapping.py:457); lambda_lt follows the schedule of mapping.py:898-904.
@@ -568,11 +591,26 @@ def map_optimize(mapper, target_frames, refer_frames, features_cl, est_c2w_list,
     ``use_graph``: after three eager iterations ONE iteration (4 frames of sampling + feature matching, fused
     render/backward, TV, Adam) is captured in a CUDA graph and replayed with fresh draws.  Replay needs static
     shapes, so it assumes every sampled ray passes the inside test of mapping.py:525 (checked once at the end;
-    the call falls back to the eager loop from the saved state otherwise) and a constant lambda_lt."""
-    if use_graph and len(new_decoders) == 0 and n_iters > 4:
+    the call falls back to the eager loop from the saved state otherwise) and a constant lambda_lt.
+    ``native`` (default: = ``use_graph``, i.e. the fast path): the whole loop runs through ``step.MappingFrameStep`` --
+    no autograd, no PyTorch kernels on the data path, nothing to capture (about 60 launches of this library per
+    iteration, so eager is already launch-cheap); same static-shape assumption and the same fallback.  The captured
+    autograd loop remains for windows whose target frames have different numbers of reference views.
+    ``history``: optional list that receives the total loss of every iteration (device scalars).
+    ``mapper.last_path`` tells which loop produced the result ("native", "graph" or "eager")."""
+    if native is None:
+        native = use_graph
+    mapper.last_path = "eager"
+    if native and n_iters > 0 and len({len(x) for x in refer_frames["kf_idx"]}) == 1:
+        out = _map_optimize_native(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr,
+                                   is_BA, new_decoders, draws_fn, tv_draws_fn, history)
+        if out is not None:
+            return out
+    elif use_graph and len(new_decoders) == 0 and n_iters > 4:
         out = _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr,
                                   is_BA, draws_fn, tv_draws_fn)
         if out is not None:
+            mapper.last_path = "graph"
             return out
     dec = mapper.decoder
     dev = dec.bound.device
@@ -754,6 +792,56 @@ class _PackedStatic:
         ev = torch.cuda.Event()
         ev.record()
         self.done[k] = ev
+
+
+def _map_optimize_native(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,
+                         new_decoders, draws_fn, tv_draws_fn, history=None):
+    """``Mapper.optimize`` (slams/mapping.py:868-910) through ``step.MappingFrameStep``: per iteration ONE pinned draw
+    buffer goes up, ``dns_pose_prepare -> dns_sample_rays -> dns_featmerge_fwd -> dns_render_fwd_bwd -> dns_featmerge_bwd
+    -> dns_tv_fwd_bwd -> dns_pose_grad -> dns_adam_multi`` run back to back, and the loop ends with ONE host read (losses,
+    error flag, rays that left the bound).  Returns None -- with the decoder restored -- when a sampled ray failed the
+    inside test of mapping.py:525 (the reference drops such rays; the static-shape step cannot), so that the caller
+    repeats the call with the compacting eager loop."""
+    from . import step as stepmod
+    dec = mapper.decoder
+    dev = dec.bound.device
+    saved = dec.flat.detach().clone()
+    n_t = len(target_frames["frames"])
+    st = stepmod.MappingFrameStep(dec, mapper.cam, target_frames["frames"], target_frames["class_tables"], features_cl,
+                                  est_c2w_list, refer_frames["kf_idx"], refer_frames["est_c2w"], target_frames["kf_idx"],
+                                  mapper.n_pixels, mapper.n_samples_ray, mapper.n_surface_ray, lr=lr, BA_cam_lr=BA_cam_lr,
+                                  is_BA=is_BA, lambdas=mapper.lambdas, opacity_sigma=mapper.opacity_sigma,
+                                  smooth_pts=mapper.smooth_pts, lambda_sm=mapper.lambda_sm, with_tv=True)
+    ring = [torch.zeros(st.draw_bytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
+    done = [None] * len(ring)
+    for it in range(n_iters):
+        k = it % len(ring)
+        if done[k] is not None:
+            done[k].synchronize()           # the staging buffer's previous copy has landed
+        st.plan.pack_draws(draws_fn(it), tv_draws_fn(it), ring[k])
+        st.upload(ring[k])
+        done[k] = torch.cuda.Event()
+        done[k].record()
+        st.lambdas["lt"] = (10.0 if it > n_iters // 2 else 0.0) if len(new_decoders) > 0 else 10.0   # mapping.py:898-904
+        res = st.step()
+        if history is not None:
+            history.append(res[6].clone())
+    v = st.result_dev.tolist()               # the single host read of the loop
+    F2 = 9 + 2 * n_t
+    outside, err = v[F2], min(v[7], v[F2 + 1])
+    mapper.last_graph_ok = outside == 0
+    if err < 0:                              # the reference raises inside the iteration (mapping.py:594-595)
+        with torch.no_grad():
+            dec.flat.copy_(saved)
+        fused.raise_on_flag(torch.tensor([0.0] * 7 + [err]))
+    if outside > 0:
+        with torch.no_grad():
+            dec.flat.copy_(saved)
+        return None
+    mapper.last_path = "native"
+    ld = {k: torch.tensor(v[i], device=dev) for i, k in enumerate(fused.LOSS_KEYS)}
+    ld["smooth_loss"] = torch.tensor(v[8], device=dev)
+    return [st.quats[f].clone() for f in range(n_t)], [st.trans[f].clone() for f in range(n_t)], ld
 
 
 def _map_optimize_graph(mapper, target_frames, refer_frames, features_cl, est_c2w_list, n_iters, lr, BA_cam_lr, is_BA,

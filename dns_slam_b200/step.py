@@ -319,6 +319,41 @@ class FrameBatchPlan:
         self.draw_view(buf, "tv", torch.float64).copy_(torch.cat((off, jit)))
         return (buf, tape) if return_tape else buf
 
+    def pack_draws(self, per_frame, tv_draws, buf=None):
+        """The draw buffer of one iteration from the draw DICTIONARIES of ``slam.map_optimize`` (``per_frame[f]`` =
+        dict(idx_uniform, class_draws=[one randint per class with more than one pixel], t_surface, t_zero),
+        ``tv_draws`` = (rand(3), rand(1,1,1,3))); single rank.  ``buf``: a (pinned) byte buffer to fill."""
+        from . import fused as _fused
+        if self.world != 1:
+            raise ValueError("pack_draws packs the draws of an unsharded batch")
+        if buf is None:
+            buf = torch.zeros(self.draw_bytes, dtype=torch.uint8)
+        for f in range(self.F):
+            d = per_frame[f]
+            idx = self.draw_view(buf, f"idx{f}", torch.int64)
+            u = d["idx_uniform"].reshape(-1)
+            if u.numel() != self.n_u:
+                raise ValueError(f"frame {f}: {u.numel()} uniform draws, the plan has {self.n_u} slots")
+            idx[:self.n_u] = u
+            k = 0
+            for _, s0, m, count, _ in self.class_slot_ranges(f):
+                if count == 1:                  # repeated without a draw (common.py:321-323): offset 0
+                    idx[self.n_u + s0:self.n_u + s0 + m] = 0
+                    continue
+                dr = d["class_draws"][k].reshape(-1)
+                k += 1
+                if dr.numel() != m:
+                    raise ValueError(f"frame {f}: class draw of {dr.numel()} values for {m} slots")
+                idx[self.n_u + s0:self.n_u + s0 + m] = dr
+            ts = d["t_surface"].detach().cpu().to(torch.float32).clone()
+            if not bool((ts == 0.5).any()):
+                ts[self.nf // 2 + 1] = 0.5                                # common.py:572-573
+            self.draw_view(buf, f"ts{f}", torch.float32).copy_(ts)
+            self.draw_view(buf, f"tz{f}", torch.float32).copy_(d["t_zero"].detach().cpu().to(torch.float32))
+        off, jit = _fused.tv_offsets(self.bound, self.smooth_pts, tv_draws[0], tv_draws[1])
+        self.draw_view(buf, "tv", torch.float64).copy_(torch.cat((off, jit)))
+        return buf
+
 
 class MappingFrameStep:
     """One mapping iteration (``slams/mapping.py:884-910``) from what a SLAM host actually holds: key frames and their
@@ -379,7 +414,8 @@ class MappingFrameStep:
                     src.append(kf_idx.index(rid))
                 else:
                     src.append(-1)
-                fixed.append(refer_c2w[i][k].detach().to(dev).float())
+                c = refer_c2w[i][k] if src[-1] == -1 else None      # views that follow a target frame need no fixed pose
+                fixed.append(c.detach().to(dev).float() if c is not None else torch.eye(4, device=dev))
         fixed = torch.stack(fixed, 0)
         self.view_src = torch.tensor(src, dtype=torch.int32, device=dev)
         self.fixed_w2c = fused.rigid_inverse(fixed).contiguous()
@@ -418,8 +454,9 @@ class MappingFrameStep:
             segs += [(self.quats[f0:].view(-1), self.d_quats[f0:].view(-1), BA_cam_lr),
                      (self.trans[f0:].view(-1), self.d_trans[f0:].view(-1), BA_cam_lr)]
         self.adam = fused.AdamSegments(segs)
-        self.result_host = torch.empty(9 + 2 * F, pin_memory=True)
-        self.result_dev = torch.empty(9 + 2 * F, device=dev)
+        # result vector: 9 losses | per frame (max depth, rays outside) | over ALL steps so far: rays outside, min n_valid
+        self.result_host = torch.empty(11 + 2 * F, pin_memory=True)
+        self.result_dev = torch.zeros(11 + 2 * F, device=dev)
 
     def draw_view(self, buf, name, dtype):
         return self.plan.draw_view(buf, name, dtype)
@@ -463,7 +500,8 @@ class MappingFrameStep:
 
     def step(self, draws=None):
         """One iteration on the draws in ``self.draws_dev`` (or the given device byte buffer).  Returns the device vector
-        [p, d, l, lt, fs, op, total incl. smoothness, n_valid (< 0: error flag), smooth | per frame: max depth, rays outside]."""
+        [p, d, l, lt, fs, op, total incl. smoothness, n_valid (< 0: error flag), smooth | per frame: max depth, rays outside |
+        rays outside and min n_valid over ALL steps of this object]."""
         draws = self.draws_dev if draws is None else draws
         dec, b, F = self.dec, self.batch, self.F
         L = _lib.lib()
@@ -510,8 +548,11 @@ class MappingFrameStep:
             self.comm.all_reduce_sum(self.packed)
             self.loss_vec[7:8] /= self.world          # n_valid is a batch constant, not a partial sum
         self.adam.step()
+        F2 = 9 + 2 * F
         self.result_dev[:9] = self.loss_vec
-        self.result_dev[9:] = self.scratch.reshape(-1)
+        self.result_dev[9:F2] = self.scratch.reshape(-1)
+        self.result_dev[F2:F2 + 1] += self.scratch[:, 1].sum()
+        torch.minimum(self.result_dev[F2 + 1:F2 + 2], self.loss_vec[7:8], out=self.result_dev[F2 + 1:F2 + 2])
         return self.result_dev
 
     def read_result(self):
@@ -522,9 +563,160 @@ class MappingFrameStep:
 
     def check(self, host_vec=None):
         v = self.result_host if host_vec is None else host_vec
-        if float(v[7]) < 0:
-            fused.raise_on_flag(v[:8])
-        outside = float(v[9:].reshape(self.F, 2)[:, 1].sum())
+        F2 = 9 + 2 * self.F
+        if float(v[7]) < 0 or float(v[F2 + 1]) < 0:          # this step, or any step since construction
+            fused.raise_on_flag(torch.cat((v[:7], torch.minimum(v[7:8], v[F2 + 1:F2 + 2]))))
+        outside = float(v[9:F2].reshape(self.F, 2)[:, 1].sum()) + float(v[F2])
         if outside > 0:
             raise RuntimeError(f"{int(outside)} sampled rays leave the scene bound before their depth (mapping.py:525 "
                                "drops them): static-shape step not applicable, use slam.map_optimize")
+
+
+class TrackingFrameStep:
+    """The pose loop of ``Tracker.run`` (slams/tracking.py:304-346) from what the host holds: the new RGB-D-label frame, the
+    previous frame's pose, the two feature maps and the iteration's draws.  Per iteration, back to back on the device and
+    without autograd or PyTorch kernels on the data path:
+
+        dns_pose_prepare (R(q); the current view follows the pose estimate, tracking.py:317-319)
+        -> dns_sample_rays (window [20, H-20) x [20, W-20), tracking.py:140-147) -> dns_featmerge_fwd (band samples only)
+        -> dns_render_fwd_bwd in TRACK mode (decoder frozen: ray and pixel-feature gradients only)
+        -> dns_featmerge_bwd (into the ray gradients) -> dns_pose_grad -> dns_track_best (best pose / loss history on the
+        device instead of the reference's per-iteration host comparison) -> dns_adam_multi over (translation, quaternion).
+
+    One object serves every frame of a sequence (``reset``): buffers, workspaces and optimiser state are allocated once.
+    ``draws``: one byte buffer ``idx`` int64 [n] | ``t_surface`` f32 [n_surface] (common.py:572-573 applied) |
+    ``t_zero`` f32 [n_surface]; ``pack_draws`` fills a pinned host image from the draw dictionary of ``slam.track_frame``."""
+
+    def __init__(self, dec, cam, n_pixels, n_iters, n_samples_ray=32, n_surface_ray=15, lambdas=None, cam_lr=1e-3,
+                 seperate_LR=False, feat_shape=None):
+        self.dec, self.cam = dec, cam
+        dev = self.dev = dec.bound.device
+        self.ns, self.nf, self.S = n_samples_ray, n_surface_ray, n_samples_ray + n_surface_ray
+        self.lambdas = dict(p=5.0, d=5.0, l=0.1)
+        self.lambdas.update(lambdas or {})
+        N, S = int(n_pixels), self.S
+        self.N, self.n_iters = N, int(n_iters)
+        H, W = cam["H"], cam["W"]
+        self.window = (20, H - 20, 20, W - 20)
+        self.quats, self.trans = torch.zeros(1, 4, device=dev), torch.zeros(1, 3, device=dev)
+        self.view_src = torch.tensor([-1, 0], dtype=torch.int32, device=dev)     # view 0: previous frame, view 1: this frame
+        self.fixed_w2c, self.fixed_cam_o = torch.zeros(2, 4, 4, device=dev), torch.zeros(2, 3, device=dev)
+        self.R_all = torch.empty(1, 3, 3, device=dev)
+        self.w2c, self.cam_o = torch.empty(2, 4, 4, device=dev), torch.empty(2, 3, device=dev)
+        self.batch = dict(gt_color=torch.empty(N, 3, device=dev), gt_depth=torch.empty(N, device=dev),
+                          gt_label=torch.empty(N, dtype=torch.int64, device=dev), rays_o=torch.empty(N, 3, device=dev),
+                          rays_d=torch.empty(N, 3, device=dev), z_vals=torch.empty(N, S, device=dev),
+                          inside=torch.empty(N, dtype=torch.uint8, device=dev),
+                          pixel=torch.empty(N, dtype=torch.int64, device=dev), scratch=torch.zeros(2, device=dev))
+        self.features = torch.empty(N, S, 32, device=dev)
+        self.fm_ws = torch.empty(int(_lib.lib().dns_featmerge_workspace_bytes(N, S)), dtype=torch.uint8, device=dev)
+        self.fm_stash = fused.featmerge_stash(N, S, 2, dev)
+        self.t_lin = torch.linspace(0.0, 1.0, steps=n_samples_ray).to(dev)
+        self.off_ts = (8 * N + 15) & ~15
+        self.off_tz = (self.off_ts + 4 * self.nf + 15) & ~15
+        self.draw_bytes = self.off_tz + 4 * self.nf
+        self.draws_dev = torch.zeros(self.draw_bytes, dtype=torch.uint8, device=dev)
+        self.grads = torch.zeros(7, device=dev)                    # d_quat [4] | d_trans [3]
+        self.d_quats, self.d_trans = self.grads[:4].view(1, 4), self.grads[4:].view(1, 3)
+        self.pose_scratch = torch.empty(12, device=dev)
+        self.adam = fused.AdamSegments([(self.trans.view(-1), self.d_trans.view(-1), cam_lr * (0.2 if seperate_LR else 1.0)),
+                                        (self.quats.view(-1), self.d_quats.view(-1), cam_lr)])      # tracking.py:119-124
+        # state vector: best [quad | T] (7) | best loss | running min of n_valid (error flag) | loss history
+        self.state = torch.zeros(9 + self.n_iters, device=dev)
+        self.best, self.best_loss, self.err_min = self.state[:7], self.state[7:8], self.state[8:9]
+        self.hist = self.state[9:]
+        self.slot = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.frame = self.feats = None
+        self.ring = [torch.zeros(self.draw_bytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
+        self.ring_done = [None] * len(self.ring)
+        self.turn = 0
+
+    def reset(self, frame, refer_w2c, feats_cl, est_c2w):
+        """A new frame: images (device tensors, used in place), the previous frame's world-to-camera matrix, the
+        [2,h,w,64] channels-last feature maps of (previous, new) frame, the start pose; fresh Adam state."""
+        from . import slam
+        dev = self.dev
+        self.frame = {k: frame[k] for k in ("color", "depth", "label")}
+        self.feats = [feats_cl.contiguous()]
+        if self.feats[0].shape[0] != 2:
+            raise ValueError("tracking uses two views: the previous frame and the new one (tracking.py:293-296)")
+        w2c = refer_w2c.detach().to(dev, torch.float32)
+        with torch.no_grad():
+            self.fixed_w2c[0].copy_(w2c)
+            self.fixed_cam_o[0].copy_(fused.rigid_inverse(w2c)[:3, 3])
+            self.quats[0].copy_(slam.quad_from_matrix(est_c2w[:3, :3]), non_blocking=True)
+            self.trans[0].copy_(est_c2w[:3, 3].detach().float(), non_blocking=True)
+            self.state.zero_()
+            self.best[:4].copy_(self.quats[0])
+            self.best[4:].copy_(self.trans[0])
+            self.best_loss.fill_(1e10)
+            self.slot.zero_()
+        self.adam.reset_state()
+
+    def pack_draws(self, d, buf):
+        idx = d["idx"].reshape(-1)
+        if idx.numel() != self.N:
+            raise ValueError(f"{idx.numel()} pixel draws for a step of {self.N} rays")
+        buf[:8 * self.N].view(torch.int64).copy_(idx)
+        ts = d["t_surface"].detach().cpu().to(torch.float32).clone()
+        if not bool((ts == 0.5).any()):
+            ts[self.nf // 2 + 1] = 0.5                                     # common.py:572-573
+        buf[self.off_ts:self.off_ts + 4 * self.nf].view(torch.float32).copy_(ts)
+        buf[self.off_tz:self.off_tz + 4 * self.nf].view(torch.float32).copy_(d["t_zero"].detach().cpu().to(torch.float32))
+        return buf
+
+    def upload_draws(self, d):
+        """Draw dictionary -> pinned staging buffer (ring of 4) -> ONE asynchronous H2D copy."""
+        k = self.turn % len(self.ring)
+        self.turn += 1
+        if self.ring_done[k] is not None:
+            self.ring_done[k].synchronize()
+        self.draws_dev.copy_(self.pack_draws(d, self.ring[k]), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.ring_done[k] = ev
+
+    def step(self):
+        dec, b, N = self.dec, self.batch, self.N
+        L = _lib.lib()
+        f32 = torch.float32
+        _lib.check(L.dns_pose_prepare(_lib.ptr(self.quats, f32), _lib.ptr(self.trans, f32), 1, _lib.ptr(self.view_src, torch.int32),
+                                      _lib.ptr(self.fixed_w2c, f32), _lib.ptr(self.fixed_cam_o, f32), 2,
+                                      _lib.ptr(self.R_all), _lib.ptr(self.w2c), _lib.ptr(self.cam_o), _lib.stream()))
+        dr = self.draws_dev
+        fused.sample_rays(self.cam, dec.bound, self.frame, dr[:8 * N].view(torch.int64), self.window, self.R_all[0], self.trans[0],
+                          self.ns, self.nf, dr[self.off_ts:self.off_ts + 4 * self.nf].view(f32),
+                          dr[self.off_tz:self.off_tz + 4 * self.nf].view(f32), t_lin=self.t_lin, out=b)
+        mask = (b["gt_depth"] > 0.01).to(torch.uint8).mul_(b["inside"])          # tracking.py:172-173
+        views = fused.Views(self.w2c, self.cam_o, self.feats, (0, N))
+        merge_p = dec.view("merge")
+        fused.featmerge_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
+                            True, ws=self.fm_ws, out=self.features, stash=self.fm_stash)
+        cfg = fused.RenderConfig(_lib.MODE_TRACK, dec.bound, dec.pe_fn.grid_fn.gstruct, b["z_vals"], b["gt_color"], b["gt_depth"],
+                                 b["gt_label"], mask, None, dec.n_class, self.lambdas)
+        losses, _, d_o, d_d, d_f = fused.render_raw(cfg, dec.view("table"), dec.view("coarse"), dec.view("color"),
+                                                    dec.view("logit"), None, b["rays_o"], b["rays_d"], self.features, None,
+                                                    True, True)
+        fused.featmerge_bwd_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
+                                d_f, self.fm_ws, None, d_o, d_d, stash=self.fm_stash)
+        fused.pose_grad_raw(self.cam, self.window, d_o, d_d, b["pixel"], (0, N), self.quats, self.d_quats, self.d_trans,
+                            self.pose_scratch)
+        _lib.check(L.dns_track_best(_lib.ptr(losses, f32), _lib.ptr(self.quats, f32), _lib.ptr(self.trans, f32),
+                                    _lib.ptr(self.best), _lib.ptr(self.best_loss), _lib.ptr(self.hist, allow_none=True),
+                                    _lib.ptr(self.slot, torch.int32), self.n_iters, _lib.ptr(self.err_min), _lib.stream()))
+        self.adam.step()
+        return losses
+
+    def run(self, frame, refer_w2c, feats_cl, est_c2w, draws_fn, n_iters=None):
+        """The whole loop of one frame; ONE host read at the end.  Returns (best [quad|T], best loss, loss history)."""
+        n = self.n_iters if n_iters is None else int(n_iters)
+        if n > self.n_iters:
+            raise ValueError("more iterations than the step was built for")
+        self.reset(frame, refer_w2c, feats_cl, est_c2w)
+        for it in range(n):
+            self.upload_draws(draws_fn(it))
+            self.step()
+        v = self.state.clone()
+        if n > 0 and float(v[8]) < 0:     # a label outside the semantic head raises (torch's cross_entropy would)
+            fused.raise_on_flag(torch.cat((v[:7] * 0, v[8:9])))
+        return v[:7], v[7], v[9:9 + n]

@@ -342,6 +342,13 @@ int dns_pose_prepare(const float* quats, const float* trans, int n_frames, const
 int dns_pose_grad(const float* d_rays_o, const float* d_rays_d, const int64_t* pixel, int n_frames,
                   const int32_t* ray_start /* host, [n_frames+1] */, int H0, int W0, int Ww, float fx, float fy, float cx,
                   float cy, const float* quats, float* d_quats, float* d_trans, float* scratch, void* stream);
+/* Best-pose bookkeeping of the tracking loop (slams/tracking.py:331-338: `if loss < current_min_loss` + the copy of the
+ * candidate pose, a host comparison per iteration in the reference): losses = the [8] vector of dns_render_fwd_bwd
+ * (total at 6, n_valid / error flag at 7); if total < *best_loss, best7 <- [quat | trans] and *best_loss <- total;
+ * hist[*slot] <- total (when hist != NULL and *slot < hist_len), *slot += 1, *err_min <- min(*err_min, losses[7]). */
+int dns_track_best(const float* losses, const float* quat, const float* trans, float* best7, float* best_loss, float* hist,
+                   int32_t* slot, int hist_len, float* err_min, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------
  * ResNet stem of the pixel-feature branch == models/encoder.py:9-17 over models/layers.py:52-114 (what is left of

@@ -69,7 +69,7 @@ def test_tracking_loop_vs_oracle():
                             freeze_decoder=True)
     fr, fcl = frame_to(inp["frame"], dev), fused.channels_last(inp["feats"].to(dev))
     b_e, l_e, h_e = slam.track_frame(trk2, fr, refer_w2c, fcl, est, n2, lr, lambda it: draws2[it])
-    b_g, l_g, h_g = slam.track_frame(trk2, fr, refer_w2c, fcl, est, n2, lr, lambda it: draws2[it], use_graph=True)
+    b_g, l_g, h_g = slam.track_frame(trk2, fr, refer_w2c, fcl, est, n2, lr, lambda it: draws2[it], use_graph=True, native=False)
     close(h_g, h_e, rtol=1e-4, atol=1e-6, name="graph vs eager loss trajectory")
     close(b_g, b_e, rtol=1e-5, atol=1e-6, name="graph vs eager best pose")
     # the captured loop is REUSED for the next frame (new images, new start pose, fresh Adam state): no new capture
@@ -81,11 +81,27 @@ def test_tracking_loop_vs_oracle():
     est2 = est.clone()
     est2[:3, 3] += torch.tensor([-0.01, 0.02, 0.0])
     b_e2, l_e2, h_e2 = slam.track_frame(trk2, fr2, refer_w2c, fcl, est2, n2, lr, lambda it: draws2[it])
-    b_g2, l_g2, h_g2 = slam.track_frame(trk2, fr2, refer_w2c, fcl, est2, n2, lr, lambda it: draws2[it], use_graph=True)
+    b_g2, l_g2, h_g2 = slam.track_frame(trk2, fr2, refer_w2c, fcl, est2, n2, lr, lambda it: draws2[it], use_graph=True,
+                                        native=False)
     assert len(loops) == 1 and next(iter(loops.values())).graph is graph_before
     close(h_g2, h_e2, rtol=1e-4, atol=1e-6, name="reused graph vs eager loss trajectory")
     close(b_g2, b_e2, rtol=1e-5, atol=1e-6, name="reused graph vs eager best pose")
     assert not torch.equal(h_g2, h_g)
+    # the NATIVE loop (step.TrackingFrameStep: no autograd, no PyTorch kernels on the data path) -- the default fast path --
+    # against the oracle trajectory and against the eager loops, on both frames with ONE cached step object
+    trk3 = slam.TrackerCore(cam, dec, s["tracking_pixels"], 32, 15, s["lambda_color"], s["lambda_depth"], s["lambda_label"],
+                            freeze_decoder=True)
+    b_n, l_n, h_n = slam.track_frame(trk3, fr, refer_w2c, fcl, est, n_it, lr, lambda it: draws[it], use_graph=True)
+    close(h_n, torch.stack(hist_o), rtol=2e-3, atol=1e-5, name="native tracking loss trajectory vs oracle")
+    assert abs(float(l_n) - float(hist_o[k])) < 2e-3 * abs(float(hist_o[k]))
+    b_n1, l_n1, h_n1 = slam.track_frame(trk3, fr, refer_w2c, fcl, est, n2, lr, lambda it: draws2[it], native=True)
+    close(h_n1, h_e, rtol=1e-4, atol=1e-6, name="native vs eager loss trajectory")
+    close(b_n1, b_e, rtol=1e-5, atol=1e-6, name="native vs eager best pose")
+    close(l_n1, l_e, rtol=1e-5, atol=1e-7, name="native vs eager best loss")
+    b_n2, l_n2, h_n2 = slam.track_frame(trk3, fr2, refer_w2c, fcl, est2, n2, lr, lambda it: draws2[it], native=True)
+    assert len(trk3._track_steps) == 2          # (3 iterations) and (6 iterations): one step object per loop length
+    close(h_n2, h_e2, rtol=1e-4, atol=1e-6, name="native vs eager loss trajectory, next frame")
+    close(b_n2, b_e2, rtol=1e-5, atol=1e-6, name="native vs eager best pose, next frame")
 
 
 def test_mapping_loop_vs_oracle():
@@ -172,6 +188,25 @@ def test_mapping_loop_vs_oracle():
     # parameters after two Adam steps: the update direction is sign-like, so compare the net displacement
     assert rel_err(dec.coarse_fn.decoder.params, odec.coarse_fn.decoder.params) < 1e-3
     assert rel_err(dec.pe_fn.grid_fn.params, odec.pe_fn.grid_fn.params) < 1e-3
+    assert mp.last_path == "eager"
+    # ---- the NATIVE loop (step.MappingFrameStep behind slam.map_optimize: the default fast path) against the same oracle
+    inp3 = cases.mapping_inputs(meta)
+    dec3 = product_decoder_from_oracle("tiny", inp3["decoder"], inp3["experts"], n_class=6)
+    mp3 = slam.MapperCore(cam, dec3, s["mapping_pixels"], 32, 15, lambdas=lam, opacity_sigma=s["opacity_sigma"],
+                          smooth_pts=s["smooth_pts"], lambda_sm=meta["lambda_sm"])
+    hist3 = []
+    q3, t3, ld3 = slam.map_optimize(mp3, target, refer, feats, est, n_it, lr, cam_lr, True, [], lambda it: draws[it],
+                                    lambda it: tv[it], use_graph=True, history=hist3)
+    assert mp3.last_path == "native", "a sampled ray left the bound: the native loop fell back"
+    close(torch.stack(hist3), torch.stack(losses_o), rtol=2e-3, atol=1e-5, name="native mapping loss trajectory")
+    close(ld3["total"], losses_o[-1], rtol=2e-3, atol=1e-5, name="native last loss")
+    for i in range(1, n_t):
+        close(q3[i], ql[i], rtol=2e-3, atol=2e-5, name=f"native quad[{i}] after BA")
+        close(t3[i], Tl[i], rtol=2e-3, atol=2e-5, name=f"native T[{i}] after BA")
+    close(q3[0], ql[0], rtol=1e-6, atol=1e-7, name="the oldest frame stays fixed")
+    assert rel_err(dec3.coarse_fn.decoder.params, odec.coarse_fn.decoder.params) < 1e-3
+    assert rel_err(dec3.pe_fn.grid_fn.params, odec.pe_fn.grid_fn.params) < 1e-3
+    assert rel_err(dec3.merge.decoder.params, odec.merge.decoder.params) < 1e-3
 
 
 def test_mapping_loop_cuda_graph_equals_eager():
@@ -187,21 +222,24 @@ def test_mapping_loop_cuda_graph_equals_eager():
     est = [sc["poses"][2 * f + 1].clone() for f in range(3)]
     lam = dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0)
     res = []
-    for use_graph in (False, True):
+    for use_graph, native, path in ((False, None, "eager"), (True, False, "graph"), (True, None, "native")):
         dec = bench_util.make_decoder("tiny", 6, dev, seed=1)
         mp = slam.MapperCore(sc["cam"], dec, s["mapping_pixels"], 32, 15, lambdas=lam, opacity_sigma=0.05,
                              smooth_pts=s["smooth_pts"], lambda_sm=0.05)
         ql, tl, ld = slam.map_optimize(mp, target, refer, sc["feats"], est, n_it, 5e-3, 5e-4, True, [],
-                                       lambda it: md[it], lambda it: tv[it], use_graph=use_graph)
+                                       lambda it: md[it], lambda it: tv[it], use_graph=use_graph, native=native)
         if use_graph:
-            assert getattr(mp, "last_graph_ok", False), "graph path fell back to eager (rays outside the bound)"
+            assert getattr(mp, "last_graph_ok", False), "fast path fell back to eager (rays outside the bound)"
+        assert mp.last_path == path
         res.append((ql, tl, ld, dec.flat.clone()))
-    (q0, t0, l0, f0), (q1, t1, l1, f1) = res
-    close(l1["total"], l0["total"], rtol=1e-3, atol=1e-6, name="last loss")
-    for i in range(1, 3):
-        close(q1[i], q0[i], rtol=1e-3, atol=1e-5, name="quad")
-        close(t1[i], t0[i], rtol=1e-3, atol=1e-5, name="T")
-    assert rel_err(f1, f0) < 1e-3
+    (q0, t0, l0, f0) = res[0]
+    for (q1, t1, l1, f1), path in zip(res[1:], ("graph", "native")):
+        close(l1["total"], l0["total"], rtol=1e-3, atol=1e-6, name=f"last loss ({path})")
+        close(l1["smooth_loss"], l0["smooth_loss"], rtol=1e-3, atol=1e-6, name=f"smoothness ({path})")
+        for i in range(1, 3):
+            close(q1[i], q0[i], rtol=1e-3, atol=1e-5, name=f"quad ({path})")
+            close(t1[i], t0[i], rtol=1e-3, atol=1e-5, name=f"T ({path})")
+        assert rel_err(f1, f0) < 1e-3, path
 
 
 def test_graph_capture_after_an_eager_loop_on_the_same_decoder():
@@ -224,7 +262,7 @@ def test_graph_capture_after_an_eager_loop_on_the_same_decoder():
     args = (mp, target, refer, sc["feats"], est, n_it, 5e-3, 5e-4, True, [], lambda it: md[it], lambda it: tv[it])
     _, _, kept = slam.map_optimize(*args, use_graph=False)          # the caller keeps this dictionary
     assert all(v.grad_fn is None and not v.requires_grad for v in kept.values())
-    _, _, ld = slam.map_optimize(*args, use_graph=True)
+    _, _, ld = slam.map_optimize(*args, use_graph=True, native=False)
     assert getattr(mp, "last_graph_ok", False)
     assert torch.isfinite(ld["total"]).all() and torch.isfinite(kept["total"]).all()
 
