@@ -340,6 +340,18 @@ def main():
     # ---------------- end to end: scene from HOST memory inside the timed region, draws from pinned memory every step,
     # the loss vector read back every step
     del st, dec, frames_dev, feats, tables         # (the caching allocator keeps the blocks: steady state of a SLAM run)
+    # one untimed rehearsal of the whole call (upload, stem, class tables, step construction, two steps): the first call after
+    # a free re-shapes the caching allocator's blocks (20-60 ms, once); a SLAM run is in that steady state from its second
+    # mapping call on
+    dec = build_decoder(args, scene, dev)
+    frames_dev, feats, tables = upload_scene(scene, host_pinned, dev, stem, args.n_class)
+    st = build_gpu_step(args, scene, dec, rank, world, comm, frames_dev, feats, tables)
+    for i in range(2):
+        st.upload(host_draws[i % len(host_draws)])
+        st.step()
+        st.read_result()
+    barrier()
+    del st, dec, frames_dev, feats, tables
     dec = build_decoder(args, scene, dev)          # weights are device state like in the reference (not per-call input)
     barrier()
     e0.record()
@@ -410,7 +422,7 @@ def main():
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": f"key frames + reference images ({frame_bytes} B) uploaded, stem and class tables run once "
-                            f"inside the timed region; {R * 8} B of draws per step"},
+                            f"inside the timed region (the call was rehearsed once, untimed); {R * 8} B of draws per step"},
             "gpu_launches": int(sum(launches.values())), "launches_per_step": {k: v // args.steps for k, v in launches.items() if v},
             "roofline": roof, "cpu_baseline": cpu, "losses_last_step": losses, "band_samples_per_ray": band_rows / R,
             "extra": extra}

@@ -1262,7 +1262,7 @@ int dns_render_counts(const dns_render_args* a, int32_t* counts4, void* stream) 
 int64_t dns_tv_workspace_bytes(int n) {
   int64_t n3 = (int64_t)n * n * n;
   int64_t Q = ((n3 + kTile - 1) / kTile) * kTile;
-  return 4096 + 32768 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + 40)) + 10 * 256;
+  return 4096 + 32768 + sizeof(float) * (kNetT + 2 * n3 + Q * (kIn1 + 32 + 64 + 40)) + 10 * 256 + kPrivBytes + 256;
 }
 
 int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
@@ -1292,6 +1292,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   float* dHc = c.take<float>(Q * 64);
   float* dOc = c.take<float>(Q * 40);   // fp32 rows of 36, or the 5-chunk tile image of the tcgen05 path
   uint4* wc_tc = c.take<uint4>(kNetTc);
+  float2* dpriv = c.take<float2>(kPrivBytes / 8);
   const bool tc = !a->use_simt;
   static unsigned long long seen = 0;
   if (first_call_on_device(seen)) {
@@ -1314,6 +1315,13 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   pa.Xst = Xst; pa.Hc = Hc; pa.dHc = dHc; pa.dOc = dOc;
   pa.Ximg = (uint4*)Xst; pa.Himg = (uint4*)Hc; pa.dHimg = (uint4*)dHc; pa.dOimg = (uint4*)dOc;
   pa.d_table = (float2*)a->d_table; pa.need_dparams = a->need_dparams; pa.need_drays = 0;
+  if (tc && a->need_dparams && a->d_table) {   // the lattice is spatially coherent: neighbouring points reduce into the SAME
+    priv_plan(a->grid, pa.priv_levels, pa.priv_end, pa.priv_copies);   // coarse cells, the contention case of PointArgs::d_priv
+    pa.d_priv = pa.priv_copies ? dpriv : nullptr;
+#ifdef DNS_ABLATE
+    if (getenv("DNS_NO_PRIV")) pa.d_priv = nullptr;
+#endif
+  }
   const size_t smem_pt = sizeof(float) * (kTile * kXld + kNetT);
   PhaseScope* pht = new PhaseScope(phTvFwd, st, 4);
   if (tc) {
@@ -1327,9 +1335,12 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   delete pht;
   if (int e = check_launch("tv fwd")) return e;
   if (a->need_dparams) {
-    PhaseScope phtb(phTvBwd, st, 3);
+    PhaseScope phtb(phTvBwd, st, pa.d_priv ? 4 : 3);
+    if (pa.d_priv) cudaMemsetAsync(pa.d_priv, 0, (size_t)pa.priv_copies * pa.priv_end * sizeof(float2), st);
     if (tc) launch_point_bwd_tc(kTv, pa, tiles, wc_tc, wc_tc, st);
     else k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
+    if (pa.d_priv)
+      k_priv_reduce<<<(pa.priv_end + 255) / 256, 256, 0, st>>>((float2*)a->d_table, pa.d_priv, pa.priv_end, pa.priv_copies);
     if (int e = check_launch("tv bwd")) return e;
     int e = 0;
     if (tc) {

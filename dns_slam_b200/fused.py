@@ -205,7 +205,7 @@ def render_counts(cfg):
 
 
 def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, features, grads, need_drays,
-               need_dfeat, forward_only=0):
+               need_dfeat, forward_only=0, ws=None):
     """One ``dns_render_fwd_bwd`` call.  ``grads``: dict with optional device buffers
     ``table/coarse/color/logit/experts`` that are ACCUMULATED into (None => no parameter grads).
     Returns (losses[8], preds dict, d_rays_o, d_rays_d, d_features)."""
@@ -260,10 +260,17 @@ def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, featur
     a.d_features = _lib.ptr(d_f, allow_none=True)
     L = _lib.lib()
     nbytes = L.dns_render_workspace_bytes(cfg.mode, N, S, Cn, n_ids)
-    ws = workspace(nbytes, dev)
+    if ws is None:          # shared growing scratch; a caller that captures the call in a CUDA graph passes its own
+        ws = workspace(nbytes, dev)
+    elif ws.numel() < nbytes:
+        raise ValueError("render_raw: the caller's workspace is too small")
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     _lib.check(L.dns_render_fwd_bwd(C.byref(a), _lib.stream()))
     return losses, preds, d_o, d_d, d_f
+
+
+def render_workspace_bytes(mode, n_rays, n_samples, n_class, n_class_ids=1):
+    return int(_lib.lib().dns_render_workspace_bytes(mode, n_rays, n_samples, n_class, n_class_ids))
 
 
 class _RenderFn(torch.autograd.Function):
@@ -337,7 +344,7 @@ def render_and_loss(decoder, samples, mode, n_class=None, lambdas=None, opacity_
 # ----------------------------------------------------------------------------------------
 def tv_offsets(bound, sample_points, rand3, rand113, voxel_size=0.1, margin=0.05):
     """float64 offset / jitter exactly as mapping.py:133-140 builds them (host side, tiny)."""
-    b = bound.detach().double().cpu()
+    b = bound.detach().double().cpu()          # (a device bound costs a synchronising read: loops pass a host copy)
     volume = b[:, 1] - b[:, 0]
     offset_max = volume - (sample_points - 1) * voxel_size - 2 * margin
     offset = rand3.detach().cpu().to(offset_max) * offset_max + margin

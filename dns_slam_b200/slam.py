@@ -545,6 +545,9 @@ class TrackLoop:
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self._one()
+                # the captured launches hold pointers into the shared scratch of fused.workspace(): keep THIS buffer
+                # alive (a later, larger call re-allocates the shared one; the graph keeps using the one it captured)
+                self._ws_ref = fused._ws_cache.get((self.dev.type, self.dev.index))
 
         def replay(j):                       # capture only records: the captured iteration is replayed too
             self.packed.update(draws_fn(start + j))
@@ -812,8 +815,13 @@ def _map_optimize_native(mapper, target_frames, refer_frames, features_cl, est_c
                                   mapper.n_pixels, mapper.n_samples_ray, mapper.n_surface_ray, lr=lr, BA_cam_lr=BA_cam_lr,
                                   is_BA=is_BA, lambdas=mapper.lambdas, opacity_sigma=mapper.opacity_sigma,
                                   smooth_pts=mapper.smooth_pts, lambda_sm=mapper.lambda_sm, with_tv=True)
-    ring = [torch.zeros(st.draw_bytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
+    rings = mapper.__dict__.setdefault("_draw_rings", {})     # pinned staging buffers, kept across calls (pinning is slow)
+    ring = rings.get(st.draw_bytes)
+    if ring is None:
+        rings.clear()
+        ring = rings[st.draw_bytes] = [torch.zeros(st.draw_bytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
     done = [None] * len(ring)
+    F2 = 9 + 2 * n_t
     for it in range(n_iters):
         k = it % len(ring)
         if done[k] is not None:
@@ -826,8 +834,9 @@ def _map_optimize_native(mapper, target_frames, refer_frames, features_cl, est_c
         res = st.step()
         if history is not None:
             history.append(res[6].clone())
+        if it == 0 and n_iters > 8 and float(res[F2]) > 0:
+            break        # early look (one extra host read): a frame that pokes out of the bound shows in the first batch
     v = st.result_dev.tolist()               # the single host read of the loop
-    F2 = 9 + 2 * n_t
     outside, err = v[F2], min(v[7], v[F2 + 1])
     mapper.last_graph_ok = outside == 0
     if err < 0:                              # the reference raises inside the iteration (mapping.py:594-595)

@@ -220,7 +220,8 @@ class FrameBatchPlan:
     (common.py:572-573 already applied), then the TV ``offset | jitter`` f64 [6] (mapping.py:133-140)."""
 
     def __init__(self, class_tables, n_rays, n_surface, window, bound, smooth_pts, rank=0, world=1):
-        self.tables, self.nf, self.window, self.bound, self.smooth_pts = class_tables, n_surface, window, bound, smooth_pts
+        self.tables, self.nf, self.window, self.smooth_pts = class_tables, n_surface, window, smooth_pts
+        self.bound = bound.detach().double().cpu()      # host copy, made ONCE: the TV offsets are host arithmetic per iteration
         self.rank, self.world = rank, world
         F = self.F = len(class_tables)
         n_f = n_rays // F
@@ -626,7 +627,10 @@ class TrackingFrameStep:
         self.best, self.best_loss, self.err_min = self.state[:7], self.state[7:8], self.state[8:9]
         self.hist = self.state[9:]
         self.slot = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.frame = self.feats = None
+        self.frame = self.feats = None      # static copies of the frame images / feature maps (a captured graph reads them)
+        self.ws = torch.empty(fused.render_workspace_bytes(_lib.MODE_TRACK, N, S, dec.n_class) + 4096, dtype=torch.uint8,
+                              device=dev)       # own workspace: the shared scratch may be re-allocated by later calls
+        self.graph = None
         self.ring = [torch.zeros(self.draw_bytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
         self.ring_done = [None] * len(self.ring)
         self.turn = 0
@@ -636,12 +640,18 @@ class TrackingFrameStep:
         [2,h,w,64] channels-last feature maps of (previous, new) frame, the start pose; fresh Adam state."""
         from . import slam
         dev = self.dev
-        self.frame = {k: frame[k] for k in ("color", "depth", "label")}
-        self.feats = [feats_cl.contiguous()]
-        if self.feats[0].shape[0] != 2:
+        if feats_cl.shape[0] != 2:
             raise ValueError("tracking uses two views: the previous frame and the new one (tracking.py:293-296)")
+        if self.frame is None or any(self.frame[k].shape != frame[k].shape for k in self.frame) \
+                or self.feats[0].shape != feats_cl.shape:
+            self.frame = {k: torch.empty_like(frame[k], device=dev).contiguous() for k in ("color", "depth", "label")}
+            self.feats = [torch.empty_like(feats_cl, device=dev).contiguous()]
+            self.graph = None
         w2c = refer_w2c.detach().to(dev, torch.float32)
         with torch.no_grad():
+            for k, v in self.frame.items():
+                v.copy_(frame[k], non_blocking=True)
+            self.feats[0].copy_(feats_cl, non_blocking=True)
             self.fixed_w2c[0].copy_(w2c)
             self.fixed_cam_o[0].copy_(fused.rigid_inverse(w2c)[:3, 3])
             self.quats[0].copy_(slam.quad_from_matrix(est_c2w[:3, :3]), non_blocking=True)
@@ -696,7 +706,7 @@ class TrackingFrameStep:
                                  b["gt_label"], mask, None, dec.n_class, self.lambdas)
         losses, _, d_o, d_d, d_f = fused.render_raw(cfg, dec.view("table"), dec.view("coarse"), dec.view("color"),
                                                     dec.view("logit"), None, b["rays_o"], b["rays_d"], self.features, None,
-                                                    True, True)
+                                                    True, True, ws=self.ws)
         fused.featmerge_bwd_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
                                 d_f, self.fm_ws, None, d_o, d_d, stash=self.fm_stash)
         fused.pose_grad_raw(self.cam, self.window, d_o, d_d, b["pixel"], (0, N), self.quats, self.d_quats, self.d_trans,
@@ -707,15 +717,36 @@ class TrackingFrameStep:
         self.adam.step()
         return losses
 
-    def run(self, frame, refer_w2c, feats_cl, est_c2w, draws_fn, n_iters=None):
-        """The whole loop of one frame; ONE host read at the end.  Returns (best [quad|T], best loss, loss history)."""
+    def run(self, frame, refer_w2c, feats_cl, est_c2w, draws_fn, n_iters=None, use_graph=True):
+        """The whole loop of one frame; ONE host read at the end.  Returns (best [quad|T], best loss, loss history).
+        ``use_graph``: the ~25 launches of ``step`` are captured ONCE (after two eager iterations of the first frame) and
+        replayed for every later iteration of every later frame -- the iteration is launch bound at tracking sizes."""
         n = self.n_iters if n_iters is None else int(n_iters)
         if n > self.n_iters:
             raise ValueError("more iterations than the step was built for")
         self.reset(frame, refer_w2c, feats_cl, est_c2w)
-        for it in range(n):
+        it = 0
+        if use_graph and self.graph is None and n > 2:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for it in range(2):
+                    self.upload_draws(draws_fn(it))
+                    self.step()
+            torch.cuda.current_stream().wait_stream(side)
+            it = 2
             self.upload_draws(draws_fn(it))
-            self.step()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):     # capture only records: the captured iteration is replayed below
+                self.step()
+            self.graph.replay()
+            it = 3
+        for it in range(it, n):
+            self.upload_draws(draws_fn(it))
+            if use_graph and self.graph is not None:
+                self.graph.replay()
+            else:
+                self.step()
         v = self.state.clone()
         if n > 0 and float(v[8]) < 0:     # a label outside the semantic head raises (torch's cross_entropy would)
             fused.raise_on_flag(torch.cat((v[:7] * 0, v[8:9])))

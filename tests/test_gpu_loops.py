@@ -326,3 +326,59 @@ def test_decoder_init_vs_reference_golden(golden_dir):
     assert moved < 5e-3, f"table update {moved:.2e}"
     for c, want in g["experts"].items():
         assert rel_err(dec.expert_params[c][:want.numel()], want) < 5e-3, f"expert {c}"
+
+
+def test_fast_mapping_loops_fall_back_when_rays_leave_the_bound():
+    """mapping.py:525 drops the rays whose depth lies beyond the scene bound; the static-shape fast loops (native step,
+    captured graph) cannot, so they must notice -- in whatever iteration it happens -- restore the decoder and hand the call
+    to the compacting eager loop (a flag that only saw the warm-up iterations and the last replay).  One frame's
+    depth is stretched so that a part of its pixels fails the inside test."""
+    from dns_slam_b200 import bench_util, slam, synthetic as syn
+    dev = _dev()
+    s = syn.SHAPES["tiny"]
+    n_it = 12
+    sc = bench_util.slam_scene("tiny", 6, dev, seed=11, n_target=2)
+    frames = [dict(f) for f in sc["frames"]]
+    d = frames[1]["depth"].clone()
+    d[: d.shape[0] // 6] *= 3.0                      # a band of pixels whose surface point is outside the bound
+    frames[1]["depth"] = d.contiguous()
+    md, tv = bench_util.mapping_draws(sc, s["mapping_pixels"], n_it, seed=12)
+    target = dict(kf_idx=sc["kf_idx"], frames=frames, class_tables=sc["class_tables"])
+    refer = dict(kf_idx=sc["refer_idx"], est_c2w=sc["refer_c2w"])
+    est = [sc["poses"][2 * f + 1].clone() for f in range(2)]
+    lam = dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0)
+    res = {}
+    for name, kw in (("eager", dict(use_graph=False)), ("native", dict(use_graph=True)), ("graph", dict(use_graph=True, native=False))):
+        dec = bench_util.make_decoder("tiny", 6, dev, seed=3)
+        mp = slam.MapperCore(sc["cam"], dec, s["mapping_pixels"], 32, 15, lambdas=lam, opacity_sigma=0.05,
+                             smooth_pts=s["smooth_pts"], lambda_sm=0.05)
+        ql, tl, ld = slam.map_optimize(mp, target, refer, sc["feats"], est, n_it, 5e-3, 5e-4, True, [],
+                                       lambda it: md[it], lambda it: tv[it], **kw)
+        assert mp.last_path == "eager", f"{name}: rays outside the bound went unnoticed"
+        if name != "eager":
+            assert mp.last_graph_ok is False
+        res[name] = (ld["total"].clone(), dec.flat.clone(), [q.clone() for q in ql])
+    for name in ("native", "graph"):       # the fallback restarts from the saved state: identical to the eager call
+        close(res[name][0], res["eager"][0], rtol=1e-5, atol=1e-7, name=f"{name} fallback loss")
+        assert rel_err(res[name][1], res["eager"][1]) < 1e-5
+        close(res[name][2][1], res["eager"][2][1], rtol=1e-5, atol=1e-7, name=f"{name} fallback pose")
+
+
+def test_native_tracking_flags_a_label_outside_the_semantic_head():
+    """torch's cross_entropy raises on a label >= C (tracking.py:203); the native loop reads the kernel's flag once."""
+    from dns_slam_b200 import bench_util, slam, synthetic as syn
+    dev = _dev()
+    s = syn.SHAPES["tiny"]
+    sc = bench_util.slam_scene("tiny", 6, dev, seed=13, n_target=2)
+    dec = bench_util.make_decoder("tiny", 6, dev, seed=4)
+    trk = slam.TrackerCore(sc["cam"], dec, s["tracking_pixels"], 32, 15, freeze_decoder=True)
+    td = bench_util.tracking_draws(sc["cam"], s["tracking_pixels"], 4, seed=1)
+    fr = dict(sc["frames"][1])
+    est, refer_w2c = sc["poses"][3].clone(), torch.inverse(sc["poses"][1])
+    feats2 = sc["feats"][1][:2].contiguous()
+    best, loss, hist = slam.track_frame(trk, fr, refer_w2c, feats2, est, 4, 1e-3, lambda it: td[it], native=True)
+    assert torch.isfinite(hist).all() and float(loss) == float(hist.min())
+    bad = dict(fr)
+    bad["label"] = torch.full_like(fr["label"], 6)
+    with pytest.raises(ValueError):
+        slam.track_frame(trk, bad, refer_w2c, feats2, est, 4, 1e-3, lambda it: td[it], native=True)
