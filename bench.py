@@ -389,7 +389,20 @@ def main():
     achieved = alg / (kern[dom] * 1e-3) / 1e9
     tv_pts = (scene["s"]["smooth_pts"] - 1) ** 3
     step_alg = R * (S * 3332 + 252) + tv_pts * TV_BYTES_PT + band_rows * N_REFER * FEAT_BYTES_ROW
-    traffic, traffic_src = None, "no ncu capture in this run (profiles/ holds the per-round captures)"
+    # DRAM traffic of the dominant kernel: bytes per sample point from the round's `ncu --set full` capture of this build
+    # (profiles/ncu_traffic.json, written by scratch/ncu_summary.py from profiles/run_ncu.sh), scaled to this launch; a
+    # run cannot measure it itself (numbers taken under a profiler are not bench values)
+    traffic, traffic_src = None, "no ncu capture on file (profiles/ncu_traffic.json missing)"
+    tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tj):
+        tr = json.load(open(tj))
+        kname = {"point_fwd": "k_point_fwd_tc2<1>", "ray": "k_ray_tc2", "point_bwd": "k_point_bwd_tc2<1>"}[dom]
+        bpp = tr.get("bytes_per_point", {}).get(kname)
+        if bpp is not None:
+            traffic = bpp * R * S
+            traffic_src = (f"profiles/{tr.get('capture')}_ncu_summary.md: {bpp:.0f} B per sample point (dram__bytes_read.sum + "
+                           f"dram__bytes_write.sum of one `ncu --set full` launch at {tr.get('points_per_launch')} points) x "
+                           f"{R * S} points of this launch")
     roof = {"bound": "hbm", "kernel": {"point_fwd": "k_point_fwd_tc2", "ray": "k_ray_tc2", "point_bwd": "k_point_bwd_tc2"}[dom],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": traffic_src,
@@ -549,7 +562,7 @@ def _config3(dev):
         wall = time.perf_counter() - t0
         mp_ = [x for x in log["log"] if x[0] == "map"]
         return {"wall_s": wall, "frames": 200, "timings": log["timings"],
-                "mapping_calls_replayed_as_cuda_graph": sum(1 for x in mp_ if x[4]), "mapping_calls": len(mp_),
+                "mapping_calls_on_the_native_loop": sum(1 for x in mp_ if x[4]), "mapping_calls": len(mp_),
                 "schedule": "scannet.yaml: 30 tracking iterations per frame, 100 mapping iterations every 5th frame"}
     except Exception as e:      # noqa: BLE001 - a failing extra must not void the headline line
         return {"error": repr(e)}

@@ -88,7 +88,7 @@ def run(shape="tiny", n_frames=4, n_class=5, track_iters=8, map_iters=8, use_gra
         for k, q, t in zip(window, quads, Ts):
             est[k] = slam.c2w_from_quad_T(q.detach(), t.detach()).cpu()
         log.append(("map", f, float(losses["p_loss"]), float(losses["d_loss"]),
-                    bool(use_graph and getattr(mapper, "last_graph_ok", True))))
+                    bool(use_graph and getattr(mapper, "last_path", "eager") != "eager")))
         if f not in keyframes:
             keyframes.append(f)
         if f + 1 == n_frames:
@@ -143,5 +143,5 @@ if __name__ == "__main__":
               f"({len(tr)} tracked frames x {s_['tracking_iters']} iterations, {len(mp_)} mapping calls x {s_['mapping_iters']} "
               f"iterations); translation drift vs the synthetic trajectory (random-colour frames, not an accuracy "
               f"figure): mean {float(err.mean()):.4f} m, max {float(err.max()):.4f} m; last map p_loss {mp_[-1][2]:.4f} d_loss {mp_[-1][3]:.4f}; "
-              f"{sum(1 for e in mp_ if e[4])} of {len(mp_)} mapping calls replayed as CUDA graphs (the others had rays "
-              f"leaving the bound and ran the eager loop); per call: {out['timings']}")
+              f"{sum(1 for e in mp_ if e[4])} of {len(mp_)} mapping calls on the native loop (the others had rays "
+              f"leaving the bound and ran the compacting eager loop); per call: {out['timings']}")
