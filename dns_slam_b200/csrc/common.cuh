@@ -95,8 +95,17 @@ inline int current_device_slot() {
 // Ablation switches exist only in -DDNS_ABLATE builds (scratch measurements); release kernels carry none.
 #ifdef DNS_ABLATE
 #define DNS_DBG(a) ((a).dbg)
+#define DNS_CLK_DECL long long _clk_prev = clock64();
+#define DNS_CLK(a, i)                                                                          \
+  if ((a).phase_clk && threadIdx.x == 0) {                                                     \
+    const long long _now = clock64();                                                          \
+    atomicAdd((a).phase_clk + (i), (unsigned long long)(_now - _clk_prev));                    \
+    _clk_prev = _now;                                                                          \
+  }
 #else
 #define DNS_DBG(a) 0
+#define DNS_CLK_DECL
+#define DNS_CLK(a, i)
 #endif
 
 // ---------------------------------------------------------------------------------------

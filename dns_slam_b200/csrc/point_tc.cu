@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, row = tid & (kTile - 1), grp = tid >> 7;
   const int n_tiles = a.perm ? a.counts[cTiles] : a.n_tiles_host;
   if (tile >= n_tiles) return;
+  DNS_CLK_DECL
   int expert = -1;
   if (MODE == kMap) expert = a.tile_class[tile];
   const bool fine = MODE == kMap && expert >= 0;
@@ -346,10 +347,12 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
   if (tid == 0) mbar_init(&bar, 1);
 
+  DNS_CLK(a, 0)   // W2 tile loads issued, TMEM allocation
   const int64_t q = (int64_t)tile * kTile + row;
   int64_t i, r;
   float zv, x[3];
   const bool valid = slot_point<MODE>(a, q, i, r, zv, x);
+  DNS_CLK(a, 1)   // perm -> ray -> point
   constexpr int DOCH = MODE == kMap ? 10 : 5;   // chunks per half of the dOut image: 5 (40 >= 33 channels) per net
   constexpr int HCH = MODE == kMap ? 8 : 4;     // chunks per half of the H / dH images
   const bool stash = a.need_dparams && !(DNS_DBG(a) & 2);
@@ -447,10 +450,12 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
                       gi ? doimg + (DOCH + 5 + c) * kTile : nullptr);
     }
   }
+  DNS_CLK(a, 2)   // dOut rows built
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  DNS_CLK(a, 3)   // first CTA barrier
   const uint32_t tmem_d = tmem_base_s;
   if (tid == 0) {  // dH = dOut . W2   (B = W2 tile MN-major: hidden contiguous; LBO 128 over out rows, SBO 768 over hidden chunks)
     const uint32_t idesc = umma_idesc_bf16(128, 32, 0, 1);
@@ -481,6 +486,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   }
   mbar_wait_cta(&bar, 0);
   tc_fence_after();
+  DNS_CLK(a, 4)   // GEMM dH issued + W1 prefetch + wait
 #pragma unroll
   for (int k = 0; k < 5; ++k) reinterpret_cast<uint4*>(W1_hi)[tid + k * kTile2] = w1r[k];   // W1_lo follows W1_hi
   const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
@@ -508,9 +514,11 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
       }
     }
   }
+  DNS_CLK(a, 5)   // dH epilogue (H image read, ReLU mask, tile + image stores)
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  DNS_CLK(a, 6)   // second CTA barrier
   if (tid == 0) {  // dX = [dHc | dHf] . [W1c ; W1f]   (B = combined W1 tile MN-major: LBO 128 over hidden rows, SBO 1024)
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, 80, 0, 1);
@@ -527,6 +535,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   }
   mbar_wait_cta(&bar, 1);
   tc_fence_after();
+  DNS_CLK(a, 7)   // GEMM dX + wait
   // dX columns: 0..47 OneBlob (group 0), 48..63 levels 0..7 (group 0), 64..79 levels 8..15 (group 1)
   float dx[3] = {0.f, 0.f, 0.f}, dg[16];
   if (grp == 0) {
@@ -547,6 +556,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   tc_fence_before();
   __syncthreads();   // every accumulator row has been read; the operand tiles are free (DXS aliases them)
   if (warp == 0) tmem_dealloc(tmem_d, 128);
+  DNS_CLK(a, 8)   // dX read back, OneBlob backward, third CTA barrier, TMEM release
   float dxg[3] = {0.f, 0.f, 0.f};
   float2* dtab = (a.need_dparams && !(DNS_DBG(a) & 4) && !(DNS_DBG(a) & (grp ? 32 : 16))) ? a.d_table : nullptr;
   const bool want_dx = a.need_drays != 0 && !(DNS_DBG(a) & 8);
@@ -556,6 +566,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
     if (grp == 0) hashgrid_bwd_range<0, 8>(a.G, a.table, dtab, x, dg, want_dx, dxg, dpriv, pl);
     else hashgrid_bwd_range<8, 16>(a.G, a.table, dtab, x, dg, want_dx, dxg, dpriv, pl);
   }
+  DNS_CLK(a, 9)   // hash-grid backward of thread 0 (levels 0..7)
   if (a.need_drays && MODE != kTv) {
     if (grp == 1) {
 #pragma unroll
@@ -571,6 +582,7 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
       }
     }
   }
+  DNS_CLK(a, 10)   // ray gradients
 }
 
 size_t point_bwd_tc2_smem() { return 16 * 2048 + 2 * kW1Tile + 4 * kW2Tile; }

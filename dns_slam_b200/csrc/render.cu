@@ -1091,6 +1091,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
 #ifdef DNS_ABLATE
     { const char* e = getenv("DNS_DBG"); pa.dbg = e ? atoi(e) : 0; }
     if (getenv("DNS_NO_PRIV")) pa.d_priv = nullptr;
+    if (const char* e = getenv("DNS_PHASE_CLK")) pa.phase_clk = (unsigned long long*)strtoull(e, nullptr, 0);   // device pointer
     if (const char* e = getenv("DNS_PRIV_COPIES")) { if (pa.d_priv && atoi(e) >= 1 && atoi(e) <= pa.priv_copies) pa.priv_copies = atoi(e); }
     if (const char* e = getenv("DNS_PRIV_LEVELS")) { if (pa.d_priv && atoi(e) >= 1 && atoi(e) <= pa.priv_levels) { pa.priv_levels = atoi(e); pa.priv_end = a->grid.offset[pa.priv_levels]; } }
 #endif

@@ -128,6 +128,7 @@ struct PointArgs {
   float* d_rays_d;
   int need_dparams, need_drays;
   int dbg;   // -DDNS_ABLATE builds only (DNS_DBG env): 2 no stash stores, 4 no table atomics, 8 no regather
+  unsigned long long* phase_clk;   // -DDNS_ABLATE builds only: [16] summed clock64 deltas of thread 0 per kernel phase
 };
 
 template <int MODE>
