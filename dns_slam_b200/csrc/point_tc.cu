@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
   float zv, x[3];
   const bool valid = slot_point<MODE>(a, q, i, r, zv, x);
   uint4* ximg = (a.need_dparams && !(DNS_DBG(a) & 2)) ? a.Ximg + (int64_t)tile * (20 * kTile) + row : nullptr;
+  float4* jimg = (MODE != kTv && a.Jst && a.need_drays)
+                     ? reinterpret_cast<float4*>(a.Jst) + ((int64_t)tile * 24 + 12 * grp) * kTile + row : nullptr;
 #define XIMG(c) (ximg ? ximg + (c) * kTile : nullptr), (ximg ? ximg + (10 + (c)) * kTile : nullptr)
   if (valid) {
     if (grp == 0) {
@@ -120,9 +122,9 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
         put_chunk_f16_img(X_hi, X_lo, 2 * c, 2048, row, pe, XIMG(2 * c));
         put_chunk_f16_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, XIMG(2 * c + 1));
       }
-      hashgrid_fwd_to_tile<0, 8>(a.G, a.table, x, X_hi, X_lo, row);
+      hashgrid_fwd_to_tile<0, 8>(a.G, a.table, x, X_hi, X_lo, row, jimg);
     } else {
-      hashgrid_fwd_to_tile<8, 16>(a.G, a.table, x, X_hi, X_lo, row);
+      hashgrid_fwd_to_tile<8, 16>(a.G, a.table, x, X_hi, X_lo, row, jimg);
     }
     if (ximg) {   // the two grid chunks this thread has just written (its own row): fp16 tile -> bf16 global image
 #pragma unroll
@@ -560,11 +562,21 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
   float dxg[3] = {0.f, 0.f, 0.f};
   float2* dtab = (a.need_dparams && !(DNS_DBG(a) & 4) && !(DNS_DBG(a) & (grp ? 32 : 16))) ? a.d_table : nullptr;
   const bool want_dx = a.need_drays != 0 && !(DNS_DBG(a) & 8);
+  // dL/dx through the grid: from the forward pass's Jacobian image when there is one (12 coalesced loads per thread),
+  // else by re-reading the corners
+  const bool from_j = MODE != kTv && a.Jst != nullptr;
   if (valid) {
     float2* dpriv = a.d_priv ? a.d_priv + (size_t)(blockIdx.x % a.priv_copies) * a.priv_end : nullptr;
     const int pl = a.d_priv ? a.priv_levels : 0;
-    if (grp == 0) hashgrid_bwd_range<0, 8>(a.G, a.table, dtab, x, dg, want_dx, dxg, dpriv, pl);
-    else hashgrid_bwd_range<8, 16>(a.G, a.table, dtab, x, dg, want_dx, dxg, dpriv, pl);
+    float dxj[3] = {0.f, 0.f, 0.f};
+    if (want_dx && from_j)    // issued before the reductions: the 12 loads fly while those drain
+      hashgrid_dx_from_jimg<8>(reinterpret_cast<const float4*>(a.Jst) + ((int64_t)tile * 24 + 12 * grp) * kTile + row, dg, dxj);
+    if (grp == 0) hashgrid_bwd_range<0, 8>(a.G, a.table, dtab, x, dg, want_dx && !from_j, dxg, dpriv, pl);
+    else hashgrid_bwd_range<8, 16>(a.G, a.table, dtab, x, dg, want_dx && !from_j, dxg, dpriv, pl);
+    if (want_dx && from_j) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dxg[c] = dxj[c];
+    }
   }
   DNS_CLK(a, 9)   // hash-grid backward of thread 0 (levels 0..7)
   if (a.need_drays && MODE != kTv) {

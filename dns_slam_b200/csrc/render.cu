@@ -916,7 +916,10 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.fine36 = c.take<float>(Pc * kOutP);
   w.coarse36 = c.take<float>(map ? Pc * kOutP : 4);
   w.dfine36 = c.take<float>(Pc * kOutP);
-  w.Jst = nullptr;   // (a per-level Jacobian stash was measured slower than re-gathering the corners)
+  // Jacobian image of the grid features (PointArgs::Jst): 24 float4 per slot, written by the forward point kernel when
+  // ray gradients are wanted.  (Round 1 tried the same values as [slot][96] ROWS -- every lane its own cache line, slower
+  // than re-reading the corners; the image is lane-contiguous like the other tile images.)
+  w.Jst = c.take<float>(w.Q * 96);
   // Stashes for the weight gradients.  SIMT path: fp32 rows.  tcgen05 path: the same regions hold bf16 hi/lo
   // tile images (32 B per value pair = the fp32 footprint; dOut rows padded 36 -> 40, ray-side rows padded to
   // whole CTAs of T rows).
@@ -1083,7 +1086,9 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     pa.lam_lt = a->lambda_lt; pa.lam_fs = a->lambda_fs; pa.lam_op = a->lambda_op;
     pa.trunc = a->opacity_trunc; pa.sigma = a->opacity_sigma;
     pa.raw = w.raw; pa.d_table = (float2*)a->d_table; pa.d_rays_o = a->d_rays_o; pa.d_rays_d = a->d_rays_d;
-    pa.need_dparams = a->need_dparams && !a->forward_only; pa.need_drays = a->need_drays;
+    pa.need_dparams = a->need_dparams && !a->forward_only;
+    pa.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d && !a->forward_only;
+    if (!tc || !pa.need_drays) pa.Jst = nullptr;
     if (tc && pa.need_dparams && a->d_table) {
       priv_plan(a->grid, pa.priv_levels, pa.priv_end, pa.priv_copies);
       pa.d_priv = pa.priv_copies ? w.dpriv : nullptr;
@@ -1091,6 +1096,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
 #ifdef DNS_ABLATE
     { const char* e = getenv("DNS_DBG"); pa.dbg = e ? atoi(e) : 0; }
     if (getenv("DNS_NO_PRIV")) pa.d_priv = nullptr;
+    if (getenv("DNS_NO_JIMG")) pa.Jst = nullptr;
     if (const char* e = getenv("DNS_PHASE_CLK")) pa.phase_clk = (unsigned long long*)strtoull(e, nullptr, 0);   // device pointer
     if (const char* e = getenv("DNS_PRIV_COPIES")) { if (pa.d_priv && atoi(e) >= 1 && atoi(e) <= pa.priv_copies) pa.priv_copies = atoi(e); }
     if (const char* e = getenv("DNS_PRIV_LEVELS")) { if (pa.d_priv && atoi(e) >= 1 && atoi(e) <= pa.priv_levels) { pa.priv_levels = atoi(e); pa.priv_end = a->grid.offset[pa.priv_levels]; } }

@@ -98,7 +98,8 @@ struct PointArgs {
   float* occ;   // TV: [n^3]
   float* docc;  // TV
   // stashes in slot order
-  float* Jst;   // [Q][96] d grid feature / d x (tcgen05 path, only when ray gradients are wanted)
+  float* Jst;   // tcgen05 path, only when ray gradients are wanted: Jacobian image [tile][24 float4 chunks][128 slots] of
+                // d(grid features) / d(x) written by the forward kernel (chunks 0..11: levels 0..7, 12..23: levels 8..15)
   float* Xst;   // [Q][80]
   float* Hc;    // [Q][32]
   float* Hf;

@@ -166,9 +166,14 @@ __device__ __forceinline__ void hashgrid_fwd_range(const dns_grid& G, const floa
 // Rolled variant for the forward tile: each level's feature pair goes straight into the bf16 hi / lo operand tile
 // (4 bytes at  chunk 6 + l/4, row, element pair l%4), so no per-thread feature array exists and the loop body is
 // emitted twice instead of eight times (the fully unrolled form showed instruction-fetch stalls in ncu).
+// `jimg` != nullptr: the level's Jacobian d(feature pair) / d(x) -- six floats, scale included -- goes into the thread's
+// slot-order Jacobian image (float4 chunk k of row `row` at jimg[k * 128]; two levels = three chunks), from which the
+// backward kernel forms dL/dx = sum_l g_l . J_l with 12 coalesced 16-byte loads per thread instead of re-reading the
+// 64 corners (one L1 wavefront per LANE: the unrelated points of a warp share no cache line).
 template <int L0, int L1>
 __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const float2* __restrict__ table, const float x[3],
-                                                     unsigned char* X_hi, unsigned char* X_lo, int row) {
+                                                     unsigned char* X_hi, unsigned char* X_lo, int row, float4* jimg = nullptr) {
+  float jj[12];
 #pragma unroll 2
   for (int l = L0; l < L1; ++l) {
     uint32_t g[3];
@@ -196,6 +201,40 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
     const int off = (6 + (l >> 2)) * 2048 + row * 16 + (l & 3) * 4;
     *reinterpret_cast<__half2*>(X_hi + off) = hh;
     *reinterpret_cast<__half2*>(X_lo + off) = ll;
+    if (jimg) {
+      const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
+      float* j6 = jj + 6 * ((l - L0) & 1);     // (the loop is unrolled by two: the parity is a compile-time constant)
+      // the same corner differences and weights as the backward's dL/dx (hashgrid_bwd_range), per feature
+      j6[0] = sc * (wy0 * wz0 * (v[1].x - v[0].x) + w[1] * wz0 * (v[3].x - v[2].x) + wy0 * w[2] * (v[5].x - v[4].x) + w[1] * w[2] * (v[7].x - v[6].x));
+      j6[1] = sc * (wx0 * wz0 * (v[2].x - v[0].x) + w[0] * wz0 * (v[3].x - v[1].x) + wx0 * w[2] * (v[6].x - v[4].x) + w[0] * w[2] * (v[7].x - v[5].x));
+      j6[2] = sc * (wx0 * wy0 * (v[4].x - v[0].x) + w[0] * wy0 * (v[5].x - v[1].x) + wx0 * w[1] * (v[6].x - v[2].x) + w[0] * w[1] * (v[7].x - v[3].x));
+      j6[3] = sc * (wy0 * wz0 * (v[1].y - v[0].y) + w[1] * wz0 * (v[3].y - v[2].y) + wy0 * w[2] * (v[5].y - v[4].y) + w[1] * w[2] * (v[7].y - v[6].y));
+      j6[4] = sc * (wx0 * wz0 * (v[2].y - v[0].y) + w[0] * wz0 * (v[3].y - v[1].y) + wx0 * w[2] * (v[6].y - v[4].y) + w[0] * w[2] * (v[7].y - v[5].y));
+      j6[5] = sc * (wx0 * wy0 * (v[4].y - v[0].y) + w[0] * wy0 * (v[5].y - v[1].y) + wx0 * w[1] * (v[6].y - v[2].y) + w[0] * w[1] * (v[7].y - v[3].y));
+      if ((l - L0) & 1) {
+        float4* dst = jimg + (3 * ((l - L0) >> 1)) * 128;
+        dst[0] = make_float4(jj[0], jj[1], jj[2], jj[3]);
+        dst[128] = make_float4(jj[4], jj[5], jj[6], jj[7]);
+        dst[256] = make_float4(jj[8], jj[9], jj[10], jj[11]);
+      }
+    }
+  }
+}
+// dL/dx of levels L0..L1-1 from the Jacobian image of the forward pass (see hashgrid_fwd_to_tile): dg = dL/d(feature pairs)
+template <int NL>
+__device__ __forceinline__ void hashgrid_dx_from_jimg(const float4* __restrict__ jimg, const float (&dg)[2 * NL], float dx[3]) {
+  static_assert(NL % 2 == 0, "two levels per three chunks");
+  dx[0] = dx[1] = dx[2] = 0.f;
+#pragma unroll
+  for (int p = 0; p < NL / 2; ++p) {
+    const float4 a = jimg[(3 * p) * 128], b = jimg[(3 * p + 1) * 128], c = jimg[(3 * p + 2) * 128];
+    const float j[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float g0 = dg[2 * (2 * p + h)], g1 = dg[2 * (2 * p + h) + 1];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dx[d] += g0 * j[6 * h + d] + g1 * j[6 * h + 3 + d];
+    }
   }
 }
 template <int L0, int L1, bool PAIR = true>
