@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
       if (grp) dst = a.fine36 + (a.p0 + i) * kOutP;
       else if (a.want_coarse_pt) dst = a.coarse36 + (a.p0 + i) * kOutP;
     }
-    float* dslot = (valid && grp == 0 && a.diff36s) ? a.diff36s + q * kOutP : nullptr;
+    float4* dslot = (valid && grp == 0 && a.diff36s) ? reinterpret_cast<float4*>(a.diff36s) : nullptr;   // image, see slot_img
     float fo32 = 0.f;
 #pragma unroll
     for (int g4 = 0; g4 < 3; ++g4) {
@@ -269,11 +269,11 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
           }
           if (dslot) {
             if (g4 < 2) {
-              float4* d4 = reinterpret_cast<float4*>(dslot + 16 * g4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) d4[k] = make_float4(dv[4 * k], dv[4 * k + 1], dv[4 * k + 2], dv[4 * k + 3]);
+              for (int k = 0; k < 4; ++k)
+                dslot[slot_img(q, 4 * g4 + k)] = make_float4(dv[4 * k], dv[4 * k + 1], dv[4 * k + 2], dv[4 * k + 3]);
             } else {
-              dslot[32] = dv[0];                                 // slot 33 belongs to group 1 (fine channel 32)
+              reinterpret_cast<float*>(dslot + slot_img(q, 8))[0] = dv[0];   // channel 33 belongs to group 1 (fine channel 32)
             }
           }
         } else {
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
         }
       }
     }
-    if (valid && grp == 1 && a.diff36s) a.diff36s[q * kOutP + 33] = fo32;
+    if (valid && grp == 1 && a.diff36s) reinterpret_cast<float*>(reinterpret_cast<float4*>(a.diff36s) + slot_img(q, 8))[1] = fo32;
     if (valid && grp == 1) {
       float front, band, vd, d = a.gt_depth[r];
       opacity_masks(zv, d, a.trunc, front, band, vd);
@@ -383,12 +383,12 @@ __global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const 
       float fo32 = 0.f;
       if (a.dfine36s) {
         // slot-order rows (written by the ray kernel and the forward kernel): unit stride, no permutation chase
-        const float4* sd = reinterpret_cast<const float4*>(a.dfine36s + q * kOutP + ch0);
-        const float4* sx = reinterpret_cast<const float4*>(a.diff36s + q * kOutP + ch0);
+        const float4* sd = reinterpret_cast<const float4*>(a.dfine36s);
+        const float4* sx = reinterpret_cast<const float4*>(a.diff36s);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           if (ch0 + 4 * k < kOutP) {
-            const float4 d = sd[k], x = sx[k];
+            const float4 d = sd[slot_img(q, 6 * grp + k)], x = sx[slot_img(q, 6 * grp + k)];
             const float dd[4] = {d.x, d.y, d.z, d.w}, xx[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

@@ -514,10 +514,17 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
     if (valid) {
       // point order, or (tcgen05 MAP path) the row of the point's SLOT: fire-and-forget here, unit stride for the reader
-      float* drow = a.inv ? a.dfine36s + (int64_t)a.inv[p - a.ray0 * S] * kOutP : a.dfine36 + p * kOutP;
-      float4* d4 = reinterpret_cast<float4*>(drow);
+      if (a.inv) {       // slot-order latent image (render.cuh slot_img): chunk c of slot sq
+        const int64_t sq = a.inv[p - a.ray0 * S];
+        float4* img = reinterpret_cast<float4*>(a.dfine36s);
 #pragma unroll
-      for (int q = 0; q < kOutP / 4; ++q) d4[q] = make_float4(lat[4 * q], lat[4 * q + 1], lat[4 * q + 2], lat[4 * q + 3]);
+        for (int q = 0; q < kOutP / 4; ++q)
+          img[slot_img(sq, q)] = make_float4(lat[4 * q], lat[4 * q + 1], lat[4 * q + 2], lat[4 * q + 3]);
+      } else {
+        float4* d4 = reinterpret_cast<float4*>(a.dfine36 + p * kOutP);
+#pragma unroll
+        for (int q = 0; q < kOutP / 4; ++q) d4[q] = make_float4(lat[4 * q], lat[4 * q + 1], lat[4 * q + 2], lat[4 * q + 3]);
+      }
     }
   }
   tc_fence_before();

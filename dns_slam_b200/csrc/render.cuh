@@ -90,8 +90,9 @@ struct PointArgs {
   float* fine36;
   float* coarse36;
   float* dfine36;
-  // tcgen05 MAP path, SLOT order [Q][36]: diff36s = coarse - fine (channels 0..32) | fine[32] (slot 33), written by the
-  // forward kernel; dfine36s written by the ray kernel.  The backward reads both with unit stride.
+  // tcgen05 MAP path, SLOT-order latent IMAGES [tile][9 chunks of 4 channels][128 slots] (slot_img): diff36s = coarse - fine
+  // (channels 0..32) | fine[32] (channel 33), written by the forward kernel; dfine36s written by the ray kernel.  A warp of
+  // the backward reads 512 contiguous bytes per chunk (rows of 36 floats put every lane into its own cache line).
   float* diff36s;
   float* dfine36s;
   int want_coarse_pt;   // also store the coarse latents in point order (coarse_out requested)
@@ -131,6 +132,9 @@ struct PointArgs {
   int dbg;   // -DDNS_ABLATE builds only (DNS_DBG env): 2 no stash stores, 4 no table atomics, 8 no regather
   unsigned long long* phase_clk;   // -DDNS_ABLATE builds only: [16] summed clock64 deltas of thread 0 per kernel phase
 };
+
+// float4 index of channel chunk `chunk` (4 channels) of slot q in a slot-order latent image
+__device__ __forceinline__ int64_t slot_img(int64_t q, int chunk) { return ((q >> 7) * 9 + chunk) * 128 + (q & 127); }
 
 template <int MODE>
 __device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_t& i, int64_t& r, float& zv, float x[3]) {
