@@ -203,9 +203,26 @@ __device__ __forceinline__ void row_geometry(const FmArgs& a, int64_t n_rows, in
 // This thread's share of the row's X = [OneBlob 48 | feature 64]: group 0 the OneBlob chunks 0..5 and feature
 // chunks 6..8 (24 channels), group 1 feature chunks 9..13 (40 channels).
 // ``img``: this row's slot in the tile image (NULL: no stash), chunk c hi at img[c * 128], lo at img[(14 + c) * 128].
+template <bool FEATURES = true>
 __device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsigned char* X_hi, unsigned char* X_lo, uint4* img) {
   const uint4 z4 = make_uint4(0, 0, 0, 0);
   const int c0 = grp ? 9 : 6, c1 = grp ? 14 : 9;
+  if (!FEATURES) {   // OneBlob chunks only (group 0); the feature chunks come from gather_features_coop
+    if (grp == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float pe[16];
+        if (g.valid) oneblob16(g.x[c], pe);
+        else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pe[e] = 0.f;
+        }
+        put_chunk(X_hi, X_lo, 2 * c, 2048, row, pe);
+        put_chunk(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8);
+      }
+    }
+    return;
+  }
   if (!g.valid) {
     for (int c = grp ? 9 : 0; c < c1; ++c) {
       *reinterpret_cast<uint4*>(X_hi + c * 2048 + row * 16) = z4;
@@ -251,6 +268,66 @@ __device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsi
   }
 }
 
+// Cooperative form of the feature part of build_x for the forward kernel.  build_x lets every thread fetch ITS row's taps:
+// the 32 lanes of a load instruction then touch 32 different cache lines (32 L1 wavefronts for 512 useful bytes), and the
+// kernel sat on that rate.  Here the row owners publish their tap descriptors in shared memory and each warp walks 16
+// rows, four at a time: the 8 lanes of a row read the tap's 64 channels as two contiguous 128-byte lines (lane k: channels
+// 4k..4k+3 and 32+4k..32+4k+3), so an instruction touches 4 lines instead of 32.  Neighbouring lanes then swap halves so
+// that each owns one 8-channel operand chunk (even k: chunk 6 + k/2, odd k: chunk 10 + k/2).  Same blend expression as
+// build_x: the tile is bit identical.
+struct TapDesc {
+  const float* f00;   // NULL: row absent or view hidden (zeros)
+  int dx, dy;         // element offsets of the x1 / y1 taps
+  float wx1, wy1;
+};
+__device__ __forceinline__ void publish_taps(const RowGeom& g, TapDesc* d) {
+  d->f00 = (g.valid && g.vis) ? g.f00 : nullptr;
+  if (g.valid && g.vis) {
+    d->dx = (int)(g.f01 - g.f00);
+    d->dy = (int)(g.f10 - g.f00);
+    d->wx1 = g.wx1;
+    d->wy1 = g.wy1;
+  }
+}
+__device__ __forceinline__ void gather_features_coop(const TapDesc* taps, int warp, int lane, unsigned char* X_hi, unsigned char* X_lo) {
+  const int k = lane & 7;
+#pragma unroll 2
+  for (int it = 0; it < 4; ++it) {
+    const int row = 16 * warp + 4 * it + (lane >> 3);
+    const TapDesc td = taps[row];
+    float lo4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4] = {0.f, 0.f, 0.f, 0.f};   // channels 4k.., 32+4k..
+    if (td.f00) {
+      const float wx1 = td.wx1, wx0 = 1.f - wx1, wy1 = td.wy1, wy0 = 1.f - wy1;
+      const float4* p00 = reinterpret_cast<const float4*>(td.f00) + k;
+      const float4* p01 = reinterpret_cast<const float4*>(td.f00 + td.dx) + k;
+      const float4* p10 = reinterpret_cast<const float4*>(td.f00 + td.dy) + k;
+      const float4* p11 = reinterpret_cast<const float4*>(td.f00 + td.dy + td.dx) + k;
+      const float4 a00 = __ldg(p00), a01 = __ldg(p01), a10 = __ldg(p10), a11 = __ldg(p11);
+      const float4 b00 = __ldg(p00 + 8), b01 = __ldg(p01 + 8), b10 = __ldg(p10 + 8), b11 = __ldg(p11 + 8);
+      lo4[0] = wy0 * (wx0 * a00.x + wx1 * a01.x) + wy1 * (wx0 * a10.x + wx1 * a11.x);
+      lo4[1] = wy0 * (wx0 * a00.y + wx1 * a01.y) + wy1 * (wx0 * a10.y + wx1 * a11.y);
+      lo4[2] = wy0 * (wx0 * a00.z + wx1 * a01.z) + wy1 * (wx0 * a10.z + wx1 * a11.z);
+      lo4[3] = wy0 * (wx0 * a00.w + wx1 * a01.w) + wy1 * (wx0 * a10.w + wx1 * a11.w);
+      hi4[0] = wy0 * (wx0 * b00.x + wx1 * b01.x) + wy1 * (wx0 * b10.x + wx1 * b11.x);
+      hi4[1] = wy0 * (wx0 * b00.y + wx1 * b01.y) + wy1 * (wx0 * b10.y + wx1 * b11.y);
+      hi4[2] = wy0 * (wx0 * b00.z + wx1 * b01.z) + wy1 * (wx0 * b10.z + wx1 * b11.z);
+      hi4[3] = wy0 * (wx0 * b00.w + wx1 * b01.w) + wy1 * (wx0 * b10.w + wx1 * b11.w);
+    }
+    // even k keeps its first set and takes the partner's first set (channels 4k..4k+7 = chunk 6 + k/2); odd k keeps its
+    // second set behind the partner's (channels 32+4(k-1)..32+4k+3 = chunk 10 + k/2)
+    const bool odd = k & 1;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float send = odd ? lo4[e] : hi4[e];
+      const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+      f[e] = odd ? got : lo4[e];
+      f[4 + e] = odd ? hi4[e] : got;
+    }
+    put_chunk(X_hi, X_lo, (odd ? 10 : 6) + (k >> 1), 2048, row, f);
+  }
+}
+
 // H = X . W1^T  (M = 128 rows, N = 32, K = 112), issued by one thread
 __device__ __forceinline__ void mma_hidden(uint32_t tmem_h, const unsigned char* X_hi, const unsigned char* X_lo,
                                            const unsigned char* W1_hi, const unsigned char* W1_lo) {
@@ -282,6 +359,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float sK[9], sW2c[16 * kMaxViews], sCamO[3 * kMaxViews];
+  __shared__ TapDesc sTaps[kTile];
   unsigned char* X_hi = sm;
   unsigned char* X_lo = sm + 14 * 2048;
   unsigned char* H_hi = sm;                  // aliases the X tile after the first GEMM
@@ -313,13 +391,20 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     RowGeom g;
     row_geometry(a, n_rows, tile, row, sK, sW2c, sCamO, g);
-    build_x(g, grp, row, X_hi, X_lo, use_img ? a.Ximg + tile * (kXImgBytes / 16) + row : nullptr);
+    if (grp == 1) publish_taps(g, sTaps + row);
+    __syncthreads();
+    build_x<false>(g, grp, row, X_hi, X_lo, nullptr);            // OneBlob chunks (group 0)
+    gather_features_coop(sTaps, warp, tid & 31, X_hi, X_lo);      // feature chunks, coalesced
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       mma_hidden(tmem_d, X_hi, X_lo, W1_hi, W1_lo);
+      if (use_img) {   // the tile image for the backward = the X tile byte for byte: ONE bulk store; the MMA commit waits
+        bulk_s2g(a.Ximg + tile * (kXImgBytes / 16), X_hi, kXImgBytes);   // until its source has been read (H aliases X)
+        bulk_wait_read();
+      }
       umma_commit(&bar);
     }
     mbar_wait_cta(&bar, phase);
@@ -377,6 +462,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
     }
     __syncthreads();   // OB / H are overwritten by the next tile's X
   }
+  if (tid == 0 && use_img) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, 64);
