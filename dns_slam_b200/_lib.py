@@ -47,7 +47,8 @@ class RenderArgs(C.Structure):
                 ("d_experts", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("d_features", _P),
                 ("workspace", _P), ("workspace_bytes", C.c_int64),
                 ("n_rays_total", C.c_int64), ("ray_offset", C.c_int64), ("gt_label_all", _P),
-                ("global_counts", _P), ("forward_only", C.c_int32), ("use_simt", C.c_int32)]
+                ("global_counts", _P), ("forward_only", C.c_int32), ("use_simt", C.c_int32),
+                ("features_band_only", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class TvArgs(C.Structure):
@@ -78,7 +79,7 @@ class FeatMergeArgs(C.Structure):
     _fields_ = [("n_rays", C.c_int32), ("n_samples", C.c_int32), ("n_frames", C.c_int32), ("n_views", C.c_int32),
                 ("ray_start", C.c_int32 * (MAX_FRAMES + 1)), ("H", C.c_int32), ("W", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("apply_trunc", C.c_int32), ("need_dparams", C.c_int32), ("need_drays", C.c_int32),
-                ("bound", (C.c_double * 2) * 3), ("K", _P), ("w2c", _P), ("cam_o", _P), ("feats", _P * MAX_FRAMES),
+                ("no_zero_fill", C.c_int32), ("bound", (C.c_double * 2) * 3), ("K", _P), ("w2c", _P), ("cam_o", _P), ("feats", _P * MAX_FRAMES),
                 ("rays_o", _P), ("rays_d", _P), ("z_vals", _P), ("gt_depth", _P), ("params", _P), ("features", _P),
                 ("d_features", _P), ("d_params", _P), ("d_rays_o", _P), ("d_rays_d", _P), ("workspace", _P),
                 ("workspace_bytes", C.c_int64), ("stash", _P), ("stash_bytes", C.c_int64)]

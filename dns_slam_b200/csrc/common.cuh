@@ -265,6 +265,11 @@ __device__ __forceinline__ void point_from_ray(const float* __restrict__ o, cons
   }
 }
 
+// Truncation band of tracking.py:167-170: front = z < 0.95 d, back = z > 1.05 d, keep = !front & !back & d > 0.
+__device__ __forceinline__ bool in_band(float zv, float d) {
+  return !(zv < __fmul_rn(d, 0.95f)) && !(zv > __fmul_rn(d, 1.05f)) && d > 0.f;
+}
+
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
 
 // ---------------------------------------------------------------------------------------

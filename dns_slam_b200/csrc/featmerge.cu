@@ -83,10 +83,6 @@ __global__ void k_prep_featmerge(const float* __restrict__ params, uint4* __rest
   }
 }
 
-// Truncation band of tracking.py:167-170: front = z < 0.95 d, back = z > 1.05 d, keep = !front & !back & d > 0.
-__device__ __forceinline__ bool in_band(float zv, float d) {
-  return !(zv < __fmul_rn(d, 0.95f)) && !(zv > __fmul_rn(d, 1.05f)) && d > 0.f;
-}
 
 // Row list of the band samples.  A block owns 4096 consecutive samples and appends its (ordered) hits with ONE
 // atomic on the counter, so the samples of a ray stay adjacent; block order is arbitrary (results do not depend on it).
@@ -804,7 +800,7 @@ int dns_featmerge_fwd(const dns_featmerge_args* a, void* stream) {
   const int64_t P = m.P;
   if (a->apply_trunc) {
     cudaMemsetAsync(w.counter, 0, sizeof(int), st);
-    cudaMemsetAsync(a->features, 0, sizeof(float) * P * 32, st);
+    if (!a->no_zero_fill) cudaMemsetAsync(a->features, 0, sizeof(float) * P * 32, st);
     const int64_t blocks = (P + 256 * kBandPer - 1) / (256 * kBandPer);
     k_band_rows<<<(unsigned)blocks, 256, 0, st>>>(a->z_vals, a->gt_depth, P, m.S, w.rows, w.counter);
   }

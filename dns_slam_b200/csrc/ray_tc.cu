@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   float* RG = RO + RPC * 8;             // [RPC][8]
   float* LG = RG + RPC * 8;             // [RPC][C4]
   float* LS = LG + RPC * C4;            // [4]
+  float* RT = LS + 4;                   // [RPC][8] ground truth of the CTA's rays, fetched at kernel start: colour 0..2, depth 3,
+                                        // label 4 (int bits), mask 5 -- the loss section (one warp per ray) then waits for no load
+  float* W2L = RT + RPC * 8;            // [C][32] layer 2 of the logit head (read twice per CTA: forward and backward)
   const int t = threadIdx.x, warp = t >> 5;
   const int grp = t >= T ? 1 : 0, row = t - grp * T;
   if (t == 0) {   // the 28 KB weight tile (fp16 halves for the forward GEMM) arrives by two bulk copies while the
@@ -85,8 +88,24 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   }
   for (int i = t; i < 32; i += NT) reinterpret_cast<float4*>(W2c)[i] = reinterpret_cast<const float4*>(a.W2cT)[i];
   if (t < 4) LS[t] = 0.f;
+  if (a.w2l_smem)
+    for (int i = t; i < C * 8; i += NT) reinterpret_cast<float4*>(W2L)[i] = __ldg(reinterpret_cast<const float4*>(a.logit + 32 * kIn2) + i);
+  if (t < RPC) {
+    const int64_t rl2 = (int64_t)blockIdx.x * RPC + t, r2 = a.ray0 + rl2;
+    if (rl2 < a.Nc) {
+      float* rt = RT + t * 8;
+      rt[0] = a.gt_color[3 * r2];
+      rt[1] = a.gt_color[3 * r2 + 1];
+      rt[2] = a.gt_color[3 * r2 + 2];
+      rt[3] = a.gt_depth[r2];
+      const int64_t lab = a.gt_label[r2];
+      rt[4] = __int_as_float((lab < 0 || lab >= C) ? -1 : (int)lab);
+      rt[5] = (a.mode == kTrack && a.mask) ? (a.mask[r2] != 0 ? 1.f : 0.f) : 1.f;
+    }
+  }
   const uint32_t tmem_cols = MT == 1 ? 128 : 256;
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  DNS_CLK_DECL
 
   const int lr = row / S, s = row - lr * S;
   const int64_t rl = (int64_t)blockIdx.x * RPC + lr;      // chunk-local ray
@@ -96,6 +115,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   const int rb = lr * S;                                  // first row of my ray
   float* xc = XC + row;
   float x[3] = {0.f, 0.f, 0.f}, zv = 0.f, occ = 0.f;
+  bool band = true;   // features_band_only: the pixel-feature row exists only for samples inside the truncation band
   // weight-gradient operands leave the kernel as bf16 hi/lo tile images: this CTA owns T rows = T/RS sub-tiles,
   // each laid out [half][chunk][RS rows] (tc.cu: k_dw_img); rows of absent points are written as zeros
   const bool stash = a.need_dparams != 0;
@@ -110,6 +130,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   // ---- stage this point's row of X = [OneBlob(x) 48 | latent 32 | pixel feature 32] as bf16 hi/lo chunks
   if (valid) {
     zv = a.z[p];
+    if (a.feat_band && grp == 1) band = in_band(zv, a.gt_depth[r]);
     if (grp == 0) {
       point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
 #pragma unroll
@@ -135,7 +156,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       }
       {
         float ft[32];
-        if (a.features) {
+        if (a.features && band) {
           const float4* s4 = reinterpret_cast<const float4*>(a.features + p * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -160,6 +181,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       if (stash) x2p[c * RS] = x2p[(14 + c) * RS] = z4;
     }
   }
+  DNS_CLK(a, 1)
   // occupancy compositing (common.py:524-532) depends on the latent row only: group 1 runs its scans while the
   // forward GEMM is in flight (its own named barrier; group 0 issues / waits for the MMAs)
   float alpha = 0.f, b = 1.f;
@@ -171,6 +193,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  DNS_CLK(a, 2)
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
   // ---- forward GEMM: H = X . W1^T  (A K-major: LBO = chunk stride, SBO = 128; B K-major: LBO = 1024, SBO = 128)
@@ -204,6 +227,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     wsh[row] = w;
   }
   mbar_wait_cta(&bar, 0);
+  DNS_CLK(a, 3)
   tc_fence_after();
   if (t == 0 && !a.fwd_only) {   // the forward GEMM has consumed the fp16 weight tile: fetch the bf16 halves over it
     mbar_expect_tx(&wbar, 2 * kW1oBytes2);
@@ -224,6 +248,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   }
   tc_fence_before();
   __syncthreads();   // every thread has read its accumulator half: region R may be reused as staging
+  DNS_CLK(a, 4)
   float rgb[3] = {0.f, 0.f, 0.f};
   if (grp == 0) {    // colour head: 32 -> 3, sigmoid (decoder.py:123)
     float pre[3] = {0.f, 0.f, 0.f};
@@ -249,6 +274,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
   }
   __syncthreads();
+  DNS_CLK(a, 5)
   for (int e = t; e < RPC * 36; e += NT) {
     int l2 = e / 36, o = e - l2 * 36;
     if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
@@ -260,13 +286,14 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
   }
   __syncthreads();
+  DNS_CLK(a, 6)
   float dz = 0.f;
   if (grp == 1) {
     dz = valid ? zv - RO[lr * 8 + 3] : 0.f;
     bs[row] = w * dz * dz;
     us[row] = w * dz;
   }
-  const float* W2l = a.logit + 32 * kIn2;
+  const float* W2l = a.w2l_smem ? W2L : a.logit + 32 * kIn2;   // (many classes x many rays per CTA: the copy does not fit)
   for (int e = t; e < RPC * C; e += NT) {
     int l2 = e / C, c = e - l2 * C;
     if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
@@ -275,7 +302,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       float acc = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float4 v = __ldg(wr + q);
+        float4 v = wr[q];
         acc = fmaf(hb[4 * q], v.x, acc);
         acc = fmaf(hb[4 * q + 1], v.y, acc);
         acc = fmaf(hb[4 * q + 2], v.z, acc);
@@ -285,6 +312,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
   }
   __syncthreads();
+  DNS_CLK(a, 7)
   // ---- per-ray losses and their gradients: one warp per ray, lanes over samples / classes
   for (int l2 = warp; l2 < RPC; l2 += (NT >> 5)) {
     const int64_t rl2 = (int64_t)blockIdx.x * RPC + l2, r2 = a.ray0 + rl2;
@@ -316,21 +344,22 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
     // scalars of the ray: evaluated by every lane (same values), written by lane 0
     const float dhat = ro[3];
-    const float gd = a.gt_depth[r2];
-    int64_t lab = a.gt_label[r2];
-    if (lab < 0 || lab >= C) {   // torch's cross_entropy raises here; the flag surfaces as losses[7] = -3
+    const float* rt = RT + l2 * 8;
+    const float gd = rt[3];
+    int lab = __float_as_int(rt[4]);
+    if (lab < 0) {   // label outside [0, C): torch's cross_entropy raises here; the flag surfaces as losses[7] = -3
       if (lane == 0) *a.err = 3;
       lab = 0;
     }
     const bool track = a.mode == kTrack;
-    const bool m = track ? (a.mask ? a.mask[r2] != 0 : true) : true;
+    const bool m = rt[5] != 0.f;
     const float n_ray = track ? (float)a.counts[cMask] : (float)a.N_total;
     float lp = 0.f, ldp = 0.f, ll = 0.f;
     float g_rgb[3] = {0.f, 0.f, 0.f}, g_d = 0.f, g_var = 0.f, g_ce = 0.f, lse = 0.f;
     if (m) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float e = ro[c] - a.gt_color[3 * r2 + c];
+        float e = ro[c] - rt[c];
         lp = fmaf(e, e, lp);
         g_rgb[c] = a.lam_p * 2.f * e / (3.f * n_ray);
       }
@@ -374,6 +403,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     }
   }
   __syncthreads();
+  DNS_CLK(a, 8)
   if (t == 0) {
     atomicAdd(a.raw + rP, LS[0]);
     atomicAdd(a.raw + rD, LS[1]);
@@ -390,7 +420,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     if ((int64_t)blockIdx.x * RPC + l2 < a.Nc) {
       const float* lg = LG + l2 * C4;
       float acc = 0.f;
-      for (int c = 0; c < C; ++c) acc = fmaf(lg[c], __ldg(W2l + c * 32 + j), acc);
+      for (int c = 0; c < C; ++c) acc = fmaf(lg[c], W2l[c * 32 + j], acc);
       QV[e] = acc;
     }
   }
@@ -404,6 +434,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     tmp[row] = part;
   }
   __syncthreads();
+  DNS_CLK(a, 9)
   float d_w = 0.f;
   if (grp == 1) {
     if (valid) {
@@ -416,6 +447,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     bs[row] = w * d_w;
   }
   __syncthreads();
+  DNS_CLK(a, 10)
   float d_u = 0.f, d_occ = 0.f;
   if (grp == 1) {
     if (valid) {
@@ -465,6 +497,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  DNS_CLK(a, 11)
   if (t == 0) {
     tc_fence_after();
     mbar_wait(&wbar, 1);   // bf16 weight halves landed
@@ -484,6 +517,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     umma_commit(&bar);
   }
   mbar_wait_cta(&bar, 1);
+  DNS_CLK(a, 12)
   tc_fence_after();
   float g3[3] = {0.f, 0.f, 0.f};
   if (grp == 0) {   // dX columns 0..47: OneBlob backward -> d(ray)
@@ -502,11 +536,11 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
 #pragma unroll
     for (int g = 3; g < 7; ++g) {
       float v[16];
-      if (g < 5 || a.need_dfeat) tmem_ld16(taddr + 16 * g, v);
+      if (g < 5 || a.need_dfeat) tmem_ld16(taddr + 16 * g, v);   // (warp-uniform condition: tcgen05.ld is warp-collective)
       if (g < 5) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) lat[1 + 16 * (g - 3) + i] = v[i];
-      } else if (a.need_dfeat && valid) {
+      } else if (a.need_dfeat && valid && band) {
         float4* d4 = reinterpret_cast<float4*>(a.d_features + p * 32 + 16 * (g - 5));
 #pragma unroll
         for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -529,6 +563,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   }
   tc_fence_before();
   __syncthreads();
+  DNS_CLK(a, 13)
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
   if (a.need_drays) {
     if (valid && grp == 0) {
@@ -539,6 +574,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       }
     }
     __syncthreads();
+  DNS_CLK(a, 14)
     for (int e = t; e < RPC * 6; e += NT) {
       int l2 = e / 6, o = e - l2 * 6;
       int64_t rr2 = (int64_t)blockIdx.x * RPC + l2;
@@ -551,6 +587,7 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
       }
     }
   }
+  DNS_CLK(a, 15)
 }
 
 // T in {128, 256}: the larger row efficiency wins (ties -> 128, two CTAs per SM); -DDNS_ABLATE builds read DNS_RAY_T
@@ -581,15 +618,23 @@ void pick_ray_block_tc2(int S, int& T, int& RPC) {
   RPC = T / S > 64 ? 64 : T / S;
 }
 
-size_t ray_tc2_smem_bytes(int T, int RPC, int C4) {
-  return (size_t)28 * T * 16 + 2 * kW1oBytes2 + sizeof(float) * (128 + 5 * T + RPC * (32 + 32 + 8 + 8 + C4) + 8);
+constexpr size_t kRaySmemMax = 226 * 1024;   // dynamic; the kernel's static shared memory needs the rest of the 227 KB
+size_t ray_tc2_smem_bytes(int T, int RPC, int C4, bool w2l) {
+  return (size_t)28 * T * 16 + 2 * kW1oBytes2 + sizeof(float) * (128 + 5 * T + RPC * (32 + 32 + 8 + 8 + 8 + C4) + 8 + (w2l ? C4 * 32 : 0));
 }
+size_t ray_tc2_smem_bytes(int T, int RPC, int C4) { return ray_tc2_smem_bytes(T, RPC, C4, false); }
 
 int launch_ray_tc2(const RayArgs& ra, uint4* w1_hi, uint4* w1_lo, int64_t n_rays_chunk, cudaStream_t st) {
   static unsigned long long seen = 0;
-  if (first_call_on_device(seen)) cudaFuncSetAttribute(k_ray_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  size_t smem = ray_tc2_smem_bytes(ra.T, ra.RPC, ra.C4);
-  k_ray_tc2<<<(int)((n_rays_chunk + ra.RPC - 1) / ra.RPC), 2 * ra.T, smem, st>>>(ra, w1_hi, w1_lo);
+  if (first_call_on_device(seen)) cudaFuncSetAttribute(k_ray_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRaySmemMax);
+  RayArgs a2 = ra;
+  a2.w2l_smem = ray_tc2_smem_bytes(ra.T, ra.RPC, ra.C4, true) <= kRaySmemMax;
+  const size_t smem = ray_tc2_smem_bytes(ra.T, ra.RPC, ra.C4, a2.w2l_smem != 0);
+  if (smem > kRaySmemMax) {
+    set_error("ray_tc2: %lld bytes of shared memory needed (n_samples x n_class too large for the tcgen05 ray kernel)", (long long)smem);
+    return DNS_ERR_UNSUPPORTED;
+  }
+  k_ray_tc2<<<(int)((n_rays_chunk + ra.RPC - 1) / ra.RPC), 2 * ra.T, smem, st>>>(a2, w1_hi, w1_lo);
   return check_launch("ray_tc2");
 }
 

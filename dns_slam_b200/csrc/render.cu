@@ -996,6 +996,10 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     set_error("render: table / d_table must be 16-byte aligned (paired corner accesses)");
     return DNS_ERR_ARG;
   }
+  if (a->features_band_only && a->use_simt) {
+    set_error("render: features_band_only is a contract of the tcgen05 path");
+    return DNS_ERR_UNSUPPORTED;
+  }
   const bool map = mode == DNS_MODE_MAP;
   const int nci = map ? (a->n_class_ids < 1 ? 1 : a->n_class_ids) : 1;
   if (nci > 4096) {
@@ -1156,12 +1160,14 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     ra.X2img = (uint4*)w.X2; ra.dH2img = (uint4*)w.dH2; ra.Hcolimg = (uint4*)w.Hcol; ra.dpreimg = (uint4*)w.dpre;
     ra.RS = T <= 96 ? T : (T == 160 ? 80 : (T == 256 ? 128 : 64));   // sub-tile rows of the ray-side images (divides T)
 #ifdef DNS_ABLATE
+    if (const char* e = getenv("DNS_PHASE_CLK_RAY")) ra.phase_clk = (unsigned long long*)strtoull(e, nullptr, 0);   // device pointer
     if (const char* e = getenv("DNS_RAY_RS")) ra.RS = atoi(e);
 #endif
     const bool fwd_only = a->forward_only != 0;
     ra.fwd_only = a->forward_only;
     ra.need_dparams = a->need_dparams && !fwd_only; ra.need_drays = a->need_drays && a->d_rays_o && a->d_rays_d && !fwd_only;
     ra.need_dfeat = a->need_dfeat && a->d_features && !fwd_only;
+    ra.feat_band = a->features_band_only;
     pa.need_drays = ra.need_drays;
     {
       PhaseScope phr(phRay, st, 1 + ((tc && ray0 == 0) ? 1 : 0));

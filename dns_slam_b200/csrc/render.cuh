@@ -11,6 +11,9 @@ enum { cMask = 0, cDpos = 1, cFront = 2, cBand = 3, cTiles = 4, cErr = 5 };
 enum { rP = 0, rD = 1, rL = 2, rLt = 3, rFs = 4, rOp = 5 };
 
 struct RayArgs {
+  unsigned long long* phase_clk;   // -DDNS_ABLATE builds only (DNS_PHASE_CLK_RAY): [24] summed clock64 deltas of thread 0
+  int feat_band;                   // dns_render_args::features_band_only
+  int w2l_smem;                    // layer 2 of the logit head copied into shared memory (set by launch_ray_tc2 when it fits)
   int mode;
   int S, T, RPC, C, C4;
   int64_t N_total, ray0, Nc;  // chunk of rays [ray0, ray0 + Nc)

@@ -205,7 +205,7 @@ def render_counts(cfg):
 
 
 def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, features, grads, need_drays,
-               need_dfeat, forward_only=0, ws=None):
+               need_dfeat, forward_only=0, ws=None, features_band_only=False):
     """One ``dns_render_fwd_bwd`` call.  ``grads``: dict with optional device buffers
     ``table/coarse/color/logit/experts`` that are ACCUMULATED into (None => no parameter grads).
     Returns (losses[8], preds dict, d_rays_o, d_rays_d, d_features)."""
@@ -218,6 +218,7 @@ def render_raw(cfg, table, coarse, color, logit, experts, rays_o, rays_d, featur
     a.need_dparams, a.need_drays, a.need_dfeat = int(need_dparams), int(need_drays), int(need_dfeat)
     a.forward_only = int(forward_only)
     a.use_simt = int(_use_simt)
+    a.features_band_only = int(bool(features_band_only) and not _use_simt)
     _lib.fill_bound(a.bound, cfg.bound)
     a.lambda_p, a.lambda_d, a.lambda_l = cfg.lam["p"], cfg.lam["d"], cfg.lam["l"]
     a.lambda_lt, a.lambda_fs, a.lambda_op = cfg.lam["lt"], cfg.lam["fs"], cfg.lam["op"]
@@ -581,7 +582,7 @@ def _K_dev(cam, dev):
 
 
 def featmerge_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, apply_trunc=True, ws=None, out=None,
-                  stash=None):
+                  stash=None, zero_fill=True):
     """One ``dns_featmerge_fwd`` call.  Returns (features [N,S,32], workspace) -- the workspace holds the band row list
     and must be handed to ``featmerge_bwd_raw`` (like ``stash``, the optional operand-tile stash)."""
     dev = z_vals.device
@@ -593,6 +594,7 @@ def featmerge_raw(cam, bound, views, rays_o, rays_d, z_vals, gt_depth, params, a
     if out is None:
         out = torch.empty(N, S, 32, device=dev)
     a.features = _lib.ptr(out, torch.float32)
+    a.no_zero_fill = int(not zero_fill and apply_trunc)   # rows outside the band stay untouched: render_raw(features_band_only=True)
     _lib.check(L.dns_featmerge_fwd(C.byref(a), _lib.stream()))
     return out, ws
 

@@ -432,7 +432,7 @@ class MappingFrameStep:
                           inside=torch.empty(N, dtype=torch.uint8, device=dev),
                           pixel=torch.empty(N, dtype=torch.int64, device=dev))
         self.scratch = torch.zeros(F, 2, device=dev)          # per frame: max depth, rays outside the bound
-        self.features = torch.empty(N, S, 32, device=dev)
+        self.features = torch.zeros(N, S, 32, device=dev)      # band rows are rewritten every step, the others never read
         self.fm_ws = torch.empty(int(_lib.lib().dns_featmerge_workspace_bytes(N, S)), dtype=torch.uint8, device=dev)
         self.fm_stash = fused.featmerge_stash(N, S, self.R, dev)      # forward operand tiles kept for the backward
         self.t_lin = torch.linspace(0.0, 1.0, steps=n_samples_ray).to(dev)
@@ -520,7 +520,7 @@ class MappingFrameStep:
         views = self._views()
         merge_p = dec.view("merge")
         fused.featmerge_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
-                            True, ws=self.fm_ws, out=self.features, stash=self.fm_stash)
+                            True, ws=self.fm_ws, out=self.features, stash=self.fm_stash, zero_fill=fused._use_simt)
         cfg = fused.RenderConfig(_lib.MODE_MAP, dec.bound, dec.pe_fn.grid_fn.gstruct, b["z_vals"], b["gt_color"], b["gt_depth"],
                                  b["gt_label"], None, dec.class_to_expert, dec.n_class, self.lambdas,
                                  opacity_trunc=self.opacity_sigma)
@@ -531,7 +531,8 @@ class MappingFrameStep:
             cfg.shard(self.n_total, self.ray_offset, labels_all, counts)
         p, g = self._flat_views(dec.flat), self._flat_views(self.grad)
         losses, _, d_o, d_d, d_f = fused.render_raw(cfg, p["table"], p["coarse"], p["color"], p["logit"], p["experts"],
-                                                    b["rays_o"], b["rays_d"], self.features, g, True, True)
+                                                    b["rays_o"], b["rays_d"], self.features, g, True, True,
+                                                    features_band_only=True)
         fused.featmerge_bwd_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
                                 d_f, self.fm_ws, g["merge"], d_o if self.opt_poses else None, d_d if self.opt_poses else None,
                                 stash=self.fm_stash)
@@ -609,7 +610,7 @@ class TrackingFrameStep:
                           rays_d=torch.empty(N, 3, device=dev), z_vals=torch.empty(N, S, device=dev),
                           inside=torch.empty(N, dtype=torch.uint8, device=dev),
                           pixel=torch.empty(N, dtype=torch.int64, device=dev), scratch=torch.zeros(2, device=dev))
-        self.features = torch.empty(N, S, 32, device=dev)
+        self.features = torch.zeros(N, S, 32, device=dev)      # band rows are rewritten every step, the others never read
         self.fm_ws = torch.empty(int(_lib.lib().dns_featmerge_workspace_bytes(N, S)), dtype=torch.uint8, device=dev)
         self.fm_stash = fused.featmerge_stash(N, S, 2, dev)
         self.t_lin = torch.linspace(0.0, 1.0, steps=n_samples_ray).to(dev)
@@ -701,12 +702,12 @@ class TrackingFrameStep:
         views = fused.Views(self.w2c, self.cam_o, self.feats, (0, N))
         merge_p = dec.view("merge")
         fused.featmerge_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
-                            True, ws=self.fm_ws, out=self.features, stash=self.fm_stash)
+                            True, ws=self.fm_ws, out=self.features, stash=self.fm_stash, zero_fill=fused._use_simt)
         cfg = fused.RenderConfig(_lib.MODE_TRACK, dec.bound, dec.pe_fn.grid_fn.gstruct, b["z_vals"], b["gt_color"], b["gt_depth"],
                                  b["gt_label"], mask, None, dec.n_class, self.lambdas)
         losses, _, d_o, d_d, d_f = fused.render_raw(cfg, dec.view("table"), dec.view("coarse"), dec.view("color"),
                                                     dec.view("logit"), None, b["rays_o"], b["rays_d"], self.features, None,
-                                                    True, True, ws=self.ws)
+                                                    True, True, ws=self.ws, features_band_only=True)
         fused.featmerge_bwd_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
                                 d_f, self.fm_ws, None, d_o, d_d, stash=self.fm_stash)
         fused.pose_grad_raw(self.cam, self.window, d_o, d_d, b["pixel"], (0, N), self.quats, self.d_quats, self.d_trans,

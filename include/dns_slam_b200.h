@@ -156,6 +156,11 @@ typedef struct dns_render_args {
    * TMEM); 1: the fp32 SIMT kernels -- kept as the A/B reference of the parity tests.  Per call: the library holds
    * no mode state. */
   int32_t use_simt;
+  /* 1: `features` comes from dns_featmerge_fwd with no_zero_fill = 1 and `d_features` goes to dns_featmerge_bwd: rows of
+   * samples OUTSIDE the truncation band (slams/tracking.py:167-170: z within +-5 % of a positive gt depth; two thirds of
+   * the samples) are taken as zero without being read, and their d_features rows are not written.  tcgen05 path only. */
+  int32_t features_band_only;
+  int32_t reserved_;
 } dns_render_args;
 
 /* table and d_table must be 16-byte aligned (the kernels fetch / reduce the x, x+1 corner pair of a cell edge
@@ -300,6 +305,9 @@ typedef struct dns_featmerge_args {
   int32_t H, W, h, w;       /* image size, feature-map size */
   int32_t apply_trunc;
   int32_t need_dparams, need_drays;   /* backward only */
+  /* forward with apply_trunc: 1 = rows of samples outside the band are left untouched instead of being zeroed (the consumer
+   * is dns_render_fwd_bwd with features_band_only = 1, which never reads them): saves a pass over [N,S,32] */
+  int32_t no_zero_fill;
   double bound[3][2];
   const float* K;           /* [3,3] */
   const float* w2c;         /* [n_frames*n_views,4,4] */

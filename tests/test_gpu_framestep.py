@@ -78,7 +78,12 @@ def test_frame_step_vs_oracle_iteration(golden_dir, n_rays, simt):
         assert torch.equal(b[k].cpu(), os_[k]), k
     assert torch.equal(b["pixel"].cpu(), os_["_idx"]), "class-balanced / uniform pixel indices"
     assert rel_err(b["rays_d"], os_["rays_d"]) < 1e-6
-    assert rel_err(st.features, os_["features"]) < 1e-3
+    # the step hands its pixel features over BAND ONLY (dns_featmerge_args.no_zero_fill / dns_render_args.features_band_only):
+    # rows of samples outside the truncation band are neither written nor read -- the oracle holds zeros there
+    from dns_slam_b200 import slam
+    band = slam.trunc_mask(b["z_vals"], b["gt_depth"])[..., None]
+    assert float(band.mean()) > 0.05 and float((os_["features"] * (1 - band.cpu())).abs().max()) == 0.0
+    assert rel_err(st.features * band, os_["features"]) < 1e-3
     for i, k in enumerate(("p", "d", "l", "lt", "fs", "op")):
         torch.testing.assert_close(res[i], o["loss"][k].detach().float(), rtol=1e-3, atol=1e-7, msg=k)
     torch.testing.assert_close(res[8], o["loss"]["sm"].detach().float(), rtol=1e-3, atol=1e-9)
@@ -181,6 +186,7 @@ def test_sharded_frame_step_sums_to_unsharded_chain(golden_dir):
     # the same frame must see the same max depth on both ranks (z sampling, common.py:581,591)
     assert torch.equal(st0.scratch[:, 0], st1.scratch[:, 0])
     # ---- unsharded chain on the rank-major concatenation: (rank, frame) pairs become the frames of one call
+    from dns_slam_b200 import slam as slam_mod
     dec, cam = st0.dec, st0.cam
     cat = {k: torch.cat([st.batch[k] for st in steps], 0).contiguous() for k in st0.batch}
     ray_start, w2c, cam_o, feats = [0], [], [], []
@@ -191,7 +197,8 @@ def test_sharded_frame_step_sums_to_unsharded_chain(golden_dir):
     views = fused.Views(torch.cat(w2c, 0), torch.cat(cam_o, 0), feats, ray_start)
     mp = dec.view("merge")
     feat, ws = fused.featmerge_raw(cam, dec.merge.bound, views, cat["rays_o"], cat["rays_d"], cat["z_vals"], cat["gt_depth"], mp)
-    assert torch.equal(feat, torch.cat([st.features for st in steps], 0))
+    band = slam_mod.trunc_mask(cat["z_vals"], cat["gt_depth"])[..., None]      # band-only hand-over inside the steps
+    assert torch.equal(feat, torch.cat([st.features for st in steps], 0) * band)
     packed = torch.zeros_like(st0.packed)
     gv = st0._flat_views(packed[:dec.flat.numel()])
     p = st0._flat_views(dec.flat)
