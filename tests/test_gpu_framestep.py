@@ -82,7 +82,7 @@ def test_frame_step_vs_oracle_iteration(golden_dir, n_rays, simt):
     # rows of samples outside the truncation band are neither written nor read -- the oracle holds zeros there
     from dns_slam_b200 import slam
     band = slam.trunc_mask(b["z_vals"], b["gt_depth"])[..., None]
-    assert float(band.mean()) > 0.05 and float((os_["features"] * (1 - band.cpu())).abs().max()) == 0.0
+    assert float(band.mean()) > 0.05 and float((os_["features"].detach() * (1 - band.cpu())).abs().max()) == 0.0
     assert rel_err(st.features * band, os_["features"]) < 1e-3
     for i, k in enumerate(("p", "d", "l", "lt", "fs", "op")):
         torch.testing.assert_close(res[i], o["loss"][k].detach().float(), rtol=1e-3, atol=1e-7, msg=k)
