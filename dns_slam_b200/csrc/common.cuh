@@ -73,6 +73,18 @@ struct DwImgArgs {
   float* out1;
   int split;
   int64_t sl0, sc0, cls0, sl1, sc1, cls1;
+  // Block-diagonal mode (diag_l > 0): the lanes are two blocks of diag_l features, the columns two blocks of diag_c; only
+  // the diagonal blocks are kept -- (lane block 0) x (column block 0) -> out0, block 1 x block 1 -> out1, element
+  // (l mod diag_l, c mod diag_c); L.n_valid / Cc.n_valid count the valid features PER BLOCK.  Two small GEMMs that share
+  // nothing but the tile loop (dOut^T H of the coarse net and of the class expert) then cost ONE pass: the kernel's time
+  // per tile is its fixed MMA / barrier chain, not the operand bytes.
+  int diag_l, diag_c;
+  // Second operand pair (L2.ptr != NULL): its lanes / columns follow those of L / Cc in the stage, and the product keeps
+  // two blocks -- L x Cc -> out0 / out1 as usual, L2 x C2 -> out2 (element (l, c) -> out2[l*sl2 + c*sc2]); the cross
+  // blocks are dropped.  Same sub-tiling (RS) for all four images.
+  DwImg L2, C2;
+  float* out2;
+  int64_t sl2, sc2;
 };
 int launch_dw_img(const DwImgArgs& a, cudaStream_t st);
 

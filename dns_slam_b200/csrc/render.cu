@@ -1195,7 +1195,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
       k_unpad33<<<(int)((Pc * DNS_LATENT + 255) / 256), 256, 0, st>>>(w.coarse36, a->coarse_out + p0 * DNS_LATENT, Pc);
 
     if (a->need_dparams && !fwd_only) {
-      PhaseScope phg(phDwGemm, st, tc ? (map ? 6 : 5) : (map ? 8 : 6));
+      PhaseScope phg(phDwGemm, st, tc ? 4 : (map ? 8 : 6));
       const int64_t Qrows = (int64_t)tiles_max * kTile;
       const int* ntd = map ? w.counts + cTiles : nullptr;
       int e = 0;
@@ -1214,23 +1214,26 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
         g.out0 = a->d_coarse; g.split = 32; g.sl0 = 1; g.sc0 = kIn1; g.cls0 = 0;
         g.out1 = map ? a->d_experts : nullptr; g.sl1 = 1; g.sc1 = kIn1; g.cls1 = 4096;
         e |= launch_dw_img(g, st);
-        g.L = DwImg{pa.dOimg, doch, 0, 5, DNS_LATENT}; g.Cc = DwImg{pa.Himg, hch, 0, 4, 32};
-        g.tile_class = nullptr;
-        g.out0 = a->d_coarse + 2560; g.split = 32; g.sl0 = 32; g.sc0 = 1; g.cls0 = 0; g.out1 = nullptr;
-        e |= launch_dw_img(g, st);
-        if (map) {
-          g.L = DwImg{pa.dOimg, doch, 5, 5, DNS_LATENT}; g.Cc = DwImg{pa.Himg, hch, 4, 4, 32};
+        if (map) {   // coarse and class-expert layer 2 in ONE pass: block-diagonal [dOc | dOf]^T [Hc | Hf]
+          g.L = DwImg{pa.dOimg, doch, 0, 10, DNS_LATENT}; g.Cc = DwImg{pa.Himg, hch, 0, 8, 32};
+          g.diag_l = 40; g.diag_c = 32;
           g.tile_class = w.tile_class;
-          g.out0 = a->d_experts + 2560; g.cls0 = 4096;
+          g.out0 = a->d_coarse + 2560; g.sl0 = 32; g.sc0 = 1; g.cls0 = 0;
+          g.out1 = a->d_experts + 2560; g.sl1 = 32; g.sc1 = 1; g.cls1 = 4096;
+          e |= launch_dw_img(g, st);
+        } else {
+          g.L = DwImg{pa.dOimg, doch, 0, 5, DNS_LATENT}; g.Cc = DwImg{pa.Himg, hch, 0, 4, 32};
+          g.tile_class = nullptr;
+          g.out0 = a->d_coarse + 2560; g.split = 32; g.sl0 = 32; g.sc0 = 1; g.cls0 = 0; g.out1 = nullptr;
           e |= launch_dw_img(g, st);
         }
         memset(&g, 0, sizeof(g));
         g.L = DwImg{ra.X2img, 14, 0, 14, kIn2}; g.Cc = DwImg{ra.dH2img, 8, 0, 8, 64};
         g.RS = ra.RS; g.subs_per_tile = T / ra.RS; g.n_tiles_host = (int)((nc + RPC - 1) / RPC);
         g.out0 = a->d_color; g.split = 32; g.sl0 = 1; g.sc0 = kIn2; g.out1 = a->d_logit; g.sl1 = 1; g.sc1 = kIn2;
-        e |= launch_dw_img(g, st);
-        g.L = DwImg{ra.dpreimg, 1, 0, 1, 3}; g.Cc = DwImg{ra.Hcolimg, 4, 0, 4, 32};
-        g.out0 = a->d_color + 32 * kIn2; g.sl0 = 32; g.sc0 = 1; g.out1 = nullptr;
+        // ... and, in the same pass, the colour head's layer 2: dpre^T H colour (second operand pair of k_dw_img)
+        g.L2 = DwImg{ra.dpreimg, 1, 0, 1, 3}; g.C2 = DwImg{ra.Hcolimg, 4, 0, 4, 32};
+        g.out2 = a->d_color + 32 * kIn2; g.sl2 = 32; g.sc2 = 1;
         e |= launch_dw_img(g, st);
         e |= launch_dw_gemm(w.dlogit, C4, C, w.Hbar, 32, 32, nc, nullptr, ray_tiles, nullptr, a->d_logit + 32 * kIn2, 32, 0, st, tc);
         if (e) return DNS_ERR_CUDA;

@@ -174,8 +174,10 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int RS = a.RS, cs = RS * 16;                         // bytes per chunk of a sub-tile
-  const int nC16 = (a.Cc.n_valid + 15) & ~15;
-  const int l_bytes = a.L.chunks_used * cs, c_bytes = a.Cc.chunks_used * cs;   // one half each
+  const bool two = a.L2.ptr != nullptr;
+  const int nC16 = two ? (a.Cc.chunks_used + a.C2.chunks_used) * 8 : (a.diag_c ? 2 * a.diag_c : ((a.Cc.n_valid + 15) & ~15));
+  const int l1_bytes = a.L.chunks_used * cs, c1_bytes = a.Cc.chunks_used * cs;
+  const int l_bytes = l1_bytes + (two ? a.L2.chunks_used * cs : 0), c_bytes = c1_bytes + (two ? a.C2.chunks_used * cs : 0);   // one half each
   const int n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles_host;
   const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int t0 = blockIdx.x * per, t1 = min(n_tiles, t0 + per);
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_bf16(128, nC16, 1, 1);
   const int64_t l_sub = (int64_t)2 * a.L.chunks_total * RS, c_sub = (int64_t)2 * a.Cc.chunks_total * RS;  // uint4 per sub-tile
+  const int64_t l2_sub = (int64_t)2 * a.L2.chunks_total * RS, c2_sub = (int64_t)2 * a.C2.chunks_total * RS;
   uint32_t gi = 0, done_phase = 0;   // sub-tiles streamed so far (stage / phase bookkeeping), flushes so far
 
   int t = t0;
@@ -216,10 +219,19 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
           mbar_expect_tx(&full[s], 2 * (l_bytes + c_bytes));
           const uint4* lsrc = a.L.ptr + (sub0 + prod) * l_sub + (int64_t)a.L.chunk0 * RS;
           const uint4* csrc = a.Cc.ptr + (sub0 + prod) * c_sub + (int64_t)a.Cc.chunk0 * RS;
-          bulk_g2s(st, lsrc, l_bytes, &full[s]);                                             // L hi
-          bulk_g2s(st + l_bytes, lsrc + (int64_t)a.L.chunks_total * RS, l_bytes, &full[s]);  // L lo
-          bulk_g2s(st + 2 * l_bytes, csrc, c_bytes, &full[s]);                               // C hi
-          bulk_g2s(st + 2 * l_bytes + c_bytes, csrc + (int64_t)a.Cc.chunks_total * RS, c_bytes, &full[s]);
+          bulk_g2s(st, lsrc, l1_bytes, &full[s]);                                             // L hi
+          bulk_g2s(st + l_bytes, lsrc + (int64_t)a.L.chunks_total * RS, l1_bytes, &full[s]);  // L lo
+          bulk_g2s(st + 2 * l_bytes, csrc, c1_bytes, &full[s]);                               // C hi
+          bulk_g2s(st + 2 * l_bytes + c_bytes, csrc + (int64_t)a.Cc.chunks_total * RS, c1_bytes, &full[s]);
+          if (two) {   // the second pair's chunks follow the first pair's in each of the four halves
+            const uint4* l2src = a.L2.ptr + (sub0 + prod) * l2_sub + (int64_t)a.L2.chunk0 * RS;
+            const uint4* c2src = a.C2.ptr + (sub0 + prod) * c2_sub + (int64_t)a.C2.chunk0 * RS;
+            const int l2b = l_bytes - l1_bytes, c2b = c_bytes - c1_bytes;
+            bulk_g2s(st + l1_bytes, l2src, l2b, &full[s]);
+            bulk_g2s(st + l_bytes + l1_bytes, l2src + (int64_t)a.L2.chunks_total * RS, l2b, &full[s]);
+            bulk_g2s(st + 2 * l_bytes + c1_bytes, c2src, c2b, &full[s]);
+            bulk_g2s(st + 2 * l_bytes + c_bytes + c1_bytes, c2src + (int64_t)a.C2.chunks_total * RS, c2b, &full[s]);
+          }
         }
       }
       if (tid == 0) {    // MMA issuer: never waits for its own MMAs, only for data
@@ -257,7 +269,32 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
         for (int c0 = 0; c0 < nC16; c0 += 16) {
           float v[16];
           tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-          if (l < a.L.n_valid) {
+          if (two) {        // L x Cc -> out0 / out1,  L2 x C2 -> out2
+            const int lanes0 = a.L.chunks_used * 8, cols0 = a.Cc.chunks_used * 8;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + i;
+              if (v[i] == 0.f) continue;
+              if (l < a.L.n_valid && c < a.Cc.n_valid) {
+                if (c < a.split) {
+                  if (o0) atomicAdd(o0 + (int64_t)l * a.sl0 + (int64_t)c * a.sc0, v[i]);
+                } else if (o1) atomicAdd(o1 + (int64_t)l * a.sl1 + (int64_t)(c - a.split) * a.sc1, v[i]);
+              } else if (l >= lanes0 && l - lanes0 < a.L2.n_valid && c >= cols0 && c - cols0 < a.C2.n_valid && a.out2) {
+                atomicAdd(a.out2 + (int64_t)(l - lanes0) * a.sl2 + (int64_t)(c - cols0) * a.sc2, v[i]);
+              }
+            }
+          } else if (a.diag_l) {   // block diagonal: lane block lb meets column block lb only
+            const int lb = l / a.diag_l, ll = l - lb * a.diag_l;
+            float* const o = lb == 0 ? o0 : (lb == 1 ? o1 : nullptr);
+            if (o && ll < a.L.n_valid) {
+              const int64_t sl = lb ? a.sl1 : a.sl0, sc = lb ? a.sc1 : a.sc0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int c = c0 + i, cc = c - lb * a.diag_c;
+                if (cc >= 0 && cc < a.Cc.n_valid && v[i] != 0.f) atomicAdd(o + (int64_t)ll * sl + (int64_t)cc * sc, v[i]);
+              }
+            }
+          } else if (l < a.L.n_valid) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int c = c0 + i;
@@ -281,14 +318,17 @@ __global__ void __launch_bounds__(kTile) k_dw_img(DwImgArgs a, int n_stages, int
 int launch_dw_img(const DwImgArgs& a, cudaStream_t st) {
   if (a.n_tiles_host <= 0) return DNS_OK;
   const int cs = a.RS * 16;
-  const int stage = 2 * (a.L.chunks_used + a.Cc.chunks_used) * cs;
+  const bool two = a.L2.ptr != nullptr;
+  const int lch = a.L.chunks_used + (two ? a.L2.chunks_used : 0), cch = a.Cc.chunks_used + (two ? a.C2.chunks_used : 0);
+  const int stage = 2 * (lch + cch) * cs;
   // the MMA footprint of the lane operand spans 16 chunks from the start of each half (the lo half starts
   // chunks_used chunks into the stage): pad the allocation by whatever reaches past the last stage
-  const int over = a.L.chunks_used + 16 - 2 * (a.L.chunks_used + a.Cc.chunks_used);
+  const int over = lch + 16 - 2 * (lch + cch);
   const int tail = over > 0 ? over * cs : 0;
-  int ns = (200 * 1024 - tail) / stage;
+  int ns = (216 * 1024 - tail) / stage;
   if (ns > kImgMaxStages) ns = kImgMaxStages;
-  if (ns < 1 || (a.RS & 15) || a.L.chunks_used > 16 || ((a.Cc.n_valid + 15) & ~15) > a.Cc.chunks_used * 8) {
+  const int ncols = two ? cch * 8 : (a.diag_c ? 2 * a.diag_c : ((a.Cc.n_valid + 15) & ~15));
+  if (ns < 1 || (a.RS & 15) || lch > 16 || ncols > cch * 8 || ncols > 128 || (two && a.diag_l) || (a.diag_l && (2 * a.diag_l > 128 || (a.diag_c & 15)))) {
     set_error("dw_img: unsupported shape (RS %d, chunks %d/%d, nC %d)", a.RS, a.L.chunks_used, a.Cc.chunks_used, a.Cc.n_valid);
     return DNS_ERR_UNSUPPORTED;
   }
