@@ -1351,7 +1351,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
   delete pht;
   if (int e = check_launch("tv fwd")) return e;
   if (a->need_dparams) {
-    PhaseScope phtb(phTvBwd, st, pa.d_priv ? 4 : 3);
+    PhaseScope phtb(phTvBwd, st, pa.d_priv ? 3 : 2);
     if (pa.d_priv) cudaMemsetAsync(pa.d_priv, 0, (size_t)pa.priv_copies * pa.priv_end * sizeof(float2), st);
     if (tc) launch_point_bwd_tc(kTv, pa, tiles, wc_tc, wc_tc, st);
     else k_point_bwd<kTv><<<tiles, kTile, smem_pt, st>>>(pa);
@@ -1365,9 +1365,9 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
       g.L = DwImg{pa.Ximg, 10, 0, 10, kIn1}; g.Cc = DwImg{pa.dHimg, 4, 0, 4, 32};
       g.RS = kTile; g.subs_per_tile = 1; g.n_tiles_host = tiles;
       g.out0 = a->d_coarse; g.split = 32; g.sl0 = 1; g.sc0 = kIn1;
-      e |= launch_dw_img(g, st);
-      g.L = DwImg{pa.dOimg, 5, 0, 5, 1}; g.Cc = DwImg{pa.Himg, 4, 0, 4, 32};
-      g.out0 = a->d_coarse + 2560; g.sl0 = 32; g.sc0 = 1;
+      // layer 2 (only the occupancy channel carries a gradient) in the same pass: second operand pair of k_dw_img
+      g.L2 = DwImg{pa.dOimg, 5, 0, 5, 1}; g.C2 = DwImg{pa.Himg, 4, 0, 4, 32};
+      g.out2 = a->d_coarse + 2560; g.sl2 = 32; g.sc2 = 1;
       e |= launch_dw_img(g, st);
     } else {
       e |= launch_dw_gemm(dHc, 64, 32, Xst, kIn1, kIn1, Q, nullptr, tiles, nullptr, a->d_coarse, kIn1, 0, st, tc);
