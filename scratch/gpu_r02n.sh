@@ -5,8 +5,8 @@ TAG=${1:-r02n}
 timeout 900 python -m pytest tests -m gpu -q --timeout 150 > gpurun_out/${TAG}_all.log 2>&1
 echo "all rc=$?"; grep -n "AssertionError\|^E   .*assert\|FAILED\|passed\|failed\|Timeout" gpurun_out/${TAG}_all.log | head -30
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
-/usr/bin/time -f "reference arm wall %e s" timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_ref.json 2> gpurun_out/${TAG}_ref.err; echo "ref rc=$?"; tail -1 gpurun_out/${TAG}_ref.err
-/usr/bin/time -f "our arm wall %e s" timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err
+timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_ref.json 2> gpurun_out/${TAG}_ref.err; echo "ref rc=$?"; tail -1 gpurun_out/${TAG}_ref.err
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err
 python - <<PY
 import json
 b=json.load(open('gpurun_out/${TAG}_bench.json'))
