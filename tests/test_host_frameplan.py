@@ -50,3 +50,33 @@ def test_rank_slices_tile_the_global_slots():
         assert torch.equal(torch.cat([p.slot_base[f] for p in parts]), whole.slot_base[f])
         us = [p.slices[f][0] for p in parts]
         assert us[0][0] == 0 and us[-1][1] == whole.n_u and all(us[i][1] == us[i + 1][0] for i in range(2))
+
+
+def test_pack_draws_equals_the_generated_buffer():
+    """``FrameBatchPlan.pack_draws`` (the draw dictionaries of slam.map_optimize -> the step's byte buffer) must produce the
+    very bytes ``make_host_draws`` writes for the same raw draws: uniform indices, per-class offsets (a single-pixel class
+    consumes no draw and gets offset 0), the forced 0.5 of common.py:572-573, the float64 TV offsets."""
+    frames, tables = _tables()
+    cam = syn.camera("tiny")
+    bound = syn.load_bound(syn.SHAPES["tiny"]["bound"])
+    plan = step.FrameBatchPlan(tables, 96, 15, (0, cam["H"], 0, cam["W"]), bound, 8)
+    buf, tape = plan.make_host_draws(torch.Generator().manual_seed(7), pinned=False, return_tape=True)
+    # rebuild the dictionaries from the tape: per frame [uniform, one randint per class with > 1 pixel, rand, rand], then TV
+    it = iter(tape)
+    per = []
+    for f in range(plan.F):
+        u = next(it)[1]
+        cd = [next(it)[1] for _, _, m, count, _ in plan.class_slot_ranges(f) if count != 1]
+        ts, tz = next(it)[1], next(it)[1]
+        per.append(dict(idx_uniform=u, class_draws=cd, t_surface=ts, t_zero=tz))
+    tv = (next(it)[1], next(it)[1])
+    packed = plan.pack_draws(per, tv)
+    assert torch.equal(packed, buf)
+    # wrong sizes are refused instead of silently shifting slots
+    bad = [dict(d) for d in per]
+    bad[0]["idx_uniform"] = bad[0]["idx_uniform"][:-1]
+    try:
+        plan.pack_draws(bad, tv)
+        raise AssertionError("short uniform draw accepted")
+    except ValueError:
+        pass
