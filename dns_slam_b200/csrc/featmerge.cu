@@ -55,6 +55,7 @@ struct FmArgs {
   float* d_rays_o;            // [N][3] +=
   float* d_rays_d;
   int need_dparams, need_drays;
+  unsigned long long* phase_clk;   // -DDNS_ABLATE builds only (DNS_PHASE_CLK_FM): [32] clock64 deltas of thread 0 (fwd 0.., bwd 16..)
   uint4* Ximg;                // optional stash: the X operand tiles of the forward pass, [tile][hi | lo][14 chunks][128 rows]
   int64_t stash_bytes;
 };
@@ -139,19 +140,27 @@ struct RowGeom {
   float wy0, wy1, wx0, wx1;
 };
 
+// sample id of row `row` of tile `tile` (-1: the row does not exist); the kernels fetch it ONE TILE AHEAD so that the
+// dependent chain rows[] -> z / rays / d_out of the next tile starts with the id already in a register
+__device__ __forceinline__ int64_t row_sample(const FmArgs& a, int64_t n_rows, int64_t n_tiles, int64_t tile, int row) {
+  if (tile >= n_tiles) return -1;
+  const int pslot = row / a.R;
+  const int64_t bi = tile * a.PPT + pslot;
+  if (pslot >= a.PPT || bi >= n_rows) return -1;
+  return a.rows ? (int64_t)a.rows[bi] : bi;
+}
 template <bool PROJECT = true>
-__device__ __forceinline__ void row_geometry(const FmArgs& a, int64_t n_rows, int64_t tile, int row, const float* sK,
+__device__ __forceinline__ void row_geometry(const FmArgs& a, int64_t p_row, int row, const float* sK,
                                              const float* sW2c, const float* sCamO, RowGeom& g) {
   const int pslot = row / a.R, v = row - pslot * a.R;
-  const int64_t bi = tile * a.PPT + pslot;
-  g.valid = pslot < a.PPT && bi < n_rows;
+  g.valid = p_row >= 0;
   g.vis = false;
   g.p = g.r = 0;
   g.view = 0;
   g.zv = 0.f;
   g.x[0] = g.x[1] = g.x[2] = 0.f;
   if (!g.valid) return;
-  g.p = a.rows ? (int64_t)a.rows[bi] : bi;
+  g.p = p_row;
   g.r = g.p / a.S;
   g.zv = a.z[g.p];
   int f = 0;
@@ -285,11 +294,12 @@ __device__ __forceinline__ void publish_taps(const RowGeom& g, TapDesc* d) {
     d->wy1 = g.wy1;
   }
 }
-__device__ __forceinline__ void gather_features_coop(const TapDesc* taps, int warp, int lane, unsigned char* X_hi, unsigned char* X_lo) {
+__device__ __forceinline__ void gather_features_coop(const TapDesc* taps, int row0, int n_it, int lane, unsigned char* X_hi,
+                                                     unsigned char* X_lo) {
   const int k = lane & 7;
 #pragma unroll 2
-  for (int it = 0; it < 4; ++it) {
-    const int row = 16 * warp + 4 * it + (lane >> 3);
+  for (int it = 0; it < n_it; ++it) {
+    const int row = row0 + 4 * it + (lane >> 3);
     const TapDesc td = taps[row];
     float lo4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4] = {0.f, 0.f, 0.f, 0.f};   // channels 4k.., 32+4k..
     if (td.f00) {
@@ -347,7 +357,8 @@ __device__ __forceinline__ void load_views(const FmArgs& a, float* sK, float* sW
   for (int i = threadIdx.x; i < 3 * nv; i += blockDim.x) sCamO[i] = a.cam_o[i];
 }
 
-constexpr int kFmFwdSmem = 28 * 2048 + kFW * 16;                       // X tile | weights
+constexpr int kFmHB = 17408;                                           // H tile (16 KB) / output staging [128][33] floats
+constexpr int kFmFwdSmem = 28 * 2048 + kFmHB + kFW * 16;               // X tile | H / staging | weights
 constexpr int kFmBwdSmem = 28 * 2048 + 8 * 2048 + 8 * 2048 + kFW * 16;  // X | H | dO / dH | weights
 
 __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
@@ -358,10 +369,12 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
   __shared__ TapDesc sTaps[kTile];
   unsigned char* X_hi = sm;
   unsigned char* X_lo = sm + 14 * 2048;
-  unsigned char* H_hi = sm;                  // aliases the X tile after the first GEMM
-  unsigned char* H_lo = sm + 4 * 2048;
-  float* OB = reinterpret_cast<float*>(sm + 8 * 2048);   // [128][33] output rows (X is dead by then)
-  unsigned char* Wt = sm + 28 * 2048;
+  // H (and, after the second GEMM, the output staging) has a region of its own: the bulk store of the X tile (the image
+  // for the backward) then only has to finish before the NEXT tile is built, not before the H epilogue
+  unsigned char* H_hi = sm + 28 * 2048;
+  unsigned char* H_lo = H_hi + 4 * 2048;
+  float* OB = reinterpret_cast<float*>(H_hi);            // [128][33] output rows (H is dead by then)
+  unsigned char* Wt = sm + 28 * 2048 + kFmHB;
   unsigned char* W1_hi = Wt;
   unsigned char* W1_lo = Wt + kFW1 * 16;
   unsigned char* W2_hi = Wt + 2 * kFW1 * 16;
@@ -384,26 +397,34 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
   // the X tiles are kept for the backward when the caller's stash holds all of them (decided on the device: no host sync)
   const bool use_img = a.Ximg != nullptr && n_tiles * (int64_t)kXImgBytes <= a.stash_bytes;
   uint32_t phase = 0;
+  DNS_CLK_DECL
+  int64_t p_next = row_sample(a, n_rows, n_tiles, blockIdx.x, row);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     RowGeom g;
-    row_geometry(a, n_rows, tile, row, sK, sW2c, sCamO, g);
+    const int64_t p_row = p_next;
+    p_next = row_sample(a, n_rows, n_tiles, tile + gridDim.x, row);      // one tile ahead
+    row_geometry(a, p_row, row, sK, sW2c, sCamO, g);
     if (grp == 1) publish_taps(g, sTaps + row);
+    if (tid == 0 && use_img) bulk_wait_read();   // the previous tile's image store has read the X region
     __syncthreads();
+    DNS_CLK(a, 1)
     build_x<false>(g, grp, row, X_hi, X_lo, nullptr);            // OneBlob chunks (group 0)
-    gather_features_coop(sTaps, warp, tid & 31, X_hi, X_lo);      // feature chunks, coalesced
+    // feature chunks, coalesced: the warps of group 0 (busy with the OneBlob) take 8 rows each, those of group 1 24
+    if (grp == 0) gather_features_coop(sTaps, 8 * warp, 2, tid & 31, X_hi, X_lo);
+    else gather_features_coop(sTaps, 32 + 24 * (warp - 4), 6, tid & 31, X_hi, X_lo);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    DNS_CLK(a, 2)
     if (tid == 0) {
       tc_fence_after();
       mma_hidden(tmem_d, X_hi, X_lo, W1_hi, W1_lo);
-      if (use_img) {   // the tile image for the backward = the X tile byte for byte: ONE bulk store; the MMA commit waits
-        bulk_s2g(a.Ximg + tile * (kXImgBytes / 16), X_hi, kXImgBytes);   // until its source has been read (H aliases X)
-        bulk_wait_read();
-      }
+      // the tile image for the backward = the X tile byte for byte: ONE bulk store, waited for at the top of the next tile
+      if (use_img) bulk_s2g(a.Ximg + tile * (kXImgBytes / 16), X_hi, kXImgBytes);
       umma_commit(&bar);
     }
     mbar_wait_cta(&bar, phase);
+    DNS_CLK(a, 3)
     phase ^= 1;
     tc_fence_after();
     {   // hidden activations of this thread's 16 units -> H tile
@@ -417,6 +438,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    DNS_CLK(a, 4)
     if (tid == 0) {   // O = H . W2^T
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 32, 0, 0);
@@ -432,6 +454,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
       umma_commit(&bar);
     }
     mbar_wait_cta(&bar, phase);
+    DNS_CLK(a, 5)
     phase ^= 1;
     tc_fence_after();
     {
@@ -442,6 +465,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+    DNS_CLK(a, 6)
     // mean over the R view rows of a sample (decoder.py:77), one float4 per thread and step
     for (int e = tid; e < a.PPT * 8; e += kFT) {
       const int pslot = e >> 3, q = e & 7;
@@ -457,6 +481,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_fwd(FmArgs a) {
       }
     }
     __syncthreads();   // OB / H are overwritten by the next tile's X
+    DNS_CLK(a, 7)
   }
   if (tid == 0 && use_img) bulk_wait_all();
   tc_fence_before();
@@ -506,16 +531,20 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
   bool have_acc = false;
   // X tiles stashed by the forward pass (same device-side rule): ONE bulk copy per tile instead of the gather + encode
   const bool use_img = a.Ximg != nullptr && n_tiles * (int64_t)kXImgBytes <= a.stash_bytes;
+  DNS_CLK_DECL
+  int64_t p_next = row_sample(a, n_rows, n_tiles, blockIdx.x, row);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     RowGeom g;
+    const int64_t p_row = p_next;
+    p_next = row_sample(a, n_rows, n_tiles, tile + gridDim.x, row);      // one tile ahead
     if (use_img) {
       if (tid == 0) {   // the previous tile's MMAs have completed (end-of-loop barrier): the X region is free
         mbar_expect_tx(&xbar, kXImgBytes);
         bulk_g2s(X_hi, a.Ximg + tile * (kXImgBytes / 16), kXImgBytes, &xbar);
       }
-      row_geometry<false>(a, n_rows, tile, row, sK, sW2c, sCamO, g);
+      row_geometry<false>(a, p_row, row, sK, sW2c, sCamO, g);
     } else {
-      row_geometry(a, n_rows, tile, row, sK, sW2c, sCamO, g);
+      row_geometry(a, p_row, row, sK, sW2c, sCamO, g);
       build_x(g, grp, row, X_hi, X_lo, nullptr);
     }
     {   // dO = d_features[sample] / R (the same for the R views of the sample): 16 channels per thread
@@ -537,6 +566,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    DNS_CLK(a, 17)
     if (tid == 0) {
       tc_fence_after();
       if (use_img) {
@@ -547,6 +577,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
       umma_commit(&bar);
     }
     mbar_wait_cta(&bar, phase);
+    DNS_CLK(a, 18)
     phase ^= 1;
     tc_fence_after();
     float hv[16];   // this thread's 16 hidden activations (kept for the ReLU mask)
@@ -558,6 +589,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    DNS_CLK(a, 19)
     if (tid == 0) {
       tc_fence_after();
       {   // dH = dO . W2   (B = W2 tile MN-major: hidden contiguous; LBO 128 over output rows, SBO 512 over hidden chunks)
@@ -587,6 +619,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
       umma_commit(&bar);
     }
     mbar_wait_cta(&bar, phase);
+    DNS_CLK(a, 20)
     phase ^= 1;
     tc_fence_after();
     {   // dH = (dO W2) [H > 0] -> the dH tile takes the place of the dO tile (its MMAs have completed)
@@ -600,6 +633,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    DNS_CLK(a, 21)
     if (tid == 0) {
       tc_fence_after();
       if (a.need_drays) {   // dX[:, 0..47] = dH . W1[:, 0..47]   (B = W1 tile MN-major: LBO 128 over hidden rows, SBO 512)
@@ -630,6 +664,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
     }
     have_acc = true;
     mbar_wait_cta(&bar, phase);
+    DNS_CLK(a, 22)
     phase ^= 1;
     tc_fence_after();
     if (a.need_drays) {
@@ -657,6 +692,7 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
     }
     tc_fence_before();
     __syncthreads();   // accumulator columns read, operand tiles free for the next tile
+    DNS_CLK(a, 23)
     tc_fence_after();
   }
   if (a.need_dparams && have_acc) {
@@ -762,6 +798,9 @@ static int fm_fill(FmArgs& m, FmWs& w, const dns_featmerge_args* a, const char* 
     m.feats[f] = a->feats[f];
   }
   m.rays_o = a->rays_o; m.rays_d = a->rays_d; m.z = a->z_vals;
+#ifdef DNS_ABLATE
+  if (const char* e = getenv("DNS_PHASE_CLK_FM")) m.phase_clk = (unsigned long long*)strtoull(e, nullptr, 0);   // device pointer
+#endif
   m.rows = a->apply_trunc ? w.rows : nullptr;
   m.n_rows_dev = a->apply_trunc ? w.counter : nullptr;
   m.n_rows_host = N * S;
