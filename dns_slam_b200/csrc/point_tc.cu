@@ -314,7 +314,13 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kTile2, 2) k_point_bwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
+#ifndef DNS_BWD_CTAS
+#define DNS_BWD_CTAS 2
+#endif
+#ifndef DNS_BWD_CARVE_PCT
+#define DNS_BWD_CARVE_PCT 58
+#endif
+__global__ void __launch_bounds__(kTile2, DNS_BWD_CTAS) k_point_bwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
                                                              const uint4* __restrict__ we_all) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar;
@@ -654,9 +660,9 @@ int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* w
   set_attrs2();
   const size_t smem = point_bwd_tc2_smem();
   static CarveState last[3];
-  if (mode == kMap) prefer_carveout(k_point_bwd_tc2<kMap>, last[0], tiles, "DNS_BWD_CARVE", 58);
-  else if (mode == kTrack) prefer_carveout(k_point_bwd_tc2<kTrack>, last[1], tiles, "DNS_BWD_CARVE", 58);
-  else prefer_carveout(k_point_bwd_tc2<kTv>, last[2], tiles, "DNS_BWD_CARVE", 58);
+  if (mode == kMap) prefer_carveout(k_point_bwd_tc2<kMap>, last[0], tiles, "DNS_BWD_CARVE", DNS_BWD_CARVE_PCT);
+  else if (mode == kTrack) prefer_carveout(k_point_bwd_tc2<kTrack>, last[1], tiles, "DNS_BWD_CARVE", DNS_BWD_CARVE_PCT);
+  else prefer_carveout(k_point_bwd_tc2<kTv>, last[2], tiles, "DNS_BWD_CARVE", DNS_BWD_CARVE_PCT);
   if (mode == kMap) k_point_bwd_tc2<kMap><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else if (mode == kTrack) k_point_bwd_tc2<kTrack><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else k_point_bwd_tc2<kTv><<<tiles, kTile2, smem, st>>>(pa, wc, we);
