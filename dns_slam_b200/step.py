@@ -257,6 +257,13 @@ class FrameBatchPlan:
         self.draw_layout["tv"] = (off, 48)
         self.draw_bytes = off + 48
 
+    def _slot_ranges(self, f):
+        """``class_slot_ranges`` cached per frame (the tables do not change during a mapping call)."""
+        cache = self.__dict__.setdefault("_slot_range_cache", {})
+        if f not in cache:
+            cache[f] = self.class_slot_ranges(f)
+        return cache[f]
+
     def class_slot_ranges(self, f):
         """[(class position, first slot, slots, pixels of the class, first pixel)] of frame f's GLOBAL class-balanced slot
         list (common.py:315-330: class 0 of the sorted list takes the remainder)."""
@@ -335,17 +342,17 @@ class FrameBatchPlan:
             u = d["idx_uniform"].reshape(-1)
             if u.numel() != self.n_u:
                 raise ValueError(f"frame {f}: {u.numel()} uniform draws, the plan has {self.n_u} slots")
-            idx[:self.n_u] = u
-            k = 0
-            for _, s0, m, count, _ in self.class_slot_ranges(f):
+            pieces, k = [u], 0          # ONE concatenation + ONE copy per frame (a slice assignment per class was 0.5 ms / iteration)
+            for _, s0, m, count, _ in self._slot_ranges(f):
                 if count == 1:                  # repeated without a draw (common.py:321-323): offset 0
-                    idx[self.n_u + s0:self.n_u + s0 + m] = 0
+                    pieces.append(torch.zeros(m, dtype=torch.int64))
                     continue
                 dr = d["class_draws"][k].reshape(-1)
                 k += 1
                 if dr.numel() != m:
                     raise ValueError(f"frame {f}: class draw of {dr.numel()} values for {m} slots")
-                idx[self.n_u + s0:self.n_u + s0 + m] = dr
+                pieces.append(dr)
+            idx.copy_(torch.cat(pieces))
             ts = d["t_surface"].detach().cpu().to(torch.float32).clone()
             if not bool((ts == 0.5).any()):
                 ts[self.nf // 2 + 1] = 0.5                                # common.py:572-573
