@@ -382,3 +382,46 @@ def test_native_tracking_flags_a_label_outside_the_semantic_head():
     bad["label"] = torch.full_like(fr["label"], 6)
     with pytest.raises(ValueError):
         slam.track_frame(trk, bad, refer_w2c, feats2, est, 4, 1e-3, lambda it: td[it], native=True)
+
+
+def test_native_loops_cover_the_optimizer_variants():
+    """Two switches of the reference's optimiser set-up on the native loops against the autograd loops: the tracker's
+    ``seperate_LR`` (translation at 0.2 x cam_lr, slams/tracking.py:119-124) and a mapping call without bundle adjustment
+    (``BA = False``: no pose parameter group, slams/mapping.py:457-466)."""
+    from dns_slam_b200 import bench_util, slam, synthetic as syn
+    dev = _dev()
+    s = syn.SHAPES["tiny"]
+    sc = bench_util.slam_scene("tiny", 6, dev, seed=21, n_target=2)
+    dec = bench_util.make_decoder("tiny", 6, dev, seed=5)
+    # ---- tracking, separate learning rates
+    trk = slam.TrackerCore(sc["cam"], dec, s["tracking_pixels"], 32, 15, freeze_decoder=True)
+    n_it = 5
+    td = bench_util.tracking_draws(sc["cam"], s["tracking_pixels"], n_it, seed=2)
+    est = sc["poses"][3].clone()
+    est[:3, 3] += torch.tensor([0.015, -0.01, 0.02])
+    args = (trk, sc["frames"][1], torch.inverse(sc["poses"][1]), sc["feats"][1][:2].contiguous(), est, n_it, 2e-3, lambda it: td[it])
+    b_e, l_e, h_e = slam.track_frame(*args, seperate_LR=True)
+    b_n, l_n, h_n = slam.track_frame(*args, seperate_LR=True, native=True)
+    close(h_n, h_e, rtol=1e-4, atol=1e-6, name="native vs eager loss trajectory (seperate_LR)")
+    close(b_n, b_e, rtol=1e-5, atol=1e-6, name="native vs eager best pose (seperate_LR)")
+    b_1, _, h_1 = slam.track_frame(*args, seperate_LR=False, native=True)
+    assert not torch.equal(h_1, h_n), "the translation learning rate must matter"
+    # ---- mapping without bundle adjustment: poses stay where they were, the decoder moves as in the eager loop
+    md, tv = bench_util.mapping_draws(sc, s["mapping_pixels"], 4, seed=3)
+    target = dict(kf_idx=sc["kf_idx"], frames=sc["frames"], class_tables=sc["class_tables"])
+    refer = dict(kf_idx=sc["refer_idx"], est_c2w=sc["refer_c2w"])
+    est_l = [sc["poses"][2 * f + 1].clone() for f in range(2)]
+    res = []
+    for native in (False, True):
+        d2 = bench_util.make_decoder("tiny", 6, dev, seed=6)
+        mp = slam.MapperCore(sc["cam"], d2, s["mapping_pixels"], 32, 15, lambdas=dict(p=5.0, d=5.0, l=0.1, lt=10.0, fs=10.0, op=10.0),
+                             opacity_sigma=0.05, smooth_pts=s["smooth_pts"], lambda_sm=0.05)
+        ql, tl, ld = slam.map_optimize(mp, target, refer, sc["feats"], est_l, 4, 5e-3, 5e-4, False, [], lambda it: md[it],
+                                       lambda it: tv[it], native=native)
+        assert mp.last_path == ("native" if native else "eager")
+        res.append((ql, tl, ld["total"].clone(), d2.flat.clone()))
+    for i in range(2):
+        close(res[1][0][i], res[0][0][i], rtol=1e-6, atol=1e-7, name="pose untouched without BA")
+        close(res[1][0][i].cpu(), slam.quad_from_matrix(est_l[i][:3, :3]), rtol=1e-6, atol=1e-7, name="pose = start pose")
+    close(res[1][2], res[0][2], rtol=1e-3, atol=1e-6, name="last loss without BA")
+    assert rel_err(res[1][3], res[0][3]) < 1e-3
