@@ -320,7 +320,7 @@ template <int MODE>
 #ifndef DNS_BWD_CARVE_PCT
 #define DNS_BWD_CARVE_PCT 58
 #endif
-__global__ void __launch_bounds__(kTile2, DNS_BWD_CTAS) k_point_bwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
+__global__ void __launch_bounds__(kTile2, MODE == kTv ? 4 : DNS_BWD_CTAS) k_point_bwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
                                                              const uint4* __restrict__ we_all) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar;
@@ -329,15 +329,18 @@ __global__ void __launch_bounds__(kTile2, DNS_BWD_CTAS) k_point_bwd_tc2(PointArg
   // (after the first GEMM): the dH tile [8 chunks hi | lo, 32 KB] and the combined W1 tile (20 KB, prefetched into
   // registers while the GEMM runs) take the place of the dOut tiles.  Two CTAs then fit a 132 KB carve-out and the
   // corner re-reads get 124 KB of L1.  (More resident CTAs with a larger carve-out were measured slower.)
+  // Single-net modes (tracking, TV) need 36 KB: dOut hi | lo (24 KB) with W2 hi | lo behind them, then dH hi | lo (16 KB) and
+  // W1 (20 KB, stored once the first GEMM has consumed dOut and W2) -- four TV CTAs per SM (64 registers, 128 TMEM columns).
+  constexpr bool kTwoNets = MODE == kMap;
   unsigned char* DOc_hi = sm;
   unsigned char* DOc_lo = sm + kDOTile;
   unsigned char* DOf_hi = sm + 2 * kDOTile;
   unsigned char* DOf_lo = sm + 3 * kDOTile;
-  unsigned char* DH_hi = sm;                        // dH tile [8 chunks] aliases the dOut tiles
-  unsigned char* DH_lo = sm + 8 * 2048;
-  unsigned char* W1_hi = sm + 16 * 2048;            // behind the dH tile, still inside the (dead) dOut tiles
+  unsigned char* DH_hi = sm;                        // dH tile [8 | 4 chunks] aliases the dOut tiles
+  unsigned char* DH_lo = sm + (kTwoNets ? 8 : 4) * 2048;
+  unsigned char* W1_hi = sm + (kTwoNets ? 16 : 8) * 2048;   // behind the dH tile, still inside the (dead) dOut tiles
   unsigned char* W1_lo = W1_hi + kW1Tile;
-  unsigned char* W2c_hi = sm + 16 * 2048 + 2 * kW1Tile;
+  unsigned char* W2c_hi = kTwoNets ? sm + 16 * 2048 + 2 * kW1Tile : sm + 2 * kDOTile;
   unsigned char* W2f_hi = W2c_hi + 2 * kW2Tile;
   float* DXS = reinterpret_cast<float*>(sm);        // [3][128] partial d/dx of group 1 (after the last GEMM)
   const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, row = tid & (kTile - 1), grp = tid >> 7;
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(kTile2, DNS_BWD_CTAS) k_point_bwd_tc2(PointArg
   const uint4* we_net = we_all + (int64_t)(fine ? expert : 0) * kNetTc;
   for (int k = tid; k < 384; k += kTile2) {   // W2 coarse / expert, hi | lo contiguous per net
     reinterpret_cast<uint4*>(W2c_hi)[k] = wc_all[640 + k];
-    reinterpret_cast<uint4*>(W2f_hi)[k] = fine ? we_net[640 + k] : make_uint4(0, 0, 0, 0);
+    if (kTwoNets) reinterpret_cast<uint4*>(W2f_hi)[k] = fine ? we_net[640 + k] : make_uint4(0, 0, 0, 0);
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
   if (tid == 0) mbar_init(&bar, 1);
@@ -571,7 +574,15 @@ __global__ void __launch_bounds__(kTile2, DNS_BWD_CTAS) k_point_bwd_tc2(PointArg
   // dL/dx through the grid: from the forward pass's Jacobian image when there is one (12 coalesced loads per thread),
   // else by re-reading the corners
   const bool from_j = MODE != kTv && a.Jst != nullptr;
-  if (valid) {
+  if (MODE == kTv && a.tv_agg_levels > 0) {
+    // coherent lattice: per-cell pre-reduction inside the warp (every lane takes part in the shuffles)
+    float2* dpriv = a.d_priv ? a.d_priv + (size_t)(blockIdx.x % a.priv_copies) * a.priv_end : nullptr;
+    const int pl = a.d_priv ? a.priv_levels : 0;
+    float* dgs = reinterpret_cast<float*>(sm) + tid;   // [16][256]: this thread's column (the operand tiles are dead)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dgs[k * kTile2] = valid ? dg[k] : 0.f;
+    hashgrid_bwd_rows(a.G, dtab, x, dgs, kTile2, 8 * grp, 8 * grp + 8, valid, q / a.n, a.tv_agg_levels, dpriv, pl);
+  } else if (valid) {
     float2* dpriv = a.d_priv ? a.d_priv + (size_t)(blockIdx.x % a.priv_copies) * a.priv_end : nullptr;
     const int pl = a.d_priv ? a.priv_levels : 0;
     float dxj[3] = {0.f, 0.f, 0.f};
@@ -603,13 +614,13 @@ __global__ void __launch_bounds__(kTile2, DNS_BWD_CTAS) k_point_bwd_tc2(PointArg
   DNS_CLK(a, 10)   // ray gradients
 }
 
-size_t point_bwd_tc2_smem() { return 16 * 2048 + 2 * kW1Tile + 4 * kW2Tile; }
+size_t point_bwd_tc2_smem(int mode) { return mode == kMap ? 16 * 2048 + 2 * kW1Tile + 4 * kW2Tile : 8 * 2048 + 2 * kW1Tile; }
 size_t point_fwd_tc2_smem() { return 2 * kXTile + 2 * kW1Tile; }
 
 static void set_attrs2() {
   static unsigned long long seen = 0;
   if (!first_call_on_device(seen)) return;
-  const int f = (int)point_fwd_tc2_smem(), b = (int)point_bwd_tc2_smem();
+  const int f = (int)point_fwd_tc2_smem(), b = (int)point_bwd_tc2_smem(kMap);
   cudaFuncSetAttribute(k_point_fwd_tc2<kTrack>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
   cudaFuncSetAttribute(k_point_fwd_tc2<kMap>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
   cudaFuncSetAttribute(k_point_fwd_tc2<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, f);
@@ -658,11 +669,11 @@ int launch_point_fwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* w
 }
 int launch_point_bwd_tc(int mode, const PointArgs& pa, int tiles, const uint4* wc, const uint4* we, cudaStream_t st) {
   set_attrs2();
-  const size_t smem = point_bwd_tc2_smem();
+  const size_t smem = point_bwd_tc2_smem(mode);
   static CarveState last[3];
   if (mode == kMap) prefer_carveout(k_point_bwd_tc2<kMap>, last[0], tiles, "DNS_BWD_CARVE", DNS_BWD_CARVE_PCT);
   else if (mode == kTrack) prefer_carveout(k_point_bwd_tc2<kTrack>, last[1], tiles, "DNS_BWD_CARVE", DNS_BWD_CARVE_PCT);
-  else prefer_carveout(k_point_bwd_tc2<kTv>, last[2], tiles, "DNS_BWD_CARVE", DNS_BWD_CARVE_PCT);
+  else prefer_carveout(k_point_bwd_tc2<kTv>, last[2], tiles, "DNS_TV_BWD_CARVE", 72);   // no gathers: room for four CTAs
   if (mode == kMap) k_point_bwd_tc2<kMap><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else if (mode == kTrack) k_point_bwd_tc2<kTrack><<<tiles, kTile2, smem, st>>>(pa, wc, we);
   else k_point_bwd_tc2<kTv><<<tiles, kTile2, smem, st>>>(pa, wc, we);

@@ -81,6 +81,7 @@ struct PointArgs {
   int n;
   double voxel, jit[3], off[3];
   const double* tv_oj;   // device override: off[3] | jit[3]
+  int tv_agg_levels;      // TV backward: levels [0, tv_agg_levels) are pre-reduced per cell inside the warp (hashgrid_bwd_rows)
   // slots
   const int* perm;        // slot -> chunk-local point, -1 = padding; NULL = identity
   const int* tile_class;  // tile -> expert row (MAP)
@@ -143,9 +144,16 @@ template <int MODE>
 __device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_t& i, int64_t& r, float& zv, float x[3]) {
   if (MODE == kTv) {
     int64_t n = a.n, n3 = n * n * n;
-    if (q >= n3) return false;
+    if (q >= n3) {
+      x[0] = x[1] = x[2] = 0.f;   // the lane still takes part in the warp shuffles of hashgrid_bwd_rows
+      return false;
+    }
     i = q;
-    int64_t idx[3] = {q / (n * n), (q / n) % n, q % n};
+    // x runs fastest over the slots: the lanes of a warp are consecutive lattice points of one x row, i.e. neighbours in the
+    // dense levels' memory order (index = x + y res + z res^2) and, at hashed levels, within one aligned block (the x prime
+    // is 1), so the forward gathers of a warp coalesce and the backward can pre-reduce per cell (hashgrid_bwd_rows).  occ /
+    // docc are therefore stored [z][y][x]; the stencil (k_tv_stencil) is symmetric in the three axes.
+    int64_t idx[3] = {q % n, (q / n) % n, q / (n * n)};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const double jit = a.tv_oj ? a.tv_oj[3 + c] : a.jit[c], off = a.tv_oj ? a.tv_oj[c] : a.off[c];

@@ -290,6 +290,85 @@ __device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const floa
     }
   }
 }
+// Hash-table scatter of the TV lattice (mapping.py:129-159).  Slots run x fastest (slot_point<kTv>), so the lanes of a warp
+// are consecutive lattice points of one x row: same y, z (bit-identical weights) and non-decreasing cells along x.  At the
+// levels whose cells are wider than the lattice spacing (l < agg_levels) several lanes in a row fall into the SAME cell and
+// the next cell's x plane is this cell's x+1 plane, so the warp first sums (1-wx).g and wx.g per cell (segmented scan over
+// the runs of equal cells: five shuffle rounds on four values), hands a run's x+1 sums to the run of the neighbouring cell,
+// and only the LAST lane of a run issues reductions: four per x plane instead of eight (six with pairing) per lane.  The
+// reduction count per lane, not bytes, is what bounds the scatter.  Must be called by all 32 lanes (dg of an invalid lane = 0);
+// `rowid` identifies the x row of the lane's lattice point.  Levels >= agg_levels take the per-lane path.
+// The level loop is rolled (dg comes from the thread's column of a shared-memory staging area, element k at dgs[k * dgs_stride]):
+// unrolled, the eight scan bodies per thread missed the instruction cache (ncu: no_instructions 31 % of the stalls).
+__device__ __forceinline__ void hashgrid_bwd_rows(const dns_grid& G, float2* d_table_all, const float x[3], const float* dgs,
+                                                  int dgs_stride, int l0, int l1, bool valid, int64_t rowid, int agg_levels,
+                                                  float2* d_priv, int priv_levels) {
+  constexpr unsigned kAll = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t row_up = __shfl_up_sync(kAll, rowid, 1);
+  const int valid_up = __shfl_up_sync(kAll, (int)valid, 1);
+  const bool same_row = lane > 0 && valid && valid_up && row_up == rowid;
+#pragma unroll 1
+  for (int l = l0; l < l1; ++l) {
+    float2* d_table = l < priv_levels ? d_priv : d_table_all;
+    const float g0 = dgs[(2 * (l - l0)) * dgs_stride], g1 = dgs[(2 * (l - l0) + 1) * dgs_stride];
+    uint32_t g[3];
+    float w[3];
+    const float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    if (l < agg_levels) {   // uniform over the grid
+      const uint32_t gx_up = __shfl_up_sync(kAll, g[0], 1);
+      const bool head = !(same_row && gx_up == g[0]);
+      const bool adj = same_row && gx_up + 1u == g[0];   // the previous run is the x-neighbour cell: its x+1 plane is my x plane
+      const unsigned heads = __ballot_sync(kAll, head);
+      const int start = 31 - __clz(heads & (kAll >> (31 - lane)));   // first lane of my run (lane 0 is always a head)
+      const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+      float a0 = (1.f - w[0]) * g0, a1 = (1.f - w[0]) * g1, b0 = w[0] * g0, b1 = w[0] * g1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float ta0 = __shfl_up_sync(kAll, a0, d), ta1 = __shfl_up_sync(kAll, a1, d);
+        const float tb0 = __shfl_up_sync(kAll, b0, d), tb1 = __shfl_up_sync(kAll, b1, d);
+        if (lane - d >= start) { a0 += ta0; a1 += ta1; b0 += tb0; b1 += tb1; }
+      }
+      // the last lane of a run holds the run's sums; the previous run ends at lane start - 1
+      const float pb0 = __shfl_sync(kAll, b0, (start - 1) & 31), pb1 = __shfl_sync(kAll, b1, (start - 1) & 31);
+      const int adj_head = __shfl_sync(kAll, (int)adj, start);
+      const int next_adj = __shfl_down_sync(kAll, (int)adj, 1);    // lane + 1 heads the next run when this lane is a tail
+      if (tail && valid && d_table_all) {
+        if (adj_head) { a0 += pb0; a1 += pb1; }
+        const bool plus = lane == 31 || !next_adj;                 // nobody takes over the x+1 plane
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float wyz = ((c & 1) ? w[1] : 1.f - w[1]) * ((c & 2) ? w[2] : 1.f - w[2]);
+          const uint32_t i0 = corner_index(G, l, g[0], g[1] + (c & 1), g[2] + (c >> 1));
+          if (a0 != 0.f || a1 != 0.f) atomicAdd(d_table + i0, make_float2(wyz * a0, wyz * a1));
+          if (plus && (b0 != 0.f || b1 != 0.f)) {
+            const uint32_t i1 = corner_index(G, l, g[0] + 1u, g[1] + (c & 1), g[2] + (c >> 1));
+            atomicAdd(d_table + i1, make_float2(wyz * b0, wyz * b1));
+          }
+        }
+      }
+    } else if (valid && d_table_all && (g0 != 0.f || g1 != 0.f)) {
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const float wyz = ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+        const float w0 = (1.f - w[0]) * wyz, w1 = w[0] * wyz;
+        const uint32_t i0 = corner_index(G, l, g[0], g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+        const uint32_t i1 = corner_index(G, l, g[0] + 1u, g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+        if ((i0 ^ i1) == 1u) {
+          const bool odd = i0 & 1u;
+          const float wa = odd ? w1 : w0, wb = odd ? w0 : w1;
+          atomicAdd(reinterpret_cast<float4*>(d_table + (i0 & ~1u)), make_float4(wa * g0, wa * g1, wb * g0, wb * g1));
+        } else {
+          atomicAdd(d_table + i0, make_float2(w0 * g0, w0 * g1));
+          atomicAdd(d_table + i1, make_float2(w1 * g0, w1 * g1));
+        }
+      }
+    }
+  }
+}
 __device__ __forceinline__ void put_chunk(unsigned char* hi_tile, unsigned char* lo_tile, int chunk, int cs, int point,
                                           const float* v8) {
   uint4 h, l;

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-DNS_SLAM_B200_LIB=$PWD/dns_slam_b200/libdns_slam_b200_ablate.so timeout 300 python scratch/tv_ab.py > gpurun_out/tv_ab.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/tv_ab.log | cut -c1-120
-timeout 500 python -m pytest tests/test_gpu_fused.py tests/test_gpu_loops.py tests/test_gpu_framestep.py tests/test_gpu_edges.py -q --timeout 150 > gpurun_out/tv_tests.log 2>&1; echo "tests rc=$?"; grep -n "^E   \|FAILED\|passed\|failed" gpurun_out/tv_tests.log | head
+DNS_SLAM_B200_LIB=$PWD/dns_slam_b200/libdns_slam_b200_ablate.so timeout 300 python scratch/tv_ab.py > gpurun_out/tv_ab.log 2>&1; echo "rc=$?"; tail -16 gpurun_out/tv_ab.log | cut -c1-150
+timeout 600 python -m pytest tests/test_gpu_fused.py tests/test_gpu_loops.py tests/test_gpu_framestep.py tests/test_gpu_edges.py tests/test_gpu_parity_configs.py -q -m gpu --timeout 200 > gpurun_out/tv_tests.log 2>&1; echo "tests rc=$?"; grep -n "^E   \|FAILED\|passed\|failed" gpurun_out/tv_tests.log | head

@@ -1,5 +1,5 @@
-"""TV smoothness term (fwd + bwd + dW) at the Replica (63^3) and ScanNet (127^3) lattices, with / without the privatised
-gradient copies (ablate build)."""
+"""TV smoothness term (fwd + bwd + dW) at the Replica (63^3) and ScanNet (127^3) lattices, with the per-cell
+warp pre-reduction of the backward scatter up to different level limits (DNS_TV_AGG, ablate build)."""
 import os, sys, torch
 sys.path.insert(0, '.')
 from dns_slam_b200 import _lib, bench_util, fused, synthetic as syn
@@ -14,8 +14,9 @@ for shape in ("replica", "scannet"):
         return fused.tv_raw(dec.pe_fn.grid_fn.gstruct, dec.bound, dec.view("table"), dec.view("coarse"), s["smooth_pts"], off, jit,
                             s["lambda_smooth"], d_t, d_c)
     ref = None
-    for tag, env in (("no priv", {"DNS_NO_PRIV": "1"}), ("priv", {}), ("no priv", {"DNS_NO_PRIV": "1"}), ("priv", {})):
-        os.environ.pop("DNS_NO_PRIV", None); os.environ.update(env)
+    for tag, env in (("agg 0", {"DNS_TV_AGG": "0"}), ("agg 0.6", {"DNS_TV_AGG": "0.6"}), ("agg 1.0", {}), ("agg 1.5", {"DNS_TV_AGG": "1.5"}),
+                     ("agg all", {"DNS_TV_AGG": "1e9"}), ("agg 0", {"DNS_TV_AGG": "0"}), ("agg 1.0", {}), ("agg 1 nopriv", {"DNS_NO_PRIV": "1"})):
+        os.environ.pop("DNS_NO_PRIV", None); os.environ.pop("DNS_TV_AGG", None); os.environ.update(env)
         for _ in range(3): tv()
         d_t.zero_(); d_c.zero_(); tv(); gt = d_t.clone()
         if ref is None: ref = gt
@@ -25,4 +26,4 @@ for shape in ("replica", "scannet"):
         for _ in range(10): tv()
         torch.cuda.synchronize(); _lib.profile_enable(False)
         ph, _ = _lib.profile_read(True)
-        print(shape, f"{tag:8s}", {k: round(v / 10, 3) for k, v in ph.items() if v}, "grad diff vs first", f"{err:.1e}", flush=True)
+        print(shape, f"{tag:12s}", {k: round(v / 10, 3) for k, v in ph.items() if v}, "grad diff vs first", f"{err:.1e}", flush=True)

@@ -232,3 +232,37 @@ def test_scannet_mapping_batch_vs_oracle():
     _check_mapping(ms, ms.forward_backward(samples), o, "scannet")
     with fused.simt_path():
         _check_mapping(ms, ms.forward_backward(samples), o, "scannet (fp32 SIMT core)", strict=True)
+
+
+@pytest.mark.parametrize("shape,sample_points", [("replica", 64), ("scannet", 48)])
+def test_tv_lattice_at_config_grids_vs_oracle(shape, sample_points):
+    """The smoothness term (slams/mapping.py:129-159) on the real encoders: the Replica lattice at its configured size (63^3
+    points, hash 2^16) and a 47^3 lattice on the ScanNet grid (2^20, dense levels 0..10; the configured 127^3 points would
+    take the CPU oracle minutes).  The lattice slots run x fastest and the backward pre-reduces the coarse levels per cell
+    inside a warp (hashgrid_bwd_rows); loss and the table / coarse-MLP gradients must match the oracle to 1e-3."""
+    from oracle import reference_path as rp
+    from dns_slam_b200 import bench_util, fused
+    dev = _dev()
+    dec = bench_util.make_decoder(shape, 40, dev, seed=4, all_experts=False)
+    bound, odec, _ = _oracle_models(shape, dec, 40)
+    g = torch.Generator().manual_seed(9)
+    r3, r113 = torch.rand(3, generator=g), torch.rand(1, 1, 1, 3, generator=g)
+    tape = rp.DrawTape([("rand", r3), ("rand", r113)])
+    for p in odec.parameters():
+        p.grad = None
+    lo = rp.smoothness(odec, bound, sample_points, tape)
+    lo.backward()
+    dec.zero_grad()
+    lg = fused.tv_loss(dec, sample_points, r3, r113)
+    lg.backward()
+    assert abs(float(lg) - float(lo)) <= TOL * abs(float(lo)) + 1e-12, (float(lg), float(lo))
+    for name, got, want in (("coarse", dec.coarse_fn.decoder.params.grad, odec.coarse_fn.decoder.params.grad),
+                            ("table", dec.pe_fn.grid_fn.params.grad, odec.pe_fn.grid_fn.params.grad)):
+        e = rel_err(got.detach().cpu().reshape(-1), want.reshape(-1))
+        assert e <= TOL, f"tv {shape} d_{name}: {e:.2e}"
+    with fused.simt_path():
+        dec.zero_grad()
+        ls = fused.tv_loss(dec, sample_points, r3, r113)
+        ls.backward()
+    e = rel_err(dec.pe_fn.grid_fn.params.grad.detach().cpu().reshape(-1), odec.pe_fn.grid_fn.params.grad.reshape(-1))
+    assert e <= 1e-4, f"tv {shape} d_table (fp32 SIMT): {e:.2e}"
