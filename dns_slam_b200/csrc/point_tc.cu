@@ -314,11 +314,14 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
 }
 
 template <int MODE>
+// Three CTAs per SM (<= 85 registers; 86 % carve-out for 3 x 64 KB): since the Jacobian image took the L1-hungry corner
+// re-read out of the mapping backward, occupancy beats L1 here -- 1024 x 96 tracking 0.069 -> 0.060 ms, 4096 x 47 mapping
+// 0.220 -> 0.207 ms, 131 072 x 47 mapping 5.35 -> 5.20 ms (round 1, with the re-read: 7.6 -> 9.6 ms).
 #ifndef DNS_BWD_CTAS
-#define DNS_BWD_CTAS 2
+#define DNS_BWD_CTAS 3
 #endif
 #ifndef DNS_BWD_CARVE_PCT
-#define DNS_BWD_CARVE_PCT 58
+#define DNS_BWD_CARVE_PCT 86
 #endif
 __global__ void __launch_bounds__(kTile2, MODE == kTv ? 4 : DNS_BWD_CTAS) k_point_bwd_tc2(PointArgs a, const uint4* __restrict__ wc_all,
                                                              const uint4* __restrict__ we_all) {
@@ -327,8 +330,8 @@ __global__ void __launch_bounds__(kTile2, MODE == kTv ? 4 : DNS_BWD_CTAS) k_poin
   __shared__ uint32_t tmem_base_s;
   // 64 KB.  Phase 1: dOut tiles coarse hi | lo | fine hi | lo (six chunks each, 48 KB) and the W2 tiles.  Phase 2
   // (after the first GEMM): the dH tile [8 chunks hi | lo, 32 KB] and the combined W1 tile (20 KB, prefetched into
-  // registers while the GEMM runs) take the place of the dOut tiles.  Two CTAs then fit a 132 KB carve-out and the
-  // corner re-reads get 124 KB of L1.  (More resident CTAs with a larger carve-out were measured slower.)
+  // registers while the GEMM runs) take the place of the dOut tiles.  Three CTAs fit the 196 KB carve-out (DNS_BWD_CTAS
+  // above); tracking, which still re-reads the corners for dL/dx, keeps what L1 is left.
   // Single-net modes (tracking, TV) need 36 KB: dOut hi | lo (24 KB) with W2 hi | lo behind them, then dH hi | lo (16 KB) and
   // W1 (20 KB, stored once the first GEMM has consumed dOut and W2) -- four TV CTAs per SM (64 registers, 128 TMEM columns).
   constexpr bool kTwoNets = MODE == kMap;
