@@ -186,6 +186,42 @@ __device__ __forceinline__ uint32_t corner_index(const dns_grid& G, int l, uint3
   return idx + G.offset[l];
 }
 
+// The eight corner indices of cell g at level l (corner c = (c & 1, (c >> 1) & 1, c >> 2)), bit for bit what corner_index
+// gives corner by corner.  Dense levels: corner = base + delta (mod 2^32) with base = gx + gy res + gz res^2, so a cell
+// whose far corner stays below the level size needs no modulo at all, and a cell outside the bound (the TV lattice of
+// mapping.py:129-159 reaches far beyond it: ncu showed 16 % of the TV forward's instructions in `idx %= size`) needs ONE
+// modulo for the base and a conditional subtraction per corner (delta <= 1 + res + res^2 < size).  Only a base within delta
+// of 2^32 (slightly negative cells) takes the per-corner form, where the 32-bit wrap-around matters.
+__device__ __forceinline__ void corner_indices8(const dns_grid& G, int l, const uint32_t g[3], uint32_t (&idx)[8]) {
+  const uint32_t size = G.size[l], off = G.offset[l];
+  if (G.hashed[l]) {
+    const uint32_t m = size - 1u;   // size == 2^log2_T
+    const uint32_t y0 = g[1] * 2654435761u, y1 = y0 + 2654435761u, z0 = g[2] * 805459861u, z1 = z0 + 805459861u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) idx[c] = (((g[0] + (c & 1)) ^ ((c & 2) ? y1 : y0) ^ ((c & 4) ? z1 : z0)) & m) + off;
+  } else {
+    const uint32_t res = G.res[l], r2 = res * res;
+    const uint32_t base = g[0] + g[1] * res + g[2] * r2, dmax = 1u + res + r2;
+    if (base <= 0xffffffffu - dmax && dmax < size) {
+      uint32_t r0 = base;
+      if (base + dmax >= size) r0 = base % size;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v = r0 + (c & 1) + ((c & 2) ? res : 0u) + ((c & 4) ? r2 : 0u);
+        if (v >= size) v -= size;
+        idx[c] = v + off;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v = base + (c & 1) + ((c & 2) ? res : 0u) + ((c & 4) ? r2 : 0u);
+        if (v >= size) v %= size;
+        idx[c] = v + off;
+      }
+    }
+  }
+}
+
 // forward of all levels for one point; out[2l+f] written with stride st
 __device__ __forceinline__ void hashgrid_fwd(const dns_grid& G, const float2* __restrict__ table,
                                              const float x[3], float* out, int st) {

@@ -102,8 +102,12 @@ __global__ void k_hashgrid_indices(dns_grid G, const float* __restrict__ x, int6
     uint32_t g[3];
     float w[3];
     for (int a = 0; a < 3; ++a) grid_pos(x[3 * p + a], G.scale[l], g[a], w[a]);
-    for (int c = 0; c < 8; ++c)
-      idx[(p * G.n_levels + l) * 8 + c] = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+    uint32_t i8[8];
+    corner_indices8(G, l, g, i8);   // the per-cell form the fused kernels use; must equal the per-corner form
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t ic = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+      idx[(p * G.n_levels + l) * 8 + c] = ic == i8[c] ? ic : 0xffffffffu;
+    }
   }
 }
 

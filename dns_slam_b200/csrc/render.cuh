@@ -153,7 +153,8 @@ __device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_
     // dense levels' memory order (index = x + y res + z res^2) and, at hashed levels, within one aligned block (the x prime
     // is 1), so the forward gathers of a warp coalesce and the backward can pre-reduce per cell (hashgrid_bwd_rows).  occ /
     // docc are therefore stored [z][y][x]; the stencil (k_tv_stencil) is symmetric in the three axes.
-    int64_t idx[3] = {q % n, (q / n) % n, q / (n * n)};
+    const uint32_t qq = (uint32_t)q, nn = (uint32_t)a.n, qn = qq / nn;   // n <= 512: 32-bit divisions
+    int64_t idx[3] = {qq - qn * nn, qn % nn, qn / nn};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const double jit = a.tv_oj ? a.tv_oj[3 + c] : a.jit[c], off = a.tv_oj ? a.tv_oj[c] : a.off[c];

@@ -183,10 +183,10 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
     grid_pos(x[1], sc, g[1], w[1]);
     grid_pos(x[2], sc, g[2], w[2]);
     float2 v[8];
+    uint32_t ci[8];
+    corner_indices8(G, l, g, ci);
 #pragma unroll
-    for (int c = 0; c < 8; c += 2)
-      load_corner_pair(table, corner_index(G, l, g[0], g[1] + ((c >> 1) & 1), g[2] + (c >> 2)),
-                       corner_index(G, l, g[0] + 1, g[1] + ((c >> 1) & 1), g[2] + (c >> 2)), v[c], v[c + 1]);
+    for (int c = 0; c < 8; c += 2) load_corner_pair(table, ci[c], ci[c + 1], v[c], v[c + 1]);
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -254,9 +254,7 @@ __device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const floa
     grid_pos(x[1], sc, g[1], w[1]);
     grid_pos(x[2], sc, g[2], w[2]);
     uint32_t idx[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      idx[c] = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+    corner_indices8(G, l, g, idx);
     if (d_table) {
       // The x and x+1 corners of a cell edge are neighbours in memory (dense levels: consecutive indices; hashed
       // levels: the x prime is 1, so an even x only flips bit 0).  When they share an aligned 16-byte pair, ONE
@@ -339,24 +337,23 @@ __device__ __forceinline__ void hashgrid_bwd_rows(const dns_grid& G, float2* d_t
       if (tail && valid && d_table_all) {
         if (adj_head) { a0 += pb0; a1 += pb1; }
         const bool plus = lane == 31 || !next_adj;                 // nobody takes over the x+1 plane
+        uint32_t ci[8];
+        corner_indices8(G, l, g, ci);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float wyz = ((c & 1) ? w[1] : 1.f - w[1]) * ((c & 2) ? w[2] : 1.f - w[2]);
-          const uint32_t i0 = corner_index(G, l, g[0], g[1] + (c & 1), g[2] + (c >> 1));
-          if (a0 != 0.f || a1 != 0.f) atomicAdd(d_table + i0, make_float2(wyz * a0, wyz * a1));
-          if (plus && (b0 != 0.f || b1 != 0.f)) {
-            const uint32_t i1 = corner_index(G, l, g[0] + 1u, g[1] + (c & 1), g[2] + (c >> 1));
-            atomicAdd(d_table + i1, make_float2(wyz * b0, wyz * b1));
-          }
+        for (int c = 0; c < 8; c += 2) {
+          const float wyz = ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+          if (a0 != 0.f || a1 != 0.f) atomicAdd(d_table + ci[c], make_float2(wyz * a0, wyz * a1));
+          if (plus && (b0 != 0.f || b1 != 0.f)) atomicAdd(d_table + ci[c + 1], make_float2(wyz * b0, wyz * b1));
         }
       }
     } else if (valid && d_table_all && (g0 != 0.f || g1 != 0.f)) {
+      uint32_t ci[8];
+      corner_indices8(G, l, g, ci);
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {
         const float wyz = ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
         const float w0 = (1.f - w[0]) * wyz, w1 = w[0] * wyz;
-        const uint32_t i0 = corner_index(G, l, g[0], g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
-        const uint32_t i1 = corner_index(G, l, g[0] + 1u, g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
+        const uint32_t i0 = ci[c], i1 = ci[c + 1];
         if ((i0 ^ i1) == 1u) {
           const bool odd = i0 & 1u;
           const float wa = odd ? w1 : w0, wb = odd ? w0 : w1;

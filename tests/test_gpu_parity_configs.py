@@ -211,6 +211,10 @@ def test_scannet_grid_indices_bit_exact():
     P = 20000
     x = torch.rand(P, 3, generator=g)
     x[:4] = torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.999999, 0.000001, 0.5], [-0.01, 0.2, 1.02]])
+    # far outside the bound, like most of the TV lattice on this scene (mapping.py:129-159 with a 12.7 m lattice in a 3.6 m
+    # room): the dense levels wrap modulo their size, negative cells wrap modulo 2^32 first (corner_indices8's three cases)
+    x[4:6004] = torch.rand(6000, 3, generator=g) * 7.0 - 3.0
+    x[6004:6008] = torch.tensor([[-1e-4, -1e-4, -1e-4], [-0.003, 0.5, 0.5], [0.5, -0.003, -0.003], [1.0001, -1e-5, 3.0]])
     idx_o, _ = enc_o.impl.corner_indices(x)
     idx_g = torch.empty(P, 16, 8, dtype=torch.int32, device=dev)
     _lib.check(_lib.lib().dns_hashgrid_indices(C.byref(enc.gstruct), _lib.ptr(x.to(dev).contiguous()), P, _lib.ptr(idx_g),
