@@ -361,7 +361,69 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
 // CUDA graph advances it on every replay (slams/tracking.py:119-124: translation / quaternion groups;
 // slams/mapping.py:464-466: decoder / quaternions / translations).
 __global__ void k_adam_tick(int* step) { *step += 1; }
-__global__ void k_adam_multi(const dns_adam_seg* __restrict__ segs, const int* __restrict__ step, float b1, float b2,
+// beta^t for the integer step count by repeated squaring in double (<= 2 log2 t multiplications, relative error ~1e-15:
+// the float bias corrections are those of pow(); every thread of the launch evaluating pow() twice cost 10 us of FP64).
+__device__ __forceinline__ double ipow(double b, int t) {
+  double r = 1.0;
+  for (; t > 0; t >>= 1, b *= b)
+    if (t & 1) r *= b;
+  return r;
+}
+// One Adam update of up to four consecutive elements held in registers.
+__device__ __forceinline__ void adam4(float4& p, const float4& g, float4& m, float4& v, float b1, float b2, float eps,
+                                      float step_size, float bc2_sqrt) {
+  float* pp = &p.x; const float* gg = &g.x; float* mm = &m.x; float* vv = &v.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float mi = mm[e] + (1.f - b1) * (gg[e] - mm[e]);       // lerp, as torch's foreach path
+    const float vi = b2 * vv[e] + (1.f - b2) * gg[e] * gg[e];
+    mm[e] = mi;
+    vv[e] = vi;
+    pp[e] = pp[e] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+// A block's pass over [base, base + len) of one segment, 16-byte accesses and kAdamBatch of them in flight per thread (the
+// scalar grid-stride form waited one DRAM latency per element: 48 us for the 1.9 M parameters of a Replica decoder, most
+// of it in the 40 blocks that own a class-expert row each).  The pointers of a segment are 16-byte aligned whenever its
+// offset in the flat buffer is a multiple of four floats; anything else takes the scalar tail loop.
+constexpr int kAdamBatch = 2;
+__device__ __forceinline__ void adam_span(const dns_adam_seg& sg, int64_t base, int64_t len, int tid, int nthreads, float b1,
+                                          float b2, float eps, float step_size, float bc2_sqrt) {
+  const bool vec = ((((uintptr_t)(sg.p + base)) | ((uintptr_t)(sg.g + base)) | ((uintptr_t)(sg.m + base)) |
+                     ((uintptr_t)(sg.v + base))) & 15) == 0;
+  const int64_t n4 = vec ? len >> 2 : 0;
+  float4* p4 = reinterpret_cast<float4*>(sg.p + base);
+  const float4* g4 = reinterpret_cast<const float4*>(sg.g + base);
+  float4* m4 = reinterpret_cast<float4*>(sg.m + base);
+  float4* v4 = reinterpret_cast<float4*>(sg.v + base);
+  for (int64_t i0 = tid; i0 < n4; i0 += (int64_t)kAdamBatch * nthreads) {
+    float4 p[kAdamBatch], g[kAdamBatch], m[kAdamBatch], v[kAdamBatch];
+#pragma unroll
+    for (int k = 0; k < kAdamBatch; ++k) {
+      const int64_t i = i0 + (int64_t)k * nthreads;
+      if (i < n4) { g[k] = g4[i]; m[k] = m4[i]; v[k] = v4[i]; p[k] = p4[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < kAdamBatch; ++k) {
+      const int64_t i = i0 + (int64_t)k * nthreads;
+      if (i < n4) {
+        adam4(p[k], g[k], m[k], v[k], b1, b2, eps, step_size, bc2_sqrt);
+        m4[i] = m[k]; v4[i] = v[k]; p4[i] = p[k];
+      }
+    }
+  }
+  for (int64_t i = base + 4 * n4 + tid; i < base + len; i += nthreads) {
+    const float gi = sg.g[i];
+    const float mi = sg.m[i] + (1.f - b1) * (gi - sg.m[i]);
+    const float vi = b2 * sg.v[i] + (1.f - b2) * gi * gi;
+    sg.m[i] = mi;
+    sg.v[i] = vi;
+    sg.p[i] = sg.p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+// 148 x 4 blocks of 256 threads at <= 64 registers: the whole grid is resident at once (at 127 registers and 1184 blocks it
+// ran four waves of latency-bound blocks: 28 us for 30 MB)
+__global__ void __launch_bounds__(256, 4) k_adam_multi(const dns_adam_seg* __restrict__ segs, const int* __restrict__ step, float b1, float b2,
                              float eps) {
   const dns_adam_seg sg = segs[blockIdx.y];
   if (sg.row_len > 0) {
@@ -372,40 +434,32 @@ __global__ void k_adam_multi(const dns_adam_seg* __restrict__ segs, const int* _
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
       const int64_t base = row * sg.row_len;
       int any = 0;
-      for (int i = threadIdx.x; i < sg.row_len; i += blockDim.x) any |= sg.g[base + i] != 0.f;
+      if ((((uintptr_t)(sg.g + base)) & 15) == 0 && (sg.row_len & 3) == 0) {
+        const float4* g4 = reinterpret_cast<const float4*>(sg.g + base);
+        for (int i = threadIdx.x; i < (sg.row_len >> 2); i += blockDim.x) {
+          const float4 g = g4[i];
+          any |= (g.x != 0.f) | (g.y != 0.f) | (g.z != 0.f) | (g.w != 0.f);
+        }
+      } else {
+        for (int i = threadIdx.x; i < sg.row_len; i += blockDim.x) any |= sg.g[base + i] != 0.f;
+      }
       any = __syncthreads_or(any);
       if (!any) continue;                    // uniform over the block
       if (threadIdx.x == 0) s_step = ++sg.row_steps[row];
       __syncthreads();
-      const double tr = (double)s_step;
-      const float bc1 = (float)(1.0 - pow((double)b1, tr)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, tr));
-      const float step_size = sg.lr / bc1;
-      for (int i = threadIdx.x; i < sg.row_len; i += blockDim.x) {
-        const int64_t k = base + i;
-        const float gi = sg.g[k];
-        const float mi = sg.m[k] + (1.f - b1) * (gi - sg.m[k]);
-        const float vi = b2 * sg.v[k] + (1.f - b2) * gi * gi;
-        sg.m[k] = mi;
-        sg.v[k] = vi;
-        sg.p[k] = sg.p[k] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-      }
+      const float bc1 = (float)(1.0 - ipow((double)b1, s_step)), bc2_sqrt = (float)sqrt(1.0 - ipow((double)b2, s_step));
+      adam_span(sg, base, sg.row_len, threadIdx.x, blockDim.x, b1, b2, eps, sg.lr / bc1, bc2_sqrt);
       __syncthreads();                       // s_step is rewritten for the next row
     }
     return;
   }
-  const double t = (double)*step;
-  const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
-  const float step_size = sg.lr / bc1;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < sg.n; i += stride) {
-    const float gi = sg.g[i];
-    const float mi = sg.m[i] + (1.f - b1) * (gi - sg.m[i]);
-    const float vi = b2 * sg.v[i] + (1.f - b2) * gi * gi;
-    sg.m[i] = mi;
-    sg.v[i] = vi;
-    sg.p[i] = sg.p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-  }
+  const int t = *step;
+  const float bc1 = (float)(1.0 - ipow((double)b1, t)), bc2_sqrt = (float)sqrt(1.0 - ipow((double)b2, t));
+  // contiguous spans per block (multiples of four floats, so an aligned segment stays aligned in every block)
+  const int64_t per = ((sg.n + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;
+  const int64_t b0 = (int64_t)blockIdx.x * per;
+  if (b0 >= sg.n) return;
+  adam_span(sg, b0, (sg.n - b0 < per ? sg.n - b0 : per), threadIdx.x, blockDim.x, b1, b2, eps, sg.lr / bc1, bc2_sqrt);
 }
 
 }  // namespace dns
@@ -556,7 +610,7 @@ int dns_adam_multi(const dns_adam_seg* segs_dev, int n_segs, int64_t max_n, int*
     return DNS_ERR_ARG;
   }
   int64_t blocks = (max_n + 255) / 256;
-  const int bx = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  const int bx = (int)(blocks < 148 * 4 ? blocks : 148 * 4);
   PhaseScope ph(phAdam, (cudaStream_t)stream, 2);
   k_adam_tick<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
   k_adam_multi<<<dim3(bx, n_segs), 256, 0, (cudaStream_t)stream>>>(segs_dev, step_dev, beta1, beta2, eps);
