@@ -54,7 +54,8 @@ for r in rr[2:]:
                f"{col(r, 'lts__t_sector_hit_rate.pct'):.1f} % | {top} |")
     traffic.setdefault(name, (rd + wr) * 1e9)
 pts = 32768 * 47
-tj = {"capture": tag, "points_per_launch": pts, "bytes_per_point": {k: v / pts for k, v in traffic.items() if ("point" in k or "ray" in k) and "<2>" not in k}   # <2>: the TV lattice, not the ray batch,
+tj = {"capture": tag, "points_per_launch": pts, "bytes_per_point": {k: v / pts for k, v in traffic.items() if ("point" in k or "ray" in k) and "<2>" not in k},   # <2>: the TV lattice, not the ray batch
+     
       "note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch, divided by the launch's sample points"}
 json.dump(tj, open("profiles/ncu_traffic.json", "w"), indent=1)
 out += ["", "DRAM bytes per sample point (`profiles/ncu_traffic.json`, what `bench.py` scales into `roofline.traffic`): " +
