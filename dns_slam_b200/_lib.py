@@ -95,7 +95,7 @@ SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_ena
            "dns_adam_step", "dns_merge_workspace_bytes", "dns_merge_fwd", "dns_merge_bwd",
            "dns_stem_workspace_bytes", "dns_stem_fwd", "dns_adam_multi", "dns_featmerge_workspace_bytes",
            "dns_featmerge_fwd", "dns_featmerge_bwd", "dns_pose_prepare", "dns_pose_grad",
-           "dns_class_tables_workspace_bytes", "dns_class_tables", "dns_track_best"]
+           "dns_class_tables_workspace_bytes", "dns_class_tables", "dns_track_best", "dns_map_step_result"]
 
 
 def lib():
@@ -149,6 +149,7 @@ def lib():
     L.dns_pose_prepare.argtypes = [_P, _P, i32, _P, _P, _P, i32, _P, _P, _P, _P]
     L.dns_pose_grad.argtypes = [_P, _P, _P, i32, C.POINTER(C.c_int32), i32, i32, i32, f32, f32, f32, f32, _P, _P, _P, _P, _P]
     L.dns_track_best.argtypes = [_P, _P, _P, _P, _P, _P, _P, i32, _P, _P]
+    L.dns_map_step_result.argtypes = [i32, _P, _P, f32, f32, f32, _P, i32, _P, _P, _P]
     L.dns_class_tables_workspace_bytes.restype = C.c_int64
     L.dns_class_tables_workspace_bytes.argtypes = [i64, i32]
     L.dns_class_tables.argtypes = [_P, i64, i32, _P, _P, _P, _P, _P, i64, _P]

@@ -118,6 +118,33 @@ __global__ void k_pose_finish(const float* __restrict__ sums, const float* __res
 // best-pose bookkeeping of the tracking loop (slams/tracking.py:331-338), one thread: the reference compares the loss
 // on the host every iteration; here the comparison, the copy of the current pose, the loss history and the running
 // error flag stay on the device
+// loss / result bookkeeping of one native mapping iteration (dns_map_step_result)
+__global__ void k_map_step_result(int phase, const float* __restrict__ losses8, const float* __restrict__ tv_loss, float tv_w,
+                                  float tv_lambda_w, float nvalid_scale, const float* __restrict__ scratch, int F,
+                                  float* loss_vec, float* result) {
+  const int t = threadIdx.x;
+  if (phase & 1) {
+    if (t < 8) {
+      float v = losses8[t];
+      if (t == 6 && tv_loss) v += tv_lambda_w * *tv_loss;
+      loss_vec[t] = v;
+    }
+    if (t == 8 && tv_loss) loss_vec[8] = tv_w * *tv_loss;
+    __syncthreads();
+  }
+  if (phase & 2) {
+    if (t == 7) loss_vec[7] *= nvalid_scale;
+    __syncthreads();
+    if (t < 9) result[t] = loss_vec[t];
+    for (int e = t; e < 2 * F; e += blockDim.x) result[9 + e] = scratch[e];
+    if (t == 0) {
+      float outside = 0.f;
+      for (int f = 0; f < F; ++f) outside += scratch[2 * f + 1];
+      result[9 + 2 * F] += outside;
+      result[10 + 2 * F] = fminf(result[10 + 2 * F], loss_vec[7]);
+    }
+  }
+}
 __global__ void k_track_best(const float* __restrict__ losses, const float* __restrict__ quat, const float* __restrict__ trans,
                              float* best7, float* best_loss, float* hist, int* slot, int hist_len, float* err_min) {
   const float l = losses[6];
@@ -185,6 +212,19 @@ int dns_track_best(const float* losses, const float* quat, const float* trans, f
   PhaseScope ph(phFinalize, (cudaStream_t)stream, 1);
   k_track_best<<<1, 1, 0, (cudaStream_t)stream>>>(losses, quat, trans, best7, best_loss, hist, slot, hist_len, err_min);
   return check_launch("track_best");
+}
+
+int dns_map_step_result(int phase, const float* losses8, const float* tv_loss, float tv_w, float tv_lambda_w,
+                        float nvalid_scale, const float* scratch, int n_frames, float* loss_vec9, float* result,
+                        void* stream) {
+  if (!(phase & 3) || !loss_vec9 || ((phase & 1) && !losses8) || ((phase & 2) && (!scratch || !result || n_frames < 0))) {
+    set_error("map_step_result: bad arguments");
+    return DNS_ERR_ARG;
+  }
+  PhaseScope ph(phFinalize, (cudaStream_t)stream, 1);
+  k_map_step_result<<<1, 64, 0, (cudaStream_t)stream>>>(phase, losses8, tv_loss, tv_w, tv_lambda_w, nvalid_scale, scratch,
+                                                        n_frames, loss_vec9, result);
+  return check_launch("map_step_result");
 }
 
 }  // extern "C"

@@ -543,25 +543,25 @@ class MappingFrameStep:
         fused.featmerge_bwd_raw(self.cam, dec.merge.bound, views, b["rays_o"], b["rays_d"], b["z_vals"], b["gt_depth"], merge_p,
                                 d_f, self.fm_ws, g["merge"], d_o if self.opt_poses else None, d_d if self.opt_poses else None,
                                 stash=self.fm_stash)
-        self.loss_vec[:8] = losses
+        sm, w = None, 1.0 / self.world
         if self.with_tv:       # parameter-only work, replicated: every rank contributes 1 / world of it
-            w = 1.0 / self.world
             sm = fused.tv_raw(dec.pe_fn.grid_fn.gstruct, dec.bound, p["table"], p["coarse"], self.smooth_pts, None, None,
                               self.lambda_sm * w, g["table"], g["coarse"], oj_dev=self.draw_view(draws, "tv", torch.float64))
-            self.loss_vec[8:9] = sm * w
-            self.loss_vec[6:7] += (self.lambda_sm * w) * sm
         if self.opt_poses:
             fused.pose_grad_raw(self.cam, self.window, d_o, d_d, b["pixel"], self.ray_start, self.quats, self.d_quats,
                                 self.d_trans, self.pose_scratch)
+        # loss vector (it travels with the gradients through the all-reduce) and the result vector: dns_map_step_result
+        def result(phase, nvalid_scale=1.0):
+            _lib.check(L.dns_map_step_result(phase, _lib.ptr(losses, f32), _lib.ptr(sm, f32, allow_none=True), w,
+                                             self.lambda_sm * w, nvalid_scale, _lib.ptr(self.scratch, f32), F,
+                                             self.loss_vec.data_ptr(), _lib.ptr(self.result_dev, f32), _lib.stream()))
         if self.world > 1:
+            result(1)
             self.comm.all_reduce_sum(self.packed)
-            self.loss_vec[7:8] /= self.world          # n_valid is a batch constant, not a partial sum
+            result(2, 1.0 / self.world)               # n_valid is a batch constant, not a partial sum
+        else:
+            result(3)
         self.adam.step()
-        F2 = 9 + 2 * F
-        self.result_dev[:9] = self.loss_vec
-        self.result_dev[9:F2] = self.scratch.reshape(-1)
-        self.result_dev[F2:F2 + 1] += self.scratch[:, 1].sum()
-        torch.minimum(self.result_dev[F2 + 1:F2 + 2], self.loss_vec[7:8], out=self.result_dev[F2 + 1:F2 + 2])
         return self.result_dev
 
     def read_result(self):

@@ -350,6 +350,16 @@ int dns_pose_prepare(const float* quats, const float* trans, int n_frames, const
 int dns_pose_grad(const float* d_rays_o, const float* d_rays_d, const int64_t* pixel, int n_frames,
                   const int32_t* ray_start /* host, [n_frames+1] */, int H0, int W0, int Ww, float fx, float fy, float cx,
                   float cy, const float* quats, float* d_quats, float* d_trans, float* scratch, void* stream);
+/* Loss / result bookkeeping of one native mapping iteration (the scalar arithmetic of slams/mapping.py:896-907 around the
+ * fused calls, on the device so that the loop holds no library kernel).  phase bit 0, before the gradient all-reduce:
+ * loss_vec[0..7] <- losses8 (dns_render_fwd_bwd), and with tv_loss != NULL loss_vec[8] <- tv_w * *tv_loss,
+ * loss_vec[6] += tv_lambda_w * *tv_loss (the smoothness term joins the total, mapping.py:895-897).  phase bit 1, after it:
+ * loss_vec[7] *= nvalid_scale (n_valid is a batch constant, not a partial sum), result[0..8] <- loss_vec,
+ * result[9 .. 9 + 2F) <- scratch [F][2] (per frame: max depth, rays outside the bound), result[9 + 2F] += sum_f scratch[f][1],
+ * result[10 + 2F] <- min(result[10 + 2F], loss_vec[7]) (running error flag over all steps). */
+int dns_map_step_result(int phase, const float* losses8, const float* tv_loss, float tv_w, float tv_lambda_w,
+                        float nvalid_scale, const float* scratch, int n_frames, float* loss_vec9, float* result,
+                        void* stream);
 /* Best-pose bookkeeping of the tracking loop (slams/tracking.py:331-338: `if loss < current_min_loss` + the copy of the
  * candidate pose, a host comparison per iteration in the reference): losses = the [8] vector of dns_render_fwd_bwd
  * (total at 6, n_valid / error flag at 7); if total < *best_loss, best7 <- [quat | trans] and *best_loss <- total;

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_framestep.py tests/test_gpu_loops.py tests/test_gpu_pipeline.py -q -m gpu --timeout 200 > gpurun_out/native_tests.log 2>&1; echo "tests rc=$?"; grep -n "^E   \|FAILED\|passed\|failed" gpurun_out/native_tests.log | head
+timeout 300 python - <<'PY'
+import sys, copy, torch
+sys.path.insert(0, '.')
+import bench
+sys.argv = sys.argv[:1]
+args = bench.parse(); dev = torch.device("cuda:0")
+scene = bench.host_scene(args.shape, args.n_class)
+for _ in range(2): print(bench._native_iteration(args, dev, scene, 2000))
+PY
