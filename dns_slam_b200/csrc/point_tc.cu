@@ -577,22 +577,21 @@ __global__ void __launch_bounds__(kTile2, MODE == kTv ? 4 : DNS_BWD_CTAS) k_poin
   // dL/dx through the grid: from the forward pass's Jacobian image when there is one (12 coalesced loads per thread),
   // else by re-reading the corners
   const bool from_j = MODE != kTv && a.Jst != nullptr;
+  // dg leaves the registers for the thread's column of a shared-memory staging area [16][256] behind DXS (the operand tiles
+  // are dead): the level loops below are rolled (code size, see hashgrid_bwd_levels)
+  float* dgs = reinterpret_cast<float*>(sm) + 3 * kTile + tid;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) dgs[k * kTile2] = valid ? dg[k] : 0.f;
+  float2* dpriv = a.d_priv ? a.d_priv + (size_t)(blockIdx.x % a.priv_copies) * a.priv_end : nullptr;
+  const int pl = a.d_priv ? a.priv_levels : 0;
   if (MODE == kTv && a.tv_agg_levels > 0) {
     // coherent lattice: per-cell pre-reduction inside the warp (every lane takes part in the shuffles)
-    float2* dpriv = a.d_priv ? a.d_priv + (size_t)(blockIdx.x % a.priv_copies) * a.priv_end : nullptr;
-    const int pl = a.d_priv ? a.priv_levels : 0;
-    float* dgs = reinterpret_cast<float*>(sm) + tid;   // [16][256]: this thread's column (the operand tiles are dead)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) dgs[k * kTile2] = valid ? dg[k] : 0.f;
     hashgrid_bwd_rows(a.G, dtab, x, dgs, kTile2, 8 * grp, 8 * grp + 8, valid, q / a.n, a.tv_agg_levels, dpriv, pl);
   } else if (valid) {
-    float2* dpriv = a.d_priv ? a.d_priv + (size_t)(blockIdx.x % a.priv_copies) * a.priv_end : nullptr;
-    const int pl = a.d_priv ? a.priv_levels : 0;
     float dxj[3] = {0.f, 0.f, 0.f};
     if (want_dx && from_j)    // issued before the reductions: the 12 loads fly while those drain
       hashgrid_dx_from_jimg<8>(reinterpret_cast<const float4*>(a.Jst) + ((int64_t)tile * 24 + 12 * grp) * kTile + row, dg, dxj);
-    if (grp == 0) hashgrid_bwd_range<0, 8>(a.G, a.table, dtab, x, dg, want_dx && !from_j, dxg, dpriv, pl);
-    else hashgrid_bwd_range<8, 16>(a.G, a.table, dtab, x, dg, want_dx && !from_j, dxg, dpriv, pl);
+    hashgrid_bwd_levels(a.G, a.table, dtab, x, dgs, kTile2, 8 * grp, 8 * grp + 8, want_dx && !from_j, dxg, dpriv, pl);
     if (want_dx && from_j) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) dxg[c] = dxj[c];

@@ -288,6 +288,57 @@ __device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const floa
     }
   }
 }
+// hashgrid_bwd_range with the level loop ROLLED: dg (element k at dgs[k * dgs_stride], the thread's column of a shared-memory
+// staging area) instead of a register array.  Unrolled over eight levels the scatter alone is ~60 KB of SASS per thread group
+// and k_point_bwd_tc2<MAP> 200 KB -- beyond the instruction cache, with every warp of the SM in a different phase (ncu:
+// no_instructions 13 % of the stall samples).
+__device__ __forceinline__ void hashgrid_bwd_levels(const dns_grid& G, const float2* __restrict__ table, float2* d_table_all,
+                                                    const float x[3], const float* dgs, int dgs_stride, int l0, int l1,
+                                                    bool want_dx, float dx[3], float2* d_priv, int priv_levels) {
+  dx[0] = dx[1] = dx[2] = 0.f;
+#pragma unroll 1
+  for (int l = l0; l < l1; ++l) {
+    float2* d_table = (d_table_all && l < priv_levels) ? d_priv : d_table_all;
+    const float g0 = dgs[(2 * (l - l0)) * dgs_stride], g1 = dgs[(2 * (l - l0) + 1) * dgs_stride];
+    if (g0 == 0.f && g1 == 0.f) continue;
+    uint32_t g[3];
+    float w[3];
+    const float sc = G.scale[l];
+    grid_pos(x[0], sc, g[0], w[0]);
+    grid_pos(x[1], sc, g[1], w[1]);
+    grid_pos(x[2], sc, g[2], w[2]);
+    uint32_t idx[8];
+    corner_indices8(G, l, g, idx);
+    if (d_table) {
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const float wyz = ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+        const float w0 = (1.f - w[0]) * wyz, w1 = w[0] * wyz;
+        const uint32_t i0 = idx[c], i1 = idx[c + 1];
+        if ((i0 ^ i1) == 1u) {   // one vector reduction for an aligned x / x+1 pair (see hashgrid_bwd_range)
+          const bool odd = i0 & 1u;
+          const float wa = odd ? w1 : w0, wb = odd ? w0 : w1;
+          atomicAdd(reinterpret_cast<float4*>(d_table + (i0 & ~1u)), make_float4(wa * g0, wa * g1, wb * g0, wb * g1));
+        } else {
+          atomicAdd(d_table + i0, make_float2(w0 * g0, w0 * g1));
+          atomicAdd(d_table + i1, make_float2(w1 * g0, w1 * g1));
+        }
+      }
+    }
+    if (want_dx) {
+      float s[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float2 v = __ldg(table + idx[c]);
+        s[c] = v.x * g0 + v.y * g1;
+      }
+      const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
+      dx[0] += sc * (wy0 * wz0 * (s[1] - s[0]) + w[1] * wz0 * (s[3] - s[2]) + wy0 * w[2] * (s[5] - s[4]) + w[1] * w[2] * (s[7] - s[6]));
+      dx[1] += sc * (wx0 * wz0 * (s[2] - s[0]) + w[0] * wz0 * (s[3] - s[1]) + wx0 * w[2] * (s[6] - s[4]) + w[0] * w[2] * (s[7] - s[5]));
+      dx[2] += sc * (wx0 * wy0 * (s[4] - s[0]) + w[0] * wy0 * (s[5] - s[1]) + wx0 * w[1] * (s[6] - s[2]) + w[0] * w[1] * (s[7] - s[3]));
+    }
+  }
+}
 // Hash-table scatter of the TV lattice (mapping.py:129-159).  Slots run x fastest (slot_point<kTv>), so the lanes of a warp
 // are consecutive lattice points of one x row: same y, z (bit-identical weights) and non-decreasing cells along x.  At the
 // levels whose cells are wider than the lattice spacing (l < agg_levels) several lanes in a row fall into the SAME cell and
