@@ -11,11 +11,16 @@ namespace dns {
 // thirteen are exact zeros there too (saturated CDFs cancel).  x far outside [0,1] takes the dense path.
 __device__ __forceinline__ void oneblob16(float x, float (&o)[16]) {
   if (x < -0.5f || x > 1.5f) {
+    // cold path, ROLLED (same operations in the same order): unrolled, its 51 quartic CDFs were ~800 instructions per
+    // coordinate in every kernel that encodes a point -- a third of k_ray_tc2's 165 KB of SASS for a path that only the
+    // out-of-bound part of the TV lattice takes.  The bin is written by an unrolled select so that o[] stays in registers.
     float prev = cdf3(0.0f - x, 16.0f);
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b < 16; ++b) {
-      float cur = cdf3((float)(b + 1) / 16.0f - x, 16.0f);
-      o[b] = cur - prev;
+      const float cur = cdf3((float)(b + 1) / 16.0f - x, 16.0f);
+      const float v = cur - prev;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = j == b ? v : o[j];
       prev = cur;
     }
     return;
@@ -33,12 +38,15 @@ __device__ __forceinline__ void oneblob16(float x, float (&o)[16]) {
   for (int b = 0; b < 16; ++b) o[b] = b == bb[0] ? vv[0] : (b == bb[1] ? vv[1] : (b == bb[2] ? vv[2] : 0.0f));
 }
 __device__ __forceinline__ float oneblob16_bwd(float x, const float (&d)[16]) {
-  if (x < -0.5f || x > 1.5f) {
+  if (x < -0.5f || x > 1.5f) {   // cold path, rolled (see oneblob16)
     float prev = pdf3(0.0f - x, 16.0f), acc = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b < 16; ++b) {
-      float cur = pdf3((float)(b + 1) / 16.0f - x, 16.0f);
-      acc += d[b] * (cur - prev);
+      const float cur = pdf3((float)(b + 1) / 16.0f - x, 16.0f);
+      float db = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) db = j == b ? d[j] : db;
+      acc += db * (cur - prev);
       prev = cur;
     }
     return -16.0f * acc;
