@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
 #define XIMG(c) (ximg ? ximg + (c) * kTile : nullptr), (ximg ? ximg + (10 + (c)) * kTile : nullptr)
   if (valid) {
     if (grp == 0) {
-#pragma unroll
+#pragma unroll 1   // one copy of the OneBlob + operand-split code instead of three (instruction-cache footprint)
       for (int c = 0; c < 3; ++c) {
         float pe[16];
-        oneblob16(x[c], pe);
+        oneblob16(c == 0 ? x[0] : (c == 1 ? x[1] : x[2]), pe);
         put_chunk_f16_img(X_hi, X_lo, 2 * c, 2048, row, pe, XIMG(2 * c));
         put_chunk_f16_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, XIMG(2 * c + 1));
       }

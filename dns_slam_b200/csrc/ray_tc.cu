@@ -133,10 +133,10 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
     if (a.feat_band && grp == 1) band = in_band(zv, a.gt_depth[r]);
     if (grp == 0) {
       point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
-#pragma unroll
+#pragma unroll 1   // one copy of the OneBlob + operand-split code instead of three (instruction-cache footprint)
       for (int c = 0; c < 3; ++c) {
         float pe[16];
-        oneblob16(x[c], pe);
+        oneblob16(c == 0 ? x[0] : (c == 1 ? x[1] : x[2]), pe);
         put_chunk_f16_img(X_hi, X_lo, 2 * c, cs, row, pe, IMG2(x2p, 14, 2 * c));
         put_chunk_f16_img(X_hi, X_lo, 2 * c + 1, cs, row, pe + 8, IMG2(x2p, 14, 2 * c + 1));
       }
@@ -522,11 +522,14 @@ __global__ void __launch_bounds__(512) k_ray_tc2(RayArgs a, const uint4* __restr
   float g3[3] = {0.f, 0.f, 0.f};
   if (grp == 0) {   // dX columns 0..47: OneBlob backward -> d(ray)
     if (a.need_drays) {
-#pragma unroll
+#pragma unroll 1   // one copy of the OneBlob backward instead of three
       for (int g = 0; g < 3; ++g) {
         float v[16];
         tmem_ld16(taddr + 16 * g, v);
-        if (valid) g3[g] = oneblob16_bwd(x[g], v) / (float)a.B.ext[g];
+        const float gx = valid ? oneblob16_bwd(g == 0 ? x[0] : (g == 1 ? x[1] : x[2]), v) / (float)a.B.ext[g] : 0.f;
+        g3[0] = g == 0 ? gx : g3[0];
+        g3[1] = g == 1 ? gx : g3[1];
+        g3[2] = g == 2 ? gx : g3[2];
       }
     }
   } else {          // columns 48..79: d(latent) (with d_occ in channel 0); columns 80..111: d(pixel feature)
