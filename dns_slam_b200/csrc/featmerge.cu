@@ -214,10 +214,10 @@ __device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsi
   const int c0 = grp ? 9 : 6, c1 = grp ? 14 : 9;
   if (!FEATURES) {   // OneBlob chunks only (group 0); the feature chunks come from gather_features_coop
     if (grp == 0) {
-#pragma unroll
+#pragma unroll 1   // one copy of the OneBlob + operand-split code (instruction-cache footprint)
       for (int c = 0; c < 3; ++c) {
         float pe[16];
-        if (g.valid) oneblob16(g.x[c], pe);
+        if (g.valid) oneblob16(c == 0 ? g.x[0] : (c == 1 ? g.x[1] : g.x[2]), pe);
         else {
 #pragma unroll
           for (int e = 0; e < 16; ++e) pe[e] = 0.f;
@@ -237,10 +237,10 @@ __device__ __forceinline__ void build_x(const RowGeom& g, int grp, int row, unsi
     return;
   }
   if (grp == 0) {
-#pragma unroll
+#pragma unroll 1   // one copy of the OneBlob + operand-split code (instruction-cache footprint)
     for (int c = 0; c < 3; ++c) {
       float pe[16];
-      oneblob16(g.x[c], pe);
+      oneblob16(c == 0 ? g.x[0] : (c == 1 ? g.x[1] : g.x[2]), pe);
       put_chunk_img(X_hi, X_lo, 2 * c, 2048, row, pe, img ? img + (2 * c) * kTile : nullptr, img ? img + (14 + 2 * c) * kTile : nullptr);
       put_chunk_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, img ? img + (2 * c + 1) * kTile : nullptr,
                     img ? img + (15 + 2 * c) * kTile : nullptr);
@@ -671,10 +671,11 @@ __global__ void __launch_bounds__(kFT, 2) k_featmerge_bwd(FmArgs a) {
       // OneBlob backward per coordinate (group 0: x, y; group 1: z), summed over the R view rows of the sample, then
       // d(point) -> d_rays_o, d_rays_d (point = o + d z)
       const int c0 = grp ? 2 : 0, c1 = grp ? 3 : 2;
+#pragma unroll 1
       for (int c = c0; c < c1; ++c) {
         float v[16];
         tmem_ld16(lane_addr + 64 + 16 * c, v);
-        DXS[row * 3 + c] = g.valid ? oneblob16_bwd(g.x[c], v) / (float)a.B.ext[c] : 0.f;
+        DXS[row * 3 + c] = g.valid ? oneblob16_bwd(c == 0 ? g.x[0] : (c == 1 ? g.x[1] : g.x[2]), v) / (float)a.B.ext[c] : 0.f;
       }
       tc_fence_before();
       __syncthreads();
