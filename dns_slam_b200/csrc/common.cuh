@@ -212,11 +212,13 @@ __device__ __forceinline__ void corner_indices8(const dns_grid& G, int l, const 
         idx[c] = v + off;
       }
     } else {
-#pragma unroll
+#pragma unroll 1   // rare (cells within delta of the 2^32 wrap): one copy of the modulo, idx[] written by an unrolled select
       for (int c = 0; c < 8; ++c) {
         uint32_t v = base + (c & 1) + ((c & 2) ? res : 0u) + ((c & 4) ? r2 : 0u);
         if (v >= size) v %= size;
-        idx[c] = v + off;
+        v += off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idx[j] = j == c ? v : idx[j];
       }
     }
   }

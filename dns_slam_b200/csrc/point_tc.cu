@@ -553,17 +553,18 @@ __global__ void __launch_bounds__(kTile2, MODE == kTv ? 4 : DNS_BWD_CTAS) k_poin
   // dX columns: 0..47 OneBlob (group 0), 48..63 levels 0..7 (group 0), 64..79 levels 8..15 (group 1)
   float dx[3] = {0.f, 0.f, 0.f}, dg[16];
   if (grp == 0) {
-#pragma unroll
-    for (int g5 = 0; g5 < 4; ++g5) {
-      float v[16];
-      if (g5 == 3 || a.need_drays) tmem_ld16(lane_addr + 16 * g5, v);
-      if (g5 < 3) {
-        if (a.need_drays && valid) dx[g5] = oneblob16_bwd(x[g5], v);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) dg[k] = v[k];
+    if (a.need_drays) {
+#pragma unroll 1   // one copy of the OneBlob backward instead of three (instruction-cache footprint)
+      for (int g5 = 0; g5 < 3; ++g5) {
+        float v[16];
+        tmem_ld16(lane_addr + 16 * g5, v);
+        const float d = valid ? oneblob16_bwd(g5 == 0 ? x[0] : (g5 == 1 ? x[1] : x[2]), v) : 0.f;
+        dx[0] = g5 == 0 ? d : dx[0];
+        dx[1] = g5 == 1 ? d : dx[1];
+        dx[2] = g5 == 2 ? d : dx[2];
       }
     }
+    tmem_ld16(lane_addr + 48, dg);
   } else {
     tmem_ld16(lane_addr + 64, dg);
   }
