@@ -122,10 +122,8 @@ __global__ void __launch_bounds__(kTile2, 3) k_point_fwd_tc2(PointArgs a, const 
         put_chunk_f16_img(X_hi, X_lo, 2 * c, 2048, row, pe, XIMG(2 * c));
         put_chunk_f16_img(X_hi, X_lo, 2 * c + 1, 2048, row, pe + 8, XIMG(2 * c + 1));
       }
-      hashgrid_fwd_to_tile<0, 8>(a.G, a.table, x, X_hi, X_lo, row, jimg);
-    } else {
-      hashgrid_fwd_to_tile<8, 16>(a.G, a.table, x, X_hi, X_lo, row, jimg);
     }
+    hashgrid_fwd_to_tile(a.G, a.table, x, X_hi, X_lo, row, 8 * grp, jimg);
     if (ximg) {   // the two grid chunks this thread has just written (its own row): fp16 tile -> bf16 global image
 #pragma unroll
       for (int c = 6 + 2 * grp; c < 8 + 2 * grp; ++c) {

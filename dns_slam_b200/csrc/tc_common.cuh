@@ -178,12 +178,16 @@ __device__ __forceinline__ void hashgrid_fwd_range(const dns_grid& G, const floa
 // slot-order Jacobian image (float4 chunk k of row `row` at jimg[k * 128]; two levels = three chunks), from which the
 // backward kernel forms dL/dx = sum_l g_l . J_l with 12 coalesced 16-byte loads per thread instead of re-reading the
 // 64 corners (one L1 wavefront per LANE: the unrelated points of a warp share no cache line).
-template <int L0, int L1>
+// The level range is a RUN-TIME argument (l0 even, eight levels): the two thread groups of a CTA run the same copy of the
+// loop body instead of one template instance each (half the instruction-cache footprint of the kernel's hottest loop).
 __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const float2* __restrict__ table, const float x[3],
-                                                     unsigned char* X_hi, unsigned char* X_lo, int row, float4* jimg = nullptr) {
+                                                     unsigned char* X_hi, unsigned char* X_lo, int row, int l0,
+                                                     float4* jimg = nullptr) {
   float jj[12];
-#pragma unroll 2
-  for (int l = L0; l < L1; ++l) {
+#pragma unroll 1
+  for (int lb = l0; lb < l0 + 8; lb += 2)
+#pragma unroll
+  for (int l = lb; l < lb + 2; ++l) {
     uint32_t g[3];
     float w[3];
     const float sc = G.scale[l];
@@ -211,7 +215,7 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
     *reinterpret_cast<__half2*>(X_lo + off) = ll;
     if (jimg) {
       const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
-      float* j6 = jj + 6 * ((l - L0) & 1);     // (the loop is unrolled by two: the parity is a compile-time constant)
+      float* j6 = jj + 6 * (l - lb);     // (the loop is unrolled by two: the parity is a compile-time constant)
       // the same corner differences and weights as the backward's dL/dx (hashgrid_bwd_range), per feature
       j6[0] = sc * (wy0 * wz0 * (v[1].x - v[0].x) + w[1] * wz0 * (v[3].x - v[2].x) + wy0 * w[2] * (v[5].x - v[4].x) + w[1] * w[2] * (v[7].x - v[6].x));
       j6[1] = sc * (wx0 * wz0 * (v[2].x - v[0].x) + w[0] * wz0 * (v[3].x - v[1].x) + wx0 * w[2] * (v[6].x - v[4].x) + w[0] * w[2] * (v[7].x - v[5].x));
@@ -219,8 +223,8 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
       j6[3] = sc * (wy0 * wz0 * (v[1].y - v[0].y) + w[1] * wz0 * (v[3].y - v[2].y) + wy0 * w[2] * (v[5].y - v[4].y) + w[1] * w[2] * (v[7].y - v[6].y));
       j6[4] = sc * (wx0 * wz0 * (v[2].y - v[0].y) + w[0] * wz0 * (v[3].y - v[1].y) + wx0 * w[2] * (v[6].y - v[4].y) + w[0] * w[2] * (v[7].y - v[5].y));
       j6[5] = sc * (wx0 * wy0 * (v[4].y - v[0].y) + w[0] * wy0 * (v[5].y - v[1].y) + wx0 * w[1] * (v[6].y - v[2].y) + w[0] * w[1] * (v[7].y - v[3].y));
-      if ((l - L0) & 1) {
-        float4* dst = jimg + (3 * ((l - L0) >> 1)) * 128;
+      if (l - lb) {
+        float4* dst = jimg + (3 * ((lb - l0) >> 1)) * 128;
         dst[0] = make_float4(jj[0], jj[1], jj[2], jj[3]);
         dst[128] = make_float4(jj[4], jj[5], jj[6], jj[7]);
         dst[256] = make_float4(jj[8], jj[9], jj[10], jj[11]);
