@@ -95,7 +95,7 @@ SYMBOLS = ["dns_last_error", "dns_version", "dns_struct_sizes", "dns_profile_ena
            "dns_adam_step", "dns_merge_workspace_bytes", "dns_merge_fwd", "dns_merge_bwd",
            "dns_stem_workspace_bytes", "dns_stem_fwd", "dns_adam_multi", "dns_featmerge_workspace_bytes",
            "dns_featmerge_fwd", "dns_featmerge_bwd", "dns_pose_prepare", "dns_pose_grad",
-           "dns_class_tables_workspace_bytes", "dns_class_tables", "dns_track_best", "dns_map_step_result"]
+           "dns_class_tables_workspace_bytes", "dns_class_tables", "dns_track_best", "dns_map_step_result", "dns_sample_rays_batch"]
 
 
 def lib():
@@ -132,6 +132,7 @@ def lib():
     L.dns_tv_workspace_bytes.argtypes = [i32]
     L.dns_tv_fwd_bwd.argtypes = [C.POINTER(TvArgs), _P]
     L.dns_sample_rays.argtypes = [C.POINTER(SampleArgs), _P]
+    L.dns_sample_rays_batch.argtypes = [C.POINTER(SampleArgs), i32, _P]
     L.dns_feature_gather.argtypes = [_P, i64, _P, i32, _P, i32, i32, _P, i32, i32, i32, _P, _P, _P, _P]
     L.dns_adam_step.argtypes = [_P, _P, _P, _P, i64, f32, f32, f32, f32, i32, _P]
     bound_t = (C.c_double * 2) * 3

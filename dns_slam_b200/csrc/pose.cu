@@ -63,9 +63,16 @@ __global__ void k_pose_prepare(const float* __restrict__ quats, const float* __r
 }
 
 // per frame: partial sums of dT (3) and G = dL/dR (9) over the frame's rays
+// all frames in one launch (blockIdx.y = frame; ray ranges by value)
+constexpr int kMaxPoseFrames = 32;
+struct PoseRanges {
+  int start[kMaxPoseFrames + 1];
+};
 __global__ void __launch_bounds__(256) k_pose_reduce(const float* __restrict__ d_o, const float* __restrict__ d_d,
-                                                     const int64_t* __restrict__ pixel, int r0, int r1, int H0, int W0,
-                                                     int Ww, float fx, float fy, float cx, float cy, float* __restrict__ out12) {
+                                                     const int64_t* __restrict__ pixel, PoseRanges rg, int f0, int H0, int W0,
+                                                     int Ww, float fx, float fy, float cx, float cy, float* __restrict__ out) {
+  const int r0 = rg.start[blockIdx.y], r1 = rg.start[blockIdx.y + 1];
+  float* const out12 = out + 12 * (f0 + blockIdx.y);
   __shared__ float red[32];
   float acc[12];
 #pragma unroll
@@ -190,14 +197,18 @@ int dns_pose_grad(const float* d_rays_o, const float* d_rays_d, const int64_t* p
     set_error("pose_grad: bad arguments");
     return DNS_ERR_ARG;
   }
-  PhaseScope ph(phFinalize, st, n_frames + 2);
+  PhaseScope ph(phFinalize, st, 3);
   cudaMemsetAsync(scratch, 0, sizeof(float) * 12 * n_frames, st);
-  for (int f = 0; f < n_frames; ++f) {
-    const int r0 = ray_start[f], r1 = ray_start[f + 1];
-    if (r1 <= r0) continue;
-    int blocks = (r1 - r0 + 255) / 256;
+  for (int f0 = 0; f0 < n_frames; f0 += kMaxPoseFrames) {
+    const int nf = n_frames - f0 < kMaxPoseFrames ? n_frames - f0 : kMaxPoseFrames;
+    PoseRanges rg;
+    int n_max = 0;
+    for (int f = 0; f <= nf; ++f) rg.start[f] = ray_start[f0 + f];
+    for (int f = 0; f < nf; ++f) n_max = rg.start[f + 1] - rg.start[f] > n_max ? rg.start[f + 1] - rg.start[f] : n_max;
+    if (n_max <= 0) continue;
+    int blocks = (n_max + 255) / 256;
     if (blocks > 148) blocks = 148;
-    k_pose_reduce<<<blocks, 256, 0, st>>>(d_rays_o, d_rays_d, pixel, r0, r1, H0, W0, Ww, fx, fy, cx, cy, scratch + 12 * f);
+    k_pose_reduce<<<dim3(blocks, nf), 256, 0, st>>>(d_rays_o, d_rays_d, pixel, rg, f0, H0, W0, Ww, fx, fy, cx, cy, scratch);
   }
   k_pose_finish<<<(n_frames + 31) / 32, 32, 0, st>>>(scratch, quats, n_frames, d_quats, d_trans);
   return check_launch("pose_grad");

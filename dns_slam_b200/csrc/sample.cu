@@ -12,8 +12,8 @@
 
 namespace dns {
 
-__global__ void k_sample_gather(dns_sample_args a) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void sample_gather_body(const dns_sample_args& a, int block) {
+  int r = block * blockDim.x + threadIdx.x;
   if (r >= a.n) return;
   int64_t idx = a.index[r];
   // class-balanced draws (utils/common.py:315-330): the draw is an offset into the pixels of the slot's class
@@ -40,15 +40,29 @@ __global__ void k_sample_gather(dns_sample_args a) {
   atomicMax(reinterpret_cast<int*>(a.scratch), __float_as_int(fmaxf(d, 0.f)));
 }
 
+__global__ void k_sample_gather(dns_sample_args a) { sample_gather_body(a, blockIdx.x); }
+
+// Several frames of one mapping iteration in ONE launch (blockIdx.y = frame): at SLAM batch sizes the per-frame launches
+// of the sampler were a chain of ~7 us kernels, 60 us of a 0.8 ms iteration.
+constexpr int kMaxSampleFrames = 8;
+struct SampleBatch {
+  dns_sample_args f[kMaxSampleFrames];
+};
+__global__ void k_sample_gather_batch(const __grid_constant__ SampleBatch b) {
+  const dns_sample_args& a = b.f[blockIdx.y];
+  if ((int)(blockIdx.x * blockDim.x) >= a.n) return;
+  sample_gather_body(a, blockIdx.x);
+}
+
 // kRaysZ rays per block, 128 threads: per-ray scalars by one thread each, then the S values, their ranks (S
 // comparisons per value) and the optional points spread over the whole block -- a single thread per ray made the
 // O(S^2) rank sort a 30 us latency chain at tracking-sized batches.
 constexpr int kRaysZ = 16;
-__global__ void __launch_bounds__(128) k_sample_z(dns_sample_args a) {
+__device__ __forceinline__ void sample_z_body(const dns_sample_args& a, int block) {
   extern __shared__ float sm[];  // [S][kRaysZ] values
   __shared__ double s_far[kRaysZ];
   __shared__ float s_d[kRaysZ];
-  const int tid = threadIdx.x, r0 = blockIdx.x * kRaysZ;
+  const int tid = threadIdx.x, r0 = block * kRaysZ;
   const int S = a.n_uniform + a.n_surface;
   const int nr = min(kRaysZ, a.n - r0);
   const float maxd = a.scratch[0];
@@ -113,6 +127,13 @@ __global__ void __launch_bounds__(128) k_sample_z(dns_sample_args a) {
       for (int c = 0; c < 3; ++c) a.pts[q * 3 + c] = __fadd_rn(a.rays_o[3 * r + c], __fmul_rn(a.rays_d[3 * r + c], z));
     }
   }
+}
+
+__global__ void __launch_bounds__(128) k_sample_z(dns_sample_args a) { sample_z_body(a, blockIdx.x); }
+__global__ void __launch_bounds__(128) k_sample_z_batch(const __grid_constant__ SampleBatch b) {
+  const dns_sample_args& a = b.f[blockIdx.y];
+  if ((int)(blockIdx.x * kRaysZ) >= a.n) return;   // uniform over the block
+  sample_z_body(a, blockIdx.x);
 }
 
 // one warp per (view, point); feats are channels-last [R][h][w][C], C == 64
@@ -192,6 +213,53 @@ int dns_sample_rays(const dns_sample_args* a, void* stream) {
   if (a->phase != 1)     // far plane, inside mask (outside count -> scratch[1]), z values
     k_sample_z<<<(a->n + kRaysZ - 1) / kRaysZ, 128, sizeof(float) * S * kRaysZ, st>>>(*a);
   return check_launch("sample_rays");
+}
+
+int dns_sample_rays_batch(const dns_sample_args* frames, int n_frames, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_frames <= 0) return DNS_OK;
+  if (!frames) {
+    set_error("sample batch: frames == NULL");
+    return DNS_ERR_ARG;
+  }
+  for (int f0 = 0; f0 < n_frames; f0 += kMaxSampleFrames) {
+    const int nf = n_frames - f0 < kMaxSampleFrames ? n_frames - f0 : kMaxSampleFrames;
+    SampleBatch b;
+    memset(&b, 0, sizeof(b));
+    int n_max = 0;
+    const int S = frames[f0].n_uniform + frames[f0].n_surface, phase = frames[f0].phase;
+    bool contiguous = true;
+    for (int f = 0; f < nf; ++f) {
+      const dns_sample_args& a = frames[f0 + f];
+      if (a.n_uniform + a.n_surface != S || a.phase != phase || a.n_uniform != frames[f0].n_uniform) {
+        set_error("sample batch: the frames of one call share n_uniform, n_surface and phase");
+        return DNS_ERR_ARG;
+      }
+      if (S < 1 || S > 256 || a.n_uniform < 0 || a.n_surface < 0) {
+        set_error("sample: need 1 <= n_uniform + n_surface <= 256");
+        return DNS_ERR_UNSUPPORTED;
+      }
+      if (a.n > 0 && a.order && (!a.slot_base || a.n_direct < 0 || a.n_direct > a.n)) {
+        set_error("sample: class-balanced draws need slot_base and 0 <= n_direct <= n");
+        return DNS_ERR_ARG;
+      }
+      b.f[f] = a;
+      if (a.n > n_max) n_max = a.n;
+      contiguous = contiguous && a.scratch == frames[f0].scratch + 2 * f;
+    }
+    if (n_max <= 0) continue;
+    PhaseScope ph(phSample, st, 3);
+    if (phase != 2) {
+      if (contiguous) cudaMemsetAsync(frames[f0].scratch, 0, 2 * sizeof(float) * nf, st);
+      else
+        for (int f = 0; f < nf; ++f)
+          if (b.f[f].n > 0) cudaMemsetAsync(b.f[f].scratch, 0, 2 * sizeof(float), st);
+      k_sample_gather_batch<<<dim3((n_max + 127) / 128, nf), 128, 0, st>>>(b);
+    }
+    if (phase != 1)
+      k_sample_z_batch<<<dim3((n_max + kRaysZ - 1) / kRaysZ, nf), 128, sizeof(float) * S * kRaysZ, st>>>(b);
+  }
+  return check_launch("sample_rays_batch");
 }
 
 int dns_feature_gather(const float* pts, int64_t P, const float* w2c, int R, const float* K, int H, int W,

@@ -73,11 +73,13 @@ def fix_surface_draw(t, n_surface):
 
 def sample_rays(cam, bound, frame, idx, window, R, T, n_samples, n_surface, t_surface, t_zero,
                 want_pts=False, t_lin=None, class_order=None, slot_base=None, n_direct=None, want_pixel=False, out=None,
-                phase=0):
+                phase=0, defer=None):
     """frame: dict(color [H,W,3] f32, depth [H,W] f32, label [H,W] i64) on the GPU; idx: flat
     window indices [n] int64 (the draws of common.py:274 / :327); window = (H0, H1, W0, W1).
     ``class_order`` / ``slot_base`` / ``n_direct``: rays >= n_direct are class-balanced draws resolved on the device
     (``order[slot_base[j] + idx]``, common.py:315-330).  ``out``: pre-allocated output slices (dict) to write into.
+    ``defer``: a list -- the filled argument block is appended to it instead of being launched; ``sample_rays_flush``
+    then runs all deferred frames in ONE pair of launches (``dns_sample_rays_batch``).
     Returns the ``samples`` fields of tracking.py:177-185 plus ``inside`` (and ``pixel`` with want_pixel)."""
     dev = frame["color"].device
     n = idx.numel()
@@ -124,11 +126,23 @@ def sample_rays(cam, bound, frame, idx, window, R, T, n_samples, n_surface, t_su
     else:
         a.n_direct = n
     a.phase = int(phase)
+    if defer is not None:
+        defer.append((a, keep))
+        return out
     _lib.check(_lib.lib().dns_sample_rays(C.byref(a), _lib.stream()))
     if not raw:
         out["inside"] = out["inside"].bool()
         out.pop("scratch")
     return out
+
+
+def sample_rays_flush(deferred):
+    """Launch the frames collected with ``sample_rays(..., defer=list)``: one gather and one z-value kernel for all of them."""
+    if not deferred:
+        return
+    arr = (_lib.SampleArgs * len(deferred))(*[a for a, _ in deferred])
+    _lib.check(_lib.lib().dns_sample_rays_batch(arr, len(deferred), _lib.stream()))
+    deferred.clear()
 
 
 def pixel_dirs(cam, idx, window):

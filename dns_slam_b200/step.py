@@ -483,6 +483,7 @@ class MappingFrameStep:
     # ------------------------------------------------------------------ stages
     def _sample(self, phase, draws):
         b = self.batch
+        pend = []          # all target frames in one pair of launches (dns_sample_rays_batch)
         for f in range(self.F):
             r0, r1 = self.ray_start[f], self.ray_start[f + 1]
             if r1 == r0:
@@ -494,7 +495,8 @@ class MappingFrameStep:
                               self.window, self.R_all[f], self.trans[f], self.ns, self.nf,
                               self.draw_view(draws, f"ts{f}", torch.float32), self.draw_view(draws, f"tz{f}", torch.float32),
                               t_lin=self.t_lin, class_order=self.tables[f][1], slot_base=self.slot_base[f],
-                              n_direct=bb - a, out=out, phase=phase)
+                              n_direct=bb - a, out=out, phase=phase, defer=pend)
+        fused.sample_rays_flush(pend)
 
     def _views(self):
         return fused.Views(self.w2c, self.cam_o, self.feats, self.ray_start)

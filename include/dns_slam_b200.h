@@ -248,6 +248,10 @@ typedef struct dns_sample_args {
 } dns_sample_args;
 
 int dns_sample_rays(const dns_sample_args* a, void* stream);
+/* The same for several frames of one iteration (the target frames of slams/mapping.py:519-531) in ONE pair of launches:
+ * frames [n_frames] (host array); all frames share n_uniform, n_surface and phase.  Results equal n_frames calls of
+ * dns_sample_rays. */
+int dns_sample_rays_batch(const dns_sample_args* frames, int n_frames, void* stream);
 
 /* Per-frame tables of the class-balanced draw (utils/common.py:312-322: torch.unique(label) + torch.nonzero per
  * class): a STABLE counting sort of the window pixels by label.  label [n_pixels] int64 with ids in [0, n_ids);
