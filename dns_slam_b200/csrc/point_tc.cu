@@ -31,9 +31,12 @@ namespace dns {
 constexpr int kTile2 = 2 * kTile;
 
 // params [n][4096] (W1[32][80] | W2[48][32]) -> bf16 hi/lo chunk tiles
-__global__ void k_prep_net80_tc(const float* __restrict__ params, uint4* __restrict__ out) {
-  const float* p = params + (int64_t)blockIdx.x * 4096;
-  uint4* o = out + (int64_t)blockIdx.x * kNetTc;
+// block 0: the coarse net -> wc; block 1 + e: class expert e -> we (one launch for both)
+__global__ void k_prep_net80_tc(const float* __restrict__ coarse, uint4* __restrict__ wc, const float* __restrict__ experts,
+                                uint4* __restrict__ we) {
+  const int e = (int)blockIdx.x - 1;
+  const float* p = e < 0 ? coarse : experts + (int64_t)e * 4096;
+  uint4* o = e < 0 ? wc : we + (int64_t)e * kNetTc;
   for (int i = threadIdx.x; i < 320 + 192; i += blockDim.x) {
     float4 a, b;
     if (i < 320) {
@@ -67,8 +70,7 @@ __global__ void k_prep_net80_tc(const float* __restrict__ params, uint4* __restr
 }
 
 int prep_nets_tc(const float* coarse, const float* experts, int n_experts, uint4* wc, uint4* we, cudaStream_t st) {
-  k_prep_net80_tc<<<1, 128, 0, st>>>(coarse, wc);
-  if (experts && n_experts > 0) k_prep_net80_tc<<<n_experts, 128, 0, st>>>(experts, we);
+  k_prep_net80_tc<<<1 + ((experts && n_experts > 0) ? n_experts : 0), 128, 0, st>>>(coarse, wc, experts, we);
   return check_launch("prep_nets_tc");
 }
 

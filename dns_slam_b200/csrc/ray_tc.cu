@@ -30,9 +30,15 @@ namespace dns {
 constexpr int kW1oBytes2 = 14 * 64 * 16;  // one bf16 half of the [64 x 112] colour|logit layer-1 weights
 
 // colour | logit layer-1 weights -> bf16 hi / lo chunk tiles [14 feature chunks][64 hidden rows][8 features]
+// (+ the colour head's layer 2 as W2cT [32][4], what k_transpose_out computes for the SIMT path: one launch fewer)
 __global__ void k_prep_w1o_tc(const float* __restrict__ color, const float* __restrict__ logit, uint4* __restrict__ hi,
-                              uint4* __restrict__ lo, uint4* __restrict__ hi16, uint4* __restrict__ lo16) {
+                              uint4* __restrict__ lo, uint4* __restrict__ hi16, uint4* __restrict__ lo16,
+                              float* __restrict__ W2cT) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (W2cT && i < 128) {
+    const int j = i >> 2, c = i & 3;
+    W2cT[i] = c < 3 ? color[32 * kIn2 + c * 32 + j] : 0.f;
+  }
   if (i >= 14 * 64) return;
   int c = i >> 6, j = i & 63;
   const float* src = (j < 32 ? color + j * kIn2 : logit + (j - 32) * kIn2) + 8 * c;
@@ -647,7 +653,7 @@ int launch_ray_tc(const RayArgs& ra, const float* color, const float* logit, uin
                   int64_t n_rays_chunk, cudaStream_t st) {
   if (prep)
     k_prep_w1o_tc<<<(14 * 64 + 127) / 128, 128, 0, st>>>(color, logit, w1_hi, w1_lo, const_cast<uint4*>(ra.w16_hi),
-                                                         const_cast<uint4*>(ra.w16_lo));
+                                                         const_cast<uint4*>(ra.w16_lo), const_cast<float*>(ra.W2cT));
   return launch_ray_tc2(ra, w1_hi, w1_lo, n_rays_chunk, st);
 }
 

@@ -891,8 +891,8 @@ static int64_t carve(RenderWs& w, char* base, int mode, int64_t Nc, int S, int C
   w.tiles = (Pc + kTile - 1) / kTile + (map ? nci : 0);
   w.Q = w.tiles * kTile;
   const int C4 = (C + 3) & ~3;
-  w.counts = c.take<int>(16);
-  w.raw = c.take<float>(16);
+  w.counts = c.take<int>(32);                          // counts [16] | raw [16]: one block, one memset per call
+  w.raw = reinterpret_cast<float*>(w.counts ? w.counts + 16 : nullptr);
   w.hist = c.take<int>(nci + 1);
   w.slot_start = c.take<int>(nci + 2);
   w.cursor = c.take<int>(nci + 1);
@@ -1033,8 +1033,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
   const bool tc = !a->use_simt;
   // weight preparation: bf16 hi/lo chunk tiles (tcgen05 path) or k-major fp32 copies (SIMT path)
   PhaseScope* ph = new PhaseScope(phPrep, st, 1 + (a->global_counts ? 0 : 1) + (map ? 2 : 1));
-  cudaMemsetAsync(w.counts, 0, 16 * sizeof(int), st);
-  cudaMemsetAsync(w.raw, 0, 16 * sizeof(float), st);
+  cudaMemsetAsync(w.counts, 0, 32 * sizeof(int), st);   // counts and raw loss partials
   if (!tc) {
     k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, w.WTc);
     if (map) k_transpose_net80<<<a->n_experts, 256, 0, st>>>(a->experts, w.WTe);
@@ -1042,7 +1041,7 @@ int dns_render_fwd_bwd(const dns_render_args* a, void* stream) {
     delete ph;
     return e;
   }
-  k_transpose_out<<<1, 256, 0, st>>>(a->color, a->logit, w.W1T2, w.W2cT);
+  if (!tc) k_transpose_out<<<1, 256, 0, st>>>(a->color, a->logit, w.W1T2, w.W2cT);   // tcgen05 path: k_prep_w1o_tc writes W2cT
   {
     if (a->global_counts) {
       cudaMemcpyAsync(w.counts, a->global_counts, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st);
@@ -1317,7 +1316,7 @@ int dns_tv_fwd_bwd(const dns_tv_args* a, void* stream) {
     cudaFuncSetAttribute(k_point_fwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_point_bwd<kTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   }
-  k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, WTc);
+  if (a->use_simt) k_transpose_net80<<<1, 256, 0, st>>>(a->coarse, WTc);   // k-major fp32 copy: SIMT kernels only
   cudaMemsetAsync(a->loss, 0, sizeof(float), st);
   PointArgs pa;
   memset(&pa, 0, sizeof(pa));
