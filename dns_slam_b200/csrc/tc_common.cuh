@@ -63,72 +63,6 @@ __device__ __forceinline__ float oneblob16_bwd(float x, const float (&d)[16]) {
   }
   return -16.0f * acc;
 }
-// Register-resident hash-grid forward / backward for the tcgen05 kernels: the 16-level loop is FULLY unrolled so
-// that the 32 features (or their gradients) are compile-time-indexed registers.  (A dynamically indexed per-thread
-// array lives in local memory; ncu showed 53 % of k_point_bwd_tc's stall samples on the first use of such a load.)
-__device__ __forceinline__ void hashgrid_fwd_regs(const dns_grid& G, const float2* __restrict__ table, const float x[3],
-                                                  float (&out)[32]) {
-#pragma unroll
-  for (int l = 0; l < 16; ++l) {
-    uint32_t g[3];
-    float w[3];
-    const float sc = G.scale[l];
-    grid_pos(x[0], sc, g[0], w[0]);
-    grid_pos(x[1], sc, g[1], w[1]);
-    grid_pos(x[2], sc, g[2], w[2]);
-    float2 v[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      v[c] = __ldg(table + corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
-      a0 += wt * v[c].x;
-      a1 += wt * v[c].y;
-    }
-    out[2 * l] = a0;
-    out[2 * l + 1] = a1;
-  }
-}
-__device__ __forceinline__ void hashgrid_bwd_regs(const dns_grid& G, const float2* __restrict__ table, float2* d_table,
-                                                  const float x[3], const float (&dg)[32], bool want_dx, float dx[3]) {
-  dx[0] = dx[1] = dx[2] = 0.f;
-#pragma unroll
-  for (int l = 0; l < 16; ++l) {
-    const float g0 = dg[2 * l], g1 = dg[2 * l + 1];
-    if (g0 == 0.f && g1 == 0.f) continue;
-    uint32_t g[3];
-    float w[3];
-    const float sc = G.scale[l];
-    grid_pos(x[0], sc, g[0], w[0]);
-    grid_pos(x[1], sc, g[1], w[1]);
-    grid_pos(x[2], sc, g[2], w[2]);
-    uint32_t idx[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      idx[c] = corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2));
-    if (d_table) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
-        atomicAdd(d_table + idx[c], make_float2(wt * g0, wt * g1));
-      }
-    }
-    if (want_dx) {
-      float s[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float2 v = __ldg(table + idx[c]);
-        s[c] = v.x * g0 + v.y * g1;
-      }
-      const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
-      dx[0] += sc * (wy0 * wz0 * (s[1] - s[0]) + w[1] * wz0 * (s[3] - s[2]) + wy0 * w[2] * (s[5] - s[4]) + w[1] * w[2] * (s[7] - s[6]));
-      dx[1] += sc * (wx0 * wz0 * (s[2] - s[0]) + w[0] * wz0 * (s[3] - s[1]) + wx0 * w[2] * (s[6] - s[4]) + w[0] * w[2] * (s[7] - s[5]));
-      dx[2] += sc * (wx0 * wy0 * (s[4] - s[0]) + w[0] * wy0 * (s[5] - s[1]) + wx0 * w[1] * (s[6] - s[2]) + w[0] * w[1] * (s[7] - s[3]));
-    }
-  }
-}
 // Table entries of the x and x+1 corners of one cell edge.  They are neighbours in memory (dense levels: consecutive
 // indices; hashed levels: the x prime is 1, so an even x only flips bit 0); when they share an aligned 16-byte pair,
 // one 16-byte load fetches both (a quarter fewer L1 / L2 requests over the 8 corners).
@@ -142,33 +76,6 @@ __device__ __forceinline__ void load_corner_pair(const float2* __restrict__ tabl
   } else {
     v0 = __ldg(table + i0);
     v1 = __ldg(table + i1);
-  }
-}
-// Level ranges of the same, for kernels that split one point's levels over two threads.
-template <int L0, int L1>
-__device__ __forceinline__ void hashgrid_fwd_range(const dns_grid& G, const float2* __restrict__ table, const float x[3],
-                                                   float (&out)[2 * (L1 - L0)]) {
-#pragma unroll
-  for (int l = L0; l < L1; ++l) {
-    uint32_t g[3];
-    float w[3];
-    const float sc = G.scale[l];
-    grid_pos(x[0], sc, g[0], w[0]);
-    grid_pos(x[1], sc, g[1], w[1]);
-    grid_pos(x[2], sc, g[2], w[2]);
-    float2 v[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      v[c] = __ldg(table + corner_index(G, l, g[0] + (c & 1), g[1] + ((c >> 1) & 1), g[2] + (c >> 2)));
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
-      a0 += wt * v[c].x;
-      a1 += wt * v[c].y;
-    }
-    out[2 * (l - L0)] = a0;
-    out[2 * (l - L0) + 1] = a1;
   }
 }
 // Rolled variant for the forward tile: each level's feature pair goes straight into the bf16 hi / lo operand tile
@@ -216,7 +123,7 @@ __device__ __forceinline__ void hashgrid_fwd_to_tile(const dns_grid& G, const fl
     if (jimg) {
       const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
       float* j6 = jj + 6 * (l - lb);     // (the loop is unrolled by two: the parity is a compile-time constant)
-      // the same corner differences and weights as the backward's dL/dx (hashgrid_bwd_range), per feature
+      // the same corner differences and weights as the backward's dL/dx (hashgrid_bwd_levels), per feature
       j6[0] = sc * (wy0 * wz0 * (v[1].x - v[0].x) + w[1] * wz0 * (v[3].x - v[2].x) + wy0 * w[2] * (v[5].x - v[4].x) + w[1] * w[2] * (v[7].x - v[6].x));
       j6[1] = sc * (wx0 * wz0 * (v[2].x - v[0].x) + w[0] * wz0 * (v[3].x - v[1].x) + wx0 * w[2] * (v[6].x - v[4].x) + w[0] * w[2] * (v[7].x - v[5].x));
       j6[2] = sc * (wx0 * wy0 * (v[4].x - v[0].x) + w[0] * wy0 * (v[5].x - v[1].x) + wx0 * w[1] * (v[6].x - v[2].x) + w[0] * w[1] * (v[7].x - v[3].x));
@@ -249,61 +156,15 @@ __device__ __forceinline__ void hashgrid_dx_from_jimg(const float4* __restrict__
     }
   }
 }
-template <int L0, int L1, bool PAIR = true>
-__device__ __forceinline__ void hashgrid_bwd_range(const dns_grid& G, const float2* __restrict__ table, float2* d_table_all,
-                                                   const float x[3], const float (&dg)[2 * (L1 - L0)], bool want_dx,
-                                                   float dx[3], float2* d_priv = nullptr, int priv_levels = 0) {
-  dx[0] = dx[1] = dx[2] = 0.f;
-#pragma unroll
-  for (int l = L0; l < L1; ++l) {
-    float2* d_table = (d_table_all && l < priv_levels) ? d_priv : d_table_all;   // this CTA's private copy of a small level
-    const float g0 = dg[2 * (l - L0)], g1 = dg[2 * (l - L0) + 1];
-    if (g0 == 0.f && g1 == 0.f) continue;
-    uint32_t g[3];
-    float w[3];
-    const float sc = G.scale[l];
-    grid_pos(x[0], sc, g[0], w[0]);
-    grid_pos(x[1], sc, g[1], w[1]);
-    grid_pos(x[2], sc, g[2], w[2]);
-    uint32_t idx[8];
-    corner_indices8(G, l, g, idx);
-    if (d_table) {
-      // The x and x+1 corners of a cell edge are neighbours in memory (dense levels: consecutive indices; hashed
-      // levels: the x prime is 1, so an even x only flips bit 0).  When they share an aligned 16-byte pair, ONE
-      // vector reduction carries both: a quarter fewer operations for the L2 atomic units that bound this kernel.
-#pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        const float wyz = ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
-        const float w0 = (1.f - w[0]) * wyz, w1 = w[0] * wyz;
-        const uint32_t i0 = idx[c], i1 = idx[c + 1];
-        if (PAIR && ((i0 ^ i1) == 1u)) {
-          const bool odd = i0 & 1u;
-          const float wa = odd ? w1 : w0, wb = odd ? w0 : w1;     // weights of entries (base, base + 1)
-          atomicAdd(reinterpret_cast<float4*>(d_table + (i0 & ~1u)), make_float4(wa * g0, wa * g1, wb * g0, wb * g1));
-        } else {
-          atomicAdd(d_table + i0, make_float2(w0 * g0, w0 * g1));
-          atomicAdd(d_table + i1, make_float2(w1 * g0, w1 * g1));
-        }
-      }
-    }
-    if (want_dx) {
-      float s[8];   // (pairing these re-reads like the forward gathers was measured slower here: 6.9 -> 7.7 ms)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float2 v = __ldg(table + idx[c]);
-        s[c] = v.x * g0 + v.y * g1;
-      }
-      const float wx0 = 1.f - w[0], wy0 = 1.f - w[1], wz0 = 1.f - w[2];
-      dx[0] += sc * (wy0 * wz0 * (s[1] - s[0]) + w[1] * wz0 * (s[3] - s[2]) + wy0 * w[2] * (s[5] - s[4]) + w[1] * w[2] * (s[7] - s[6]));
-      dx[1] += sc * (wx0 * wz0 * (s[2] - s[0]) + w[0] * wz0 * (s[3] - s[1]) + wx0 * w[2] * (s[6] - s[4]) + w[0] * w[2] * (s[7] - s[5]));
-      dx[2] += sc * (wx0 * wy0 * (s[4] - s[0]) + w[0] * wy0 * (s[5] - s[1]) + wx0 * w[1] * (s[6] - s[2]) + w[0] * w[1] * (s[7] - s[3]));
-    }
-  }
-}
-// hashgrid_bwd_range with the level loop ROLLED: dg (element k at dgs[k * dgs_stride], the thread's column of a shared-memory
-// staging area) instead of a register array.  Unrolled over eight levels the scatter alone is ~60 KB of SASS per thread group
-// and k_point_bwd_tc2<MAP> 200 KB -- beyond the instruction cache, with every warp of the SM in a different phase (ncu:
-// no_instructions 13 % of the stall samples).
+// Hash-table scatter (and, for tracking, the corner re-read of dL/dx) of levels [l0, l1) of one point.  The level loop is
+// ROLLED: dg comes from the thread's column of a shared-memory staging area (element k at dgs[k * dgs_stride]) instead of a
+// register array.  Unrolled over eight levels (round 1 / start of round 2) the scatter alone was ~60 KB of SASS per thread
+// group and k_point_bwd_tc2<MAP> 200 KB -- beyond the instruction cache, with every warp of the SM in a different phase
+// (ncu: no_instructions 13 % of the stall samples).
+// The x and x+1 corners of a cell edge are neighbours in memory (dense levels: consecutive indices; hashed levels: the x
+// prime is 1, so an even x only flips bit 0).  When they share an aligned 16-byte pair, ONE vector reduction carries both:
+// a quarter fewer operations for the L2 atomic units that bound this kernel.  (Pairing the re-reads of the tracking path
+// like the forward gathers was measured slower: 6.9 -> 7.7 ms.)
 __device__ __forceinline__ void hashgrid_bwd_levels(const dns_grid& G, const float2* __restrict__ table, float2* d_table_all,
                                                     const float x[3], const float* dgs, int dgs_stride, int l0, int l1,
                                                     bool want_dx, float dx[3], float2* d_priv, int priv_levels) {
@@ -327,7 +188,7 @@ __device__ __forceinline__ void hashgrid_bwd_levels(const dns_grid& G, const flo
         const float wyz = ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
         const float w0 = (1.f - w[0]) * wyz, w1 = w[0] * wyz;
         const uint32_t i0 = idx[c], i1 = idx[c + 1];
-        if ((i0 ^ i1) == 1u) {   // one vector reduction for an aligned x / x+1 pair (see hashgrid_bwd_range)
+        if ((i0 ^ i1) == 1u) {   // one vector reduction for an aligned x / x+1 pair
           const bool odd = i0 & 1u;
           const float wa = odd ? w1 : w0, wb = odd ? w0 : w1;
           atomicAdd(reinterpret_cast<float4*>(d_table + (i0 & ~1u)), make_float4(wa * g0, wa * g1, wb * g0, wb * g1));
