@@ -158,6 +158,91 @@ def test_sample_rays_bit_exact(golden_dir):
     assert bool((out2["z_vals"][:, 1:] >= out2["z_vals"][:, :-1]).all())
 
 
+def test_sample_rays_batch_equals_per_frame_calls(golden_dir):
+    """dns_sample_rays_batch (all target frames of an iteration in one pair of launches) gives bit for bit what one
+    dns_sample_rays call per frame gives: different ray counts per frame (one frame empty), own poses, own scratch."""
+    from oracle import cases
+    from dns_slam_b200 import fused, slam, synthetic as syn
+    from gpu_util import frame_to
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "tracking_tiny.pt"), weights_only=False)
+    meta = g["meta"]
+    inp = cases.tracking_inputs(meta)
+    cam = inp["cam"]
+    fr = frame_to(inp["frame"], dev)
+    window = (0, cam["H"], 0, cam["W"])
+    gen = torch.Generator().manual_seed(3)
+    ns, nf = meta["n_samples"], meta["n_surface"]
+    S = ns + nf
+    counts = (37, 0, 130, 5)
+    frames = []
+    for f, n in enumerate(counts):
+        q = torch.randn(4, generator=gen)
+        frames.append(dict(idx=torch.randint(0, cam["H"] * cam["W"], (n,), generator=gen).to(dev),
+                           R=slam.get_rotation_from_quad(q).to(dev), T=torch.randn(3, generator=gen).to(dev),
+                           ts=fused.fix_surface_draw(torch.rand(nf, generator=gen), nf).to(dev),
+                           tz=torch.rand(nf, generator=gen).to(dev)))
+
+    def buffers():
+        return [dict(gt_color=torch.full((n, 3), -1.0, device=dev), gt_depth=torch.full((n,), -1.0, device=dev),
+                     gt_label=torch.full((n,), -1, dtype=torch.int64, device=dev), rays_o=torch.full((n, 3), -1.0, device=dev),
+                     rays_d=torch.full((n, 3), -1.0, device=dev), z_vals=torch.full((n, S), -1.0, device=dev),
+                     inside=torch.full((n,), 7, dtype=torch.uint8, device=dev), pixel=torch.full((n,), -1, dtype=torch.int64, device=dev),
+                     scratch=torch.full((2,), -1.0, device=dev)) for n in counts]
+    one, many = buffers(), buffers()
+    pend = []
+    for f, n in enumerate(counts):
+        for outs, defer in ((one, None), (many, pend)):
+            if n == 0 and defer is None:
+                continue
+            fused.sample_rays(cam, inp["bound"], fr, frames[f]["idx"], window, frames[f]["R"], frames[f]["T"], ns, nf,
+                              frames[f]["ts"], frames[f]["tz"], out=outs[f], defer=defer)
+    assert len(pend) == len(counts)
+    fused.sample_rays_flush(pend)
+    assert not pend
+    for f, n in enumerate(counts):
+        for k in one[f]:
+            if n == 0 and k == "scratch":
+                continue     # an empty frame is not touched by either path
+            assert torch.equal(one[f][k], many[f][k]), (f, k)
+    assert float(one[2]["scratch"][0]) > 0.0   # the frame's max depth went through
+
+
+def test_map_step_result_kernel():
+    """dns_map_step_result against the scalar arithmetic it replaces (loss vector, per-frame scratch, running flags)."""
+    from dns_slam_b200 import _lib
+    dev = _dev()
+    L = _lib.lib()
+    f32 = torch.float32
+    gen = torch.Generator().manual_seed(1)
+    F = 4
+    losses = torch.rand(8, generator=gen).to(dev)
+    sm = torch.rand(1, generator=gen).to(dev)
+    scratch = torch.rand(F, 2, generator=gen).to(dev)
+    scratch[:, 1] = torch.tensor([0.0, 2.0, 0.0, 1.0])
+    loss_vec = torch.full((9,), -5.0, device=dev)
+    result = torch.zeros(11 + 2 * F, device=dev)
+    result[10 + 2 * F] = 1e9
+    w, lam = 0.5, 1e-3
+    for rep in range(2):
+        _lib.check(L.dns_map_step_result(1, _lib.ptr(losses, f32), _lib.ptr(sm, f32), w, lam * w, 1.0, _lib.ptr(scratch, f32), F,
+                                         _lib.ptr(loss_vec, f32), _lib.ptr(result, f32), _lib.stream()))
+        want = torch.cat((losses, sm * w)).clone()
+        want[6] = losses[6] + (lam * w) * sm[0]
+        assert torch.allclose(loss_vec, want, rtol=0, atol=1e-7)
+        _lib.check(L.dns_map_step_result(2, None, None, 0.0, 0.0, 0.25, _lib.ptr(scratch, f32), F, _lib.ptr(loss_vec, f32),
+                                         _lib.ptr(result, f32), _lib.stream()))
+        want[7] = want[7] * 0.25
+        assert torch.allclose(result[:9], want, rtol=0, atol=1e-7)
+        assert torch.equal(result[9:9 + 2 * F], scratch.reshape(-1))
+        assert float(result[9 + 2 * F]) == 3.0 * (rep + 1)           # rays outside the bound accumulate over the steps
+        assert abs(float(result[10 + 2 * F]) - float(want[7])) < 1e-7
+    # without a TV term, both phases in one call
+    _lib.check(L.dns_map_step_result(3, _lib.ptr(losses, f32), None, 0.0, 0.0, 1.0, _lib.ptr(scratch, f32), F,
+                                     _lib.ptr(loss_vec, f32), _lib.ptr(result, f32), _lib.stream()))
+    assert torch.allclose(result[:8], losses, rtol=0, atol=0)
+
+
 def test_feature_gather(golden_dir):
     from oracle import cases, reference_path as rp
     from dns_slam_b200 import fused
