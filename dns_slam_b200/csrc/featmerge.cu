@@ -161,7 +161,7 @@ __device__ __forceinline__ void row_geometry(const FmArgs& a, int64_t p_row, int
   g.x[0] = g.x[1] = g.x[2] = 0.f;
   if (!g.valid) return;
   g.p = p_row;
-  g.r = g.p / a.S;
+  g.r = g.p < 0x7fffffffLL ? (int64_t)((uint32_t)g.p / (uint32_t)a.S) : g.p / a.S;   // 32-bit division whenever the index allows
   g.zv = a.z[g.p];
   int f = 0;
   while (f + 1 < a.F && g.r >= a.ray_start[f + 1]) ++f;

@@ -168,7 +168,7 @@ __device__ __forceinline__ bool slot_point(const PointArgs& a, int64_t q, int64_
     i = a.perm ? (int64_t)a.perm[q] : q;
     if (i < 0 || i >= a.Pc) return false;
     int64_t p = a.p0 + i;
-    r = p / a.S;
+    r = p < 0x7fffffffLL ? (int64_t)((uint32_t)p / (uint32_t)a.S) : p / a.S;   // 32-bit division whenever the index allows
     zv = a.z[p];
     point_from_ray(a.rays_o + 3 * r, a.rays_d + 3 * r, zv, a.B, x);
     return true;

@@ -28,11 +28,21 @@ __device__ __forceinline__ void oneblob16(float x, float (&o)[16]) {
   const int bx = (int)floorf(x * 16.0f);
   int bb[3];
   float vv[3];
+  // the upper edge of a bin is the lower edge of the next one unless the bins wrap around (15 -> 0): the same expression on
+  // the same operands, so the value is reused (4 CDF triples per coordinate instead of 6)
+  float up_prev = 0.f;
+  int b_prev = -2;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int b = (bx + k - 1) & 15;
     bb[k] = b;
-    vv[k] = cdf3((float)(b + 1) / 16.0f - x, 16.0f) - cdf3((float)b / 16.0f - x, 16.0f);
+    float lo;
+    if (b == b_prev + 1) lo = up_prev;
+    else lo = cdf3((float)b / 16.0f - x, 16.0f);
+    const float up = cdf3((float)(b + 1) / 16.0f - x, 16.0f);
+    vv[k] = up - lo;
+    up_prev = up;
+    b_prev = b;
   }
 #pragma unroll
   for (int b = 0; b < 16; ++b) o[b] = b == bb[0] ? vv[0] : (b == bb[1] ? vv[1] : (b == bb[2] ? vv[2] : 0.0f));
@@ -52,14 +62,21 @@ __device__ __forceinline__ float oneblob16_bwd(float x, const float (&d)[16]) {
     return -16.0f * acc;
   }
   const int bx = (int)floorf(x * 16.0f);
-  float acc = 0.f;
+  float acc = 0.f, up_prev = 0.f;
+  int b_prev = -2;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int b = (bx + k - 1) & 15;
     float db = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) db = j == b ? d[j] : db;
-    acc += db * (pdf3((float)(b + 1) / 16.0f - x, 16.0f) - pdf3((float)b / 16.0f - x, 16.0f));
+    float lo;   // shared bin edge, see oneblob16
+    if (b == b_prev + 1) lo = up_prev;
+    else lo = pdf3((float)b / 16.0f - x, 16.0f);
+    const float up = pdf3((float)(b + 1) / 16.0f - x, 16.0f);
+    acc += db * (up - lo);
+    up_prev = up;
+    b_prev = b;
   }
   return -16.0f * acc;
 }
