@@ -1,5 +1,7 @@
 #!/bin/bash
 # L2 residency of the hash / gradient table against the streamed stash: access-policy window (ablate build, DNS_L2_WIN) and
+# (the switches live in scratch/l2_residency_experiment.patch: `patch -p0 < scratch/l2_residency_experiment.patch`, then
+#  `make ablate` and `make variant VARIANT=cs VFLAGS=-DDNS_STASH_CS`; measured slower, not part of the library)
 # streaming stores of the tile images (variant build -DDNS_STASH_CS)
 mkdir -p gpurun_out; : > gpurun_out/l2.log
 A=$PWD/dns_slam_b200/libdns_slam_b200_ablate.so
